@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — MaxSum edge-message updates/s on BASELINE.json's configs (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun)
+    python bench.py --impl reference ...                   CPU arm: the oracle port, all host threads
+
+A "step" is ONE synchronous MaxSum cycle over the whole factor graph: every factor->variable
+min-marginal and every variable->factor message recomputed (2*E edge-message updates), damping,
+send gate and value selection included.  N=1 workload: BASELINE.json configs[1]
+(random binary DCOP, 100k vars, d=10, mean degree 4).  N>1: weak scaling, one C2-sized shard of a
+single N*100k-variable graph per GPU, variable-cut partition, one NCCL halo exchange per cycle.
+
+Timing: every timed step is bracketed by CUDA events on the launching stream; L2 is flushed
+(256 MiB memset) between steps, outside the event pairs; per-rank time = sum over the K steps;
+the job time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "maxsum_edge_message_updates_per_s"
+UNIT = "updates/s"
+E2E_CYCLES = 30  # cycles per end-to-end solve (upload -> cycles -> read assignment)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_instance(inst, L):
+    tsz = np.concatenate([np.full(c.n_factors, c.table_size, np.int64) for c in L.classes]) \
+        if L.classes else np.zeros(0, np.int64)
+    # canonical table sizes (factor order of `inst`): invert the class permutation
+    t = np.zeros(L.n_factors, np.int64)
+    t[:] = tsz[L.factor_perm]
+    return dict(inst, var_ptr=L.var_ptr, var_edge=L.canon_var_edge, init_value=L.init_value,
+                table_off=np.concatenate([[0], np.cumsum(t)]))
+
+
+def cpu_baseline(inst, L, seconds=12.0, dtype=np.float32):
+    """The CPU oracle (C port of the reference algorithm, OpenMP over all host threads) timed on a
+    bounded number of cycles of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    o = orc.MaxSumOracle(oracle_instance(inst, L), dtype).init()
+    o.step(1)
+    t0 = time.perf_counter()
+    o.step(1)
+    one = time.perf_counter() - t0
+    n = int(max(2, min(200, seconds / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    o.step(n)
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return {"value": 2.0 * L.n_edges * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} cycles of the same instance, oracle/dcop_oracle.c "
+                      f"{'f32' if dtype == np.float32 else 'f64'}, OpenMP {cores} threads, {dt:.1f}s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--vars-per-gpu", type=int, default=100_000)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from pydcop_b200 import build_layout
+    from pydcop_b200.generators import algorithmic_bytes_per_cycle, config_c2
+
+    n_vars = args.vars_per_gpu * max(1, world)
+    config = {"workload": f"random binary DCOP {n_vars} vars d=10 deg=4 (BASELINE configs[1] "
+                          f"{'x%d weak' % world if world > 1 else ''})".strip(),
+              "n_vars": n_vars, "n_factors": 2 * n_vars, "n_edges": 4 * n_vars, "d": 10,
+              "params": "damping 0.5 both, stability 0.1, noise 0.01, start_messages leafs",
+              "partition": "variable-cut contiguous blocks" if world > 1 else "single GPU",
+              "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
+              "step": "one synchronous MaxSum cycle over all edges"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        inst = config_c2(seed=0, n_vars=n_vars)
+        L = build_layout(**inst)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc
+        o = orc.MaxSumOracle(oracle_instance(inst, L), np.float32).init()
+        o.step(max(1, args.warmup))
+        t0 = time.perf_counter()
+        o.step(args.steps)
+        dt = time.perf_counter() - t0
+        val = 2.0 * L.n_edges * args.steps / dt
+        cores = os.cpu_count() or 1
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} cycles, oracle/dcop_oracle.c f32 (C port of "
+                                       f"the pure-Python reference), OpenMP {cores} threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pydcop_b200.engine import MaxSumEngine
+
+    inst = config_c2(seed=0, n_vars=n_vars)
+    if world > 1:
+        from pydcop_b200.multigpu import ShardedMaxSum
+        runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision)
+        L = runner.global_layout
+    else:
+        L = build_layout(**inst)
+        runner = MaxSumEngine(L, device=dev, precision=args.precision, record_sent=True)
+    vb = 4 if args.precision == "f32" else 8
+    alg_bytes = algorithmic_bytes_per_cycle(L, vb)
+    updates_per_step = 2 * L.n_edges
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    runner.init()
+    for _ in range(max(3, args.warmup)):
+        runner.step(1)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = runner.launch_count
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        runner.step(1)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    launches = runner.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = updates_per_step / (ms_per_step * 1e-3)
+
+    # end to end through the public API: pinned host arrays -> device, E2E_CYCLES cycles, values back
+    e2e = None
+    if world == 1:
+        host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
+                (("tables", L.tables.astype(np.float32 if vb == 4 else np.float64)),
+                 ("unary", L.unary.astype(np.float32 if vb == 4 else np.float64)),
+                 ("slot_off", L.slot_off), ("slot_edge", L.slot_edge), ("slot_var", L.slot_var),
+                 ("var_ptr", L.var_ptr))}
+        out_host = torch.empty(L.n_vars, dtype=torch.int32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in host.values())
+        d2h = out_host.numel() * 4
+        times = []
+        for it in range(3 + 5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            runner.tables.copy_(host["tables"], non_blocking=True)
+            runner.unary.copy_(host["unary"], non_blocking=True)
+            runner.slot_off.copy_(host["slot_off"], non_blocking=True)
+            runner.slot_edge.copy_(host["slot_edge"], non_blocking=True)
+            runner.slot_var.copy_(host["slot_var"], non_blocking=True)
+            runner.var_ptr.copy_(host["var_ptr"], non_blocking=True)
+            runner.init()
+            runner.step(E2E_CYCLES)
+            out_host.copy_(runner.value[:L.n_vars], non_blocking=True)
+            b.record()
+            torch.cuda.synchronize(dev)
+            if it >= 3:
+                times.append(a.elapsed_time(b))
+        e2e_ms = float(np.mean(times))
+        e2e = {"value": updates_per_step * E2E_CYCLES / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "solve": f"upload tables+unary+CSR from pinned host, init + {E2E_CYCLES} cycles, "
+                        f"assignment back to host; {e2e_ms:.3f} ms per solve"}
+
+    if rank != 0:
+        return
+    peaks, peak_kind = load_peaks()
+    peak = float(peaks["hbm_gbs"])
+    per_gpu_bytes = alg_bytes / max(1, world)
+    achieved = per_gpu_bytes / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": config, "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                     "algorithmic_bytes_per_step": int(per_gpu_bytes),
+                     "bytes_per_update": alg_bytes / updates_per_step,
+                     "kernel": "f2v + v2f kernels of one cycle (whole step; per-kernel split in "
+                               "profiles/)"},
+        "e2e": e2e,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(inst, L)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

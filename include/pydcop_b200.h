@@ -1,0 +1,190 @@
+/* pydcop_b200 — C-ABI of the B200-native factor-graph message-passing engine.
+ *
+ * The reference (Orange-OpenSource/pyDcop) is pure Python and has NO FFI: its boundary for this
+ * path is the algorithm-module surface `pydcop.algorithms.<name>` (GRAPH_TYPE / algo_params /
+ * build_computation / computation_memory / communication_load,
+ * pydcop/algorithms/__init__.py:508-566, pydcop/infrastructure/computations.py:1156-1165).
+ * pydcop_b200/algorithms/{maxsum_gpu,dsa_gpu}.py implement that surface; THIS header is the
+ * boundary one level below it: what a reference maintainer binds with ctypes to
+ * replace, for all edges at once, the per-computation Python hot loops cited on each entry point.
+ *
+ * Conventions
+ *   - plain C, opaque handles, int return codes (0 = FG_OK), no exceptions, no torch types;
+ *   - every `dev_*` pointer is CALLER-OWNED DEVICE memory (the Python host passes
+ *     torch.Tensor.data_ptr()); the library allocates no device memory of its own;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - all calls are asynchronous on `stream`; the caller synchronises;
+ *   - value type T is float (precision = FG_F32) or double (FG_F64) for every cost/message array;
+ *   - there is NO CPU fallback: without a CUDA device every launch entry point returns
+ *     FG_ERR_CUDA and fg_last_error() says why.
+ *
+ * Data layout: factors are grouped into CLASSES of identical shape
+ * (arity, domain sizes).  Inside a class everything is affine in the factor index f:
+ *   table of f        = dev_tables + table_base + f * table_size          (row-major, axis i <->
+ *                                                                           scope position i)
+ *   message row (f,j) = msg_base + f * row_total + row_off[j], length dom[j]
+ * so the factor->variable kernel needs no index arrays at all.  The variable side sees the same
+ * message arrays through a CSR: variable v owns slots [var_ptr[v], var_ptr[v+1]); slot s points
+ * at message row slot_off[s] of edge slot_edge[s] (slots are in the reference's `links` order,
+ * pydcop/algorithms/maxsum.py:466).
+ */
+#ifndef PYDCOP_B200_H
+#define PYDCOP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_ABI_VERSION 1
+#define FG_MAX_ARITY 8
+#define FG_MAX_DOM 256
+
+enum { FG_OK = 0, FG_ERR_ARG = 1, FG_ERR_CUDA = 2, FG_ERR_UNSUPPORTED = 3 };
+enum { FG_F32 = 0, FG_F64 = 1 };
+enum { FG_START_LEAFS = 0, FG_START_LEAFS_VARS = 1, FG_START_ALL = 2 }; /* maxsum.py:219 */
+enum { FG_DSA_A = 0, FG_DSA_B = 1, FG_DSA_C = 2 };                      /* dsa.py:133 */
+
+/* One class of same-shaped factors (constraints). */
+typedef struct {
+  int32_t arity;                 /* 1..FG_MAX_ARITY */
+  int32_t dom[FG_MAX_ARITY];     /* domain size per scope position */
+  int32_t row_off[FG_MAX_ARITY]; /* offset of position j's message row inside a factor's rows */
+  int32_t row_total;             /* sum(dom) */
+  int32_t n_factors;
+  int32_t first_factor;          /* global factor index of the first factor of the class */
+  int32_t first_edge;            /* global edge index of its first edge; edge(f,j)=first_edge+f*arity+j */
+  int64_t table_size;            /* prod(dom) */
+  int64_t table_base;            /* element offset into dev_tables */
+  int64_t msg_base;              /* element offset into the message arrays */
+} fg_class_t;
+
+/* ------------------------------------------------------------------------------------------
+ * MaxSum  (replaces MaxSumFactorComputation.on_new_cycle maxsum.py:339-379 +
+ * factor_costs_for_var :382-447, MaxSumVariableComputation.on_new_cycle :525-565 +
+ * select_value :584-620 + costs_for_factor :623-676, apply_damping :679-685, approx_match
+ * :688-710, and both on_start methods :305-328, :495-523 — for ALL factors/variables at once)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t abi_version; /* FG_ABI_VERSION */
+  int32_t precision;   /* FG_F32 | FG_F64 */
+  int32_t n_vars, n_factors, n_edges, n_classes;
+  int64_t n_msg;       /* total message elements = sum over edges of dom */
+  const fg_class_t *classes; /* HOST array [n_classes], copied by fg_maxsum_create */
+
+  /* problem (device, read-only) */
+  const void *dev_tables;       /* T[sum table_size] */
+  const void *dev_unary;        /* T[sum dom_size]  variable costs (+noise), maxsum.py:477-487 */
+  const int32_t *dev_dom_size;  /* [n_vars] */
+  const int64_t *dev_unary_off; /* [n_vars+1] */
+  const int32_t *dev_var_ptr;   /* [n_vars+1] */
+  const int64_t *dev_slot_off;  /* [n_edges] message-row offset of slot s */
+  const int32_t *dev_slot_edge; /* [n_edges] edge id of slot s */
+  const int32_t *dev_slot_var;  /* [n_edges] variable of slot s */
+  const int32_t *dev_init_value; /* [n_vars] initial_value index or -1 (maxsum.py:497-500) */
+
+  /* state (device, read-write).  q = variable->factor, r = factor->variable; [0]/[1] are the
+   * Jacobi double buffers, the engine tracks which one is current. */
+  void *dev_q[2], *dev_r[2];       /* T[n_msg] each */
+  uint8_t *dev_q_valid, *dev_r_valid; /* [n_edges] edge order: receiver holds a message */
+  uint8_t *dev_q_cnt;              /* [n_edges] SLOT order: bit0 has-prev, bits1.. send count */
+  uint8_t *dev_r_cnt;              /* [n_edges] edge order: same encoding */
+  uint8_t *dev_q_sent, *dev_r_sent; /* [n_edges] edge order: message posted in the last cycle
+                                       (may be NULL: not recorded) */
+  int32_t *dev_value;              /* [n_vars] selected value index (select_value) */
+  void *dev_value_cost;            /* T[n_vars] its cost */
+
+  /* algorithm parameters (maxsum.py:212-220) */
+  int32_t mode_max;      /* 0 'min', 1 'max' */
+  int32_t damp_vars, damp_factors; /* damping_nodes in {vars,both} / {factors,both} */
+  int32_t start_messages; /* FG_START_* */
+  double damping, stability;
+} fg_maxsum_desc_t;
+
+typedef struct fg_maxsum *fg_maxsum_t;
+
+int fg_abi_version(void);
+/* Number of CUDA devices visible to the library (0 when none / driver missing). */
+int fg_device_count(void);
+
+int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out);
+int fg_maxsum_destroy(fg_maxsum_t h);
+const char *fg_maxsum_last_error(fg_maxsum_t h);
+/* cycle 0: every computation's on_start (maxsum.py:305-328, 495-523). */
+int fg_maxsum_init(fg_maxsum_t h, void *stream);
+/* n_cycles synchronous cycles (one = every factor's and every variable's on_new_cycle). */
+int fg_maxsum_step(fg_maxsum_t h, int32_t n_cycles, void *stream);
+/* Split-phase variant for the multi-GPU host loop: launch the compute of ONE cycle (writes the
+ * `next` buffers), let the caller exchange halos on them, then commit (swap buffers). */
+int fg_maxsum_cycle_compute(fg_maxsum_t h, void *stream);
+int fg_maxsum_cycle_commit(fg_maxsum_t h);
+/* Index (0/1) of the CURRENT message buffers and the number of cycles done so far. */
+int fg_maxsum_current(fg_maxsum_t h, int32_t *buf_index, int64_t *cycle);
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t fg_maxsum_launch_count(fg_maxsum_t h);
+
+/* Gather / scatter of boundary message rows for the halo exchange (replaces
+ * Messaging.post_msg for cut edges, pydcop/infrastructure/communication.py:588-698).
+ * rows: `n_rows` (offset,len) pairs in dev_row_off/dev_row_len; packed back to back. */
+int fg_halo_pack(int32_t precision, const void *dev_src, void *dev_packed,
+                 const int64_t *dev_row_off, const int64_t *dev_packed_off,
+                 const int32_t *dev_row_len, int64_t n_rows, void *stream);
+int fg_halo_unpack(int32_t precision, void *dev_dst, const void *dev_packed,
+                   const int64_t *dev_row_off, const int64_t *dev_packed_off,
+                   const int32_t *dev_row_len, int64_t n_rows, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DSA  (replaces DsaComputation.on_start dsa.py:277-299 and evaluate_cycle :320-357 with
+ * find_optimal relations.py:1594-1638, assignment_cost :1479-1532, variant_a/b/c dsa.py:359-405,
+ * probabilistic_change :407-417, exists_violated_constraint :419-431, find_optimum
+ * relations.py:1367-1400 — for ALL variables at once).  Random draws are Philox4x32-10 keyed by
+ * (seed; variable, cycle): u = 53-bit uniform, choice = (word*n)>>32 (oracle/philox.py).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t abi_version, precision;
+  int32_t n_vars, n_factors, n_edges, n_classes;
+  const fg_class_t *classes;     /* HOST [n_classes] */
+  const void *dev_tables;        /* T[...] */
+  const int32_t *dev_dom_size;   /* [n_vars] */
+  const int32_t *dev_edge_var;   /* [n_edges] variable of edge e (class-major edge order) */
+  const int32_t *dev_edge_class; /* [n_edges] class of edge e */
+  const int32_t *dev_var_ptr;    /* [n_vars+1] */
+  const int32_t *dev_slot_edge;  /* [n_edges] incident edges of v in node.constraints order */
+  const uint8_t *dev_has_nbr;    /* [n_vars] variable has >= 1 neighbour (dsa.py:278) */
+  const double *dev_prob;        /* [n_vars] change threshold (p_mode fixed|arity, dsa.py:252-263) */
+  void *dev_con_opt;             /* T[n_factors] per-constraint optimum, filled by fg_dsa_init */
+  int32_t *dev_value[2];         /* [n_vars] current / next value index (double buffer) */
+  void *dev_value_cost;          /* T[n_vars] cost reported with the last selection */
+  int32_t mode_max, variant;     /* FG_DSA_* */
+  int32_t stop_cycle;            /* 0 = never (dsa.py:134,352) */
+  uint64_t seed;
+} fg_dsa_desc_t;
+
+typedef struct fg_dsa *fg_dsa_t;
+
+int fg_dsa_create(const fg_dsa_desc_t *desc, fg_dsa_t *out);
+int fg_dsa_destroy(fg_dsa_t h);
+const char *fg_dsa_last_error(fg_dsa_t h);
+/* on_start: per-constraint optima + random initial values (isolated variables keep the value
+ * the host stored in dev_value[0], dsa.py:278-289). */
+int fg_dsa_init(fg_dsa_t h, void *stream);
+/* up to n_cycles evaluate_cycle rounds (stops at stop_cycle). */
+int fg_dsa_step(fg_dsa_t h, int32_t n_cycles, void *stream);
+int fg_dsa_cycle_compute(fg_dsa_t h, void *stream);
+int fg_dsa_cycle_commit(fg_dsa_t h);
+int fg_dsa_current(fg_dsa_t h, int32_t *buf_index, int64_t *cycle);
+int64_t fg_dsa_launch_count(fg_dsa_t h);
+
+/* Solution cost (next-tier row §8f.1; pydcop/dcop/dcop.py:319-367): sum over factors of
+ * table[value of scope] + sum over variables of unary[value]; one double in dev_out[0], number of
+ * factors at +/-infinity ("violations") in dev_out[1]. */
+int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_class_t *classes,
+                     const void *dev_tables, const int32_t *dev_edge_var,
+                     const int32_t *dev_value, const void *dev_unary,
+                     const int64_t *dev_unary_off, int32_t n_vars, double *dev_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYDCOP_B200_H */

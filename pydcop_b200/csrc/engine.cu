@@ -1,0 +1,416 @@
+// C-ABI of the pydcop_b200 engine (include/pydcop_b200.h): handle management and kernel launch
+// sequencing.  No torch, no host-side arithmetic on messages, no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "dsa_generic.cuh"
+#include "maxsum_generic.cuh"
+#include "maxsum_fast.cuh"
+#include "dsa_fast.cuh"
+
+namespace {
+
+template <typename T> constexpr size_t tsize() { return sizeof(T); }
+inline size_t prec_size(int precision) { return precision == FG_F64 ? 8 : 4; }
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+struct fg_maxsum {
+  fg_maxsum_desc_t d;
+  std::vector<fg_class_t> classes;
+  MaxSumFastPlan fast;
+  int cur = 0;
+  int64_t cycle = 0;
+  int64_t launches = 0;
+  char err[512] = {0};
+};
+
+struct fg_dsa {
+  fg_dsa_desc_t d;
+  std::vector<fg_class_t> classes;
+  fg_class_t *dev_classes = nullptr;
+  int cur = 0;
+  int64_t cycle = 0;
+  int64_t launches = 0;
+  char err[512] = {0};
+};
+
+static char g_static_err[256] = "invalid handle";
+
+extern "C" int fg_abi_version(void) { return FG_ABI_VERSION; }
+
+extern "C" int fg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static int check_class(const fg_class_t &c, char *err, size_t n) {
+  if (c.arity < 1 || c.arity > FG_MAX_ARITY) { snprintf(err, n, "class arity %d out of range", c.arity); return FG_ERR_ARG; }
+  int64_t ts = 1; int rt = 0;
+  for (int i = 0; i < c.arity; ++i) {
+    if (c.dom[i] < 1 || c.dom[i] > FG_MAX_DOM) { snprintf(err, n, "domain size %d out of range", c.dom[i]); return FG_ERR_ARG; }
+    if (c.row_off[i] != rt) { snprintf(err, n, "row_off mismatch"); return FG_ERR_ARG; }
+    ts *= c.dom[i]; rt += c.dom[i];
+  }
+  if (ts != c.table_size || rt != c.row_total) { snprintf(err, n, "class size mismatch"); return FG_ERR_ARG; }
+  return FG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxSum
+// ---------------------------------------------------------------------------------------------
+extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) {
+  if (!desc || !out) return FG_ERR_ARG;
+  *out = nullptr;
+  if (desc->abi_version != FG_ABI_VERSION) return FG_ERR_ARG;
+  if (desc->precision != FG_F32 && desc->precision != FG_F64) return FG_ERR_ARG;
+  fg_maxsum *h = new (std::nothrow) fg_maxsum();
+  if (!h) return FG_ERR_ARG;
+  h->d = *desc;
+  h->classes.assign(desc->classes, desc->classes + desc->n_classes);
+  h->d.classes = h->classes.data();
+  *out = h;
+  for (auto &c : h->classes) {
+    int rc = check_class(c, h->err, sizeof(h->err));
+    if (rc != FG_OK) return rc;
+  }
+  if (fg_device_count() <= 0) {
+    snprintf(h->err, sizeof(h->err), "no CUDA device visible: pydcop_b200 has no CPU fallback");
+    return FG_ERR_CUDA;
+  }
+  maxsum_fast_plan(h->d, h->classes, h->fast);
+  return FG_OK;
+}
+
+extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
+  delete h;
+  return FG_OK;
+}
+
+extern "C" const char *fg_maxsum_last_error(fg_maxsum_t h) { return h ? h->err : g_static_err; }
+
+template <typename T>
+static int maxsum_init_t(fg_maxsum *h, cudaStream_t st) {
+  const fg_maxsum_desc_t &d = h->d;
+  const size_t mb = (size_t)d.n_msg * sizeof(T);
+  for (int b = 0; b < 2; ++b) {
+    CUDA_TRY(h, cudaMemsetAsync(d.dev_q[b], 0, mb, st));
+    CUDA_TRY(h, cudaMemsetAsync(d.dev_r[b], 0, mb, st));
+  }
+  uint8_t *bytes[] = {d.dev_q_valid, d.dev_r_valid, d.dev_q_cnt, d.dev_r_cnt, d.dev_q_sent, d.dev_r_sent};
+  for (uint8_t *p : bytes)
+    if (p && d.n_edges) CUDA_TRY(h, cudaMemsetAsync(p, 0, (size_t)d.n_edges, st));
+  VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_slot_off, d.dev_slot_edge, d.dev_slot_var};
+  if (d.n_vars) {
+    k_v2f_start<T><<<blocks_for(d.n_vars, 128), 128, 0, st>>>(
+        g, d.n_vars, (const T *)d.dev_unary, d.dev_init_value, (T *)d.dev_q[0], d.dev_q_valid,
+        d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, d.mode_max, d.start_messages);
+    ++h->launches;
+  }
+  for (const fg_class_t &c : h->classes) {
+    bool posts = (c.arity == 1 && d.start_messages <= FG_START_LEAFS_VARS) || d.start_messages == FG_START_ALL;
+    if (!posts || c.n_factors == 0) continue;
+    k_f2v_start<T><<<blocks_for((int64_t)c.n_factors * c.arity, 128), 128, 0, st>>>(
+        c, (const T *)d.dev_tables, (T *)d.dev_r[0], d.dev_r_valid, d.dev_r_sent, d.mode_max);
+    ++h->launches;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->cur = 0;
+  h->cycle = 0;
+  return FG_OK;
+}
+
+extern "C" int fg_maxsum_init(fg_maxsum_t h, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->d.precision == FG_F64 ? maxsum_init_t<double>(h, st) : maxsum_init_t<float>(h, st);
+}
+
+template <typename T>
+static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
+  const fg_maxsum_desc_t &d = h->d;
+  const int cur = h->cur, nxt = cur ^ 1;
+  const bool first = (h->cycle == 0);  // cycle 1 consults the validity arrays
+  MaxSumParams p{d.mode_max, d.damp_vars, d.damp_factors, d.damping, 1.0 - d.damping, d.stability};
+  const T *q_cur = (const T *)d.dev_q[cur], *r_cur = (const T *)d.dev_r[cur];
+  T *q_next = (T *)d.dev_q[nxt], *r_next = (T *)d.dev_r[nxt];
+  // factor -> variable
+  for (size_t ci = 0; ci < h->classes.size(); ++ci) {
+    const fg_class_t &c = h->classes[ci];
+    if (c.n_factors == 0) continue;
+    if (!first && maxsum_fast_f2v<T>(h->fast, (int)ci, c, d, q_cur, r_cur, r_next, p, st, h->launches)) continue;
+    const int64_t n = (int64_t)c.n_factors * c.arity;
+    if (first)
+      k_f2v_generic<T, 1><<<blocks_for(n, 128), 128, 0, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next,
+                                                             d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
+    else
+      k_f2v_generic<T, 0><<<blocks_for(n, 128), 128, 0, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next,
+                                                             d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
+    ++h->launches;
+  }
+  // variable -> factor (+ value selection)
+  if (d.n_edges) {
+    if (!(!first && maxsum_fast_v2f<T>(h->fast, d, r_cur, q_cur, q_next, p, st, h->launches))) {
+      VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_slot_off, d.dev_slot_edge, d.dev_slot_var};
+      if (first)
+        k_v2f_generic<T, 1><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
+            g, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
+            d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+      else
+        k_v2f_generic<T, 0><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
+            g, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
+            d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+      ++h->launches;
+    }
+  }
+  if (first && d.n_edges) {  // every edge has posted in cycle 1: all messages are valid from now on
+    CUDA_TRY(h, cudaMemsetAsync(d.dev_q_valid, 1, (size_t)d.n_edges, st));
+    CUDA_TRY(h, cudaMemsetAsync(d.dev_r_valid, 1, (size_t)d.n_edges, st));
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return FG_OK;
+}
+
+extern "C" int fg_maxsum_cycle_compute(fg_maxsum_t h, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->d.precision == FG_F64 ? maxsum_compute_t<double>(h, st) : maxsum_compute_t<float>(h, st);
+}
+
+extern "C" int fg_maxsum_cycle_commit(fg_maxsum_t h) {
+  if (!h) return FG_ERR_ARG;
+  h->cur ^= 1;
+  ++h->cycle;
+  return FG_OK;
+}
+
+extern "C" int fg_maxsum_step(fg_maxsum_t h, int32_t n_cycles, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  for (int i = 0; i < n_cycles; ++i) {
+    int rc = fg_maxsum_cycle_compute(h, stream);
+    if (rc != FG_OK) return rc;
+    fg_maxsum_cycle_commit(h);
+  }
+  return FG_OK;
+}
+
+extern "C" int fg_maxsum_current(fg_maxsum_t h, int32_t *buf_index, int64_t *cycle) {
+  if (!h) return FG_ERR_ARG;
+  if (buf_index) *buf_index = h->cur;
+  if (cycle) *cycle = h->cycle;
+  return FG_OK;
+}
+
+extern "C" int64_t fg_maxsum_launch_count(fg_maxsum_t h) { return h ? h->launches : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// halo pack / unpack: one warp per boundary row
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool PACK>
+__global__ void k_halo_rows(T *__restrict__ arr, T *__restrict__ packed, const int64_t *__restrict__ row_off,
+                            const int64_t *__restrict__ packed_off, const int32_t *__restrict__ row_len,
+                            int64_t n_rows) {
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= n_rows) return;
+  const int64_t a = row_off[w], b = packed_off[w];
+  const int n = row_len[w];
+  for (int x = lane; x < n; x += 32) {
+    if (PACK) packed[b + x] = arr[a + x];
+    else arr[a + x] = packed[b + x];
+  }
+}
+
+template <bool PACK>
+static int halo_rows(int32_t precision, void *arr, void *packed, const int64_t *row_off,
+                     const int64_t *packed_off, const int32_t *row_len, int64_t n_rows, void *stream) {
+  if (n_rows <= 0) return FG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned blocks = blocks_for(n_rows * 32, 256);
+  if (precision == FG_F64)
+    k_halo_rows<double, PACK><<<blocks, 256, 0, st>>>((double *)arr, (double *)packed, row_off, packed_off, row_len, n_rows);
+  else
+    k_halo_rows<float, PACK><<<blocks, 256, 0, st>>>((float *)arr, (float *)packed, row_off, packed_off, row_len, n_rows);
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
+extern "C" int fg_halo_pack(int32_t precision, const void *dev_src, void *dev_packed, const int64_t *dev_row_off,
+                            const int64_t *dev_packed_off, const int32_t *dev_row_len, int64_t n_rows, void *stream) {
+  return halo_rows<true>(precision, const_cast<void *>(dev_src), dev_packed, dev_row_off, dev_packed_off, dev_row_len, n_rows, stream);
+}
+
+extern "C" int fg_halo_unpack(int32_t precision, void *dev_dst, const void *dev_packed, const int64_t *dev_row_off,
+                              const int64_t *dev_packed_off, const int32_t *dev_row_len, int64_t n_rows, void *stream) {
+  return halo_rows<false>(precision, dev_dst, const_cast<void *>(dev_packed), dev_row_off, dev_packed_off, dev_row_len, n_rows, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// DSA
+// ---------------------------------------------------------------------------------------------
+extern "C" int fg_dsa_create(const fg_dsa_desc_t *desc, fg_dsa_t *out) {
+  if (!desc || !out) return FG_ERR_ARG;
+  *out = nullptr;
+  if (desc->abi_version != FG_ABI_VERSION) return FG_ERR_ARG;
+  if (desc->precision != FG_F32 && desc->precision != FG_F64) return FG_ERR_ARG;
+  fg_dsa *h = new (std::nothrow) fg_dsa();
+  if (!h) return FG_ERR_ARG;
+  h->d = *desc;
+  h->classes.assign(desc->classes, desc->classes + desc->n_classes);
+  h->d.classes = h->classes.data();
+  *out = h;
+  for (auto &c : h->classes) {
+    int rc = check_class(c, h->err, sizeof(h->err));
+    if (rc != FG_OK) return rc;
+  }
+  if (fg_device_count() <= 0) {
+    snprintf(h->err, sizeof(h->err), "no CUDA device visible: pydcop_b200 has no CPU fallback");
+    return FG_ERR_CUDA;
+  }
+  // the class table is the one device allocation the library owns (a few hundred bytes)
+  size_t bytes = sizeof(fg_class_t) * (h->classes.empty() ? 1 : h->classes.size());
+  CUDA_TRY(h, cudaMalloc(&h->dev_classes, bytes));
+  if (!h->classes.empty())
+    CUDA_TRY(h, cudaMemcpy(h->dev_classes, h->classes.data(), sizeof(fg_class_t) * h->classes.size(), cudaMemcpyHostToDevice));
+  return FG_OK;
+}
+
+extern "C" int fg_dsa_destroy(fg_dsa_t h) {
+  if (h && h->dev_classes) cudaFree(h->dev_classes);
+  delete h;
+  return FG_OK;
+}
+
+extern "C" const char *fg_dsa_last_error(fg_dsa_t h) { return h ? h->err : g_static_err; }
+
+static DsaSide dsa_side(const fg_dsa *h) {
+  const fg_dsa_desc_t &d = h->d;
+  return DsaSide{h->dev_classes, d.dev_dom_size, d.dev_edge_var, d.dev_edge_class, d.dev_var_ptr,
+                 d.dev_slot_edge, d.dev_has_nbr, d.dev_prob};
+}
+
+template <typename T>
+static int dsa_init_t(fg_dsa *h, cudaStream_t st) {
+  const fg_dsa_desc_t &d = h->d;
+  for (const fg_class_t &c : h->classes) {
+    if (!c.n_factors) continue;
+    k_dsa_con_opt<T><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const T *)d.dev_tables, (T *)d.dev_con_opt, d.mode_max);
+    ++h->launches;
+  }
+  if (d.n_vars) {
+    k_dsa_init<<<blocks_for(d.n_vars, 128), 128, 0, st>>>(dsa_side(h), d.n_vars, d.seed, d.dev_value[0]);
+    ++h->launches;
+    CUDA_TRY(h, cudaMemcpyAsync(d.dev_value[1], d.dev_value[0], sizeof(int32_t) * (size_t)d.n_vars, cudaMemcpyDeviceToDevice, st));
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->cur = 0;
+  h->cycle = 0;
+  return FG_OK;
+}
+
+extern "C" int fg_dsa_init(fg_dsa_t h, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->d.precision == FG_F64 ? dsa_init_t<double>(h, st) : dsa_init_t<float>(h, st);
+}
+
+template <typename T>
+static int dsa_compute_t(fg_dsa *h, cudaStream_t st) {
+  const fg_dsa_desc_t &d = h->d;
+  if (!d.n_vars) return FG_OK;
+  const int32_t *val = d.dev_value[h->cur];
+  int32_t *val_next = d.dev_value[h->cur ^ 1];
+  if (!dsa_fast_step<T>(h->d, h->classes, val, val_next, (uint32_t)h->cycle, st, h->launches)) {
+    k_dsa_step_generic<T><<<blocks_for(d.n_vars, 128), 128, 0, st>>>(
+        dsa_side(h), d.n_vars, (const T *)d.dev_tables, (const T *)d.dev_con_opt, val, val_next,
+        (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed, (uint32_t)h->cycle);
+    ++h->launches;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return FG_OK;
+}
+
+extern "C" int fg_dsa_cycle_compute(fg_dsa_t h, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  if (h->d.stop_cycle && h->cycle >= h->d.stop_cycle) return FG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->d.precision == FG_F64 ? dsa_compute_t<double>(h, st) : dsa_compute_t<float>(h, st);
+}
+
+extern "C" int fg_dsa_cycle_commit(fg_dsa_t h) {
+  if (!h) return FG_ERR_ARG;
+  if (h->d.stop_cycle && h->cycle >= h->d.stop_cycle) return FG_OK;
+  h->cur ^= 1;
+  ++h->cycle;
+  return FG_OK;
+}
+
+extern "C" int fg_dsa_step(fg_dsa_t h, int32_t n_cycles, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  for (int i = 0; i < n_cycles; ++i) {
+    if (h->d.stop_cycle && h->cycle >= h->d.stop_cycle) break;
+    int rc = fg_dsa_cycle_compute(h, stream);
+    if (rc != FG_OK) return rc;
+    fg_dsa_cycle_commit(h);
+  }
+  return FG_OK;
+}
+
+extern "C" int fg_dsa_current(fg_dsa_t h, int32_t *buf_index, int64_t *cycle) {
+  if (!h) return FG_ERR_ARG;
+  if (buf_index) *buf_index = h->cur;
+  if (cycle) *cycle = h->cycle;
+  return FG_OK;
+}
+
+extern "C" int64_t fg_dsa_launch_count(fg_dsa_t h) { return h ? h->launches : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// solution cost (dcop.py:319-367)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_cost_factors(const fg_class_t c, const T *__restrict__ tables, const int32_t *__restrict__ edge_var,
+                               const int32_t *__restrict__ value, double *__restrict__ out) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double cst = 0.0, viol = 0.0;
+  if (f < c.n_factors) {
+    int64_t idx = 0, stride = 1;
+    const int e0 = c.first_edge + f * c.arity;
+    for (int i = c.arity - 1; i >= 0; --i) { idx += (int64_t)value[edge_var[e0 + i]] * stride; stride *= c.dom[i]; }
+    double t = (double)tables[c.table_base + (int64_t)f * c.table_size + idx];
+    if (isinf(t)) viol = 1.0; else cst = t;
+  }
+  for (int o = 16; o; o >>= 1) { cst += __shfl_xor_sync(0xffffffffu, cst, o); viol += __shfl_xor_sync(0xffffffffu, viol, o); }
+  if ((threadIdx.x & 31) == 0) { if (cst != 0.0) atomicAdd(out, cst); if (viol != 0.0) atomicAdd(out + 1, viol); }
+}
+
+template <typename T>
+__global__ void k_cost_unary(const T *__restrict__ unary, const int64_t *__restrict__ unary_off,
+                             const int32_t *__restrict__ value, int n_vars, double *__restrict__ out) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double cst = (v < n_vars) ? (double)unary[unary_off[v] + value[v]] : 0.0;
+  for (int o = 16; o; o >>= 1) cst += __shfl_xor_sync(0xffffffffu, cst, o);
+  if ((threadIdx.x & 31) == 0 && cst != 0.0) atomicAdd(out, cst);
+}
+
+extern "C" int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_class_t *classes, const void *dev_tables,
+                                const int32_t *dev_edge_var, const int32_t *dev_value, const void *dev_unary,
+                                const int64_t *dev_unary_off, int32_t n_vars, double *dev_out, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(dev_out, 0, 2 * sizeof(double), st) != cudaSuccess) return FG_ERR_CUDA;
+  for (int i = 0; i < n_classes; ++i) {
+    const fg_class_t &c = classes[i];
+    if (!c.n_factors) continue;
+    if (precision == FG_F64) k_cost_factors<double><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const double *)dev_tables, dev_edge_var, dev_value, dev_out);
+    else k_cost_factors<float><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const float *)dev_tables, dev_edge_var, dev_value, dev_out);
+  }
+  if (dev_unary && n_vars) {
+    if (precision == FG_F64) k_cost_unary<double><<<blocks_for(n_vars, 128), 128, 0, st>>>((const double *)dev_unary, dev_unary_off, dev_value, n_vars, dev_out);
+    else k_cost_unary<float><<<blocks_for(n_vars, 128), 128, 0, st>>>((const float *)dev_unary, dev_unary_off, dev_value, n_vars, dev_out);
+  }
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}

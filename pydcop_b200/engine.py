@@ -1,0 +1,325 @@
+"""Python host of the B200 engine: device memory (torch), streams, and the C-ABI calls.
+
+`MaxSumEngine` / `DsaEngine` are what the pyDcop plugin modules (pydcop_b200/algorithms/) and
+bench.py drive.  All arithmetic on messages happens in libpydcop_b200.so (hand-written sm_100a
+kernels); torch only owns the buffers.  There is no CPU path: constructing an engine without a
+CUDA device raises EngineError.
+"""
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import EngineError, FgClass, FgDsaDesc, FgMaxSumDesc
+from .layout import FactorGraphLayout
+
+PRECISIONS = {"f32": (_cabi.FG_F32, torch.float32, np.float32),
+              "f64": (_cabi.FG_F64, torch.float64, np.float64)}
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise EngineError("no CUDA device: pydcop_b200 runs the MaxSum/DSA hot path on the GPU "
+                          "only (no CPU fallback)")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise EngineError(f"device must be a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _class_array(layout: FactorGraphLayout):
+    arr = (FgClass * max(1, len(layout.classes)))()
+    for i, c in enumerate(layout.classes):
+        fc = arr[i]
+        fc.arity = c.arity
+        for j in range(c.arity):
+            fc.dom[j] = c.dom[j]
+            fc.row_off[j] = c.row_off[j]
+        fc.row_total = c.row_total
+        fc.n_factors, fc.first_factor, fc.first_edge = c.n_factors, c.first_factor, c.first_edge
+        fc.table_size, fc.table_base, fc.msg_base = c.table_size, c.table_base, c.msg_base
+    return arr
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0) if t is not None \
+        else C.c_void_p(0)
+
+
+class _EngineBase:
+    def _dev(self, a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=self.device, dtype=dtype)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        if rc != _cabi.FG_OK:
+            raise EngineError(f"{what} failed (rc={rc}): {self._last_error()}")
+
+
+class MaxSumEngine(_EngineBase):
+    """All-edges-at-once synchronous MaxSum.
+
+    Parameters mirror the reference's algo_params (pydcop/algorithms/maxsum.py:212-220); `noise`
+    is applied by the caller to `layout.unary` (see pydcop_b200.noise.add_noise).
+    State after `init()` is the reference's cycle 0 (on_start); each `step()` cycle is one
+    synchronous round of every factor's and every variable's on_new_cycle.
+    """
+
+    def __init__(self, layout: FactorGraphLayout, device=None, precision="f32", mode="min",
+                 damping=0.5, damping_nodes="both", stability=0.1, start_messages="leafs",
+                 record_sent=True):
+        self.lib = _cabi.load()
+        self.device = _require_cuda(device)
+        self.layout = L = layout
+        self.precision = precision
+        prec, tdt, self.np_dtype = PRECISIONS[precision]
+        if damping_nodes not in ("vars", "factors", "both", "none"):
+            raise ValueError(f"invalid damping_nodes {damping_nodes!r}")
+        if start_messages not in _cabi.START_MESSAGES:
+            raise ValueError(f"invalid start_messages {start_messages!r}")
+        if mode not in ("min", "max"):
+            raise ValueError(f"invalid mode {mode!r}")
+        with torch.cuda.device(self.device):
+            self.tables = self._dev(L.tables, tdt)
+            self.unary = self._dev(L.unary, tdt)
+            self.dom_size = self._dev(L.dom_size, torch.int32)
+            self.unary_off = self._dev(L.unary_off, torch.int64)
+            self.var_ptr = self._dev(L.var_ptr, torch.int32)
+            self.slot_off = self._dev(L.slot_off, torch.int64)
+            self.slot_edge = self._dev(L.slot_edge, torch.int32)
+            self.slot_var = self._dev(L.slot_var, torch.int32)
+            self.init_value = self._dev(L.init_value, torch.int32)
+            z = lambda n, dt: torch.zeros(max(int(n), 1), dtype=dt, device=self.device)  # noqa
+            self.q = [z(L.n_msg, tdt), z(L.n_msg, tdt)]
+            self.r = [z(L.n_msg, tdt), z(L.n_msg, tdt)]
+            self.q_valid, self.r_valid = z(L.n_edges, torch.uint8), z(L.n_edges, torch.uint8)
+            self.q_cnt, self.r_cnt = z(L.n_edges, torch.uint8), z(L.n_edges, torch.uint8)
+            self.q_sent = z(L.n_edges, torch.uint8) if record_sent else None
+            self.r_sent = z(L.n_edges, torch.uint8) if record_sent else None
+            self.value = z(L.n_vars, torch.int32)
+            self.value_cost = z(L.n_vars, tdt)
+        self._classes = _class_array(L)
+        d = FgMaxSumDesc()
+        d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
+        d.n_vars, d.n_factors, d.n_edges = L.n_vars, L.n_factors, L.n_edges
+        d.n_classes, d.n_msg = len(L.classes), L.n_msg
+        d.classes = C.cast(self._classes, C.POINTER(FgClass))
+        d.dev_tables, d.dev_unary = _ptr(self.tables), _ptr(self.unary)
+        d.dev_dom_size, d.dev_unary_off = _ptr(self.dom_size), _ptr(self.unary_off)
+        d.dev_var_ptr, d.dev_slot_off = _ptr(self.var_ptr), _ptr(self.slot_off)
+        d.dev_slot_edge, d.dev_slot_var = _ptr(self.slot_edge), _ptr(self.slot_var)
+        d.dev_init_value = _ptr(self.init_value)
+        for b in range(2):
+            d.dev_q[b], d.dev_r[b] = self.q[b].data_ptr(), self.r[b].data_ptr()
+        d.dev_q_valid, d.dev_r_valid = _ptr(self.q_valid), _ptr(self.r_valid)
+        d.dev_q_cnt, d.dev_r_cnt = _ptr(self.q_cnt), _ptr(self.r_cnt)
+        d.dev_q_sent, d.dev_r_sent = _ptr(self.q_sent), _ptr(self.r_sent)
+        d.dev_value, d.dev_value_cost = _ptr(self.value), _ptr(self.value_cost)
+        d.mode_max = int(mode == "max")
+        d.damp_vars = int(damping_nodes in ("vars", "both"))
+        d.damp_factors = int(damping_nodes in ("factors", "both"))
+        d.start_messages = _cabi.START_MESSAGES[start_messages]
+        d.damping, d.stability = float(damping), float(stability)
+        self._desc = d
+        self._h = C.c_void_p()
+        rc = self.lib.fg_maxsum_create(C.byref(d), C.byref(self._h))
+        self._check(rc, "fg_maxsum_create")
+
+    def _last_error(self):
+        return (self.lib.fg_maxsum_last_error(self._h) or b"").decode()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.fg_maxsum_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- driving -----------------------------------------------------------------------------
+    def init(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_maxsum_init(self._h, self._stream()), "fg_maxsum_init")
+        return self
+
+    def step(self, n_cycles=1):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_maxsum_step(self._h, int(n_cycles), self._stream()),
+                        "fg_maxsum_step")
+        return self
+
+    def cycle_compute(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_maxsum_cycle_compute(self._h, self._stream()),
+                        "fg_maxsum_cycle_compute")
+
+    def cycle_commit(self):
+        self._check(self.lib.fg_maxsum_cycle_commit(self._h), "fg_maxsum_cycle_commit")
+
+    @property
+    def cur(self):
+        b, c = C.c_int32(), C.c_int64()
+        self.lib.fg_maxsum_current(self._h, C.byref(b), C.byref(c))
+        return b.value
+
+    @property
+    def cycle(self):
+        b, c = C.c_int32(), C.c_int64()
+        self.lib.fg_maxsum_current(self._h, C.byref(b), C.byref(c))
+        return c.value
+
+    @property
+    def launch_count(self):
+        return int(self.lib.fg_maxsum_launch_count(self._h))
+
+    # -- readback (canonical edge order) -----------------------------------------------------
+    def messages(self):
+        """(q, r) receiver-side message state as float64 numpy arrays in canonical edge order."""
+        g = torch.from_numpy(self.layout.message_gather_index()).to(self.device)
+        cur = self.cur
+        q = self.q[cur][g].double().cpu().numpy() if g.numel() else np.zeros(0)
+        r = self.r[cur][g].double().cpu().numpy() if g.numel() else np.zeros(0)
+        return q, r
+
+    def flags(self):
+        """dict of canonical-edge-order numpy arrays: q_valid, r_valid, q_sent, r_sent, q_cnt, r_cnt."""
+        L = self.layout
+        out = {"q_valid": L.edges_to_canonical(self.q_valid.cpu().numpy()[:L.n_edges]),
+               "r_valid": L.edges_to_canonical(self.r_valid.cpu().numpy()[:L.n_edges]),
+               "r_cnt": L.edges_to_canonical(self.r_cnt.cpu().numpy()[:L.n_edges]),
+               "q_cnt": L.slots_to_canonical_edges(self.q_cnt.cpu().numpy()[:L.n_edges])}
+        if self.q_sent is not None:
+            out["q_sent"] = L.slots_to_canonical_edges(self.q_sent.cpu().numpy()[:L.n_edges])
+            out["r_sent"] = L.edges_to_canonical(self.r_sent.cpu().numpy()[:L.n_edges])
+        return out
+
+    def values(self):
+        n = self.layout.n_vars
+        return self.value[:n].cpu().numpy(), self.value_cost[:n].double().cpu().numpy()
+
+
+class DsaEngine(_EngineBase):
+    """All-variables-at-once DSA-A/B/C (pydcop/algorithms/dsa.py:130-135 parameters)."""
+
+    def __init__(self, layout: FactorGraphLayout, device=None, precision="f32", mode="min",
+                 probability=0.7, p_mode="fixed", variant="B", stop_cycle=0, seed=0,
+                 isolated_value=None):
+        self.lib = _cabi.load()
+        self.device = _require_cuda(device)
+        self.layout = L = layout
+        prec, tdt, self.np_dtype = PRECISIONS[precision]
+        if variant not in _cabi.DSA_VARIANTS:
+            raise ValueError(f"invalid variant {variant!r}")
+        if p_mode not in ("fixed", "arity"):
+            raise ValueError(f"invalid p_mode {p_mode!r}")
+        arity = np.array([c.arity for c in L.classes], dtype=np.int64)
+        n_count = np.zeros(L.n_vars, dtype=np.int64)
+        if L.n_edges:
+            np.add.at(n_count, L.slot_var, arity[L.edge_class[L.slot_edge]] - 1)
+        has_nbr = (n_count > 0).astype(np.uint8)
+        if p_mode == "arity":  # dsa.py:257-260: 1 / n_count * 1.2
+            with np.errstate(divide="ignore"):
+                prob = np.where(n_count > 0, 1.0 / np.maximum(n_count, 1) * 1.2, 0.0)
+        else:
+            prob = np.full(L.n_vars, float(probability))
+        # isolated variables (dsa.py:278-289): argopt of (own cost, value), tuple order
+        if isolated_value is None:
+            isolated_value = np.zeros(L.n_vars, dtype=np.int32)
+            for v in np.nonzero(has_nbr == 0)[0]:
+                c = L.unary[L.unary_off[v]:L.unary_off[v + 1]]
+                if mode == "min":
+                    isolated_value[v] = int(np.argmin(c))
+                else:
+                    isolated_value[v] = int(len(c) - 1 - np.argmax(c[::-1]))
+        self.has_nbr_host, self.n_count = has_nbr, n_count
+        with torch.cuda.device(self.device):
+            self.tables = self._dev(L.tables, tdt)
+            self.dom_size = self._dev(L.dom_size, torch.int32)
+            self.edge_var = self._dev(L.edge_var, torch.int32)
+            self.edge_class = self._dev(L.edge_class, torch.int32)
+            self.var_ptr = self._dev(L.var_ptr, torch.int32)
+            self.slot_edge = self._dev(L.slot_edge, torch.int32)
+            self.has_nbr = self._dev(has_nbr, torch.uint8)
+            self.prob = self._dev(prob, torch.float64)
+            z = lambda n, dt: torch.zeros(max(int(n), 1), dtype=dt, device=self.device)  # noqa
+            self.con_opt = z(L.n_factors, tdt)
+            self.value = [self._dev(isolated_value, torch.int32) if L.n_vars else z(1, torch.int32),
+                          z(L.n_vars, torch.int32)]
+            self.value_cost = z(L.n_vars, tdt)
+        self._classes = _class_array(L)
+        d = FgDsaDesc()
+        d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
+        d.n_vars, d.n_factors, d.n_edges, d.n_classes = L.n_vars, L.n_factors, L.n_edges, len(L.classes)
+        d.classes = C.cast(self._classes, C.POINTER(FgClass))
+        d.dev_tables, d.dev_dom_size = _ptr(self.tables), _ptr(self.dom_size)
+        d.dev_edge_var, d.dev_edge_class = _ptr(self.edge_var), _ptr(self.edge_class)
+        d.dev_var_ptr, d.dev_slot_edge = _ptr(self.var_ptr), _ptr(self.slot_edge)
+        d.dev_has_nbr, d.dev_prob, d.dev_con_opt = _ptr(self.has_nbr), _ptr(self.prob), _ptr(self.con_opt)
+        d.dev_value[0], d.dev_value[1] = self.value[0].data_ptr(), self.value[1].data_ptr()
+        d.dev_value_cost = _ptr(self.value_cost)
+        d.mode_max, d.variant = int(mode == "max"), _cabi.DSA_VARIANTS[variant]
+        d.stop_cycle, d.seed = int(stop_cycle), int(seed) & (2 ** 64 - 1)
+        self._desc = d
+        self._h = C.c_void_p()
+        self._check(self.lib.fg_dsa_create(C.byref(d), C.byref(self._h)), "fg_dsa_create")
+
+    def _last_error(self):
+        return (self.lib.fg_dsa_last_error(self._h) or b"").decode()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.fg_dsa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_dsa_init(self._h, self._stream()), "fg_dsa_init")
+        return self
+
+    def step(self, n_cycles=1):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_dsa_step(self._h, int(n_cycles), self._stream()), "fg_dsa_step")
+        return self
+
+    def cycle_compute(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_dsa_cycle_compute(self._h, self._stream()), "fg_dsa_cycle_compute")
+
+    def cycle_commit(self):
+        self._check(self.lib.fg_dsa_cycle_commit(self._h), "fg_dsa_cycle_commit")
+
+    def _current(self):
+        b, c = C.c_int32(), C.c_int64()
+        self.lib.fg_dsa_current(self._h, C.byref(b), C.byref(c))
+        return b.value, c.value
+
+    @property
+    def cur(self):
+        return self._current()[0]
+
+    @property
+    def cycle(self):
+        return self._current()[1]
+
+    @property
+    def launch_count(self):
+        return int(self.lib.fg_dsa_launch_count(self._h))
+
+    def values(self):
+        return self.value[self.cur][:self.layout.n_vars].cpu().numpy()

@@ -1,0 +1,84 @@
+"""Host layout (pydcop_b200/layout.py): class-major packing is a pure re-ordering.
+
+Checked without a GPU by running the CPU oracle on the canonical instance and on the instance
+re-expressed in the layout's internal order, then mapping back."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import GOLDEN_DIR, golden_names
+from pydcop_b200.layout import build_layout, layout_from_instance, default_var_csr
+
+
+def _internal_instance(L):
+    """Re-express the packed layout as a canonical-style instance (factor-major, no padding)."""
+    factor_ptr, edge_var, tables, table_off = [0], [], [], [0]
+    for c in L.classes:
+        for f in range(c.n_factors):
+            e0 = c.first_edge + f * c.arity
+            edge_var.extend(L.edge_var[e0:e0 + c.arity])
+            factor_ptr.append(len(edge_var))
+            t0 = c.table_base + f * c.table_size
+            tables.append(L.tables[t0:t0 + c.table_size])
+            table_off.append(table_off[-1] + c.table_size)
+    return dict(dom_size=L.dom_size, factor_ptr=np.array(factor_ptr), edge_var=np.array(edge_var),
+                tables=np.concatenate(tables) if tables else np.zeros(0),
+                table_off=np.array(table_off), unary=L.unary, var_ptr=L.var_ptr,
+                var_edge=L.slot_edge, init_value=L.init_value)
+
+
+@pytest.mark.parametrize("name", ["ms_rand_mixed", "ms_arity4_mixed", "ms_secp_simple1", "ms_ising_4x4"])
+def test_layout_is_a_pure_permutation(name):
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    L = layout_from_instance(inst)
+    assert sum(c.n_factors for c in L.classes) == L.n_factors
+    assert sorted(L.edge_perm.tolist()) == list(range(L.n_edges))
+    # class bases are aligned for bulk copies
+    for c in L.classes:
+        assert c.table_base % 32 == 0 and c.msg_base % 32 == 0
+    a = orc.MaxSumOracle(inst, mode=meta["mode"], **meta["params"]).init().step(8)
+    b = orc.MaxSumOracle(_internal_instance(L), mode=meta["mode"], **meta["params"]).init().step(8)
+    # map b's (internal, unpadded) messages back to canonical order
+    d_int = L.dom_size[L.edge_var]
+    off_int = np.concatenate([[0], np.cumsum(d_int)])
+    d_can = np.diff(L.canon_msg_off)
+    start = off_int[L.edge_perm] - L.canon_msg_off[:-1]
+    g = np.repeat(start, d_can) + np.arange(L.n_msg_canonical)
+    assert np.array_equal(a.q, b.q[g]) and np.array_equal(a.r, b.r[g])
+    assert np.array_equal(a.value, b.value)
+    assert np.array_equal(a.r_sent, b.r_sent[L.edge_perm])
+    # the padded gather index used for device readback addresses the same rows
+    gi = L.message_gather_index()
+    assert len(gi) == L.n_msg_canonical and gi.max(initial=-1) < L.n_msg
+    assert np.array_equal(np.diff(gi)[np.diff(np.repeat(np.arange(L.n_edges), d_can)) == 0], 
+                          np.ones((np.diff(np.repeat(np.arange(L.n_edges), d_can)) == 0).sum()))
+
+
+def test_default_var_csr_matches_reference_links_order():
+    for name in golden_names("ms_"):
+        inst, _ = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+        vp, ve = default_var_csr(len(inst["dom_size"]), inst["edge_var"])
+        assert np.array_equal(vp, inst["var_ptr"]) and np.array_equal(ve, inst["var_edge"]), name
+
+
+def test_empty_and_degenerate_graphs():
+    L = build_layout([3, 2], [0], [], [])            # no factors at all
+    assert L.n_edges == 0 and L.n_msg == 0 and len(L.classes) == 0
+    L = build_layout([3], [0, 1], [0], [1.0, 2.0, 3.0])  # single unary factor
+    assert L.classes[0].arity == 1 and L.classes[0].dom == (3,)
+    with pytest.raises(ValueError):
+        build_layout([3], [0, 1], [0], [1.0, 2.0])   # wrong table size
+    with pytest.raises(ValueError):
+        build_layout([3], [0, 1], [1], [1.0, 2.0, 3.0])  # variable out of range
+    with pytest.raises(ValueError):
+        build_layout([300], [0, 1], [0], np.zeros(300))  # domain too large
+
+
+def test_layout_scales_vectorised():
+    rng = np.random.default_rng(0)
+    V, F, d = 20000, 40000, 10
+    ev = np.stack([rng.integers(0, V, F), rng.integers(0, V, F)], 1).reshape(-1)
+    L = build_layout(np.full(V, d), np.arange(F + 1) * 2, ev, rng.integers(0, 10, F * d * d))
+    assert L.n_edges == 2 * F and len(L.classes) == 1 and L.n_msg >= 2 * F * d
