@@ -229,8 +229,8 @@ def main():
         host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
                 (("tables", L.tables.astype(np.float32 if vb == 4 else np.float64)),
                  ("unary", L.unary.astype(np.float32 if vb == 4 else np.float64)),
-                 ("slot_off", L.slot_off), ("slot_edge", L.slot_edge), ("slot_var", L.slot_var),
-                 ("var_ptr", L.var_ptr))}
+                 ("slot_roff", L.slot_roff), ("edge_qoff", L.edge_qoff),
+                 ("slot_edge", L.slot_edge), ("slot_var", L.slot_var), ("var_ptr", L.var_ptr))}
         out_host = torch.empty(L.n_vars, dtype=torch.int32).pin_memory()
         h2d = sum(t.numel() * t.element_size() for t in host.values())
         d2h = out_host.numel() * 4
@@ -241,7 +241,8 @@ def main():
             a.record()
             runner.tables.copy_(host["tables"], non_blocking=True)
             runner.unary.copy_(host["unary"], non_blocking=True)
-            runner.slot_off.copy_(host["slot_off"], non_blocking=True)
+            runner.slot_roff.copy_(host["slot_roff"], non_blocking=True)
+            runner.edge_qoff.copy_(host["edge_qoff"], non_blocking=True)
             runner.slot_edge.copy_(host["slot_edge"], non_blocking=True)
             runner.slot_var.copy_(host["slot_var"], non_blocking=True)
             runner.var_ptr.copy_(host["var_ptr"], non_blocking=True)

@@ -23,10 +23,12 @@
  *   table of f        = dev_tables + table_base + f * table_size          (row-major, axis i <->
  *                                                                           scope position i)
  *   message row (f,j) = msg_base + f * row_total + row_off[j], length dom[j]
- * so the factor->variable kernel needs no index arrays at all.  The variable side sees the same
- * message arrays through a CSR: variable v owns slots [var_ptr[v], var_ptr[v+1]); slot s points
- * at message row slot_off[s] of edge slot_edge[s] (slots are in the reference's `links` order,
- * pydcop/algorithms/maxsum.py:466).
+ * (this is the layout of the factor->variable array r, written by the factor side).  The variable
+ * side owns a CSR: variable v has slots [var_ptr[v], var_ptr[v+1]) in the reference's `links` order
+ * (pydcop/algorithms/maxsum.py:466); the variable->factor array q is stored in SLOT order:
+ *   q row of slot s   = var_qbase[v] + (s - var_ptr[v]) * dom_size[v]
+ * so each side WRITES its own messages with perfectly coalesced stores and reads the other side's
+ * through one gather index: edge_qoff[e] (factor side reads q), slot_roff[s] (variable side reads r).
  */
 #ifndef PYDCOP_B200_H
 #define PYDCOP_B200_H
@@ -70,7 +72,10 @@ typedef struct {
   int32_t abi_version; /* FG_ABI_VERSION */
   int32_t precision;   /* FG_F32 | FG_F64 */
   int32_t n_vars, n_factors, n_edges, n_classes;
-  int64_t n_msg;       /* total message elements = sum over edges of dom */
+  int64_t n_msg_r;     /* elements of each r buffer (class-major edge order, padded bases) */
+  int64_t n_msg_q;     /* elements of each q buffer (slot order) */
+  int32_t uniform_dom; /* D if every variable has domain size D, else 0 (enables fast kernels) */
+  int32_t max_degree;  /* largest number of factors on one variable */
   const fg_class_t *classes; /* HOST array [n_classes], copied by fg_maxsum_create */
 
   /* problem (device, read-only) */
@@ -79,19 +84,23 @@ typedef struct {
   const int32_t *dev_dom_size;  /* [n_vars] */
   const int64_t *dev_unary_off; /* [n_vars+1] */
   const int32_t *dev_var_ptr;   /* [n_vars+1] */
-  const int64_t *dev_slot_off;  /* [n_edges] message-row offset of slot s */
+  const int64_t *dev_var_qbase; /* [n_vars+1] q offset of the first slot of v */
+  const int64_t *dev_slot_roff; /* [n_edges] slot order: offset in r of the row of slot s's edge */
+  const int64_t *dev_edge_qoff; /* [n_edges] edge order: offset in q of the row of edge e */
+  const uint32_t *dev_slot_roff32; /* same as 32-bit offsets, or NULL when they do not fit */
+  const uint32_t *dev_edge_qoff32;
   const int32_t *dev_slot_edge; /* [n_edges] edge id of slot s */
   const int32_t *dev_slot_var;  /* [n_edges] variable of slot s */
   const int32_t *dev_init_value; /* [n_vars] initial_value index or -1 (maxsum.py:497-500) */
 
   /* state (device, read-write).  q = variable->factor, r = factor->variable; [0]/[1] are the
    * Jacobi double buffers, the engine tracks which one is current. */
-  void *dev_q[2], *dev_r[2];       /* T[n_msg] each */
+  void *dev_q[2], *dev_r[2];       /* T[n_msg_q] / T[n_msg_r] each */
   uint8_t *dev_q_valid, *dev_r_valid; /* [n_edges] edge order: receiver holds a message */
   uint8_t *dev_q_cnt;              /* [n_edges] SLOT order: bit0 has-prev, bits1.. send count */
   uint8_t *dev_r_cnt;              /* [n_edges] edge order: same encoding */
-  uint8_t *dev_q_sent, *dev_r_sent; /* [n_edges] edge order: message posted in the last cycle
-                                       (may be NULL: not recorded) */
+  uint8_t *dev_q_sent, *dev_r_sent; /* [n_edges] q_sent SLOT order, r_sent edge order: message
+                                       posted in the last cycle (may be NULL: not recorded) */
   int32_t *dev_value;              /* [n_vars] selected value index (select_value) */
   void *dev_value_cost;            /* T[n_vars] its cost */
 
@@ -183,6 +192,13 @@ int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_class_t *cla
                      const void *dev_tables, const int32_t *dev_edge_var,
                      const int32_t *dev_value, const void *dev_unary,
                      const int64_t *dev_unary_off, int32_t n_vars, double *dev_out, void *stream);
+
+/* Diagnostic: evaluates the send-gate predicate approx_match (maxsum.py:688-710) on n pairs with
+ * the division-free fast form used by the tiled kernels (out_fast) and the literal form
+ * (out_exact); the two must agree on every input.  T arrays of n elements, uint8 outputs. */
+int fg_selftest_approx_match(int32_t precision, int64_t n, const void *dev_c, const void *dev_prev,
+                             double stability, uint8_t *dev_out_fast, uint8_t *dev_out_exact,
+                             void *stream);
 
 #ifdef __cplusplus
 }

@@ -29,9 +29,13 @@ P = C.c_void_p
 class FgMaxSumDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("precision", C.c_int32),
                 ("n_vars", C.c_int32), ("n_factors", C.c_int32), ("n_edges", C.c_int32),
-                ("n_classes", C.c_int32), ("n_msg", C.c_int64), ("classes", C.POINTER(FgClass)),
+                ("n_classes", C.c_int32), ("n_msg_r", C.c_int64), ("n_msg_q", C.c_int64),
+                ("uniform_dom", C.c_int32), ("max_degree", C.c_int32),
+                ("classes", C.POINTER(FgClass)),
                 ("dev_tables", P), ("dev_unary", P), ("dev_dom_size", P), ("dev_unary_off", P),
-                ("dev_var_ptr", P), ("dev_slot_off", P), ("dev_slot_edge", P), ("dev_slot_var", P),
+                ("dev_var_ptr", P), ("dev_var_qbase", P), ("dev_slot_roff", P), ("dev_edge_qoff", P),
+                ("dev_slot_roff32", P), ("dev_edge_qoff32", P),
+                ("dev_slot_edge", P), ("dev_slot_var", P),
                 ("dev_init_value", P),
                 ("dev_q", P * 2), ("dev_r", P * 2), ("dev_q_valid", P), ("dev_r_valid", P),
                 ("dev_q_cnt", P), ("dev_r_cnt", P), ("dev_q_sent", P), ("dev_r_sent", P),
@@ -75,6 +79,7 @@ SYMBOLS = {
     "fg_dsa_cycle_commit": (C.c_int, [P]),
     "fg_dsa_current": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fg_dsa_launch_count": (C.c_int64, [P]),
+    "fg_selftest_approx_match": (C.c_int, [C.c_int32, C.c_int64, P, P, C.c_double, P, P, P]),
     "fg_solution_cost": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(FgClass), P, P, P, P, P,
                                    C.c_int32, P, P]),
 }

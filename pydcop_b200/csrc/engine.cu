@@ -97,15 +97,15 @@ extern "C" const char *fg_maxsum_last_error(fg_maxsum_t h) { return h ? h->err :
 template <typename T>
 static int maxsum_init_t(fg_maxsum *h, cudaStream_t st) {
   const fg_maxsum_desc_t &d = h->d;
-  const size_t mb = (size_t)d.n_msg * sizeof(T);
+  const size_t mbq = (size_t)d.n_msg_q * sizeof(T), mbr = (size_t)d.n_msg_r * sizeof(T);
   for (int b = 0; b < 2; ++b) {
-    CUDA_TRY(h, cudaMemsetAsync(d.dev_q[b], 0, mb, st));
-    CUDA_TRY(h, cudaMemsetAsync(d.dev_r[b], 0, mb, st));
+    if (mbq) CUDA_TRY(h, cudaMemsetAsync(d.dev_q[b], 0, mbq, st));
+    if (mbr) CUDA_TRY(h, cudaMemsetAsync(d.dev_r[b], 0, mbr, st));
   }
   uint8_t *bytes[] = {d.dev_q_valid, d.dev_r_valid, d.dev_q_cnt, d.dev_r_cnt, d.dev_q_sent, d.dev_r_sent};
   for (uint8_t *p : bytes)
     if (p && d.n_edges) CUDA_TRY(h, cudaMemsetAsync(p, 0, (size_t)d.n_edges, st));
-  VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_slot_off, d.dev_slot_edge, d.dev_slot_var};
+  VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_var_qbase, d.dev_slot_roff, d.dev_slot_edge, d.dev_slot_var};
   if (d.n_vars) {
     k_v2f_start<T><<<blocks_for(d.n_vars, 128), 128, 0, st>>>(
         g, d.n_vars, (const T *)d.dev_unary, d.dev_init_value, (T *)d.dev_q[0], d.dev_q_valid,
@@ -147,16 +147,16 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
     const int64_t n = (int64_t)c.n_factors * c.arity;
     if (first)
       k_f2v_generic<T, 1><<<blocks_for(n, 128), 128, 0, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next,
-                                                             d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
+                                                             d.dev_edge_qoff, d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
     else
       k_f2v_generic<T, 0><<<blocks_for(n, 128), 128, 0, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next,
-                                                             d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
+                                                             d.dev_edge_qoff, d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
     ++h->launches;
   }
   // variable -> factor (+ value selection)
   if (d.n_edges) {
     if (!(!first && maxsum_fast_v2f<T>(h->fast, d, r_cur, q_cur, q_next, p, st, h->launches))) {
-      VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_slot_off, d.dev_slot_edge, d.dev_slot_var};
+      VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_var_qbase, d.dev_slot_roff, d.dev_slot_edge, d.dev_slot_var};
       if (first)
         k_v2f_generic<T, 1><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
             g, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
@@ -412,5 +412,28 @@ extern "C" int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_c
     if (precision == FG_F64) k_cost_unary<double><<<blocks_for(n_vars, 128), 128, 0, st>>>((const double *)dev_unary, dev_unary_off, dev_value, n_vars, dev_out);
     else k_cost_unary<float><<<blocks_for(n_vars, 128), 128, 0, st>>>((const float *)dev_unary, dev_unary_off, dev_value, n_vars, dev_out);
   }
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_selftest_match(int64_t n, const T *__restrict__ c, const T *__restrict__ prev, T stab,
+                                 uint8_t *__restrict__ out_fast, uint8_t *__restrict__ out_exact) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out_fast[i] = approx_match_fast<T>(c[i], prev[i], stab) ? 1 : 0;
+  out_exact[i] = approx_match1<T>(c[i], prev[i], stab) ? 1 : 0;
+}
+
+extern "C" int fg_selftest_approx_match(int32_t precision, int64_t n, const void *dev_c, const void *dev_prev,
+                                        double stability, uint8_t *dev_out_fast, uint8_t *dev_out_exact, void *stream) {
+  if (n <= 0) return FG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == FG_F64)
+    k_selftest_match<double><<<blocks_for(n, 256), 256, 0, st>>>(n, (const double *)dev_c, (const double *)dev_prev, stability, dev_out_fast, dev_out_exact);
+  else
+    k_selftest_match<float><<<blocks_for(n, 256), 256, 0, st>>>(n, (const float *)dev_c, (const float *)dev_prev, (float)stability, dev_out_fast, dev_out_exact);
   return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }

@@ -10,17 +10,20 @@
 // for value xv is returned one value at a time through `emit(xv, value)`.
 template <typename T, int QMODE, typename Emit>
 __device__ __forceinline__ void factor_marginal_generic(const fg_class_t &c, const T *__restrict__ table,
-                                                        const T *__restrict__ q, int64_t row_base,
+                                                        const T *__restrict__ q,
+                                                        const int64_t *__restrict__ edge_qoff_f,
                                                         const uint8_t *__restrict__ q_valid_f, int j,
                                                         bool mode_max, Emit emit) {
   const int a = c.arity;
-  int64_t stride[FG_MAX_ARITY];
+  int64_t stride[FG_MAX_ARITY], qoff[FG_MAX_ARITY];
   bool use[FG_MAX_ARITY];
   {
     int64_t s = 1;
     for (int i = a - 1; i >= 0; --i) { stride[i] = s; s *= c.dom[i]; }
-    for (int i = 0; i < a; ++i)
+    for (int i = 0; i < a; ++i) {
       use[i] = (i != j) && (QMODE == 0 || (QMODE == 1 && q_valid_f[i] != 0));
+      qoff[i] = use[i] ? edge_qoff_f[i] : 0;
+    }
   }
   const int dj = c.dom[j];
   for (int xv = 0; xv < dj; ++xv) {
@@ -33,7 +36,7 @@ __device__ __forceinline__ void factor_marginal_generic(const fg_class_t &c, con
       T sum = (T)0;
       for (int i = 0; i < a; ++i) {
         idx += x[i] * stride[i];
-        if (use[i]) sum += q[row_base + c.row_off[i] + x[i]];
+        if (use[i]) sum += q[qoff[i] + x[i]];
       }
       T cur = table[idx] + sum;
       opt_update(opt, cur, mode_max);
@@ -56,7 +59,8 @@ template <typename T, int QMODE>
 __global__ void __launch_bounds__(128)
 k_f2v_generic(const fg_class_t c, const T *__restrict__ tables, const T *__restrict__ q_cur,
               const T *__restrict__ r_cur, T *__restrict__ r_next,
-              const uint8_t *__restrict__ q_valid, uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
+              const int64_t *__restrict__ edge_qoff, const uint8_t *__restrict__ q_valid,
+              uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
   int64_t le = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (le >= (int64_t)c.n_factors * c.arity) return;
   int f = (int)(le / c.arity), j = (int)(le % c.arity);
@@ -71,7 +75,8 @@ k_f2v_generic(const fg_class_t c, const T *__restrict__ tables, const T *__restr
   const bool damp = p.damp_factors && has_prev;
   bool match = has_prev;
   factor_marginal_generic<T, QMODE>(
-      c, table, q_cur, row_base, q_valid + (c.first_edge + f * c.arity), j, p.mode_max != 0,
+      c, table, q_cur, edge_qoff + (c.first_edge + f * c.arity),
+      q_valid + (c.first_edge + f * c.arity), j, p.mode_max != 0,
       [&](int xv, T cand) {
         T prev = r_cur[row + xv];
         if (damp) cand = lam * prev + oml * cand;
@@ -98,7 +103,7 @@ k_f2v_start(const fg_class_t c, const T *__restrict__ tables, T *__restrict__ r_
   const T *table = tables + c.table_base + (int64_t)f * c.table_size;
   int64_t row_base = c.msg_base + (int64_t)f * c.row_total;
   int64_t row = row_base + c.row_off[j];
-  factor_marginal_generic<T, 2>(c, table, (const T *)nullptr, row_base, nullptr, j, mode_max != 0,
+  factor_marginal_generic<T, 2>(c, table, (const T *)nullptr, nullptr, nullptr, j, mode_max != 0,
                                 [&](int xv, T cand) { r_cur[row + xv] = cand; });
   r_valid[e] = 1;
   if (r_sent) r_sent[e] = 1;
@@ -111,7 +116,8 @@ struct VarSide {
   const int32_t *dom_size;
   const int64_t *unary_off;
   const int32_t *var_ptr;
-  const int64_t *slot_off;
+  const int64_t *var_qbase;  // q row of slot s of v = var_qbase[v] + (s - var_ptr[v]) * dom_size[v]
+  const int64_t *slot_roff;  // r row of slot s
   const int32_t *slot_edge;
   const int32_t *slot_var;
 };
@@ -132,7 +138,7 @@ __device__ __forceinline__ void select_value_generic(const VarSide &g, const T *
     if (RMODE != 2)
       for (int s = s0; s < s1; ++s) {
         if (RMODE == 1 && !r_valid[g.slot_edge[s]]) continue;
-        c += r[g.slot_off[s] + x];
+        c += r[g.slot_roff[s] + x];
       }
     if (x == 0 || (mode_max ? (c > best_c) : (c < best_c))) { best = x; best_c = c; }
   }
@@ -154,7 +160,7 @@ k_v2f_generic(VarSide g, int n_slots, const T *__restrict__ unary, const T *__re
   const int d = g.dom_size[v];
   const int s0 = g.var_ptr[v], s1 = g.var_ptr[v + 1];
   const int64_t u0 = g.unary_off[v];
-  const int64_t row = g.slot_off[s];
+  const int64_t row = g.var_qbase[v] + (int64_t)(s - s0) * d;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
   if (s == s0)
     select_value_generic<T, RMODE>(g, unary, r_cur, r_valid, v, p.mode_max != 0, value, value_cost);
@@ -165,7 +171,7 @@ k_v2f_generic(VarSide g, int n_slots, const T *__restrict__ unary, const T *__re
     for (int t = s0; t < s1; ++t) {
       if (t == s) continue;
       if (RMODE == 1 && !r_valid[g.slot_edge[t]]) continue;
-      T c = r_cur[g.slot_off[t] + x];
+      T c = r_cur[g.slot_roff[t] + x];
       sum_cost += c;
       m += c;
     }
@@ -208,7 +214,7 @@ k_v2f_start(VarSide g, int n_vars, const T *__restrict__ unary, const int32_t *_
   const int64_t u0 = g.unary_off[v];
   if (((s1 - s0) == 1 && start_messages == FG_START_LEAFS) || start_messages >= FG_START_LEAFS_VARS) {
     for (int s = s0; s < s1; ++s) {
-      const int64_t row = g.slot_off[s];
+      const int64_t row = g.var_qbase[v] + (int64_t)(s - s0) * d;
       const T avg = (T)0 / (T)d;
       for (int x = 0; x < d; ++x) q_cur[row + x] = unary[u0 + x] - avg;
       q_valid[g.slot_edge[s]] = 1;

@@ -92,12 +92,18 @@ class MaxSumEngine(_EngineBase):
             self.dom_size = self._dev(L.dom_size, torch.int32)
             self.unary_off = self._dev(L.unary_off, torch.int64)
             self.var_ptr = self._dev(L.var_ptr, torch.int32)
-            self.slot_off = self._dev(L.slot_off, torch.int64)
+            self.var_qbase = self._dev(L.var_qbase, torch.int64)
+            self.slot_roff = self._dev(L.slot_roff, torch.int64)
+            self.edge_qoff = self._dev(L.edge_qoff, torch.int64)
+            fits32 = max(L.n_msg, L.n_msg_q) < 2 ** 32
+            # uint32 offsets, stored as int32 bit patterns (torch has no uint32 arithmetic)
+            self.slot_roff32 = self._dev(L.slot_roff.astype(np.uint32).view(np.int32), torch.int32) if fits32 else None
+            self.edge_qoff32 = self._dev(L.edge_qoff.astype(np.uint32).view(np.int32), torch.int32) if fits32 else None
             self.slot_edge = self._dev(L.slot_edge, torch.int32)
             self.slot_var = self._dev(L.slot_var, torch.int32)
             self.init_value = self._dev(L.init_value, torch.int32)
             z = lambda n, dt: torch.zeros(max(int(n), 1), dtype=dt, device=self.device)  # noqa
-            self.q = [z(L.n_msg, tdt), z(L.n_msg, tdt)]
+            self.q = [z(L.n_msg_q, tdt), z(L.n_msg_q, tdt)]
             self.r = [z(L.n_msg, tdt), z(L.n_msg, tdt)]
             self.q_valid, self.r_valid = z(L.n_edges, torch.uint8), z(L.n_edges, torch.uint8)
             self.q_cnt, self.r_cnt = z(L.n_edges, torch.uint8), z(L.n_edges, torch.uint8)
@@ -109,11 +115,14 @@ class MaxSumEngine(_EngineBase):
         d = FgMaxSumDesc()
         d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
         d.n_vars, d.n_factors, d.n_edges = L.n_vars, L.n_factors, L.n_edges
-        d.n_classes, d.n_msg = len(L.classes), L.n_msg
+        d.n_classes, d.n_msg_r, d.n_msg_q = len(L.classes), L.n_msg, L.n_msg_q
+        d.uniform_dom, d.max_degree = L.uniform_dom, L.max_degree
         d.classes = C.cast(self._classes, C.POINTER(FgClass))
         d.dev_tables, d.dev_unary = _ptr(self.tables), _ptr(self.unary)
         d.dev_dom_size, d.dev_unary_off = _ptr(self.dom_size), _ptr(self.unary_off)
-        d.dev_var_ptr, d.dev_slot_off = _ptr(self.var_ptr), _ptr(self.slot_off)
+        d.dev_var_ptr, d.dev_var_qbase = _ptr(self.var_ptr), _ptr(self.var_qbase)
+        d.dev_slot_roff, d.dev_edge_qoff = _ptr(self.slot_roff), _ptr(self.edge_qoff)
+        d.dev_slot_roff32, d.dev_edge_qoff32 = _ptr(self.slot_roff32), _ptr(self.edge_qoff32)
         d.dev_slot_edge, d.dev_slot_var = _ptr(self.slot_edge), _ptr(self.slot_var)
         d.dev_init_value = _ptr(self.init_value)
         for b in range(2):
@@ -186,8 +195,9 @@ class MaxSumEngine(_EngineBase):
     def messages(self):
         """(q, r) receiver-side message state as float64 numpy arrays in canonical edge order."""
         g = torch.from_numpy(self.layout.message_gather_index()).to(self.device)
+        gq = torch.from_numpy(self.layout.message_gather_index_q()).to(self.device)
         cur = self.cur
-        q = self.q[cur][g].double().cpu().numpy() if g.numel() else np.zeros(0)
+        q = self.q[cur][gq].double().cpu().numpy() if g.numel() else np.zeros(0)
         r = self.r[cur][g].double().cpu().numpy() if g.numel() else np.zeros(0)
         return q, r
 

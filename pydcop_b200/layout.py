@@ -56,7 +56,8 @@ class FactorGraphLayout:
     n_vars: int
     n_factors: int
     n_edges: int
-    n_msg: int                 # internal message elements (with class padding)
+    n_msg: int                 # internal r-array elements (class-major edge order, padded bases)
+    n_msg_q: int               # internal q-array elements (slot order)
     n_msg_canonical: int
     classes: List[FactorClass]
     dom_size: np.ndarray       # int32 [V]
@@ -66,7 +67,11 @@ class FactorGraphLayout:
     var_ptr: np.ndarray        # int32 [V+1]
     slot_edge: np.ndarray      # int32 [E]  internal edge id of slot s
     slot_var: np.ndarray       # int32 [E]
-    slot_off: np.ndarray       # int64 [E]  internal message-row offset of slot s
+    slot_roff: np.ndarray      # int64 [E]  offset in r of the row of slot s's edge
+    var_qbase: np.ndarray      # int64 [V+1] offset in q of the first slot of v
+    edge_qoff: np.ndarray      # int64 [E]  internal edge order: offset in q of the edge's row
+    uniform_dom: int           # D when all variables share one domain size, else 0
+    max_degree: int
     edge_var: np.ndarray       # int32 [E]  internal edge order
     edge_class: np.ndarray     # int32 [E]  internal edge order
     edge_msg_off: np.ndarray   # int64 [E]  internal edge order -> internal message offset
@@ -77,16 +82,26 @@ class FactorGraphLayout:
     canon_var_edge: np.ndarray  # int32 [E] canonical edge id of slot s
     init_value: np.ndarray     # int32 [V] (-1 = none)
     msg_gather: Optional[np.ndarray] = field(default=None, repr=False)
+    msg_gather_q: Optional[np.ndarray] = field(default=None, repr=False)
 
     # -- canonical <-> internal helpers (used by tests / readback, not by the hot path) ---------
     def message_gather_index(self):
-        """Index array g with canonical_messages = internal_messages[g]."""
+        """Index array g with canonical_r = internal_r[g] (canonical = edge order of the input)."""
         if self.msg_gather is None:
             d = np.diff(self.canon_msg_off)
             start = self.edge_msg_off[self.edge_perm] - self.canon_msg_off[:-1]
             self.msg_gather = (np.repeat(start, d)
                                + np.arange(self.n_msg_canonical, dtype=np.int64))
         return self.msg_gather
+
+    def message_gather_index_q(self):
+        """Index array g with canonical_q = internal_q[g]."""
+        if self.msg_gather_q is None:
+            d = np.diff(self.canon_msg_off)
+            start = self.edge_qoff[self.edge_perm] - self.canon_msg_off[:-1]
+            self.msg_gather_q = (np.repeat(start, d)
+                                 + np.arange(self.n_msg_canonical, dtype=np.int64))
+        return self.msg_gather_q
 
     def edges_to_canonical(self, arr_internal):
         return np.asarray(arr_internal)[self.edge_perm]
@@ -206,7 +221,16 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     if E and not np.array_equal(edge_var[var_edge], slot_var):
         raise ValueError("var_edge lists an edge under the wrong variable")
     slot_edge = edge_perm[var_edge].astype(np.int32)
-    slot_off = edge_msg_off[slot_edge]
+    slot_roff = edge_msg_off[slot_edge]
+    deg = np.diff(var_ptr).astype(np.int64)
+    var_qbase = np.zeros(V + 1, dtype=np.int64)
+    np.cumsum(deg * dom_size.astype(np.int64), out=var_qbase[1:])
+    slot_qoff = (var_qbase[:-1][slot_var]
+                 + (np.arange(E, dtype=np.int64) - var_ptr[:-1].astype(np.int64)[slot_var])
+                 * dom_size.astype(np.int64)[slot_var]) if E else np.zeros(0, np.int64)
+    edge_qoff = np.zeros(E, dtype=np.int64)
+    edge_qoff[slot_edge] = slot_qoff
+    uniform_dom = int(dom_size[0]) if V and (dom_size == dom_size[0]).all() else 0
 
     unary_off = np.zeros(V + 1, dtype=np.int64)
     np.cumsum(dom_size, out=unary_off[1:])
@@ -216,10 +240,12 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     init_value = (np.full(V, -1, np.int32) if init_value is None else _as(init_value, np.int32))
 
     return FactorGraphLayout(
-        n_vars=V, n_factors=F, n_edges=E, n_msg=int(n_msg),
+        n_vars=V, n_factors=F, n_edges=E, n_msg=int(n_msg), n_msg_q=int(var_qbase[-1]),
         n_msg_canonical=int(canon_msg_off[-1]), classes=classes, dom_size=dom_size,
         unary_off=unary_off, unary=unary, tables=tables_int, var_ptr=var_ptr,
-        slot_edge=slot_edge, slot_var=slot_var, slot_off=slot_off, edge_var=int_edge_var,
+        slot_edge=slot_edge, slot_var=slot_var, slot_roff=slot_roff, var_qbase=var_qbase,
+        edge_qoff=edge_qoff, uniform_dom=uniform_dom, max_degree=int(deg.max(initial=0)),
+        edge_var=int_edge_var,
         edge_class=edge_class, edge_msg_off=edge_msg_off, edge_perm=edge_perm,
         factor_perm=factor_perm, canon_edge_var=edge_var, canon_msg_off=canon_msg_off,
         canon_var_edge=var_edge, init_value=init_value)
