@@ -17,7 +17,6 @@ the job time is the max over ranks.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -40,49 +39,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled in-process (NVML) every 10 ms during the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.mx = index, [], 0, None
+        self._stop = threading.Event()
+        self._t = None
+        self._err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self._err = repr(e)
+            return
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            except Exception as e:  # noqa: BLE001
+                self._err = repr(e)
+                return
+            time.sleep(0.01)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])), mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["unavailable: %s" % self._err]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx,
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b),
+                "samples": len(self.sm)}
 
 
 def oracle_instance(inst, L):
@@ -91,7 +98,7 @@ def oracle_instance(inst, L):
     # canonical table sizes (factor order of `inst`): invert the class permutation
     t = np.zeros(L.n_factors, np.int64)
     t[:] = tsz[L.factor_perm]
-    return dict(inst, var_ptr=L.var_ptr, var_edge=L.canon_var_edge, init_value=L.init_value,
+    return dict(inst, var_ptr=L.canon_var_ptr, var_edge=L.canon_var_edge,
                 table_off=np.concatenate([[0], np.cumsum(t)]))
 
 
@@ -118,7 +125,7 @@ def cpu_baseline(inst, L, seconds=12.0, dtype=np.float32):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--vars-per-gpu", type=int, default=100_000)

@@ -62,6 +62,21 @@ typedef struct {
   int64_t msg_base;              /* element offset into the message arrays */
 } fg_class_t;
 
+/* One class of same-shaped variables: identical domain size and degree.  Variables are stored in
+ * class-major ("internal") order; inside a class everything is affine in the variable's rank i:
+ *   unary row   = dev_unary + unary_base + i * dom
+ *   slots       = first_slot + i * degree + g            (g = 0..degree-1, the `links` order)
+ *   q row (i,g) = q_base + (i * degree + g) * dom
+ * degree == -1 marks the irregular class (variables of degree > 16): CSR through dev_var_ptr,
+ * q rows still dense from q_base in slot order. */
+typedef struct {
+  int32_t dom, degree;
+  int32_t n_vars, first_var, first_slot;
+  int32_t n_slots;     /* total slots of the class */
+  int64_t unary_base;
+  int64_t q_base;
+} fg_varclass_t;
+
 /* ------------------------------------------------------------------------------------------
  * MaxSum  (replaces MaxSumFactorComputation.on_new_cycle maxsum.py:339-379 +
  * factor_costs_for_var :382-447, MaxSumVariableComputation.on_new_cycle :525-565 +
@@ -77,6 +92,8 @@ typedef struct {
   int32_t uniform_dom; /* D if every variable has domain size D, else 0 (enables fast kernels) */
   int32_t max_degree;  /* largest number of factors on one variable */
   const fg_class_t *classes; /* HOST array [n_classes], copied by fg_maxsum_create */
+  int32_t n_varclasses, reserved0;
+  const fg_varclass_t *varclasses; /* HOST array [n_varclasses], copied by fg_maxsum_create */
 
   /* problem (device, read-only) */
   const void *dev_tables;       /* T[sum table_size] */
@@ -156,6 +173,8 @@ typedef struct {
   const fg_class_t *classes;     /* HOST [n_classes] */
   const void *dev_tables;        /* T[...] */
   const int32_t *dev_dom_size;   /* [n_vars] */
+  const int32_t *dev_var_id;     /* [n_vars] caller's (canonical) id of each internal variable: the
+                                    Philox counter, so draws do not depend on the internal order */
   const int32_t *dev_edge_var;   /* [n_edges] variable of edge e (class-major edge order) */
   const int32_t *dev_edge_class; /* [n_edges] class of edge e */
   const int32_t *dev_var_ptr;    /* [n_vars+1] */

@@ -26,12 +26,20 @@ class FgClass(C.Structure):
 P = C.c_void_p
 
 
+class FgVarClass(C.Structure):
+    _fields_ = [("dom", C.c_int32), ("degree", C.c_int32), ("n_vars", C.c_int32),
+                ("first_var", C.c_int32), ("first_slot", C.c_int32), ("n_slots", C.c_int32),
+                ("unary_base", C.c_int64), ("q_base", C.c_int64)]
+
+
 class FgMaxSumDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("precision", C.c_int32),
                 ("n_vars", C.c_int32), ("n_factors", C.c_int32), ("n_edges", C.c_int32),
                 ("n_classes", C.c_int32), ("n_msg_r", C.c_int64), ("n_msg_q", C.c_int64),
                 ("uniform_dom", C.c_int32), ("max_degree", C.c_int32),
                 ("classes", C.POINTER(FgClass)),
+                ("n_varclasses", C.c_int32), ("reserved0", C.c_int32),
+                ("varclasses", C.POINTER(FgVarClass)),
                 ("dev_tables", P), ("dev_unary", P), ("dev_dom_size", P), ("dev_unary_off", P),
                 ("dev_var_ptr", P), ("dev_var_qbase", P), ("dev_slot_roff", P), ("dev_edge_qoff", P),
                 ("dev_slot_roff32", P), ("dev_edge_qoff32", P),
@@ -48,7 +56,8 @@ class FgDsaDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("precision", C.c_int32),
                 ("n_vars", C.c_int32), ("n_factors", C.c_int32), ("n_edges", C.c_int32),
                 ("n_classes", C.c_int32), ("classes", C.POINTER(FgClass)),
-                ("dev_tables", P), ("dev_dom_size", P), ("dev_edge_var", P), ("dev_edge_class", P),
+                ("dev_tables", P), ("dev_dom_size", P), ("dev_var_id", P), ("dev_edge_var", P),
+                ("dev_edge_class", P),
                 ("dev_var_ptr", P), ("dev_slot_edge", P), ("dev_has_nbr", P), ("dev_prob", P),
                 ("dev_con_opt", P), ("dev_value", P * 2), ("dev_value_cost", P),
                 ("mode_max", C.c_int32), ("variant", C.c_int32), ("stop_cycle", C.c_int32),

@@ -22,6 +22,7 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 struct fg_maxsum {
   fg_maxsum_desc_t d;
   std::vector<fg_class_t> classes;
+  std::vector<fg_varclass_t> varclasses;
   MaxSumFastPlan fast;
   int cur = 0;
   int64_t cycle = 0;
@@ -74,16 +75,25 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
   h->d = *desc;
   h->classes.assign(desc->classes, desc->classes + desc->n_classes);
   h->d.classes = h->classes.data();
+  if (desc->n_varclasses > 0 && desc->varclasses)
+    h->varclasses.assign(desc->varclasses, desc->varclasses + desc->n_varclasses);
+  h->d.varclasses = h->varclasses.data();
   *out = h;
   for (auto &c : h->classes) {
     int rc = check_class(c, h->err, sizeof(h->err));
     if (rc != FG_OK) return rc;
   }
+  int64_t covered = 0;
+  for (auto &vc : h->varclasses) covered += vc.n_slots;
+  if (covered != desc->n_edges) {
+    snprintf(h->err, sizeof(h->err), "variable classes cover %lld slots, expected %d", (long long)covered, desc->n_edges);
+    return FG_ERR_ARG;
+  }
   if (fg_device_count() <= 0) {
     snprintf(h->err, sizeof(h->err), "no CUDA device visible: pydcop_b200 has no CPU fallback");
     return FG_ERR_CUDA;
   }
-  maxsum_fast_plan(h->d, h->classes, h->fast);
+  maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
   return FG_OK;
 }
 
@@ -155,17 +165,23 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
   }
   // variable -> factor (+ value selection)
   if (d.n_edges) {
-    if (!(!first && maxsum_fast_v2f<T>(h->fast, d, r_cur, q_cur, q_next, p, st, h->launches))) {
-      VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_var_qbase, d.dev_slot_roff, d.dev_slot_edge, d.dev_slot_var};
-      if (first)
-        k_v2f_generic<T, 1><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
-            g, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
-            d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
-      else
-        k_v2f_generic<T, 0><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
-            g, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
-            d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+    VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_var_qbase, d.dev_slot_roff, d.dev_slot_edge, d.dev_slot_var};
+    if (first) {
+      k_v2f_generic<T, 1><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
+          g, 0, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
+          d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
       ++h->launches;
+    } else {
+      for (size_t li = 0; li < h->fast.v2f.size(); ++li) {
+        if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
+      }
+      for (int vi : h->fast.slow_varclasses) {
+        const fg_varclass_t &vc = h->varclasses[vi];
+        k_v2f_generic<T, 0><<<blocks_for(vc.n_slots, 128), 128, 0, st>>>(
+            g, vc.first_slot, vc.n_slots, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
+            d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+        ++h->launches;
+      }
     }
   }
   if (first && d.n_edges) {  // every edge has posted in cycle 1: all messages are valid from now on
@@ -289,7 +305,7 @@ extern "C" const char *fg_dsa_last_error(fg_dsa_t h) { return h ? h->err : g_sta
 
 static DsaSide dsa_side(const fg_dsa *h) {
   const fg_dsa_desc_t &d = h->d;
-  return DsaSide{h->dev_classes, d.dev_dom_size, d.dev_edge_var, d.dev_edge_class, d.dev_var_ptr,
+  return DsaSide{h->dev_classes, d.dev_dom_size, d.dev_var_id, d.dev_edge_var, d.dev_edge_class, d.dev_var_ptr,
                  d.dev_slot_edge, d.dev_has_nbr, d.dev_prob};
 }
 

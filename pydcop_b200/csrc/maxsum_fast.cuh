@@ -146,7 +146,7 @@ struct F2VCfg {
   static constexpr int PAD = (QUADS && (Q % 2 == 0)) ? E16 : 0;  // odd 16-B stride: no bank conflicts
   static constexpr int SP = S + PAD;
   static constexpr int PER_FACTOR = (SP + 3 * R) * (int)sizeof(T);
-  static constexpr int NF = fg_clamp(((40 * 1024) / PER_FACTOR) / 32 * 32, 32, 512);
+  static constexpr int NF = fg_clamp(((20 * 1024) / PER_FACTOR) / 32 * 32, 32, 512);
   static constexpr int NT = fg_clamp(NF * A, 64, 256);
   // vector width (elements) for table rows (D contiguous elements at multiples of D inside a
   // factor whose stride is SP) and for message rows
@@ -327,133 +327,237 @@ k_f2v_tile(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// variable -> factor
+// variable -> factor: one thread per variable, variables grouped in (domain, degree) classes
 // ------------------------------------------------------------------------------------------------
-#define FG_V2F_TS 256       // slots per tile
-#define FG_V2F_MAXDEG 32    // fast path requires max_degree <= this
-#define FG_V2F_RS (FG_V2F_TS + 2 * FG_V2F_MAXDEG)
+#define FG_V2F_MAX_ENTRIES 24
+#define FG_V2F_NT 128
+
+struct V2FEntry {
+  fg_varclass_t vc;
+  int32_t tile_begin;  // first block of this class in the launch
+  int32_t nv_tile;     // variables per block
+  int32_t bucket;      // 0: K<=2  1: K<=4  2: K<=8 (register resident)  3: K<=16 (shared resident)
+};
+struct V2FTable {
+  int32_t n;
+  int32_t total_tiles;
+  V2FEntry e[FG_V2F_MAX_ENTRIES];
+};
 
 template <typename T, int D>
 struct V2FCfg {
   static constexpr int VR_BYTES = fg_gcd(16, D * (int)sizeof(T));
   static constexpr int VR = VR_BYTES / (int)sizeof(T);
-  static constexpr size_t SMEM = (size_t)(D * FG_V2F_RS + 2 * FG_V2F_TS * D) * sizeof(T) + 16;
 };
 
+__host__ __device__ inline int v2f_kp(int K) { return K | 1; }  // odd column stride: conflict-free
+__host__ __device__ inline size_t v2f_per_var_bytes(int K, int D, size_t elem) {
+  return (size_t)(D * v2f_kp(K) + K * D + D + K) * elem;
+}
+
+// Phase 1, one thread per variable.  The K gathered r rows of the variable sit TRANSPOSED in
+// shared memory (col[x*RS + g]); every r value is read once, all K un-normalised messages
+// (costs_for_factor, maxsum.py:623-676: value-major, then factor order) and the selection total
+// (select_value, maxsum.py:584-620) are accumulated from it, and the raw message value is
+// written back in place.  Rows g >= K contribute +0, which is exact.
+template <typename T, int D, int KMAX>
+__device__ __forceinline__ void v2f_phase1(int K, T *__restrict__ col, int RS, const T *__restrict__ unrow,
+                                           T *__restrict__ avg, bool mx, int32_t *value_out, T *cost_out) {
+  T sum[KMAX];
+#pragma unroll
+  for (int f = 0; f < KMAX; ++f) sum[f] = (T)0;
+  int best = 0;
+  T best_c = (T)0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) {
+    T c[KMAX];
+#pragma unroll
+    for (int g = 0; g < KMAX; ++g) c[g] = (g < K) ? col[x * RS + g] : (T)0;
+    const T u = unrow[x];
+    T tot = u;
+#pragma unroll
+    for (int g = 0; g < KMAX; ++g) tot += c[g];
+    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+#pragma unroll
+    for (int f = 0; f < KMAX; ++f) {
+      if (f < K) {
+        T m = u;
+#pragma unroll
+        for (int g = 0; g < KMAX; ++g) {
+          if (g == f) continue;
+          sum[f] += c[g];
+          m += c[g];
+        }
+        col[x * RS + f] = m;
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < KMAX; ++f)
+    if (f < K) avg[f] = sum[f] / (T)D;
+  *value_out = best;
+  *cost_out = best_c;
+}
+
+// same with run-time loops (degree 9..16)
+template <typename T, int D>
+__device__ __forceinline__ void v2f_phase1_rt(int K, T *__restrict__ col, int RS, const T *__restrict__ unrow,
+                                              T *__restrict__ avg, bool mx, int32_t *value_out, T *cost_out) {
+  int best = 0;
+  T best_c = (T)0;
+  for (int x = 0; x < D; ++x) {
+    T tot = unrow[x];
+    for (int g = 0; g < K; ++g) tot += col[x * RS + g];
+    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+  }
+  *value_out = best;
+  *cost_out = best_c;
+  // the raw messages cannot overwrite the rows in place before every f has read them: keep the
+  // K values of one x in registers (K <= 16)
+  T sumf[16];
+  for (int f = 0; f < 16; ++f) sumf[f] = (T)0;
+  for (int x = 0; x < D; ++x) {
+    T c[16];
+#pragma unroll
+    for (int g = 0; g < 16; ++g) c[g] = (g < K) ? col[x * RS + g] : (T)0;
+    const T u = unrow[x];
+#pragma unroll
+    for (int f = 0; f < 16; ++f) {
+      if (f < K) {
+        T m = u;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          if (g == f) continue;
+          sumf[f] += c[g];
+          m += c[g];
+        }
+        col[x * RS + f] = m;
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 16; ++f)
+    if (f < K) avg[f] = sumf[f] / (T)D;
+}
+
 template <typename T, int D, typename OffT>
-__global__ void __launch_bounds__(FG_V2F_TS)
-k_v2f_tile(int n_slots, const int32_t *__restrict__ var_ptr, const int32_t *__restrict__ slot_var,
-           const OffT *__restrict__ slot_roff, const T *__restrict__ unary, const T *__restrict__ r_cur,
-           const T *__restrict__ q_cur, T *__restrict__ q_next, uint8_t *__restrict__ q_cnt,
-           uint8_t *__restrict__ q_sent, int32_t *__restrict__ value, T *__restrict__ value_cost,
-           MaxSumParams p) {
+__global__ void __launch_bounds__(FG_V2F_NT)
+k_v2f_classes(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
+              const T *__restrict__ r_cur, const T *__restrict__ q_cur, T *__restrict__ q_next,
+              uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
+              T *__restrict__ value_cost, MaxSumParams p) {
   using C = V2FCfg<T, D>;
-  constexpr int TS = FG_V2F_TS, RS = FG_V2F_RS;
+  constexpr int NT = FG_V2F_NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T *rtT = reinterpret_cast<T *>(smem_raw);  // [D][RS] transposed gathered r rows
-  T *qin = rtT + D * RS;                     // [TS][D]
-  T *qout = qin + TS * D;                    // [TS][D]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(qout + TS * D);
+  // which class / tile is this block?
+  int ci = 0;
+#pragma unroll 1
+  for (int i = 1; i < tab.n; ++i)
+    if ((int)blockIdx.x >= tab.e[i].tile_begin) ci = i;
+  const V2FEntry &en = tab.e[ci];
+  const int K = en.vc.degree;
+  const int KP = v2f_kp(K);
+  const int NV = en.nv_tile;
+  const int RS = NV * KP;
+  const int v0 = ((int)blockIdx.x - en.tile_begin) * NV;
+  const int nv = min(NV, en.vc.n_vars - v0);
+  const int nslots = nv * K;
+  const int slot0 = en.vc.first_slot + v0 * K;
+  const int64_t qoff = en.vc.q_base + (int64_t)v0 * K * D;
+  const int64_t uoff = en.vc.unary_base + (int64_t)v0 * D;
+
+  T *qio = reinterpret_cast<T *>(smem_raw);  // [NV*K][D]  q_old rows in, q_next rows out (in place)
+  T *un = qio + NV * K * D;                  // [NV][D]
+  T *rtT = un + NV * D;                      // [D][RS]    gathered r rows, transposed
+  T *avg = rtT + D * RS;                     // [NV*K]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (((size_t)(NV * K * D + NV * D + D * RS + NV * K) * sizeof(T) + 15) & ~(size_t)15));
 
   const int tid = threadIdx.x;
-  const int t0 = blockIdx.x * TS;
-  const int n = min(TS, n_slots - t0);
-  const bool full = (n == TS);
-  const bool tma_q = full && ((TS * D * (int)sizeof(T)) % 16 == 0);
+  const bool full = (nv == NV);
+  const uint32_t qbytes = (uint32_t)(NV * K * D) * (uint32_t)sizeof(T);
+  const uint32_t ubytes = (uint32_t)(NV * D) * (uint32_t)sizeof(T);
+  const bool tma_q = full && (qbytes % 16 == 0) && (((qoff * (int64_t)sizeof(T)) & 15) == 0);
+  const bool tma_u = full && (ubytes % 16 == 0) && (((uoff * (int64_t)sizeof(T)) & 15) == 0) &&
+                     ((((size_t)NV * K * D * sizeof(T)) & 15) == 0);
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(bar, tma_q ? TS * D * (uint32_t)sizeof(T) : 0u);
-    if (tma_q) tma_load_1d(qin, q_cur + (int64_t)t0 * D, TS * D * (uint32_t)sizeof(T), bar);
+    mbar_expect_tx(bar, (tma_q ? qbytes : 0u) + (tma_u ? ubytes : 0u));
+    if (tma_q) tma_load_1d(qio, q_cur + qoff, qbytes, bar);
+    if (tma_u) tma_load_1d(un, unary + uoff, ubytes, bar);
   }
-  if (!tma_q) coop_copy_in<T>(qin, q_cur + (int64_t)t0 * D, n * D, tid, TS);
-  // rows of every variable touching this tile: [s_lo, s_hi)
-  const int s_lo = var_ptr[slot_var[t0]];
-  const int s_hi = var_ptr[slot_var[t0 + n - 1] + 1];
-  for (int i = s_lo + tid; i < s_hi; i += TS) {
-    const T *src = r_cur + (int64_t)slot_roff[i];
+  if (!tma_q)
+    for (int i = tid; i < nslots * D; i += NT) cp_async_b<(int)sizeof(T)>(qio + i, q_cur + qoff + i);
+  if (!tma_u)
+    for (int i = tid; i < nv * D; i += NT) cp_async_b<(int)sizeof(T)>(un + i, unary + uoff + i);
+  // gather the r rows (one row per thread, vector loads) and transpose them into shared memory
+  for (int sl = tid; sl < nslots; sl += NT) {
+    const T *src = r_cur + (int64_t)slot_roff[slot0 + sl];
     T row[D];
     ld_row<T, D, C::VR>(src, row);
+    const int i = sl / K, g = sl - i * K;
+    T *dst = rtT + i * KP + g;
 #pragma unroll
-    for (int x = 0; x < D; ++x) rtT[x * RS + (i - s_lo)] = row[x];
+    for (int x = 0; x < D; ++x) dst[x * RS] = row[x];
   }
   cp_async_wait_all();
   mbar_wait(bar, 0);
   __syncthreads();
 
-  if (tid < n) {
-    const int s = t0 + tid;
-    const int v = slot_var[s];
-    const int s0 = var_ptr[v], s1 = var_ptr[v + 1];
-    const bool mx = p.mode_max != 0;
+  const bool mx = p.mode_max != 0;
+  if (tid < nv) {  // phase 1: one thread per variable
+    const int i = tid;
+    int32_t val;
+    T cst;
+    T *col = rtT + i * KP;
+    switch (en.bucket) {
+      case 0: v2f_phase1<T, D, 2>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
+      case 1: v2f_phase1<T, D, 4>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
+      case 2: v2f_phase1<T, D, 8>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
+      default: v2f_phase1_rt<T, D>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
+    }
+    const int v = en.vc.first_var + v0 + i;
+    value[v] = val;
+    value_cost[v] = cst;
+  }
+  __syncthreads();
+  {  // phase 2: one thread per slot: normalise, damping, send gate
     const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
-    T un[D];
-    ld_row<T, D, C::VR>(unary + (int64_t)v * D, un);
-    const int a = s0 - s_lo, b = s1 - s_lo, me = s - s_lo;
-    if (s == s0) {  // select_value (maxsum.py:584-620)
-      int best = 0;
-      T best_c = (T)0;
+    for (int sl = tid; sl < nslots; sl += NT) {
+      const int i = sl / K, f = sl - i * K;
+      const T a = avg[sl];
+      const T *src = rtT + i * KP + f;
+      T cand[D], prev[D];
 #pragma unroll
-      for (int x = 0; x < D; ++x) {
-        T cst = un[x];
-        for (int t = a; t < b; ++t) cst += rtT[x * RS + t];
-        if (x == 0 || (mx ? (cst > best_c) : (cst < best_c))) { best = x; best_c = cst; }
-      }
-      value[v] = best;
-      value_cost[v] = best_c;
+      for (int x = 0; x < D; ++x) cand[x] = src[x * RS] - a;
+      ld_row<T, D, C::VR>(qio + sl * D, prev);
+      uint8_t cnt = q_cnt[slot0 + sl];
+      const bool sent = damp_gate_row<T, D>(cand, prev, cnt, p.damp_vars != 0, lam, oml, stab);
+      st_row<T, D, C::VR>(qio + sl * D, cand);
+      q_cnt[slot0 + sl] = cnt;
+      if (q_sent) q_sent[slot0 + sl] = sent ? 1 : 0;
     }
-    // costs_for_factor (maxsum.py:623-676), reference order: value-major, then factor
-    T cand[D];
-    T sum_cost = (T)0;
-#pragma unroll
-    for (int x = 0; x < D; ++x) {
-      T m = un[x];
-      for (int t = a; t < b; ++t) {
-        if (t == me) continue;
-        const T cst = rtT[x * RS + t];
-        sum_cost += cst;
-        m += cst;
-      }
-      cand[x] = m;
-    }
-    const T avg = sum_cost / (T)D;
-#pragma unroll
-    for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg;
-    T prev[D];
-    ld_row<T, D, C::VR>(qin + tid * D, prev);
-    uint8_t cnt = q_cnt[s];
-    const bool sent = damp_gate_row<T, D>(cand, prev, cnt, p.damp_vars != 0, lam, oml, stab);
-    st_row<T, D, C::VR>(qout + tid * D, cand);
-    q_cnt[s] = cnt;
-    if (q_sent) q_sent[s] = sent ? 1 : 0;
   }
   if (tma_q) {
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
-      tma_store_1d(q_next + (int64_t)t0 * D, qout, TS * D * (uint32_t)sizeof(T));
+      tma_store_1d(q_next + qoff, qio, qbytes);
       tma_store_commit();
       tma_store_wait_read();
     }
   } else {
     __syncthreads();
-    coop_copy_out<T>(q_next + (int64_t)t0 * D, qout, n * D, tid, TS);
+    for (int i = tid; i < nslots * D; i += NT) q_next[qoff + i] = qio[i];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
-struct MaxSumFastPlan {
-  bool v2f = false;               // uniform domain, supported D, max degree small enough
-  bool off32 = false;             // 32-bit gather offsets available
-  std::vector<uint8_t> f2v;       // per class: fast kernel available
-  bool attrs_set = false;
-};
-
 #define FG_FAST_DOMS(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(16) X(20)
 #define FG_FAST_DOMS_A3(X) X(2) X(3) X(4) X(5) X(8)
 
@@ -475,58 +579,43 @@ inline bool fg_fast_disabled() {
   return e && e[0] == '1';
 }
 
-inline void maxsum_fast_plan(const fg_maxsum_desc_t &d, const std::vector<fg_class_t> &classes, MaxSumFastPlan &plan) {
-  plan.f2v.assign(classes.size(), 0);
-  plan.off32 = d.dev_slot_roff32 != nullptr && d.dev_edge_qoff32 != nullptr;
-  if (fg_fast_disabled()) return;
-  for (size_t i = 0; i < classes.size(); ++i) {
-    const fg_class_t &c = classes[i];
-    bool uni = true;
-    for (int j = 1; j < c.arity; ++j) uni = uni && c.dom[j] == c.dom[0];
-    if (!uni) continue;
-    if (c.arity <= 2 && fg_fast_dom(c.dom[0])) plan.f2v[i] = 1;
-    if (c.arity == 3 && fg_fast_dom_a3(c.dom[0])) plan.f2v[i] = 1;
-  }
-  plan.v2f = d.uniform_dom > 0 && fg_fast_dom(d.uniform_dom) && d.max_degree <= FG_V2F_MAXDEG && d.n_edges > 0;
-}
-
-template <typename T, int A, int D, typename OffT>
+template <typename T, int A, int D>
 inline void launch_f2v_tile(const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur, T *r_next,
-                            const OffT *edge_qoff, const MaxSumParams &p, cudaStream_t st) {
+                            const MaxSumParams &p, cudaStream_t st) {
   using C = F2VCfg<T, A, D>;
-  auto kern = k_f2v_tile<T, A, D, OffT>;
+  auto kern = k_f2v_tile<T, A, D, uint32_t>;
   static bool attr_done = false;  // one per instantiation
   if (!attr_done) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr_done = true;
   }
   const unsigned blocks = (unsigned)((c.n_factors + C::NF - 1) / C::NF);
-  kern<<<blocks, C::NT, C::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, edge_qoff, d.dev_r_cnt,
+  kern<<<blocks, C::NT, C::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, d.dev_edge_qoff32, d.dev_r_cnt,
                                        d.dev_r_sent, p);
 }
 
-template <typename T, typename OffT>
+template <typename T>
 inline bool dispatch_f2v(const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur, T *r_next,
-                         const OffT *edge_qoff, const MaxSumParams &p, cudaStream_t st) {
+                         const MaxSumParams &p, cudaStream_t st) {
   const int D = c.dom[0];
   switch (c.arity) {
     case 1:
       switch (D) {
-#define X(n) case n: launch_f2v_tile<T, 1, n, OffT>(c, d, q_cur, r_cur, r_next, edge_qoff, p, st); return true;
+#define X(n) case n: launch_f2v_tile<T, 1, n>(c, d, q_cur, r_cur, r_next, p, st); return true;
         FG_FAST_DOMS(X)
 #undef X
       }
       return false;
     case 2:
       switch (D) {
-#define X(n) case n: launch_f2v_tile<T, 2, n, OffT>(c, d, q_cur, r_cur, r_next, edge_qoff, p, st); return true;
+#define X(n) case n: launch_f2v_tile<T, 2, n>(c, d, q_cur, r_cur, r_next, p, st); return true;
         FG_FAST_DOMS(X)
 #undef X
       }
       return false;
     case 3:
       switch (D) {
-#define X(n) case n: launch_f2v_tile<T, 3, n, OffT>(c, d, q_cur, r_cur, r_next, edge_qoff, p, st); return true;
+#define X(n) case n: launch_f2v_tile<T, 3, n>(c, d, q_cur, r_cur, r_next, p, st); return true;
         FG_FAST_DOMS_A3(X)
 #undef X
       }
@@ -535,50 +624,115 @@ inline bool dispatch_f2v(const fg_class_t &c, const fg_maxsum_desc_t &d, const T
   return false;
 }
 
-template <typename T>
-inline bool maxsum_fast_f2v(const MaxSumFastPlan &plan, int ci, const fg_class_t &c, const fg_maxsum_desc_t &d,
-                            const T *q_cur, const T *r_cur, T *r_next, const MaxSumParams &p, cudaStream_t st,
-                            int64_t &launches) {
-  if (!plan.f2v[ci]) return false;
-  bool ok = plan.off32 ? dispatch_f2v<T, uint32_t>(c, d, q_cur, r_cur, r_next, d.dev_edge_qoff32, p, st)
-                       : dispatch_f2v<T, int64_t>(c, d, q_cur, r_cur, r_next, d.dev_edge_qoff, p, st);
-  if (ok) ++launches;
-  return ok;
-}
+struct V2FLaunch {
+  V2FTable tab;
+  size_t smem = 0;
+};
 
-template <typename T, int D, typename OffT>
-inline void launch_v2f_tile(const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
-                            const OffT *slot_roff, const MaxSumParams &p, cudaStream_t st) {
-  using C = V2FCfg<T, D>;
-  auto kern = k_v2f_tile<T, D, OffT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    attr_done = true;
+inline int v2f_bucket(int K) { return K <= 2 ? 0 : (K <= 4 ? 1 : (K <= 8 ? 2 : 3)); }
+
+// Split the regular variable classes (degree 1..16, one domain size D) into launches of at most
+// FG_V2F_MAX_ENTRIES classes each.
+inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<V2FLaunch> &out) {
+  V2FLaunch cur;
+  cur.tab.n = 0;
+  cur.tab.total_tiles = 0;
+  auto flush = [&]() {
+    if (cur.tab.n) out.push_back(cur);
+    cur = V2FLaunch();
+    cur.tab.n = 0;
+    cur.tab.total_tiles = 0;
+  };
+  for (const fg_varclass_t &vc : vcs) {
+    if (vc.dom != D || vc.degree < 1 || vc.n_vars == 0) continue;
+    const size_t per_var = v2f_per_var_bytes(vc.degree, D, elem);
+    int nv = (int)((40 * 1024) / per_var) / 32 * 32;
+    nv = nv < 32 ? 32 : (nv > FG_V2F_NT ? FG_V2F_NT : nv);
+    V2FEntry e;
+    e.vc = vc;
+    e.tile_begin = cur.tab.total_tiles;
+    e.nv_tile = nv;
+    e.bucket = v2f_bucket(vc.degree);
+    cur.tab.e[cur.tab.n++] = e;
+    cur.tab.total_tiles += (vc.n_vars + nv - 1) / nv;
+    const size_t sm = (size_t)nv * per_var + 48;
+    if (sm > cur.smem) cur.smem = sm;
+    if (cur.tab.n == FG_V2F_MAX_ENTRIES) flush();
   }
-  const unsigned blocks = (unsigned)((d.n_edges + FG_V2F_TS - 1) / FG_V2F_TS);
-  kern<<<blocks, FG_V2F_TS, C::SMEM, st>>>(d.n_edges, d.dev_var_ptr, d.dev_slot_var, slot_roff, (const T *)d.dev_unary,
-                                            r_cur, q_cur, q_next, d.dev_q_cnt, d.dev_q_sent, d.dev_value,
-                                            (T *)d.dev_value_cost, p);
+  flush();
 }
 
-template <typename T, typename OffT>
-inline bool dispatch_v2f(const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next, const OffT *slot_roff,
-                         const MaxSumParams &p, cudaStream_t st) {
-  switch (d.uniform_dom) {
-#define X(n) case n: launch_v2f_tile<T, n, OffT>(d, r_cur, q_cur, q_next, slot_roff, p, st); return true;
+template <typename T, int D>
+inline void launch_v2f_classes(const V2FLaunch &L, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
+                               const MaxSumParams &p, cudaStream_t st) {
+  auto kern = k_v2f_classes<T, D, uint32_t>;
+  static size_t attr_smem = 0;
+  if (L.smem > attr_smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    attr_smem = L.smem;
+  }
+  kern<<<(unsigned)L.tab.total_tiles, FG_V2F_NT, L.smem, st>>>(L.tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur,
+                                                               q_next, d.dev_q_cnt, d.dev_q_sent, d.dev_value,
+                                                               (T *)d.dev_value_cost, p);
+}
+
+template <typename T>
+inline bool dispatch_v2f_classes(int D, const V2FLaunch &L, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur,
+                                 T *q_next, const MaxSumParams &p, cudaStream_t st) {
+  switch (D) {
+#define X(n) case n: launch_v2f_classes<T, n>(L, d, r_cur, q_cur, q_next, p, st); return true;
     FG_FAST_DOMS(X)
 #undef X
   }
   return false;
 }
 
+struct MaxSumFastPlan {
+  bool off32 = false;                    // 32-bit gather offsets available (required by the fast kernels)
+  std::vector<uint8_t> f2v;              // per factor class: tiled kernel available
+  std::vector<V2FLaunch> v2f;            // fused launches over regular variable classes
+  std::vector<int> v2f_dom;              // domain size of each launch
+  std::vector<int> slow_varclasses;      // variable classes left to the generic kernel
+};
+
+inline void maxsum_fast_plan(const fg_maxsum_desc_t &d, const std::vector<fg_class_t> &classes,
+                             const std::vector<fg_varclass_t> &vcs, MaxSumFastPlan &plan) {
+  plan.f2v.assign(classes.size(), 0);
+  plan.v2f.clear();
+  plan.v2f_dom.clear();
+  plan.slow_varclasses.clear();
+  plan.off32 = d.dev_slot_roff32 != nullptr && d.dev_edge_qoff32 != nullptr;
+  const bool fast = plan.off32 && !fg_fast_disabled();
+  for (size_t i = 0; fast && i < classes.size(); ++i) {
+    const fg_class_t &c = classes[i];
+    bool uni = true;
+    for (int j = 1; j < c.arity; ++j) uni = uni && c.dom[j] == c.dom[0];
+    if (!uni) continue;
+    if (c.arity <= 2 && fg_fast_dom(c.dom[0])) plan.f2v[i] = 1;
+    if (c.arity == 3 && fg_fast_dom_a3(c.dom[0])) plan.f2v[i] = 1;
+  }
+  const size_t elem = d.precision == FG_F64 ? 8 : 4;
+  std::vector<uint8_t> taken(vcs.size(), 0);
+  for (size_t i = 0; fast && i < vcs.size(); ++i) {
+    if (taken[i] || vcs[i].degree < 1 || !fg_fast_dom(vcs[i].dom)) continue;
+    const int D = vcs[i].dom;
+    std::vector<fg_varclass_t> same;
+    for (size_t j = i; j < vcs.size(); ++j)
+      if (!taken[j] && vcs[j].dom == D && vcs[j].degree >= 1) { same.push_back(vcs[j]); taken[j] = 1; }
+    std::vector<V2FLaunch> ls;
+    v2f_build_launches(same, D, elem, ls);
+    for (auto &l : ls) { plan.v2f.push_back(l); plan.v2f_dom.push_back(D); }
+  }
+  for (size_t i = 0; i < vcs.size(); ++i)
+    if (!taken[i] && vcs[i].n_slots > 0) plan.slow_varclasses.push_back((int)i);
+}
+
 template <typename T>
-inline bool maxsum_fast_v2f(const MaxSumFastPlan &plan, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur,
-                            T *q_next, const MaxSumParams &p, cudaStream_t st, int64_t &launches) {
-  if (!plan.v2f) return false;
-  bool ok = plan.off32 ? dispatch_v2f<T, uint32_t>(d, r_cur, q_cur, q_next, d.dev_slot_roff32, p, st)
-                       : dispatch_v2f<T, int64_t>(d, r_cur, q_cur, q_next, d.dev_slot_roff, p, st);
+inline bool maxsum_fast_f2v(const MaxSumFastPlan &plan, int ci, const fg_class_t &c, const fg_maxsum_desc_t &d,
+                            const T *q_cur, const T *r_cur, T *r_next, const MaxSumParams &p, cudaStream_t st,
+                            int64_t &launches) {
+  if (!plan.f2v[ci]) return false;
+  const bool ok = dispatch_f2v<T>(c, d, q_cur, r_cur, r_next, p, st);
   if (ok) ++launches;
   return ok;
 }

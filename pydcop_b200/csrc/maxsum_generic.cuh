@@ -150,12 +150,13 @@ __device__ __forceinline__ void select_value_generic(const VarSide &g, const T *
 // of a variable's first slot also runs select_value.  RMODE as QMODE above, for f->v messages.
 template <typename T, int RMODE>
 __global__ void __launch_bounds__(128)
-k_v2f_generic(VarSide g, int n_slots, const T *__restrict__ unary, const T *__restrict__ r_cur,
+k_v2f_generic(VarSide g, int slot_begin, int n_slots, const T *__restrict__ unary, const T *__restrict__ r_cur,
               const T *__restrict__ q_cur, T *__restrict__ q_next,
               const uint8_t *__restrict__ r_valid, uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
               T *__restrict__ value_cost, MaxSumParams p) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
+  s += slot_begin;
   const int v = g.slot_var[s];
   const int d = g.dom_size[v];
   const int s0 = g.var_ptr[v], s1 = g.var_ptr[v + 1];

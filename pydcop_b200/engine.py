@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import EngineError, FgClass, FgDsaDesc, FgMaxSumDesc
+from ._cabi import EngineError, FgClass, FgDsaDesc, FgMaxSumDesc, FgVarClass
 from .layout import FactorGraphLayout
 
 PRECISIONS = {"f32": (_cabi.FG_F32, torch.float32, np.float32),
@@ -42,6 +42,16 @@ def _class_array(layout: FactorGraphLayout):
         fc.row_total = c.row_total
         fc.n_factors, fc.first_factor, fc.first_edge = c.n_factors, c.first_factor, c.first_edge
         fc.table_size, fc.table_base, fc.msg_base = c.table_size, c.table_base, c.msg_base
+    return arr
+
+
+def _varclass_array(layout: FactorGraphLayout):
+    arr = (FgVarClass * max(1, len(layout.var_classes)))()
+    for i, c in enumerate(layout.var_classes):
+        vc = arr[i]
+        vc.dom, vc.degree, vc.n_vars = c.dom, c.degree, c.n_vars
+        vc.first_var, vc.first_slot, vc.n_slots = c.first_var, c.first_slot, c.n_slots
+        vc.unary_base, vc.q_base = c.unary_base, c.q_base
     return arr
 
 
@@ -118,6 +128,9 @@ class MaxSumEngine(_EngineBase):
         d.n_classes, d.n_msg_r, d.n_msg_q = len(L.classes), L.n_msg, L.n_msg_q
         d.uniform_dom, d.max_degree = L.uniform_dom, L.max_degree
         d.classes = C.cast(self._classes, C.POINTER(FgClass))
+        self._varclasses = _varclass_array(L)
+        d.n_varclasses = len(L.var_classes)
+        d.varclasses = C.cast(self._varclasses, C.POINTER(FgVarClass))
         d.dev_tables, d.dev_unary = _ptr(self.tables), _ptr(self.unary)
         d.dev_dom_size, d.dev_unary_off = _ptr(self.dom_size), _ptr(self.unary_off)
         d.dev_var_ptr, d.dev_var_qbase = _ptr(self.var_ptr), _ptr(self.var_qbase)
@@ -214,8 +227,11 @@ class MaxSumEngine(_EngineBase):
         return out
 
     def values(self):
-        n = self.layout.n_vars
-        return self.value[:n].cpu().numpy(), self.value_cost[:n].double().cpu().numpy()
+        """(value index, reported cost) per variable, in the caller's canonical variable order."""
+        L = self.layout
+        n = L.n_vars
+        return (L.vars_to_canonical(self.value[:n].cpu().numpy()),
+                L.vars_to_canonical(self.value_cost[:n].double().cpu().numpy()))
 
 
 class DsaEngine(_EngineBase):
@@ -243,10 +259,12 @@ class DsaEngine(_EngineBase):
         else:
             prob = np.full(L.n_vars, float(probability))
         # isolated variables (dsa.py:278-289): argopt of (own cost, value), tuple order
-        if isolated_value is None:
+        if isolated_value is not None:   # given in canonical order
+            isolated_value = np.asarray(isolated_value, dtype=np.int32)[L.var_order]
+        else:
             isolated_value = np.zeros(L.n_vars, dtype=np.int32)
             for v in np.nonzero(has_nbr == 0)[0]:
-                c = L.unary[L.unary_off[v]:L.unary_off[v + 1]]
+                c = L.unary[L.unary_off[v]:L.unary_off[v] + L.dom_size[v]]
                 if mode == "min":
                     isolated_value[v] = int(np.argmin(c))
                 else:
@@ -255,6 +273,7 @@ class DsaEngine(_EngineBase):
         with torch.cuda.device(self.device):
             self.tables = self._dev(L.tables, tdt)
             self.dom_size = self._dev(L.dom_size, torch.int32)
+            self.var_id = self._dev(L.var_order, torch.int32)
             self.edge_var = self._dev(L.edge_var, torch.int32)
             self.edge_class = self._dev(L.edge_class, torch.int32)
             self.var_ptr = self._dev(L.var_ptr, torch.int32)
@@ -272,6 +291,7 @@ class DsaEngine(_EngineBase):
         d.n_vars, d.n_factors, d.n_edges, d.n_classes = L.n_vars, L.n_factors, L.n_edges, len(L.classes)
         d.classes = C.cast(self._classes, C.POINTER(FgClass))
         d.dev_tables, d.dev_dom_size = _ptr(self.tables), _ptr(self.dom_size)
+        d.dev_var_id = _ptr(self.var_id)
         d.dev_edge_var, d.dev_edge_class = _ptr(self.edge_var), _ptr(self.edge_class)
         d.dev_var_ptr, d.dev_slot_edge = _ptr(self.var_ptr), _ptr(self.slot_edge)
         d.dev_has_nbr, d.dev_prob, d.dev_con_opt = _ptr(self.has_nbr), _ptr(self.prob), _ptr(self.con_opt)
@@ -332,4 +352,6 @@ class DsaEngine(_EngineBase):
         return int(self.lib.fg_dsa_launch_count(self._h))
 
     def values(self):
-        return self.value[self.cur][:self.layout.n_vars].cpu().numpy()
+        """Current value index per variable, canonical variable order."""
+        L = self.layout
+        return L.vars_to_canonical(self.value[self.cur][:L.n_vars].cpu().numpy())

@@ -25,6 +25,7 @@ import numpy as np
 MAX_ARITY = 8
 MAX_DOM = 256
 ALIGN = 32  # elements: class bases are 128-B aligned (f32) for bulk async copies
+MAX_CLASS_DEGREE = 16  # variables of larger degree share one irregular (CSR-driven) class
 
 
 @dataclass
@@ -52,6 +53,20 @@ class FactorClass:
 
 
 @dataclass
+class VarClass:
+    """Variables of identical (domain size, degree): unary rows, q rows and slots are affine in
+    the variable's rank inside the class.  degree == -1: irregular class (CSR via var_ptr)."""
+    dom: int
+    degree: int
+    n_vars: int
+    first_var: int
+    first_slot: int
+    unary_base: int
+    q_base: int
+    n_slots: int = 0
+
+
+@dataclass
 class FactorGraphLayout:
     n_vars: int
     n_factors: int
@@ -60,6 +75,9 @@ class FactorGraphLayout:
     n_msg_q: int               # internal q-array elements (slot order)
     n_msg_canonical: int
     classes: List[FactorClass]
+    var_classes: List[VarClass]
+    # NOTE: every per-variable / per-slot array below is in INTERNAL variable order (variables
+    # sorted by class); var_perm / var_order translate from / to the caller's canonical order.
     dom_size: np.ndarray       # int32 [V]
     unary_off: np.ndarray      # int64 [V+1]
     unary: np.ndarray          # float64 [sum dom]
@@ -77,10 +95,15 @@ class FactorGraphLayout:
     edge_msg_off: np.ndarray   # int64 [E]  internal edge order -> internal message offset
     edge_perm: np.ndarray      # int32 [E]  canonical edge -> internal edge
     factor_perm: np.ndarray    # int32 [F]  canonical factor -> internal factor
-    canon_edge_var: np.ndarray  # int32 [E]
+    var_perm: np.ndarray       # int32 [V]  canonical variable -> internal variable
+    var_order: np.ndarray      # int32 [V]  internal variable -> canonical variable
+    canon_edge_var: np.ndarray  # int32 [E]  canonical edge -> canonical variable
     canon_msg_off: np.ndarray  # int64 [E+1]
-    canon_var_edge: np.ndarray  # int32 [E] canonical edge id of slot s
-    init_value: np.ndarray     # int32 [V] (-1 = none)
+    canon_var_ptr: np.ndarray  # int32 [V+1] canonical CSR (the reference's `links` order)
+    canon_var_edge: np.ndarray  # int32 [E]
+    canon_dom_size: np.ndarray  # int32 [V]
+    slot_canon_edge: np.ndarray  # int32 [E] canonical edge id of INTERNAL slot s
+    init_value: np.ndarray     # int32 [V] (-1 = none), internal order
     msg_gather: Optional[np.ndarray] = field(default=None, repr=False)
     msg_gather_q: Optional[np.ndarray] = field(default=None, repr=False)
 
@@ -108,8 +131,19 @@ class FactorGraphLayout:
 
     def slots_to_canonical_edges(self, arr_slot):
         out = np.zeros(self.n_edges, dtype=np.asarray(arr_slot).dtype)
-        out[self.canon_var_edge] = np.asarray(arr_slot)
+        out[self.slot_canon_edge] = np.asarray(arr_slot)
         return out
+
+    def vars_to_canonical(self, arr_internal):
+        return np.asarray(arr_internal)[self.var_perm]
+
+    def canonical_unary(self):
+        """Unary costs back in canonical order, without class padding."""
+        d = self.canon_dom_size.astype(np.int64)
+        start = self.unary_off[:-1][self.var_perm]
+        idx = np.repeat(start, d) + (np.arange(int(d.sum()), dtype=np.int64)
+                                     - np.repeat(np.cumsum(d) - d, d))
+        return self.unary[idx]
 
 
 def _as(a, dt):
@@ -211,44 +245,94 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     canon_msg_off = np.zeros(E + 1, dtype=np.int64)
     np.cumsum(edge_dom, out=canon_msg_off[1:])
 
+    # ---------------- variable side: classes of identical (domain size, degree) ----------------
     if var_ptr is None or var_edge is None:
         var_ptr, var_edge = default_var_csr(V, edge_var)
-    var_ptr = _as(var_ptr, np.int32)
-    var_edge = _as(var_edge, np.int32)
-    if var_ptr[-1] != E or len(var_edge) != E:
+    c_var_ptr = _as(var_ptr, np.int32)
+    c_var_edge = _as(var_edge, np.int32)
+    if c_var_ptr[-1] != E or len(c_var_edge) != E:
         raise ValueError("var_ptr / var_edge must cover every edge exactly once")
-    slot_var = np.repeat(np.arange(V, dtype=np.int32), np.diff(var_ptr)).astype(np.int32)
-    if E and not np.array_equal(edge_var[var_edge], slot_var):
+    c_slot_var = np.repeat(np.arange(V, dtype=np.int32), np.diff(c_var_ptr)).astype(np.int32)
+    if E and not np.array_equal(edge_var[c_var_edge], c_slot_var):
         raise ValueError("var_edge lists an edge under the wrong variable")
-    slot_edge = edge_perm[var_edge].astype(np.int32)
+    c_deg = np.diff(c_var_ptr).astype(np.int64)
+    c_unary_off = np.zeros(V + 1, dtype=np.int64)
+    np.cumsum(dom_size, out=c_unary_off[1:])
+    c_unary = (np.zeros(int(c_unary_off[-1])) if unary is None
+               else _as(unary, np.float64).reshape(-1))
+    if c_unary.size != c_unary_off[-1]:
+        raise ValueError("unary has the wrong number of elements")
+    c_init = np.full(V, -1, np.int32) if init_value is None else _as(init_value, np.int32)
+
+    # class key: (domain size, degree), degrees above MAX_CLASS_DEGREE share one irregular class
+    kdeg = np.where(c_deg <= MAX_CLASS_DEGREE, c_deg, MAX_CLASS_DEGREE + 1)
+    vkey = dom_size.astype(np.int64) * (MAX_CLASS_DEGREE + 2) + kdeg
+    var_order = np.argsort(vkey, kind="stable").astype(np.int32)   # internal -> canonical
+    var_perm = np.empty(V, dtype=np.int32)
+    var_perm[var_order] = np.arange(V, dtype=np.int32)              # canonical -> internal
+    i_dom = dom_size[var_order]
+    i_deg = c_deg[var_order]
+    i_var_ptr = np.zeros(V + 1, dtype=np.int32)
+    np.cumsum(i_deg, out=i_var_ptr[1:])
+    slot_var = np.repeat(np.arange(V, dtype=np.int32), i_deg).astype(np.int32)
+    # canonical slot feeding each internal slot (per-variable `links` order is preserved)
+    src_slot = (c_var_ptr[:-1].astype(np.int64)[var_order][slot_var]
+                + (np.arange(E, dtype=np.int64) - i_var_ptr[:-1].astype(np.int64)[slot_var])) \
+        if E else np.zeros(0, np.int64)
+    slot_canon_edge = c_var_edge[src_slot].astype(np.int32) if E else np.zeros(0, np.int32)
+    slot_edge = edge_perm[slot_canon_edge].astype(np.int32)
     slot_roff = edge_msg_off[slot_edge]
-    deg = np.diff(var_ptr).astype(np.int64)
+
+    var_classes: List[VarClass] = []
+    i_unary_off = np.zeros(V + 1, dtype=np.int64)
     var_qbase = np.zeros(V + 1, dtype=np.int64)
-    np.cumsum(deg * dom_size.astype(np.int64), out=var_qbase[1:])
+    ukeys, ustart, ucount = (np.unique(vkey[var_order], return_index=True, return_counts=True)
+                             if V else (np.zeros(0, np.int64),) * 3)
+    unary_base = q_base = 0
+    for k, st, n in zip(ukeys, ustart, ucount):
+        st, n = int(st), int(n)
+        D = int(i_dom[st])
+        K = int(k % (MAX_CLASS_DEGREE + 2))
+        regular = K <= MAX_CLASS_DEGREE
+        vc = VarClass(D, K if regular else -1, n, st, int(i_var_ptr[st]), unary_base, q_base,
+                      int(i_deg[st:st + n].sum()))
+        var_classes.append(vc)
+        i_unary_off[st:st + n] = unary_base + np.arange(n, dtype=np.int64) * D
+        slots_before = (i_var_ptr[st:st + n].astype(np.int64) - int(i_var_ptr[st]))
+        var_qbase[st:st + n] = q_base + slots_before * D
+        unary_base += n * D
+        unary_base += (-unary_base) % ALIGN
+        q_base += int(i_deg[st:st + n].sum()) * D
+        q_base += (-q_base) % ALIGN
+    i_unary_off[V] = unary_base
+    var_qbase[V] = q_base
+    i_unary = np.zeros(int(unary_base))
+    if V:
+        dst = np.repeat(i_unary_off[:-1], i_dom) + (np.arange(int(i_dom.sum()), dtype=np.int64)
+                                                    - np.repeat(np.cumsum(i_dom) - i_dom, i_dom))
+        srcu = np.repeat(c_unary_off[:-1][var_order], i_dom) + (
+            np.arange(int(i_dom.sum()), dtype=np.int64) - np.repeat(np.cumsum(i_dom) - i_dom, i_dom))
+        i_unary[dst] = c_unary[srcu]
     slot_qoff = (var_qbase[:-1][slot_var]
-                 + (np.arange(E, dtype=np.int64) - var_ptr[:-1].astype(np.int64)[slot_var])
-                 * dom_size.astype(np.int64)[slot_var]) if E else np.zeros(0, np.int64)
+                 + (np.arange(E, dtype=np.int64) - i_var_ptr[:-1].astype(np.int64)[slot_var])
+                 * i_dom.astype(np.int64)[slot_var]) if E else np.zeros(0, np.int64)
     edge_qoff = np.zeros(E, dtype=np.int64)
     edge_qoff[slot_edge] = slot_qoff
     uniform_dom = int(dom_size[0]) if V and (dom_size == dom_size[0]).all() else 0
-
-    unary_off = np.zeros(V + 1, dtype=np.int64)
-    np.cumsum(dom_size, out=unary_off[1:])
-    unary = np.zeros(int(unary_off[-1])) if unary is None else _as(unary, np.float64).reshape(-1)
-    if unary.size != unary_off[-1]:
-        raise ValueError("unary has the wrong number of elements")
-    init_value = (np.full(V, -1, np.int32) if init_value is None else _as(init_value, np.int32))
+    int_edge_var = var_perm[int_edge_var] if E else int_edge_var
 
     return FactorGraphLayout(
-        n_vars=V, n_factors=F, n_edges=E, n_msg=int(n_msg), n_msg_q=int(var_qbase[-1]),
-        n_msg_canonical=int(canon_msg_off[-1]), classes=classes, dom_size=dom_size,
-        unary_off=unary_off, unary=unary, tables=tables_int, var_ptr=var_ptr,
-        slot_edge=slot_edge, slot_var=slot_var, slot_roff=slot_roff, var_qbase=var_qbase,
-        edge_qoff=edge_qoff, uniform_dom=uniform_dom, max_degree=int(deg.max(initial=0)),
-        edge_var=int_edge_var,
+        n_vars=V, n_factors=F, n_edges=E, n_msg=int(n_msg), n_msg_q=int(q_base),
+        n_msg_canonical=int(canon_msg_off[-1]), classes=classes, var_classes=var_classes,
+        dom_size=i_dom.astype(np.int32), unary_off=i_unary_off, unary=i_unary, tables=tables_int,
+        var_ptr=i_var_ptr, slot_edge=slot_edge, slot_var=slot_var, slot_roff=slot_roff,
+        var_qbase=var_qbase, edge_qoff=edge_qoff, uniform_dom=uniform_dom,
+        max_degree=int(c_deg.max(initial=0)), edge_var=int_edge_var.astype(np.int32),
         edge_class=edge_class, edge_msg_off=edge_msg_off, edge_perm=edge_perm,
-        factor_perm=factor_perm, canon_edge_var=edge_var, canon_msg_off=canon_msg_off,
-        canon_var_edge=var_edge, init_value=init_value)
+        factor_perm=factor_perm, var_perm=var_perm, var_order=var_order,
+        canon_edge_var=edge_var, canon_msg_off=canon_msg_off, canon_var_ptr=c_var_ptr,
+        canon_var_edge=c_var_edge, canon_dom_size=dom_size, slot_canon_edge=slot_canon_edge,
+        init_value=c_init[var_order].astype(np.int32))
 
 
 def layout_from_instance(inst) -> FactorGraphLayout:

@@ -25,8 +25,10 @@ def _internal_instance(L):
             table_off.append(table_off[-1] + c.table_size)
     return dict(dom_size=L.dom_size, factor_ptr=np.array(factor_ptr), edge_var=np.array(edge_var),
                 tables=np.concatenate(tables) if tables else np.zeros(0),
-                table_off=np.array(table_off), unary=L.unary, var_ptr=L.var_ptr,
-                var_edge=L.slot_edge, init_value=L.init_value)
+                table_off=np.array(table_off),
+                unary=np.concatenate([L.unary[L.unary_off[v]:L.unary_off[v] + L.dom_size[v]]
+                                      for v in range(L.n_vars)]) if L.n_vars else np.zeros(0),
+                var_ptr=L.var_ptr, var_edge=L.slot_edge, init_value=L.init_value)
 
 
 @pytest.mark.parametrize("name", ["ms_rand_mixed", "ms_arity4_mixed", "ms_secp_simple1", "ms_ising_4x4"])
@@ -47,7 +49,8 @@ def test_layout_is_a_pure_permutation(name):
     start = off_int[L.edge_perm] - L.canon_msg_off[:-1]
     g = np.repeat(start, d_can) + np.arange(L.n_msg_canonical)
     assert np.array_equal(a.q, b.q[g]) and np.array_equal(a.r, b.r[g])
-    assert np.array_equal(a.value, b.value)
+    assert np.array_equal(a.value, L.vars_to_canonical(b.value))
+    assert np.array_equal(L.canonical_unary(), np.asarray(inst["unary"], dtype=np.float64))
     assert np.array_equal(a.r_sent, b.r_sent[L.edge_perm])
     # the padded gather index used for device readback addresses the same rows
     gi = L.message_gather_index()
@@ -61,6 +64,9 @@ def test_default_var_csr_matches_reference_links_order():
         inst, _ = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
         vp, ve = default_var_csr(len(inst["dom_size"]), inst["edge_var"])
         assert np.array_equal(vp, inst["var_ptr"]) and np.array_equal(ve, inst["var_edge"]), name
+        L = layout_from_instance(inst)
+        assert sum(c.n_slots for c in L.var_classes) == L.n_edges
+        assert sum(c.n_vars for c in L.var_classes) == L.n_vars
 
 
 def test_empty_and_degenerate_graphs():
