@@ -131,6 +131,8 @@ def main():
     ap.add_argument("--vars-per-gpu", type=int, default=100_000)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="lean run for ncu: init + warmup + steps back to back, no flush/e2e/JSON")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,6 +200,11 @@ def main():
     alg_bytes = algorithmic_bytes_per_cycle(L, vb)
     updates_per_step = 2 * L.n_edges
 
+    if args.profile:
+        runner.init()
+        runner.step(max(3, args.warmup) + args.steps)
+        torch.cuda.synchronize(dev)
+        return
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     runner.init()
     for _ in range(max(3, args.warmup)):

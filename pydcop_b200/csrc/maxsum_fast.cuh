@@ -91,17 +91,16 @@ template <> struct MatchEps<double> { __device__ static double lo() { return 1.0
 // decides (the margins are wider than the worst-case rounding of the quotient).
 template <typename T>
 __device__ __forceinline__ bool approx_match_fast(T c, T prev_c, T stab) {
-  if (prev_c == c) return true;
   const T s = prev_c + c;
-  if (s == (T)0) return false;
   const T d2 = (T)2 * fg_abs<T>(prev_c - c);
   const T as = fg_abs<T>(s);
   const T rhs = stab * as;
-  if (rhs > MatchEps<T>::tiny() && rhs < Inf<T>::pos()) {
-    if (d2 < rhs * MatchEps<T>::lo()) return true;
-    if (d2 > rhs * MatchEps<T>::hi()) return false;
-  }
-  return (d2 / as) < stab;
+  const bool safe = (rhs > MatchEps<T>::tiny()) && (rhs < Inf<T>::pos());
+  const bool lt = d2 < rhs * MatchEps<T>::lo();
+  const bool gt = d2 > rhs * MatchEps<T>::hi();
+  bool res = lt;
+  if (!(safe && (lt || gt))) res = (s != (T)0) && ((d2 / as) < stab);  // rare: a few ulps from the threshold
+  return (prev_c == c) || res;
 }
 
 // damping + approx_match + gate for one message row held in registers.
@@ -157,71 +156,32 @@ struct F2VCfg {
   static constexpr size_t SMEM = (size_t)(NF * SP + 3 * NF * R) * sizeof(T) + 16;
 };
 
-template <typename T, int A, int D, typename OffT>
-__global__ void __launch_bounds__(F2VCfg<T, A, D>::NT)
-k_f2v_tile(const fg_class_t c, const T *__restrict__ tables, const T *__restrict__ q_cur,
-           const T *__restrict__ r_cur, T *__restrict__ r_next, const OffT *__restrict__ edge_qoff,
-           uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
-  using C = F2VCfg<T, A, D>;
-  constexpr int S = C::S, R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, INNER = C::INNER;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  T *tab = reinterpret_cast<T *>(smem_raw);
-  T *qt = tab + NF * SP;   // q rows of the tile's edges  [f][j][x]
-  T *rt = qt + NF * R;     // previous r rows (contiguous copy of the class-major array)
-  T *ot = rt + NF * R;     // produced r rows
-  uint64_t *bar = reinterpret_cast<uint64_t *>(ot + NF * R);
-
-  const int tid = threadIdx.x;
-  const int f0 = blockIdx.x * NF;
-  const int nf = min(NF, c.n_factors - f0);
-  const T *gtab = tables + c.table_base + (int64_t)f0 * S;
-  const int64_t rbase = c.msg_base + (int64_t)f0 * R;
-  const int e_base = c.first_edge + f0 * A;
-
-  const bool full = (nf == NF);
-  const bool tma_tab = full && C::PAD == 0 && ((NF * S * (int)sizeof(T)) % 16 == 0);
-  const bool tma_rows = full && ((NF * R * (int)sizeof(T)) % 16 == 0);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t bytes = 0;
-    if (tma_tab) bytes += NF * S * (uint32_t)sizeof(T);
-    if (tma_rows) bytes += NF * R * (uint32_t)sizeof(T);
-    mbar_expect_tx(bar, bytes);  // bytes == 0: plain arrival completes the phase
-    if (tma_tab) tma_load_1d(tab, gtab, NF * S * (uint32_t)sizeof(T), bar);
-    if (tma_rows) tma_load_1d(rt, r_cur + rbase, NF * R * (uint32_t)sizeof(T), bar);
-  }
-  if (!tma_tab) {
-    if constexpr (C::QUADS) {  // 16-byte units into the (possibly padded) per-factor stride
-      constexpr int Q = C::Q, E16 = C::E16;
-      for (int u = tid; u < nf * Q; u += NT) {
-        const int f = u / Q, w = u - f * Q;
-        cp_async_16(tab + f * SP + w * E16, gtab + (int64_t)f * S + w * E16);
-      }
-    } else {
-      for (int i = tid; i < nf * S; i += NT) cp_async_b<(int)sizeof(T)>(tab + i, gtab + i);
-    }
-  }
-  if (!tma_rows) coop_copy_in<T>(rt, r_cur + rbase, nf * R, tid, NT);
-  // gather the q rows: thread le <-> edge (f, j) = (le / A, le % A) so edge_qoff reads are coalesced
-  for (int le = tid; le < nf * A; le += NT) {
-    const int64_t off = (int64_t)edge_qoff[e_base + le];
-    const T *src = q_cur + off;
-    T *dst = qt + le * D;
+// pairwise (tree) optimum of N values: same result as the sequential scan, more ILP
+template <typename T, int N>
+__device__ __forceinline__ T opt_tree(const T (&v)[N], bool mx) {
+  T w[N];
 #pragma unroll
-    for (int i = 0; i < D / C::VR; ++i) cp_async_b<C::VR_BYTES>(dst + i * C::VR, src + i * C::VR);
+  for (int i = 0; i < N; ++i) w[i] = v[i];
+#pragma unroll
+  for (int n = N; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) w[i] = fg_opt<T>(w[i], w[n - 1 - i], mx);
   }
-  cp_async_wait_all();
-  mbar_wait(bar, 0);
-  __syncthreads();
+  return w[0];
+}
 
+// All edges of one staged tile: min-marginal (factor_costs_for_var, maxsum.py:382-447), damping,
+// send gate; results into `ot` (same [f][j][x] layout as the class-major r array).
+template <typename T, int A, int D>
+__device__ __forceinline__ void f2v_compute_tile(const T *__restrict__ tab, const T *__restrict__ qt,
+                                                 const T *__restrict__ rt, T *__restrict__ ot, int nf, int e_base,
+                                                 uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent,
+                                                 const MaxSumParams &p, int tid) {
+  using C = F2VCfg<T, A, D>;
+  constexpr int R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, INNER = C::INNER;
   const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
   const T init = mx ? -Inf<T>::pos() : Inf<T>::pos();
-
   for (int le = tid; le < NF * A; le += NT) {
     const int j = le / NF, f = le - j * NF;  // warp-uniform j (NF % 32 == 0)
     if (f >= nf) continue;
@@ -239,10 +199,9 @@ k_f2v_tile(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
         for (int x0 = 0; x0 < D; ++x0) {
           T row[D];
           ld_row<T, D, C::VT>(tf + x0 * D, row);
-          T o = init;
 #pragma unroll
-          for (int x1 = 0; x1 < D; ++x1) o = fg_opt<T>(o, row[x1] + qo[x1], mx);
-          cand[x0] = o;
+          for (int x1 = 0; x1 < D; ++x1) row[x1] = row[x1] + qo[x1];
+          cand[x0] = opt_tree<T, D>(row, mx);
         }
       } else {
 #pragma unroll
@@ -264,15 +223,16 @@ k_f2v_tile(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
         ld_row<T, D, C::VR>(qf + 2 * D, q2);
 #pragma unroll 1
         for (int x0 = 0; x0 < D; ++x0) {
-          T o = init;
+          T part[D];
 #pragma unroll
           for (int x1 = 0; x1 < D; ++x1) {
             T row[D];
             ld_row<T, D, C::VT>(tf + x0 * INNER + x1 * D, row);
 #pragma unroll
-            for (int x2 = 0; x2 < D; ++x2) o = fg_opt<T>(o, row[x2] + (q1[x1] + q2[x2]), mx);
+            for (int x2 = 0; x2 < D; ++x2) row[x2] = row[x2] + (q1[x1] + q2[x2]);
+            part[x1] = opt_tree<T, D>(row, mx);
           }
-          of[x0] = o;
+          of[x0] = opt_tree<T, D>(part, mx);
         }
         ld_row<T, D, C::VR>(of, cand);
       } else {
@@ -292,7 +252,8 @@ k_f2v_tile(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
             ld_row<T, D, C::VT>(tf + x0 * INNER + x1 * D, row);
             if (j == 1) {
 #pragma unroll
-              for (int x2 = 0; x2 < D; ++x2) cand[x1] = fg_opt<T>(cand[x1], row[x2] + s[x2], mx);
+              for (int x2 = 0; x2 < D; ++x2) row[x2] = row[x2] + s[x2];
+              cand[x1] = fg_opt<T>(cand[x1], opt_tree<T, D>(row, mx), mx);
             } else {
 #pragma unroll
               for (int x2 = 0; x2 < D; ++x2) cand[x2] = fg_opt<T>(cand[x2], row[x2] + s[x1], mx);
@@ -311,19 +272,151 @@ k_f2v_tile(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     r_cnt[e] = cnt;
     if (r_sent) r_sent[e] = sent ? 1 : 0;
   }
-  // publish the tile
-  if (tma_rows) {
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tma_store_1d(r_next + rbase, ot, NF * R * (uint32_t)sizeof(T));
-      tma_store_commit();
-      tma_store_wait_read();
-    }
-  } else {
-    __syncthreads();
-    coop_copy_out<T>(r_next + rbase, ot, nf * R, tid, NT);
+}
+
+// Persistent, software-pipelined factor->variable kernel.  Each CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; while tile k is being computed the loads of tiles
+// k+1 .. k+NS-1 are in flight (bulk async copies on per-stage mbarriers, cp.async gathers in
+// per-tile commit groups, gather indices prefetched one more tile ahead in registers).
+#define FG_F2V_NS 3
+template <typename T, int A, int D>
+struct F2VPipe {
+  using C = F2VCfg<T, A, D>;
+  static constexpr int NS = FG_F2V_NS;
+  static constexpr int STAGE = C::NF * C::SP + 2 * C::NF * C::R;  // tab | qt | rt (elements)
+  static constexpr int EPT = (C::NF * A + C::NT - 1) / C::NT;     // edges per thread per tile
+  static constexpr size_t SMEM = (size_t)(NS * STAGE + C::NF * C::R) * sizeof(T) + 64;
+};
+
+template <typename T, int A, int D, typename OffT>
+__global__ void __launch_bounds__(F2VCfg<T, A, D>::NT)
+k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict__ q_cur,
+           const T *__restrict__ r_cur, T *__restrict__ r_next, const OffT *__restrict__ edge_qoff,
+           uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
+  using C = F2VCfg<T, A, D>;
+  using P = F2VPipe<T, A, D>;
+  constexpr int S = C::S, R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, NS = P::NS, EPT = P::EPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *stage0 = reinterpret_cast<T *>(smem_raw);
+  T *ot = stage0 + NS * P::STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ot + NF * R);
+
+  const int tid = threadIdx.x;
+  const int n_tiles = (c.n_factors + NF - 1) / NF;
+  const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
   }
+  __syncthreads();
+
+  // gather indices of my k-th tile -> registers
+  auto load_idx = [&](int k, OffT (&idx)[EPT]) {
+    if (k < n_my) {
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      const int f0 = tile * NF;
+      const int nf = min(NF, c.n_factors - f0);
+      const int e_base = c.first_edge + f0 * A;
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int le = tid + u * NT;
+        idx[u] = (le < nf * A) ? edge_qoff[e_base + le] : (OffT)0;
+      }
+    }
+  };
+  // start every load of my k-th tile into stage k % NS
+  auto issue = [&](int k, const OffT (&idx)[EPT]) {
+    if (k < n_my) {
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      const int f0 = tile * NF;
+      const int nf = min(NF, c.n_factors - f0);
+      T *tab = stage0 + (k % NS) * P::STAGE;
+      T *qt = tab + NF * SP;
+      T *rt = qt + NF * R;
+      const T *gtab = tables + c.table_base + (int64_t)f0 * S;
+      const int64_t rbase = c.msg_base + (int64_t)f0 * R;
+      const bool full = (nf == NF);
+      const bool tma_tab = full && C::PAD == 0 && ((NF * S * (int)sizeof(T)) % 16 == 0);
+      const bool tma_rows = full && ((NF * R * (int)sizeof(T)) % 16 == 0);
+      if (tid == 0) {
+        uint32_t bytes = 0;
+        if (tma_tab) bytes += NF * S * (uint32_t)sizeof(T);
+        if (tma_rows) bytes += NF * R * (uint32_t)sizeof(T);
+        mbar_expect_tx(&bars[k % NS], bytes);  // bytes == 0: the plain arrival completes the phase
+        if (tma_tab) tma_load_1d(tab, gtab, NF * S * (uint32_t)sizeof(T), &bars[k % NS]);
+        if (tma_rows) tma_load_1d(rt, r_cur + rbase, NF * R * (uint32_t)sizeof(T), &bars[k % NS]);
+      }
+      if (!tma_tab) {
+        if constexpr (C::QUADS) {  // 16-byte units into the (possibly padded) per-factor stride
+          constexpr int Q = C::Q, E16 = C::E16;
+          for (int u = tid; u < nf * Q; u += NT) {
+            const int f = u / Q, w = u - f * Q;
+            cp_async_16(tab + f * SP + w * E16, gtab + (int64_t)f * S + w * E16);
+          }
+        } else {
+          for (int i = tid; i < nf * S; i += NT) cp_async_b<(int)sizeof(T)>(tab + i, gtab + i);
+        }
+      }
+      if (!tma_rows) coop_copy_in<T>(rt, r_cur + rbase, nf * R, tid, NT);
+      // q rows: thread le <-> edge (f, j) = (le / A, le % A)
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int le = tid + u * NT;
+        if (le < nf * A) {
+          const T *src = q_cur + (int64_t)idx[u];
+          T *dst = qt + le * D;
+#pragma unroll
+          for (int i = 0; i < D / C::VR; ++i) cp_async_b<C::VR_BYTES>(dst + i * C::VR, src + i * C::VR);
+        }
+      }
+    }
+    cp_async_commit();  // one group per tile slot, even when empty: uniform accounting
+  };
+
+  OffT idx[EPT];
+  // prologue: tiles 0 .. NS-2 in flight, indices of tile NS-1 on their way
+#pragma unroll 1
+  for (int k = 0; k < NS - 1; ++k) {
+    load_idx(k, idx);
+    issue(k, idx);
+  }
+  load_idx(NS - 1, idx);
+
+#pragma unroll 1
+  for (int k = 0; k < n_my; ++k) {
+    OffT idx_next[EPT];
+    load_idx(k + NS, idx_next);
+    issue(k + NS - 1, idx);  // into the stage tile k-1 has just vacated
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) idx[u] = idx_next[u];
+    cp_async_wait_group<NS - 1>();  // my gathers / padded copies of tile k have landed
+    mbar_wait(&bars[k % NS], (uint32_t)((k / NS) & 1));
+    if (tid == 0) tma_store_wait_read();  // previous tile's bulk store has finished reading `ot`
+    __syncthreads();
+
+    const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+    const int f0 = tile * NF;
+    const int nf = min(NF, c.n_factors - f0);
+    const T *tab = stage0 + (k % NS) * P::STAGE;
+    f2v_compute_tile<T, A, D>(tab, tab + NF * SP, tab + NF * SP + NF * R, ot, nf, c.first_edge + f0 * A, r_cnt,
+                              r_sent, p, tid);
+    const int64_t rbase = c.msg_base + (int64_t)f0 * R;
+    if (nf == NF && ((NF * R * (int)sizeof(T)) % 16 == 0)) {
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(r_next + rbase, ot, NF * R * (uint32_t)sizeof(T));
+        tma_store_commit();
+      }
+    } else {
+      __syncthreads();
+      coop_copy_out<T>(r_next + rbase, ot, nf * R, tid, NT);
+      __syncthreads();
+    }
+  }
+  cp_async_wait_all();
+  if (tid == 0) tma_store_wait_read();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -583,14 +676,20 @@ template <typename T, int A, int D>
 inline void launch_f2v_tile(const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur, T *r_next,
                             const MaxSumParams &p, cudaStream_t st) {
   using C = F2VCfg<T, A, D>;
-  auto kern = k_f2v_tile<T, A, D, uint32_t>;
-  static bool attr_done = false;  // one per instantiation
-  if (!attr_done) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    attr_done = true;
+  auto kern = k_f2v_pipe<T, A, D, uint32_t>;
+  using PP = F2VPipe<T, A, D>;
+  static int ctas_per_sm = 0, n_sm = 0;  // one per instantiation
+  if (!ctas_per_sm) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP::SMEM);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::NT, PP::SMEM);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  const unsigned blocks = (unsigned)((c.n_factors + C::NF - 1) / C::NF);
-  kern<<<blocks, C::NT, C::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, d.dev_edge_qoff32, d.dev_r_cnt,
+  const int n_tiles = (c.n_factors + C::NF - 1) / C::NF;
+  const unsigned blocks = (unsigned)min(n_tiles, n_sm * ctas_per_sm);
+  kern<<<blocks, C::NT, PP::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, d.dev_edge_qoff32, d.dev_r_cnt,
                                        d.dev_r_sent, p);
 }
 
