@@ -172,17 +172,20 @@ __device__ __forceinline__ T opt_tree(const T (&v)[N], bool mx) {
 
 // All edges of one staged tile: min-marginal (factor_costs_for_var, maxsum.py:382-447), damping,
 // send gate; results into `ot` (same [f][j][x] layout as the class-major r array).
-template <typename T, int A, int D>
+template <typename T, int A, int D, int EPT>
 __device__ __forceinline__ void f2v_compute_tile(const T *__restrict__ tab, const T *__restrict__ qt,
                                                  const T *__restrict__ rt, T *__restrict__ ot, int nf, int e_base,
-                                                 uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent,
-                                                 const MaxSumParams &p, int tid) {
+                                                 const uint8_t (&cnt_in)[EPT], uint8_t *__restrict__ r_cnt,
+                                                 uint8_t *__restrict__ r_sent, const MaxSumParams &p, int tid) {
   using C = F2VCfg<T, A, D>;
   constexpr int R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, INNER = C::INNER;
   const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
   const T init = mx ? -Inf<T>::pos() : Inf<T>::pos();
-  for (int le = tid; le < NF * A; le += NT) {
+#pragma unroll
+  for (int u = 0; u < EPT; ++u) {
+    const int le = tid + u * NT;
+    if (le >= NF * A) break;
     const int j = le / NF, f = le - j * NF;  // warp-uniform j (NF % 32 == 0)
     if (f >= nf) continue;
     const T *tf = tab + f * SP;
@@ -266,7 +269,7 @@ __device__ __forceinline__ void f2v_compute_tile(const T *__restrict__ tab, cons
     T prev[D];
     ld_row<T, D, C::VR>(rt + f * R + j * D, prev);
     const int e = e_base + f * A + j;
-    uint8_t cnt = r_cnt[e];
+    uint8_t cnt = cnt_in[u];  // prefetched one tile ahead (a global load here would stall the tile)
     const bool sent = damp_gate_row<T, D>(cand, prev, cnt, p.damp_factors != 0, lam, oml, stab);
     st_row<T, D, C::VR>(of, cand);
     r_cnt[e] = cnt;
@@ -278,14 +281,16 @@ __device__ __forceinline__ void f2v_compute_tile(const T *__restrict__ tab, cons
 // blockIdx.x, blockIdx.x + gridDim.x, ...; while tile k is being computed the loads of tiles
 // k+1 .. k+NS-1 are in flight (bulk async copies on per-stage mbarriers, cp.async gathers in
 // per-tile commit groups, gather indices prefetched one more tile ahead in registers).
-#define FG_F2V_NS 3
+#define FG_SMEM_LIMIT (220 * 1024)
 template <typename T, int A, int D>
 struct F2VPipe {
   using C = F2VCfg<T, A, D>;
-  static constexpr int NS = FG_F2V_NS;
   static constexpr int STAGE = C::NF * C::SP + 2 * C::NF * C::R;  // tab | qt | rt (elements)
   static constexpr int EPT = (C::NF * A + C::NT - 1) / C::NT;     // edges per thread per tile
-  static constexpr size_t SMEM = (size_t)(NS * STAGE + C::NF * C::R) * sizeof(T) + 64;
+  static constexpr size_t smem_for(int ns) { return (size_t)(ns * STAGE + 2 * C::NF * C::R) * sizeof(T) + 64; }
+  static constexpr int NS = smem_for(3) <= FG_SMEM_LIMIT ? 3 : 2;
+  static constexpr bool FITS = smem_for(2) <= FG_SMEM_LIMIT;
+  static constexpr size_t SMEM = smem_for(NS);
 };
 
 template <typename T, int A, int D, typename OffT>
@@ -298,8 +303,8 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
   constexpr int S = C::S, R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, NS = P::NS, EPT = P::EPT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T *stage0 = reinterpret_cast<T *>(smem_raw);
-  T *ot = stage0 + NS * P::STAGE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(ot + NF * R);
+  T *ot0 = stage0 + NS * P::STAGE;  // two output buffers: the bulk store of tile k-1 may still be reading
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ot0 + 2 * NF * R);
 
   const int tid = threadIdx.x;
   const int n_tiles = (c.n_factors + NF - 1) / NF;
@@ -374,7 +379,24 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     cp_async_commit();  // one group per tile slot, even when empty: uniform accounting
   };
 
+  // send-gate counters of my k-th tile -> registers, in the compute mapping (le -> (j, f))
+  auto load_cnt = [&](int k, uint8_t (&cn)[EPT]) {
+    if (k < n_my) {
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      const int f0 = tile * NF;
+      const int nf = min(NF, c.n_factors - f0);
+      const int e_base = c.first_edge + f0 * A;
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int le = tid + u * NT;
+        const int j = le / NF, f = le - j * NF;
+        cn[u] = (le < NF * A && f < nf) ? r_cnt[e_base + f * A + j] : (uint8_t)0;
+      }
+    }
+  };
+
   OffT idx[EPT];
+  uint8_t cnt[EPT];
   // prologue: tiles 0 .. NS-2 in flight, indices of tile NS-1 on their way
 #pragma unroll 1
   for (int k = 0; k < NS - 1; ++k) {
@@ -382,25 +404,31 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     issue(k, idx);
   }
   load_idx(NS - 1, idx);
+  load_cnt(0, cnt);
 
 #pragma unroll 1
   for (int k = 0; k < n_my; ++k) {
     OffT idx_next[EPT];
+    uint8_t cnt_next[EPT];
     load_idx(k + NS, idx_next);
+    load_cnt(k + 1, cnt_next);
     issue(k + NS - 1, idx);  // into the stage tile k-1 has just vacated
 #pragma unroll
     for (int u = 0; u < EPT; ++u) idx[u] = idx_next[u];
     cp_async_wait_group<NS - 1>();  // my gathers / padded copies of tile k have landed
     mbar_wait(&bars[k % NS], (uint32_t)((k / NS) & 1));
-    if (tid == 0) tma_store_wait_read();  // previous tile's bulk store has finished reading `ot`
+    if (tid == 0) tma_store_wait_read1();  // the bulk store of tile k-2 has finished reading ot[k & 1]
     __syncthreads();
 
     const int tile = (int)blockIdx.x + k * (int)gridDim.x;
     const int f0 = tile * NF;
     const int nf = min(NF, c.n_factors - f0);
     const T *tab = stage0 + (k % NS) * P::STAGE;
-    f2v_compute_tile<T, A, D>(tab, tab + NF * SP, tab + NF * SP + NF * R, ot, nf, c.first_edge + f0 * A, r_cnt,
-                              r_sent, p, tid);
+    T *ot = ot0 + (k & 1) * NF * R;
+    f2v_compute_tile<T, A, D, EPT>(tab, tab + NF * SP, tab + NF * SP + NF * R, ot, nf, c.first_edge + f0 * A, cnt,
+                                   r_cnt, r_sent, p, tid);
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) cnt[u] = cnt_next[u];
     const int64_t rbase = c.msg_base + (int64_t)f0 * R;
     if (nf == NF && ((NF * R * (int)sizeof(T)) % 16 == 0)) {
       fence_proxy_async_smem();
@@ -693,28 +721,40 @@ inline void launch_f2v_tile(const fg_class_t &c, const fg_maxsum_desc_t &d, cons
                                        d.dev_r_sent, p);
 }
 
+template <typename T, int A, int D>
+inline bool try_f2v_tile(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
+                         T *r_next, const MaxSumParams &p, cudaStream_t st) {
+  if constexpr (F2VPipe<T, A, D>::FITS) {
+    if (!probe) launch_f2v_tile<T, A, D>(c, d, q_cur, r_cur, r_next, p, st);
+    return true;
+  } else {
+    return false;  // staging does not fit in shared memory: generic kernel
+  }
+}
+
+// probe == true: only report whether a tiled kernel exists for the class
 template <typename T>
-inline bool dispatch_f2v(const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur, T *r_next,
-                         const MaxSumParams &p, cudaStream_t st) {
+inline bool dispatch_f2v(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
+                         T *r_next, const MaxSumParams &p, cudaStream_t st) {
   const int D = c.dom[0];
   switch (c.arity) {
     case 1:
       switch (D) {
-#define X(n) case n: launch_f2v_tile<T, 1, n>(c, d, q_cur, r_cur, r_next, p, st); return true;
+#define X(n) case n: return try_f2v_tile<T, 1, n>(probe, c, d, q_cur, r_cur, r_next, p, st);
         FG_FAST_DOMS(X)
 #undef X
       }
       return false;
     case 2:
       switch (D) {
-#define X(n) case n: launch_f2v_tile<T, 2, n>(c, d, q_cur, r_cur, r_next, p, st); return true;
+#define X(n) case n: return try_f2v_tile<T, 2, n>(probe, c, d, q_cur, r_cur, r_next, p, st);
         FG_FAST_DOMS(X)
 #undef X
       }
       return false;
     case 3:
       switch (D) {
-#define X(n) case n: launch_f2v_tile<T, 3, n>(c, d, q_cur, r_cur, r_next, p, st); return true;
+#define X(n) case n: return try_f2v_tile<T, 3, n>(probe, c, d, q_cur, r_cur, r_next, p, st);
         FG_FAST_DOMS_A3(X)
 #undef X
       }
@@ -807,8 +847,11 @@ inline void maxsum_fast_plan(const fg_maxsum_desc_t &d, const std::vector<fg_cla
     bool uni = true;
     for (int j = 1; j < c.arity; ++j) uni = uni && c.dom[j] == c.dom[0];
     if (!uni) continue;
-    if (c.arity <= 2 && fg_fast_dom(c.dom[0])) plan.f2v[i] = 1;
-    if (c.arity == 3 && fg_fast_dom_a3(c.dom[0])) plan.f2v[i] = 1;
+    MaxSumParams dummy{};
+    const bool ok = d.precision == FG_F64
+                        ? dispatch_f2v<double>(true, c, d, nullptr, nullptr, nullptr, dummy, nullptr)
+                        : dispatch_f2v<float>(true, c, d, nullptr, nullptr, nullptr, dummy, nullptr);
+    if (ok) plan.f2v[i] = 1;
   }
   const size_t elem = d.precision == FG_F64 ? 8 : 4;
   std::vector<uint8_t> taken(vcs.size(), 0);
@@ -831,7 +874,7 @@ inline bool maxsum_fast_f2v(const MaxSumFastPlan &plan, int ci, const fg_class_t
                             const T *q_cur, const T *r_cur, T *r_next, const MaxSumParams &p, cudaStream_t st,
                             int64_t &launches) {
   if (!plan.f2v[ci]) return false;
-  const bool ok = dispatch_f2v<T>(c, d, q_cur, r_cur, r_next, p, st);
+  const bool ok = dispatch_f2v<T>(false, c, d, q_cur, r_cur, r_next, p, st);
   if (ok) ++launches;
   return ok;
 }
