@@ -105,18 +105,37 @@ __device__ __forceinline__ bool approx_match_fast(T c, T prev_c, T stab) {
 
 // damping + approx_match + gate for one message row held in registers.
 // cand: fresh message (in) / message to store (out).  Returns `sent`.
+// The match predicate is evaluated division-free for the whole row (straight-line code); only if
+// some element sits within a few ulps of the threshold (or in the denormal / overflow range) the
+// literal form with the IEEE division is evaluated for that element.
 template <typename T, int D>
 __device__ __forceinline__ bool damp_gate_row(T (&cand)[D], const T (&prev)[D], uint8_t &cnt, bool damp_side,
                                               T lam, T oml, T stab) {
   const bool has_prev = cnt & 1;
   bool match = has_prev;
   if (has_prev) {
+    bool all_ok = true, unsure = false;
 #pragma unroll
     for (int x = 0; x < D; ++x) {
       T c = cand[x];
       if (damp_side) c = lam * prev[x] + oml * c;
       cand[x] = c;
-      if (!approx_match_fast<T>(c, prev[x], stab)) match = false;
+      const T s = prev[x] + c;
+      const T d2 = (T)2 * fg_abs<T>(prev[x] - c);
+      const T rhs = stab * fg_abs<T>(s);
+      const bool safe = (rhs > MatchEps<T>::tiny()) && (rhs < Inf<T>::pos());
+      const bool lt = d2 < rhs * MatchEps<T>::lo();
+      const bool gt = d2 > rhs * MatchEps<T>::hi();
+      const bool eq = prev[x] == c;
+      unsure = unsure || (!eq && !(safe && (lt || gt)));
+      all_ok = all_ok && (eq || lt);
+    }
+    match = all_ok;
+    if (unsure) {  // rare
+      match = true;
+#pragma unroll
+      for (int x = 0; x < D; ++x)
+        if (!approx_match1<T>(cand[x], prev[x], stab)) match = false;
     }
   }
   const bool sent = gate_decide(match, cnt);
@@ -282,13 +301,16 @@ __device__ __forceinline__ void f2v_compute_tile(const T *__restrict__ tab, cons
 // k+1 .. k+NS-1 are in flight (bulk async copies on per-stage mbarriers, cp.async gathers in
 // per-tile commit groups, gather indices prefetched one more tile ahead in registers).
 #define FG_SMEM_LIMIT (220 * 1024)
+#ifndef FG_F2V_NS
+#define FG_F2V_NS 2
+#endif
 template <typename T, int A, int D>
 struct F2VPipe {
   using C = F2VCfg<T, A, D>;
   static constexpr int STAGE = C::NF * C::SP + 2 * C::NF * C::R;  // tab | qt | rt (elements)
   static constexpr int EPT = (C::NF * A + C::NT - 1) / C::NT;     // edges per thread per tile
   static constexpr size_t smem_for(int ns) { return (size_t)(ns * STAGE + 2 * C::NF * C::R) * sizeof(T) + 64; }
-  static constexpr int NS = smem_for(3) <= FG_SMEM_LIMIT ? 3 : 2;
+  static constexpr int NS = FG_F2V_NS <= 2 ? 2 : (smem_for(FG_F2V_NS) <= FG_SMEM_LIMIT ? FG_F2V_NS : 2);
   static constexpr bool FITS = smem_for(2) <= FG_SMEM_LIMIT;
   static constexpr size_t SMEM = smem_for(NS);
 };
@@ -614,6 +636,15 @@ k_v2f_classes(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *_
     for (int i = tid; i < nslots * D; i += NT) cp_async_b<(int)sizeof(T)>(qio + i, q_cur + qoff + i);
   if (!tma_u)
     for (int i = tid; i < nv * D; i += NT) cp_async_b<(int)sizeof(T)>(un + i, unary + uoff + i);
+  // send-gate counters of the slots this thread finishes in phase 2: fetched now, used after two
+  // barriers (a global load there would stall the whole tile)
+  constexpr int MAXR = 6;
+  uint8_t cntp[MAXR];
+#pragma unroll
+  for (int u = 0; u < MAXR; ++u) {
+    const int sl = tid + u * NT;
+    cntp[u] = (sl < nslots) ? q_cnt[slot0 + sl] : (uint8_t)0;
+  }
   // gather the r rows (one row per thread, vector loads) and transpose them into shared memory
   for (int sl = tid; sl < nslots; sl += NT) {
     const T *src = r_cur + (int64_t)slot_roff[slot0 + sl];
@@ -647,7 +678,10 @@ k_v2f_classes(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *_
   __syncthreads();
   {  // phase 2: one thread per slot: normalise, damping, send gate
     const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
-    for (int sl = tid; sl < nslots; sl += NT) {
+#pragma unroll
+    for (int u = 0; u < MAXR; ++u) {
+      const int sl = tid + u * NT;
+      if (sl >= nslots) break;
       const int i = sl / K, f = sl - i * K;
       const T a = avg[sl];
       const T *src = rtT + i * KP + f;
@@ -655,7 +689,7 @@ k_v2f_classes(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *_
 #pragma unroll
       for (int x = 0; x < D; ++x) cand[x] = src[x * RS] - a;
       ld_row<T, D, C::VR>(qio + sl * D, prev);
-      uint8_t cnt = q_cnt[slot0 + sl];
+      uint8_t cnt = cntp[u];
       const bool sent = damp_gate_row<T, D>(cand, prev, cnt, p.damp_vars != 0, lam, oml, stab);
       st_row<T, D, C::VR>(qio + sl * D, cand);
       q_cnt[slot0 + sl] = cnt;
@@ -787,6 +821,7 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
     const size_t per_var = v2f_per_var_bytes(vc.degree, D, elem);
     int nv = (int)((40 * 1024) / per_var) / 32 * 32;
     nv = nv < 32 ? 32 : (nv > FG_V2F_NT ? FG_V2F_NT : nv);
+    while (nv > 32 && nv * vc.degree > 6 * FG_V2F_NT) nv -= 32;  // phase 2 handles <= 6 slots per thread
     V2FEntry e;
     e.vc = vc;
     e.tile_begin = cur.tab.total_tiles;
