@@ -14,6 +14,7 @@
 // Floating-point operand order is the reference's (see common.cuh); results are bit-identical to
 // the generic kernels and to the CPU oracle of the same precision.
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -474,16 +475,18 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 // ------------------------------------------------------------------------------------------------
 #define FG_V2F_MAX_ENTRIES 24
 #define FG_V2F_NT 128
+#define FG_V2F_ROUNDS 2   // a thread finishes at most this many slots per tile
 
 struct V2FEntry {
   fg_varclass_t vc;
-  int32_t tile_begin;  // first block of this class in the launch
-  int32_t nv_tile;     // variables per block
-  int32_t bucket;      // 0: K<=2  1: K<=4  2: K<=8 (register resident)  3: K<=16 (shared resident)
+  int32_t tile_begin;  // first tile of this class in the launch
+  int32_t nv_tile;     // variables per tile
 };
 struct V2FTable {
   int32_t n;
   int32_t total_tiles;
+  int32_t stage_elems;  // elements of one stage buffer (max over the classes)
+  int32_t out_elems;    // elements of the output buffer
   V2FEntry e[FG_V2F_MAX_ENTRIES];
 };
 
@@ -493,221 +496,207 @@ struct V2FCfg {
   static constexpr int VR = VR_BYTES / (int)sizeof(T);
 };
 
-__host__ __device__ inline int v2f_kp(int K) { return K | 1; }  // odd column stride: conflict-free
-__host__ __device__ inline size_t v2f_per_var_bytes(int K, int D, size_t elem) {
-  return (size_t)(D * v2f_kp(K) + K * D + D + K) * elem;
-}
+struct V2FTile {
+  int K, nv_full, nv, nslots, slot0, var0;
+  int64_t qoff, uoff;
+};
 
-// Phase 1, one thread per variable.  The K gathered r rows of the variable sit TRANSPOSED in
-// shared memory (col[x*RS + g]); every r value is read once, all K un-normalised messages
-// (costs_for_factor, maxsum.py:623-676: value-major, then factor order) and the selection total
-// (select_value, maxsum.py:584-620) are accumulated from it, and the raw message value is
-// written back in place.  Rows g >= K contribute +0, which is exact.
-template <typename T, int D, int KMAX>
-__device__ __forceinline__ void v2f_phase1(int K, T *__restrict__ col, int RS, const T *__restrict__ unrow,
-                                           T *__restrict__ avg, bool mx, int32_t *value_out, T *cost_out) {
-  T sum[KMAX];
-#pragma unroll
-  for (int f = 0; f < KMAX; ++f) sum[f] = (T)0;
-  int best = 0;
-  T best_c = (T)0;
-#pragma unroll
-  for (int x = 0; x < D; ++x) {
-    T c[KMAX];
-#pragma unroll
-    for (int g = 0; g < KMAX; ++g) c[g] = (g < K) ? col[x * RS + g] : (T)0;
-    const T u = unrow[x];
-    T tot = u;
-#pragma unroll
-    for (int g = 0; g < KMAX; ++g) tot += c[g];
-    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-#pragma unroll
-    for (int f = 0; f < KMAX; ++f) {
-      if (f < K) {
-        T m = u;
-#pragma unroll
-        for (int g = 0; g < KMAX; ++g) {
-          if (g == f) continue;
-          sum[f] += c[g];
-          m += c[g];
-        }
-        col[x * RS + f] = m;
-      }
-    }
-  }
-#pragma unroll
-  for (int f = 0; f < KMAX; ++f)
-    if (f < K) avg[f] = sum[f] / (T)D;
-  *value_out = best;
-  *cost_out = best_c;
-}
-
-// same with run-time loops (degree 9..16)
-template <typename T, int D>
-__device__ __forceinline__ void v2f_phase1_rt(int K, T *__restrict__ col, int RS, const T *__restrict__ unrow,
-                                              T *__restrict__ avg, bool mx, int32_t *value_out, T *cost_out) {
-  int best = 0;
-  T best_c = (T)0;
-  for (int x = 0; x < D; ++x) {
-    T tot = unrow[x];
-    for (int g = 0; g < K; ++g) tot += col[x * RS + g];
-    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-  }
-  *value_out = best;
-  *cost_out = best_c;
-  // the raw messages cannot overwrite the rows in place before every f has read them: keep the
-  // K values of one x in registers (K <= 16)
-  T sumf[16];
-  for (int f = 0; f < 16; ++f) sumf[f] = (T)0;
-  for (int x = 0; x < D; ++x) {
-    T c[16];
-#pragma unroll
-    for (int g = 0; g < 16; ++g) c[g] = (g < K) ? col[x * RS + g] : (T)0;
-    const T u = unrow[x];
-#pragma unroll
-    for (int f = 0; f < 16; ++f) {
-      if (f < K) {
-        T m = u;
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          if (g == f) continue;
-          sumf[f] += c[g];
-          m += c[g];
-        }
-        col[x * RS + f] = m;
-      }
-    }
-  }
-#pragma unroll
-  for (int f = 0; f < 16; ++f)
-    if (f < K) avg[f] = sumf[f] / (T)D;
-}
-
-template <typename T, int D, typename OffT>
-__global__ void __launch_bounds__(FG_V2F_NT)
-k_v2f_classes(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
-              const T *__restrict__ r_cur, const T *__restrict__ q_cur, T *__restrict__ q_next,
-              uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
-              T *__restrict__ value_cost, MaxSumParams p) {
-  using C = V2FCfg<T, D>;
-  constexpr int NT = FG_V2F_NT;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // which class / tile is this block?
+__device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D) {
   int ci = 0;
 #pragma unroll 1
   for (int i = 1; i < tab.n; ++i)
-    if ((int)blockIdx.x >= tab.e[i].tile_begin) ci = i;
+    if (t >= tab.e[i].tile_begin) ci = i;
   const V2FEntry &en = tab.e[ci];
-  const int K = en.vc.degree;
-  const int KP = v2f_kp(K);
-  const int NV = en.nv_tile;
-  const int RS = NV * KP;
-  const int v0 = ((int)blockIdx.x - en.tile_begin) * NV;
-  const int nv = min(NV, en.vc.n_vars - v0);
-  const int nslots = nv * K;
-  const int slot0 = en.vc.first_slot + v0 * K;
-  const int64_t qoff = en.vc.q_base + (int64_t)v0 * K * D;
-  const int64_t uoff = en.vc.unary_base + (int64_t)v0 * D;
+  V2FTile o;
+  o.K = en.vc.degree;
+  o.nv_full = en.nv_tile;
+  const int v0 = (t - en.tile_begin) * en.nv_tile;
+  o.nv = min(en.nv_tile, en.vc.n_vars - v0);
+  o.nslots = o.nv * o.K;
+  o.slot0 = en.vc.first_slot + v0 * o.K;
+  o.var0 = en.vc.first_var + v0;
+  o.qoff = en.vc.q_base + (int64_t)v0 * o.K * D;
+  o.uoff = en.vc.unary_base + (int64_t)v0 * D;
+  return o;
+}
 
-  T *qio = reinterpret_cast<T *>(smem_raw);  // [NV*K][D]  q_old rows in, q_next rows out (in place)
-  T *un = qio + NV * K * D;                  // [NV][D]
-  T *rtT = un + NV * D;                      // [D][RS]    gathered r rows, transposed
-  T *avg = rtT + D * RS;                     // [NV*K]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (((size_t)(NV * K * D + NV * D + D * RS + NV * K) * sizeof(T) + 15) & ~(size_t)15));
+// Persistent, software-pipelined variable->factor kernel over the (domain D, degree K) classes of
+// one launch.  A tile is nv variables of one class = nv*K consecutive slots; one thread per slot
+// computes costs_for_factor (maxsum.py:623-676; value-major then factor order), damping and the
+// send gate; one thread per variable runs select_value (maxsum.py:584-620).  While tile k is being
+// computed, the r-row gather (cp.async through slot_roff), the q_old tile and the unary tile
+// (bulk async copies) of tile k+1 are in flight; gather indices and gate counters are prefetched
+// in registers.
+template <typename T, int D, typename OffT>
+__global__ void __launch_bounds__(FG_V2F_NT)
+k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
+           const T *__restrict__ r_cur, const T *__restrict__ q_cur, T *__restrict__ q_next,
+           uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
+           T *__restrict__ value_cost, MaxSumParams p) {
+  using C = V2FCfg<T, D>;
+  constexpr int NT = FG_V2F_NT, NS = 2, RND = FG_V2F_ROUNDS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *stage0 = reinterpret_cast<T *>(smem_raw);        // per stage: rrow | qio | un
+  T *qout = stage0 + NS * tab.stage_elems;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(qout + tab.out_elems);
 
   const int tid = threadIdx.x;
-  const bool full = (nv == NV);
-  const uint32_t qbytes = (uint32_t)(NV * K * D) * (uint32_t)sizeof(T);
-  const uint32_t ubytes = (uint32_t)(NV * D) * (uint32_t)sizeof(T);
-  const bool tma_q = full && (qbytes % 16 == 0) && (((qoff * (int64_t)sizeof(T)) & 15) == 0);
-  const bool tma_u = full && (ubytes % 16 == 0) && (((uoff * (int64_t)sizeof(T)) & 15) == 0) &&
-                     ((((size_t)NV * K * D * sizeof(T)) & 15) == 0);
+  const int n_my = ((int)blockIdx.x < tab.total_tiles)
+                       ? (tab.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, (tma_q ? qbytes : 0u) + (tma_u ? ubytes : 0u));
-    if (tma_q) tma_load_1d(qio, q_cur + qoff, qbytes, bar);
-    if (tma_u) tma_load_1d(un, unary + uoff, ubytes, bar);
-  }
-  if (!tma_q)
-    for (int i = tid; i < nslots * D; i += NT) cp_async_b<(int)sizeof(T)>(qio + i, q_cur + qoff + i);
-  if (!tma_u)
-    for (int i = tid; i < nv * D; i += NT) cp_async_b<(int)sizeof(T)>(un + i, unary + uoff + i);
-  // send-gate counters of the slots this thread finishes in phase 2: fetched now, used after two
-  // barriers (a global load there would stall the whole tile)
-  constexpr int MAXR = 6;
-  uint8_t cntp[MAXR];
+
+  auto tile_of = [&](int k) { return v2f_tile(tab, (int)blockIdx.x + k * (int)gridDim.x, D); };
+  auto load_idx = [&](int k, OffT (&idx)[RND]) {
+    if (k < n_my) {
+      const V2FTile t = tile_of(k);
 #pragma unroll
-  for (int u = 0; u < MAXR; ++u) {
-    const int sl = tid + u * NT;
-    cntp[u] = (sl < nslots) ? q_cnt[slot0 + sl] : (uint8_t)0;
-  }
-  // gather the r rows (one row per thread, vector loads) and transpose them into shared memory
-  for (int sl = tid; sl < nslots; sl += NT) {
-    const T *src = r_cur + (int64_t)slot_roff[slot0 + sl];
-    T row[D];
-    ld_row<T, D, C::VR>(src, row);
-    const int i = sl / K, g = sl - i * K;
-    T *dst = rtT + i * KP + g;
+      for (int u = 0; u < RND; ++u) {
+        const int sl = tid + u * NT;
+        idx[u] = (sl < t.nslots) ? slot_roff[t.slot0 + sl] : (OffT)0;
+      }
+    }
+  };
+  auto load_cnt = [&](int k, uint8_t (&cn)[RND]) {
+    if (k < n_my) {
+      const V2FTile t = tile_of(k);
 #pragma unroll
-    for (int x = 0; x < D; ++x) dst[x * RS] = row[x];
+      for (int u = 0; u < RND; ++u) {
+        const int sl = tid + u * NT;
+        cn[u] = (sl < t.nslots) ? q_cnt[t.slot0 + sl] : (uint8_t)0;
+      }
+    }
+  };
+  auto issue = [&](int k, const OffT (&idx)[RND]) {
+    if (k < n_my) {
+      const V2FTile t = tile_of(k);
+      T *rrow = stage0 + (k % NS) * tab.stage_elems;
+      T *qio = rrow + t.nv_full * t.K * D;
+      T *un = qio + t.nv_full * t.K * D;
+      const uint32_t qbytes = (uint32_t)(t.nslots * D) * (uint32_t)sizeof(T);
+      const uint32_t ubytes = (uint32_t)(t.nv * D) * (uint32_t)sizeof(T);
+      const bool tma_q = (qbytes % 16 == 0) && (((t.qoff * (int64_t)sizeof(T)) & 15) == 0) &&
+                         ((((size_t)t.nv_full * t.K * D * sizeof(T)) & 15) == 0);
+      const bool tma_u = (ubytes % 16 == 0) && (((t.uoff * (int64_t)sizeof(T)) & 15) == 0) &&
+                         ((((size_t)t.nv_full * t.K * D * sizeof(T)) & 15) == 0);
+      if (tid == 0) {
+        mbar_expect_tx(&bars[k % NS], (tma_q ? qbytes : 0u) + (tma_u ? ubytes : 0u));
+        if (tma_q) tma_load_1d(qio, q_cur + t.qoff, qbytes, &bars[k % NS]);
+        if (tma_u) tma_load_1d(un, unary + t.uoff, ubytes, &bars[k % NS]);
+      }
+      if (!tma_q)
+        for (int i = tid; i < t.nslots * D; i += NT) cp_async_b<(int)sizeof(T)>(qio + i, q_cur + t.qoff + i);
+      if (!tma_u)
+        for (int i = tid; i < t.nv * D; i += NT) cp_async_b<(int)sizeof(T)>(un + i, unary + t.uoff + i);
+#pragma unroll
+      for (int u = 0; u < RND; ++u) {
+        const int sl = tid + u * NT;
+        if (sl < t.nslots) {
+          const T *src = r_cur + (int64_t)idx[u];
+          T *dst = rrow + sl * D;
+#pragma unroll
+          for (int i = 0; i < D / C::VR; ++i) cp_async_b<C::VR_BYTES>(dst + i * C::VR, src + i * C::VR);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  OffT idx[RND];
+  uint8_t cnt[RND];
+  load_idx(0, idx);
+  issue(0, idx);
+  load_idx(1, idx);
+  load_cnt(0, cnt);
+  const bool mx = p.mode_max != 0;
+  const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
+
+#pragma unroll 1
+  for (int k = 0; k < n_my; ++k) {
+    OffT idx_next[RND];
+    uint8_t cnt_next[RND];
+    load_idx(k + 2, idx_next);
+    load_cnt(k + 1, cnt_next);
+    issue(k + 1, idx);  // into the stage tile k-1 has vacated
+#pragma unroll
+    for (int u = 0; u < RND; ++u) idx[u] = idx_next[u];
+    cp_async_wait_group<1>();
+    mbar_wait(&bars[k % NS], (uint32_t)((k / NS) & 1));
+    if (tid == 0) tma_store_wait_read();  // the previous tile's bulk store no longer reads qout
+    __syncthreads();
+
+    const V2FTile t = tile_of(k);
+    const int K = t.K;
+    const T *rrow = stage0 + (k % NS) * tab.stage_elems;
+    const T *qio = rrow + t.nv_full * K * D;
+    const T *un = qio + t.nv_full * K * D;
+    if (tid < t.nv) {  // select_value: costs summed in `links` order, first optimum wins
+      const T *base = rrow + tid * K * D;
+      const T *ur = un + tid * D;
+      int best = 0;
+      T best_c = (T)0;
+#pragma unroll
+      for (int x = 0; x < D; ++x) {
+        T tot = ur[x];
+        for (int g = 0; g < K; ++g) tot += base[g * D + x];
+        if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+      }
+      value[t.var0 + tid] = best;
+      value_cost[t.var0 + tid] = best_c;
+    }
+#pragma unroll
+    for (int u = 0; u < RND; ++u) {
+      const int sl = tid + u * NT;
+      if (sl < t.nslots) {
+        const int i = sl / K, f = sl - i * K;
+        const T *base = rrow + i * K * D;
+        T un_r[D], cand[D], prev[D];
+        ld_row<T, D, C::VR>(un + i * D, un_r);
+        T sum_cost = (T)0;
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+          T m = un_r[x];
+#pragma unroll 4
+          for (int g = 0; g < K; ++g) {
+            const T cst = (g != f) ? base[g * D + x] : (T)0;  // +0 for the own factor is exact
+            sum_cost += cst;
+            m += cst;
+          }
+          cand[x] = m;
+        }
+        const T avg = sum_cost / (T)D;
+#pragma unroll
+        for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg;
+        ld_row<T, D, C::VR>(qio + sl * D, prev);
+        uint8_t c8 = cnt[u];
+        const bool sent = damp_gate_row<T, D>(cand, prev, c8, p.damp_vars != 0, lam, oml, stab);
+        st_row<T, D, C::VR>(qout + sl * D, cand);
+        q_cnt[t.slot0 + sl] = c8;
+        if (q_sent) q_sent[t.slot0 + sl] = sent ? 1 : 0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RND; ++u) cnt[u] = cnt_next[u];
+    const uint32_t obytes = (uint32_t)(t.nslots * D) * (uint32_t)sizeof(T);
+    if ((obytes % 16 == 0) && (((t.qoff * (int64_t)sizeof(T)) & 15) == 0)) {
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(q_next + t.qoff, qout, obytes);
+        tma_store_commit();
+      }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < t.nslots * D; i += NT) q_next[t.qoff + i] = qout[i];
+      __syncthreads();
+    }
   }
   cp_async_wait_all();
-  mbar_wait(bar, 0);
-  __syncthreads();
-
-  const bool mx = p.mode_max != 0;
-  if (tid < nv) {  // phase 1: one thread per variable
-    const int i = tid;
-    int32_t val;
-    T cst;
-    T *col = rtT + i * KP;
-    switch (en.bucket) {
-      case 0: v2f_phase1<T, D, 2>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
-      case 1: v2f_phase1<T, D, 4>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
-      case 2: v2f_phase1<T, D, 8>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
-      default: v2f_phase1_rt<T, D>(K, col, RS, un + i * D, avg + i * K, mx, &val, &cst); break;
-    }
-    const int v = en.vc.first_var + v0 + i;
-    value[v] = val;
-    value_cost[v] = cst;
-  }
-  __syncthreads();
-  {  // phase 2: one thread per slot: normalise, damping, send gate
-    const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
-#pragma unroll
-    for (int u = 0; u < MAXR; ++u) {
-      const int sl = tid + u * NT;
-      if (sl >= nslots) break;
-      const int i = sl / K, f = sl - i * K;
-      const T a = avg[sl];
-      const T *src = rtT + i * KP + f;
-      T cand[D], prev[D];
-#pragma unroll
-      for (int x = 0; x < D; ++x) cand[x] = src[x * RS] - a;
-      ld_row<T, D, C::VR>(qio + sl * D, prev);
-      uint8_t cnt = cntp[u];
-      const bool sent = damp_gate_row<T, D>(cand, prev, cnt, p.damp_vars != 0, lam, oml, stab);
-      st_row<T, D, C::VR>(qio + sl * D, cand);
-      q_cnt[slot0 + sl] = cnt;
-      if (q_sent) q_sent[slot0 + sl] = sent ? 1 : 0;
-    }
-  }
-  if (tma_q) {
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tma_store_1d(q_next + qoff, qio, qbytes);
-      tma_store_commit();
-      tma_store_wait_read();
-    }
-  } else {
-    __syncthreads();
-    for (int i = tid; i < nslots * D; i += NT) q_next[qoff + i] = qio[i];
-  }
+  if (tid == 0) tma_store_wait_read();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -802,35 +791,48 @@ struct V2FLaunch {
   size_t smem = 0;
 };
 
-inline int v2f_bucket(int K) { return K <= 2 ? 0 : (K <= 4 ? 1 : (K <= 8 ? 2 : 3)); }
-
 // Split the regular variable classes (degree 1..16, one domain size D) into launches of at most
-// FG_V2F_MAX_ENTRIES classes each.
+// FG_V2F_MAX_ENTRIES classes each, choosing the tile size of every class.
 inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<V2FLaunch> &out) {
   V2FLaunch cur;
-  cur.tab.n = 0;
-  cur.tab.total_tiles = 0;
-  auto flush = [&]() {
-    if (cur.tab.n) out.push_back(cur);
+  auto reset = [&]() {
     cur = V2FLaunch();
     cur.tab.n = 0;
     cur.tab.total_tiles = 0;
+    cur.tab.stage_elems = 0;
+    cur.tab.out_elems = 0;
   };
+  auto flush = [&]() {
+    if (cur.tab.n) {
+      // 16-byte aligned section sizes
+      const int al = (int)(16 / elem);
+      cur.tab.stage_elems = (cur.tab.stage_elems + al - 1) / al * al;
+      cur.tab.out_elems = (cur.tab.out_elems + al - 1) / al * al;
+      cur.smem = (size_t)(2 * cur.tab.stage_elems + cur.tab.out_elems) * elem + 64;
+      out.push_back(cur);
+    }
+    reset();
+  };
+  reset();
   for (const fg_varclass_t &vc : vcs) {
     if (vc.dom != D || vc.degree < 1 || vc.n_vars == 0) continue;
-    const size_t per_var = v2f_per_var_bytes(vc.degree, D, elem);
-    int nv = (int)((40 * 1024) / per_var) / 32 * 32;
-    nv = nv < 32 ? 32 : (nv > FG_V2F_NT ? FG_V2F_NT : nv);
-    while (nv > 32 && nv * vc.degree > 6 * FG_V2F_NT) nv -= 32;  // phase 2 handles <= 6 slots per thread
+    const int K = vc.degree;
+    const size_t per_var = (size_t)(2 * K * D + D) * elem;  // stage bytes per variable
+    int nv = (int)((14 * 1024) / per_var);
+    const int cap = (FG_V2F_ROUNDS * FG_V2F_NT) / K;        // slots per tile <= ROUNDS * NT
+    if (nv > cap) nv = cap;
+    nv = nv / 8 * 8;
+    if (nv < 8) nv = 8;
+    if (nv > FG_V2F_NT) nv = FG_V2F_NT;
     V2FEntry e;
     e.vc = vc;
     e.tile_begin = cur.tab.total_tiles;
     e.nv_tile = nv;
-    e.bucket = v2f_bucket(vc.degree);
     cur.tab.e[cur.tab.n++] = e;
     cur.tab.total_tiles += (vc.n_vars + nv - 1) / nv;
-    const size_t sm = (size_t)nv * per_var + 48;
-    if (sm > cur.smem) cur.smem = sm;
+    const int st = nv * (2 * K * D + D), ot = nv * K * D;
+    if (st > cur.tab.stage_elems) cur.tab.stage_elems = st;
+    if (ot > cur.tab.out_elems) cur.tab.out_elems = ot;
     if (cur.tab.n == FG_V2F_MAX_ENTRIES) flush();
   }
   flush();
@@ -839,15 +841,24 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
 template <typename T, int D>
 inline void launch_v2f_classes(const V2FLaunch &L, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
                                const MaxSumParams &p, cudaStream_t st) {
-  auto kern = k_v2f_classes<T, D, uint32_t>;
+  auto kern = k_v2f_pipe<T, D, uint32_t>;
   static size_t attr_smem = 0;
+  static int n_sm = 0;
   if (L.smem > attr_smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     attr_smem = L.smem;
   }
-  kern<<<(unsigned)L.tab.total_tiles, FG_V2F_NT, L.smem, st>>>(L.tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur,
-                                                               q_next, d.dev_q_cnt, d.dev_q_sent, d.dev_value,
-                                                               (T *)d.dev_value_cost, p);
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2F_NT, L.smem);
+  if (per_sm < 1) per_sm = 1;
+  const unsigned blocks = (unsigned)std::min(L.tab.total_tiles, n_sm * per_sm);
+  kern<<<blocks, FG_V2F_NT, L.smem, st>>>(L.tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
+                                          d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
 }
 
 template <typename T>
