@@ -487,6 +487,7 @@ struct V2FTable {
   int32_t total_tiles;
   int32_t stage_elems;  // elements of one stage buffer (max over the classes)
   int32_t out_elems;    // elements of the output buffer
+  int32_t avg_elems;    // elements of the per-slot normalisation scratch
   V2FEntry e[FG_V2F_MAX_ENTRIES];
 };
 
@@ -497,18 +498,24 @@ struct V2FCfg {
 };
 
 struct V2FTile {
-  int K, nv_full, nv, nslots, slot0, var0;
+  int K, VS, nv_full, nv, nslots, slot0, var0, valid;
   int64_t qoff, uoff;
 };
 
-__device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D) {
-  int ci = 0;
-#pragma unroll 1
-  for (int i = 1; i < tab.n; ++i)
-    if (t >= tab.e[i].tile_begin) ci = i;
-  const V2FEntry &en = tab.e[ci];
+// variable stride (elements) of the gathered rows of one variable: K*D rounded up so that
+// the stride counted in row-vector units is odd -> one-thread-per-variable reads hit distinct banks
+__host__ __device__ inline int v2f_vstride(int K, int D, int VR) { return (((K * D) / VR) | 1) * VR; }
+
+// tile t of the launch; `ci` is a cursor that only moves forward (tiles are visited in order)
+__device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D, int VR, int &ci) {
   V2FTile o;
+  o.valid = t < tab.total_tiles;
+  if (!o.valid) { o.K = 1; o.VS = D; o.nv_full = o.nv = o.nslots = o.slot0 = o.var0 = 0; o.qoff = o.uoff = 0; return o; }
+#pragma unroll 1
+  while (ci + 1 < tab.n && t >= tab.e[ci + 1].tile_begin) ++ci;
+  const V2FEntry &en = tab.e[ci];
   o.K = en.vc.degree;
+  o.VS = v2f_vstride(o.K, D, VR);
   o.nv_full = en.nv_tile;
   const int v0 = (t - en.tile_begin) * en.nv_tile;
   o.nv = min(en.nv_tile, en.vc.n_vars - v0);
@@ -520,13 +527,89 @@ __device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D) {
   return o;
 }
 
+// Phase 1, one thread per variable.  The K gathered r rows of the variable are at col[g*D + x].
+// Every r value is read once; all K un-normalised messages (costs_for_factor, maxsum.py:623-676:
+// value-major, then factor order) and the selection total (select_value, maxsum.py:584-620) are
+// accumulated from it, and the raw message value is written back in place.  Rows g >= K
+// contribute +0, which is exact.
+template <typename T, int D, int KMAX>
+__device__ __forceinline__ void v2f_phase1(int K, T *__restrict__ col, const T *__restrict__ unrow,
+                                           T *__restrict__ avg, bool mx, int32_t *value_out, T *cost_out) {
+  T sum[KMAX];
+#pragma unroll
+  for (int f = 0; f < KMAX; ++f) sum[f] = (T)0;
+  int best = 0;
+  T best_c = (T)0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) {
+    T c[KMAX];
+#pragma unroll
+    for (int g = 0; g < KMAX; ++g) c[g] = (g < K) ? col[g * D + x] : (T)0;
+    const T u = unrow[x];
+    T tot = u;
+#pragma unroll
+    for (int g = 0; g < KMAX; ++g) tot += c[g];
+    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+#pragma unroll
+    for (int f = 0; f < KMAX; ++f) {
+      if (f < K) {
+        T m = u;
+#pragma unroll
+        for (int g = 0; g < KMAX; ++g) {
+          if (g == f) continue;
+          sum[f] += c[g];
+          m += c[g];
+        }
+        col[f * D + x] = m;
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < KMAX; ++f)
+    if (f < K) avg[f] = sum[f] / (T)D;
+  *value_out = best;
+  *cost_out = best_c;
+}
+
+// same with run-time loops over the factors (degree > 8).  The raw messages are written to a
+// separate scratch area (`raw`, K rows) because later factors still need the original rows.
+template <typename T, int D>
+__device__ __forceinline__ void v2f_phase1_rt(int K, const T *__restrict__ col, T *__restrict__ raw,
+                                              const T *__restrict__ unrow, T *__restrict__ avg, bool mx,
+                                              int32_t *value_out, T *cost_out) {
+  int best = 0;
+  T best_c = (T)0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) {
+    T tot = unrow[x];
+    for (int g = 0; g < K; ++g) tot += col[g * D + x];
+    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+  }
+  *value_out = best;
+  *cost_out = best_c;
+  for (int f = 0; f < K; ++f) {
+    T sum_cost = (T)0;
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      T m = unrow[x];
+      for (int g = 0; g < K; ++g) {
+        if (g == f) continue;
+        const T cst = col[g * D + x];
+        sum_cost += cst;
+        m += cst;
+      }
+      raw[f * D + x] = m;
+    }
+    avg[f] = sum_cost / (T)D;
+  }
+}
+
 // Persistent, software-pipelined variable->factor kernel over the (domain D, degree K) classes of
-// one launch.  A tile is nv variables of one class = nv*K consecutive slots; one thread per slot
-// computes costs_for_factor (maxsum.py:623-676; value-major then factor order), damping and the
-// send gate; one thread per variable runs select_value (maxsum.py:584-620).  While tile k is being
-// computed, the r-row gather (cp.async through slot_roff), the q_old tile and the unary tile
-// (bulk async copies) of tile k+1 are in flight; gather indices and gate counters are prefetched
-// in registers.
+// one launch.  A tile is nv variables of one class = nv*K consecutive slots.  While tile k is being
+// computed, the r-row gather (cp.async through slot_roff), the q_old tile and the unary tile (bulk
+// async copies) of tile k+1 are in flight; gather indices and gate counters are prefetched in
+// registers.  Compute: phase 1 one thread per variable (messages + value selection, every r value
+// read once), phase 2 one thread per slot (normalise, damping, send gate).
 template <typename T, int D, typename OffT>
 __global__ void __launch_bounds__(FG_V2F_NT)
 k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
@@ -536,13 +619,12 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
   using C = V2FCfg<T, D>;
   constexpr int NT = FG_V2F_NT, NS = 2, RND = FG_V2F_ROUNDS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T *stage0 = reinterpret_cast<T *>(smem_raw);        // per stage: rrow | qio | un
-  T *qout = stage0 + NS * tab.stage_elems;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(qout + tab.out_elems);
+  T *stage0 = reinterpret_cast<T *>(smem_raw);  // per stage: rrow | qio | un
+  T *qout = stage0 + NS * tab.stage_elems;      // output rows; also the scratch of the run-time-K path
+  T *avg = qout + tab.out_elems;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(avg + tab.avg_elems);
 
   const int tid = threadIdx.x;
-  const int n_my = ((int)blockIdx.x < tab.total_tiles)
-                       ? (tab.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -550,39 +632,33 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
   }
   __syncthreads();
 
-  auto tile_of = [&](int k) { return v2f_tile(tab, (int)blockIdx.x + k * (int)gridDim.x, D); };
-  auto load_idx = [&](int k, OffT (&idx)[RND]) {
-    if (k < n_my) {
-      const V2FTile t = tile_of(k);
+  int cursor = 0;
+  auto tile_at = [&](int k) { return v2f_tile(tab, (int)blockIdx.x + k * (int)gridDim.x, D, C::VR, cursor); };
+  auto load_idx = [&](const V2FTile &t, OffT (&idx)[RND]) {
 #pragma unroll
-      for (int u = 0; u < RND; ++u) {
-        const int sl = tid + u * NT;
-        idx[u] = (sl < t.nslots) ? slot_roff[t.slot0 + sl] : (OffT)0;
-      }
+    for (int u = 0; u < RND; ++u) {
+      const int sl = tid + u * NT;
+      idx[u] = (t.valid && sl < t.nslots) ? slot_roff[t.slot0 + sl] : (OffT)0;
     }
   };
-  auto load_cnt = [&](int k, uint8_t (&cn)[RND]) {
-    if (k < n_my) {
-      const V2FTile t = tile_of(k);
+  auto load_cnt = [&](const V2FTile &t, uint8_t (&cn)[RND]) {
 #pragma unroll
-      for (int u = 0; u < RND; ++u) {
-        const int sl = tid + u * NT;
-        cn[u] = (sl < t.nslots) ? q_cnt[t.slot0 + sl] : (uint8_t)0;
-      }
+    for (int u = 0; u < RND; ++u) {
+      const int sl = tid + u * NT;
+      cn[u] = (t.valid && sl < t.nslots) ? q_cnt[t.slot0 + sl] : (uint8_t)0;
     }
   };
-  auto issue = [&](int k, const OffT (&idx)[RND]) {
-    if (k < n_my) {
-      const V2FTile t = tile_of(k);
+  auto issue = [&](int k, const V2FTile &t, const OffT (&idx)[RND]) {
+    if (t.valid) {
       T *rrow = stage0 + (k % NS) * tab.stage_elems;
-      T *qio = rrow + t.nv_full * t.K * D;
+      T *qio = rrow + t.nv_full * t.VS;
       T *un = qio + t.nv_full * t.K * D;
       const uint32_t qbytes = (uint32_t)(t.nslots * D) * (uint32_t)sizeof(T);
       const uint32_t ubytes = (uint32_t)(t.nv * D) * (uint32_t)sizeof(T);
-      const bool tma_q = (qbytes % 16 == 0) && (((t.qoff * (int64_t)sizeof(T)) & 15) == 0) &&
-                         ((((size_t)t.nv_full * t.K * D * sizeof(T)) & 15) == 0);
-      const bool tma_u = (ubytes % 16 == 0) && (((t.uoff * (int64_t)sizeof(T)) & 15) == 0) &&
-                         ((((size_t)t.nv_full * t.K * D * sizeof(T)) & 15) == 0);
+      const bool al = ((((size_t)t.nv_full * t.VS * sizeof(T)) & 15) == 0) &&
+                      ((((size_t)t.nv_full * t.K * D * sizeof(T)) & 15) == 0);
+      const bool tma_q = al && (qbytes % 16 == 0) && (((t.qoff * (int64_t)sizeof(T)) & 15) == 0);
+      const bool tma_u = al && (ubytes % 16 == 0) && (((t.uoff * (int64_t)sizeof(T)) & 15) == 0);
       if (tid == 0) {
         mbar_expect_tx(&bars[k % NS], (tma_q ? qbytes : 0u) + (tma_u ? ubytes : 0u));
         if (tma_q) tma_load_1d(qio, q_cur + t.qoff, qbytes, &bars[k % NS]);
@@ -596,10 +672,11 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
       for (int u = 0; u < RND; ++u) {
         const int sl = tid + u * NT;
         if (sl < t.nslots) {
+          const int i = sl / t.K, g = sl - i * t.K;
           const T *src = r_cur + (int64_t)idx[u];
-          T *dst = rrow + sl * D;
+          T *dst = rrow + i * t.VS + g * D;
 #pragma unroll
-          for (int i = 0; i < D / C::VR; ++i) cp_async_b<C::VR_BYTES>(dst + i * C::VR, src + i * C::VR);
+          for (int w = 0; w < D / C::VR; ++w) cp_async_b<C::VR_BYTES>(dst + w * C::VR, src + w * C::VR);
         }
       }
     }
@@ -608,20 +685,21 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
 
   OffT idx[RND];
   uint8_t cnt[RND];
-  load_idx(0, idx);
-  issue(0, idx);
-  load_idx(1, idx);
-  load_cnt(0, cnt);
+  V2FTile t_cur = tile_at(0), t_n1 = tile_at(1), t_n2 = tile_at(2);
+  load_idx(t_cur, idx);
+  issue(0, t_cur, idx);
+  load_idx(t_n1, idx);
+  load_cnt(t_cur, cnt);
   const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
 
 #pragma unroll 1
-  for (int k = 0; k < n_my; ++k) {
+  for (int k = 0; t_cur.valid; ++k) {
     OffT idx_next[RND];
     uint8_t cnt_next[RND];
-    load_idx(k + 2, idx_next);
-    load_cnt(k + 1, cnt_next);
-    issue(k + 1, idx);  // into the stage tile k-1 has vacated
+    load_idx(t_n2, idx_next);
+    load_cnt(t_n1, cnt_next);
+    issue(k + 1, t_n1, idx);  // into the stage tile k-1 has vacated
 #pragma unroll
     for (int u = 0; u < RND; ++u) idx[u] = idx_next[u];
     cp_async_wait_group<1>();
@@ -629,48 +707,34 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
     if (tid == 0) tma_store_wait_read();  // the previous tile's bulk store no longer reads qout
     __syncthreads();
 
-    const V2FTile t = tile_of(k);
+    const V2FTile t = t_cur;
     const int K = t.K;
-    const T *rrow = stage0 + (k % NS) * tab.stage_elems;
-    const T *qio = rrow + t.nv_full * K * D;
+    T *rrow = stage0 + (k % NS) * tab.stage_elems;
+    const T *qio = rrow + t.nv_full * t.VS;
     const T *un = qio + t.nv_full * K * D;
-    if (tid < t.nv) {  // select_value: costs summed in `links` order, first optimum wins
-      const T *base = rrow + tid * K * D;
-      const T *ur = un + tid * D;
-      int best = 0;
-      T best_c = (T)0;
-#pragma unroll
-      for (int x = 0; x < D; ++x) {
-        T tot = ur[x];
-        for (int g = 0; g < K; ++g) tot += base[g * D + x];
-        if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-      }
-      value[t.var0 + tid] = best;
-      value_cost[t.var0 + tid] = best_c;
+    const bool rt_path = K > 8;
+    if (tid < t.nv) {  // phase 1: one thread per variable
+      int32_t val;
+      T cst;
+      T *col = rrow + tid * t.VS;
+      if (K <= 4) v2f_phase1<T, D, 4>(K, col, un + tid * D, avg + tid * K, mx, &val, &cst);
+      else if (K <= 8) v2f_phase1<T, D, 8>(K, col, un + tid * D, avg + tid * K, mx, &val, &cst);
+      else v2f_phase1_rt<T, D>(K, col, qout + tid * K * D, un + tid * D, avg + tid * K, mx, &val, &cst);
+      value[t.var0 + tid] = val;
+      value_cost[t.var0 + tid] = cst;
     }
+    __syncthreads();
+    // phase 2: one thread per slot: normalise, damping, send gate
 #pragma unroll
     for (int u = 0; u < RND; ++u) {
       const int sl = tid + u * NT;
       if (sl < t.nslots) {
         const int i = sl / K, f = sl - i * K;
-        const T *base = rrow + i * K * D;
-        T un_r[D], cand[D], prev[D];
-        ld_row<T, D, C::VR>(un + i * D, un_r);
-        T sum_cost = (T)0;
+        T cand[D], prev[D];
+        ld_row<T, D, C::VR>(rt_path ? (const T *)(qout + sl * D) : (const T *)(rrow + i * t.VS + f * D), cand);
+        const T a = avg[sl];
 #pragma unroll
-        for (int x = 0; x < D; ++x) {
-          T m = un_r[x];
-#pragma unroll 4
-          for (int g = 0; g < K; ++g) {
-            const T cst = (g != f) ? base[g * D + x] : (T)0;  // +0 for the own factor is exact
-            sum_cost += cst;
-            m += cst;
-          }
-          cand[x] = m;
-        }
-        const T avg = sum_cost / (T)D;
-#pragma unroll
-        for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg;
+        for (int x = 0; x < D; ++x) cand[x] = cand[x] - a;
         ld_row<T, D, C::VR>(qio + sl * D, prev);
         uint8_t c8 = cnt[u];
         const bool sent = damp_gate_row<T, D>(cand, prev, c8, p.damp_vars != 0, lam, oml, stab);
@@ -694,6 +758,9 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
       for (int i = tid; i < t.nslots * D; i += NT) q_next[t.qoff + i] = qout[i];
       __syncthreads();
     }
+    t_cur = t_n1;
+    t_n1 = t_n2;
+    t_n2 = tile_at(k + 3);
   }
   cp_async_wait_all();
   if (tid == 0) tma_store_wait_read();
@@ -801,6 +868,7 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
     cur.tab.total_tiles = 0;
     cur.tab.stage_elems = 0;
     cur.tab.out_elems = 0;
+    cur.tab.avg_elems = 0;
   };
   auto flush = [&]() {
     if (cur.tab.n) {
@@ -808,7 +876,8 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
       const int al = (int)(16 / elem);
       cur.tab.stage_elems = (cur.tab.stage_elems + al - 1) / al * al;
       cur.tab.out_elems = (cur.tab.out_elems + al - 1) / al * al;
-      cur.smem = (size_t)(2 * cur.tab.stage_elems + cur.tab.out_elems) * elem + 64;
+      cur.tab.avg_elems = (cur.tab.avg_elems + al - 1) / al * al;
+      cur.smem = (size_t)(2 * cur.tab.stage_elems + cur.tab.out_elems + cur.tab.avg_elems) * elem + 64;
       out.push_back(cur);
     }
     reset();
@@ -817,8 +886,10 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
   for (const fg_varclass_t &vc : vcs) {
     if (vc.dom != D || vc.degree < 1 || vc.n_vars == 0) continue;
     const int K = vc.degree;
-    const size_t per_var = (size_t)(2 * K * D + D) * elem;  // stage bytes per variable
-    int nv = (int)((14 * 1024) / per_var);
+    const int VR = fg_gcd(16, D * (int)elem) / (int)elem;
+    const int VS = v2f_vstride(K, D, VR);
+    const size_t per_var = (size_t)(VS + K * D + D) * elem;  // stage bytes per variable
+    int nv = (int)((22 * 1024) / per_var);
     const int cap = (FG_V2F_ROUNDS * FG_V2F_NT) / K;        // slots per tile <= ROUNDS * NT
     if (nv > cap) nv = cap;
     nv = nv / 8 * 8;
@@ -830,9 +901,10 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
     e.nv_tile = nv;
     cur.tab.e[cur.tab.n++] = e;
     cur.tab.total_tiles += (vc.n_vars + nv - 1) / nv;
-    const int st = nv * (2 * K * D + D), ot = nv * K * D;
+    const int st = nv * (VS + K * D + D), ot = nv * K * D;
     if (st > cur.tab.stage_elems) cur.tab.stage_elems = st;
     if (ot > cur.tab.out_elems) cur.tab.out_elems = ot;
+    if (ot / D > cur.tab.avg_elems) cur.tab.avg_elems = ot / D;
     if (cur.tab.n == FG_V2F_MAX_ENTRIES) flush();
   }
   flush();
