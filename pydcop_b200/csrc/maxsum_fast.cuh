@@ -527,89 +527,12 @@ __device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D, i
   return o;
 }
 
-// Phase 1, one thread per variable.  The K gathered r rows of the variable are at col[g*D + x].
-// Every r value is read once; all K un-normalised messages (costs_for_factor, maxsum.py:623-676:
-// value-major, then factor order) and the selection total (select_value, maxsum.py:584-620) are
-// accumulated from it, and the raw message value is written back in place.  Rows g >= K
-// contribute +0, which is exact.
-template <typename T, int D, int KMAX>
-__device__ __forceinline__ void v2f_phase1(int K, T *__restrict__ col, const T *__restrict__ unrow,
-                                           T *__restrict__ avg, bool mx, int32_t *value_out, T *cost_out) {
-  T sum[KMAX];
-#pragma unroll
-  for (int f = 0; f < KMAX; ++f) sum[f] = (T)0;
-  int best = 0;
-  T best_c = (T)0;
-#pragma unroll
-  for (int x = 0; x < D; ++x) {
-    T c[KMAX];
-#pragma unroll
-    for (int g = 0; g < KMAX; ++g) c[g] = (g < K) ? col[g * D + x] : (T)0;
-    const T u = unrow[x];
-    T tot = u;
-#pragma unroll
-    for (int g = 0; g < KMAX; ++g) tot += c[g];
-    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-#pragma unroll
-    for (int f = 0; f < KMAX; ++f) {
-      if (f < K) {
-        T m = u;
-#pragma unroll
-        for (int g = 0; g < KMAX; ++g) {
-          if (g == f) continue;
-          sum[f] += c[g];
-          m += c[g];
-        }
-        col[f * D + x] = m;
-      }
-    }
-  }
-#pragma unroll
-  for (int f = 0; f < KMAX; ++f)
-    if (f < K) avg[f] = sum[f] / (T)D;
-  *value_out = best;
-  *cost_out = best_c;
-}
-
-// same with run-time loops over the factors (degree > 8).  The raw messages are written to a
-// separate scratch area (`raw`, K rows) because later factors still need the original rows.
-template <typename T, int D>
-__device__ __forceinline__ void v2f_phase1_rt(int K, const T *__restrict__ col, T *__restrict__ raw,
-                                              const T *__restrict__ unrow, T *__restrict__ avg, bool mx,
-                                              int32_t *value_out, T *cost_out) {
-  int best = 0;
-  T best_c = (T)0;
-#pragma unroll
-  for (int x = 0; x < D; ++x) {
-    T tot = unrow[x];
-    for (int g = 0; g < K; ++g) tot += col[g * D + x];
-    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-  }
-  *value_out = best;
-  *cost_out = best_c;
-  for (int f = 0; f < K; ++f) {
-    T sum_cost = (T)0;
-#pragma unroll
-    for (int x = 0; x < D; ++x) {
-      T m = unrow[x];
-      for (int g = 0; g < K; ++g) {
-        if (g == f) continue;
-        const T cst = col[g * D + x];
-        sum_cost += cst;
-        m += cst;
-      }
-      raw[f * D + x] = m;
-    }
-    avg[f] = sum_cost / (T)D;
-  }
-}
-
 // Persistent, software-pipelined variable->factor kernel over the (domain D, degree K) classes of
 // one launch.  A tile is nv variables of one class = nv*K consecutive slots.  While tile k is being
 // computed, the r-row gather (cp.async through slot_roff), the q_old tile and the unary tile (bulk
 // async copies) of tile k+1 are in flight; gather indices and gate counters are prefetched in
-// registers.  Compute: phase 1 one thread per variable (messages + value selection, every r value
-// read once), phase 2 one thread per slot (normalise, damping, send gate).
+// registers.  Compute: one thread per slot (message, damping, send gate), one thread per variable
+// (value selection).
 template <typename T, int D, typename OffT>
 __global__ void __launch_bounds__(FG_V2F_NT)
 k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
@@ -712,29 +635,51 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
     T *rrow = stage0 + (k % NS) * tab.stage_elems;
     const T *qio = rrow + t.nv_full * t.VS;
     const T *un = qio + t.nv_full * K * D;
-    const bool rt_path = K > 8;
-    if (tid < t.nv) {  // phase 1: one thread per variable
-      int32_t val;
-      T cst;
-      T *col = rrow + tid * t.VS;
-      if (K <= 4) v2f_phase1<T, D, 4>(K, col, un + tid * D, avg + tid * K, mx, &val, &cst);
-      else if (K <= 8) v2f_phase1<T, D, 8>(K, col, un + tid * D, avg + tid * K, mx, &val, &cst);
-      else v2f_phase1_rt<T, D>(K, col, qout + tid * K * D, un + tid * D, avg + tid * K, mx, &val, &cst);
-      value[t.var0 + tid] = val;
-      value_cost[t.var0 + tid] = cst;
+    {  // select_value (maxsum.py:584-620): one thread per variable, variables spread over the warps
+      const int vi = (tid & 31) * (NT / 32) + (tid >> 5);
+      if (vi < t.nv) {
+        const T *col = rrow + vi * t.VS;
+        const T *ur = un + vi * D;
+        int best = 0;
+        T best_c = (T)0;
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+          T tot = ur[x];
+          for (int g = 0; g < K; ++g) tot += col[g * D + x];
+          if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+        }
+        value[t.var0 + vi] = best;
+        value_cost[t.var0 + vi] = best_c;
+      }
     }
-    __syncthreads();
-    // phase 2: one thread per slot: normalise, damping, send gate
+    // one thread per slot: costs_for_factor (value-major, then factor order), damping, send gate
 #pragma unroll
     for (int u = 0; u < RND; ++u) {
       const int sl = tid + u * NT;
       if (sl < t.nslots) {
         const int i = sl / K, f = sl - i * K;
+        const T *col = rrow + i * t.VS;
         T cand[D], prev[D];
-        ld_row<T, D, C::VR>(rt_path ? (const T *)(qout + sl * D) : (const T *)(rrow + i * t.VS + f * D), cand);
-        const T a = avg[sl];
+        ld_row<T, D, C::VR>(un + i * D, cand);
+        T sum_cost = (T)0;
 #pragma unroll
-        for (int x = 0; x < D; ++x) cand[x] = cand[x] - a;
+        for (int x = 0; x < D; ++x) {
+          T m = cand[x];
+          for (int g = 0; g < f; ++g) {
+            const T cst = col[g * D + x];
+            sum_cost += cst;
+            m += cst;
+          }
+          for (int g = f + 1; g < K; ++g) {
+            const T cst = col[g * D + x];
+            sum_cost += cst;
+            m += cst;
+          }
+          cand[x] = m;
+        }
+        const T avg_c = sum_cost / (T)D;
+#pragma unroll
+        for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg_c;
         ld_row<T, D, C::VR>(qio + sl * D, prev);
         uint8_t c8 = cnt[u];
         const bool sent = damp_gate_row<T, D>(cand, prev, c8, p.damp_vars != 0, lam, oml, stab);
@@ -883,13 +828,21 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
     reset();
   };
   reset();
-  for (const fg_varclass_t &vc : vcs) {
+  std::vector<fg_varclass_t> order(vcs);
+  std::stable_sort(order.begin(), order.end(),
+                   [](const fg_varclass_t &a, const fg_varclass_t &b) { return a.degree > b.degree; });  // costly tiles first
+  for (const fg_varclass_t &vc : order) {
     if (vc.dom != D || vc.degree < 1 || vc.n_vars == 0) continue;
     const int K = vc.degree;
     const int VR = fg_gcd(16, D * (int)elem) / (int)elem;
     const int VS = v2f_vstride(K, D, VR);
     const size_t per_var = (size_t)(VS + K * D + D) * elem;  // stage bytes per variable
-    int nv = (int)((22 * 1024) / per_var);
+    static const int stage_kb = [] {
+      const char *e = getenv("PYDCOP_B200_V2F_STAGE_KB");
+      const int v = e ? atoi(e) : 0;
+      return v > 0 ? v : 14;
+    }();
+    int nv = (int)((size_t)(stage_kb * 1024) / per_var);
     const int cap = (FG_V2F_ROUNDS * FG_V2F_NT) / K;        // slots per tile <= ROUNDS * NT
     if (nv > cap) nv = cap;
     nv = nv / 8 * 8;
