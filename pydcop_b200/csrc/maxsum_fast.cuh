@@ -527,6 +527,70 @@ __device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D, i
   return o;
 }
 
+// costs_for_factor (maxsum.py:623-676) for slot f of a variable whose K gathered r rows are at
+// col[g*D + x]: value-major, then factor order; the own factor contributes +0 (exact).
+// K > 0: compile-time degree (fully unrolled); K == 0: run-time degree `k_rt`.
+template <typename T, int D, int K>
+__device__ __forceinline__ void v2f_slot_msg(const T *__restrict__ col, int f, int k_rt, T (&cand)[D]) {
+  T sum_cost = (T)0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) {
+    T m = cand[x];  // in: the variable's own cost
+    if constexpr (K > 0) {
+#pragma unroll
+      for (int g = 0; g < K; ++g) {
+        const T cst = (g != f) ? col[g * D + x] : (T)0;
+        sum_cost += cst;
+        m += cst;
+      }
+    } else {
+      for (int g = 0; g < k_rt; ++g) {
+        const T cst = (g != f) ? col[g * D + x] : (T)0;
+        sum_cost += cst;
+        m += cst;
+      }
+    }
+    cand[x] = m;
+  }
+  const T avg_c = sum_cost / (T)D;
+#pragma unroll
+  for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg_c;
+}
+
+// select_value (maxsum.py:584-620): costs summed in `links` order, first optimum wins
+template <typename T, int D, int K>
+__device__ __forceinline__ void v2f_select(const T *__restrict__ col, const T *__restrict__ ur, int k_rt, bool mx,
+                                           int32_t *value_out, T *cost_out) {
+  int best = 0;
+  T best_c = (T)0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) {
+    T tot = ur[x];
+    if constexpr (K > 0) {
+#pragma unroll
+      for (int g = 0; g < K; ++g) tot += col[g * D + x];
+    } else {
+      for (int g = 0; g < k_rt; ++g) tot += col[g * D + x];
+    }
+    if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+  }
+  *value_out = best;
+  *cost_out = best_c;
+}
+
+#define FG_V2F_K_SWITCH(K_, CALL)              \
+  switch (K_) {                                \
+    case 1: { constexpr int KK = 1; CALL; } break; \
+    case 2: { constexpr int KK = 2; CALL; } break; \
+    case 3: { constexpr int KK = 3; CALL; } break; \
+    case 4: { constexpr int KK = 4; CALL; } break; \
+    case 5: { constexpr int KK = 5; CALL; } break; \
+    case 6: { constexpr int KK = 6; CALL; } break; \
+    case 7: { constexpr int KK = 7; CALL; } break; \
+    case 8: { constexpr int KK = 8; CALL; } break; \
+    default: { constexpr int KK = 0; CALL; } break; \
+  }
+
 // Persistent, software-pipelined variable->factor kernel over the (domain D, degree K) classes of
 // one launch.  A tile is nv variables of one class = nv*K consecutive slots.  While tile k is being
 // computed, the r-row gather (cp.async through slot_roff), the q_old tile and the unary tile (bulk
@@ -635,24 +699,17 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
     T *rrow = stage0 + (k % NS) * tab.stage_elems;
     const T *qio = rrow + t.nv_full * t.VS;
     const T *un = qio + t.nv_full * K * D;
-    {  // select_value (maxsum.py:584-620): one thread per variable, variables spread over the warps
+    {  // one thread per variable, variables spread over the warps
       const int vi = (tid & 31) * (NT / 32) + (tid >> 5);
       if (vi < t.nv) {
-        const T *col = rrow + vi * t.VS;
-        const T *ur = un + vi * D;
-        int best = 0;
-        T best_c = (T)0;
-#pragma unroll
-        for (int x = 0; x < D; ++x) {
-          T tot = ur[x];
-          for (int g = 0; g < K; ++g) tot += col[g * D + x];
-          if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-        }
-        value[t.var0 + vi] = best;
-        value_cost[t.var0 + vi] = best_c;
+        int32_t val;
+        T cst;
+        FG_V2F_K_SWITCH(K, (v2f_select<T, D, KK>(rrow + vi * t.VS, un + vi * D, K, mx, &val, &cst)))
+        value[t.var0 + vi] = val;
+        value_cost[t.var0 + vi] = cst;
       }
     }
-    // one thread per slot: costs_for_factor (value-major, then factor order), damping, send gate
+    // one thread per slot: message, damping, send gate
 #pragma unroll
     for (int u = 0; u < RND; ++u) {
       const int sl = tid + u * NT;
@@ -661,25 +718,7 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
         const T *col = rrow + i * t.VS;
         T cand[D], prev[D];
         ld_row<T, D, C::VR>(un + i * D, cand);
-        T sum_cost = (T)0;
-#pragma unroll
-        for (int x = 0; x < D; ++x) {
-          T m = cand[x];
-          for (int g = 0; g < f; ++g) {
-            const T cst = col[g * D + x];
-            sum_cost += cst;
-            m += cst;
-          }
-          for (int g = f + 1; g < K; ++g) {
-            const T cst = col[g * D + x];
-            sum_cost += cst;
-            m += cst;
-          }
-          cand[x] = m;
-        }
-        const T avg_c = sum_cost / (T)D;
-#pragma unroll
-        for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg_c;
+        FG_V2F_K_SWITCH(K, (v2f_slot_msg<T, D, KK>(col, f, K, cand)))
         ld_row<T, D, C::VR>(qio + sl * D, prev);
         uint8_t c8 = cnt[u];
         const bool sent = damp_gate_row<T, D>(cand, prev, c8, p.damp_vars != 0, lam, oml, stab);
