@@ -20,6 +20,8 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 }  // namespace
 
 struct fg_maxsum {
+  cudaStream_t side_stream = nullptr;   // variable side runs here, concurrently with the factor side
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   fg_maxsum_desc_t d;
   std::vector<fg_class_t> classes;
   std::vector<fg_varclass_t> varclasses;
@@ -94,10 +96,20 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
+  if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   return FG_OK;
 }
 
 extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
+  if (h) {
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  }
   delete h;
   return FG_OK;
 }
@@ -149,6 +161,13 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
   MaxSumParams p{d.mode_max, d.damp_vars, d.damp_factors, d.damping, 1.0 - d.damping, d.stability};
   const T *q_cur = (const T *)d.dev_q[cur], *r_cur = (const T *)d.dev_r[cur];
   T *q_next = (T *)d.dev_q[nxt], *r_next = (T *)d.dev_r[nxt];
+  // fork BEFORE anything of this cycle is enqueued, so the side stream only waits for the past
+  cudaStream_t st_f = st;
+  const bool fork = !first && h->side_stream != nullptr && d.n_edges > 0;
+  if (fork) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st_f));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+  }
   // factor -> variable
   for (size_t ci = 0; ci < h->classes.size(); ++ci) {
     const fg_class_t &c = h->classes[ci];
@@ -163,7 +182,10 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
                                                              d.dev_edge_qoff, d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
     ++h->launches;
   }
-  // variable -> factor (+ value selection)
+  // variable -> factor (+ value selection).  Both sides only READ the current buffers and WRITE
+  // disjoint next buffers (Jacobi), so from cycle 2 on the variable side runs on a second stream,
+  // concurrently with the factor side: one is HBM-streaming, the other gather/latency-bound.
+  if (fork) st = h->side_stream;
   if (d.n_edges) {
     VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_var_qbase, d.dev_slot_roff, d.dev_slot_edge, d.dev_slot_var};
     if (first) {
@@ -183,6 +205,11 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
         ++h->launches;
       }
     }
+  }
+  if (fork) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(st_f, h->ev_join, 0));
+    st = st_f;
   }
   if (first && d.n_edges) {  // every edge has posted in cycle 1: all messages are valid from now on
     CUDA_TRY(h, cudaMemsetAsync(d.dev_q_valid, 1, (size_t)d.n_edges, st));

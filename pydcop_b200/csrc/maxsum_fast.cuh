@@ -769,6 +769,12 @@ inline bool fg_fast_dom_a3(int d) {
   return false;
 }
 
+inline int fg_env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+
 inline bool fg_fast_disabled() {
   const char *e = getenv("PYDCOP_B200_NO_FAST");
   return e && e[0] == '1';
@@ -788,6 +794,9 @@ inline void launch_f2v_tile(const fg_class_t &c, const fg_maxsum_desc_t &d, cons
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::NT, PP::SMEM);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // the two sides of a cycle run concurrently on two streams: leave room for the other kernel
+    const int cap = fg_env_int("PYDCOP_B200_F2V_CPS", 3);
+    if (ctas_per_sm > cap) ctas_per_sm = cap;
   }
   const int n_tiles = (c.n_factors + C::NF - 1) / C::NF;
   const unsigned blocks = (unsigned)min(n_tiles, n_sm * ctas_per_sm);
@@ -876,11 +885,7 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
     const int VR = fg_gcd(16, D * (int)elem) / (int)elem;
     const int VS = v2f_vstride(K, D, VR);
     const size_t per_var = (size_t)(VS + K * D + D) * elem;  // stage bytes per variable
-    static const int stage_kb = [] {
-      const char *e = getenv("PYDCOP_B200_V2F_STAGE_KB");
-      const int v = e ? atoi(e) : 0;
-      return v > 0 ? v : 14;
-    }();
+    static const int stage_kb = fg_env_int("PYDCOP_B200_V2F_STAGE_KB", 10);
     int nv = (int)((size_t)(stage_kb * 1024) / per_var);
     const int cap = (FG_V2F_ROUNDS * FG_V2F_NT) / K;        // slots per tile <= ROUNDS * NT
     if (nv > cap) nv = cap;
@@ -920,6 +925,8 @@ inline void launch_v2f_classes(const V2FLaunch &L, const fg_maxsum_desc_t &d, co
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2F_NT, L.smem);
   if (per_sm < 1) per_sm = 1;
+  static const int cap = fg_env_int("PYDCOP_B200_V2F_CPS", 4);
+  if (per_sm > cap) per_sm = cap;
   const unsigned blocks = (unsigned)std::min(L.tab.total_tiles, n_sm * per_sm);
   kern<<<blocks, FG_V2F_NT, L.smem, st>>>(L.tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
                                           d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
