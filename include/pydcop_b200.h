@@ -47,6 +47,7 @@ enum { FG_OK = 0, FG_ERR_ARG = 1, FG_ERR_CUDA = 2, FG_ERR_UNSUPPORTED = 3 };
 enum { FG_F32 = 0, FG_F64 = 1 };
 enum { FG_START_LEAFS = 0, FG_START_LEAFS_VARS = 1, FG_START_ALL = 2 }; /* maxsum.py:219 */
 enum { FG_DSA_A = 0, FG_DSA_B = 1, FG_DSA_C = 2 };                      /* dsa.py:133 */
+enum { FG_CLASS_GHOST = 1 };
 
 /* One class of same-shaped factors (constraints). */
 typedef struct {
@@ -55,6 +56,8 @@ typedef struct {
   int32_t row_off[FG_MAX_ARITY]; /* offset of position j's message row inside a factor's rows */
   int32_t row_total;             /* sum(dom) */
   int32_t n_factors;
+  int32_t flags;                 /* FG_CLASS_GHOST: rows exist but the class is never computed
+                                    (multi-GPU halo stubs, filled by the exchange) */
   int32_t first_factor;          /* global factor index of the first factor of the class */
   int32_t first_edge;            /* global edge index of its first edge; edge(f,j)=first_edge+f*arity+j */
   int64_t table_size;            /* prod(dom) */
@@ -73,6 +76,7 @@ typedef struct {
   int32_t dom, degree;
   int32_t n_vars, first_var, first_slot;
   int32_t n_slots;     /* total slots of the class */
+  int32_t flags, reserved;  /* FG_CLASS_GHOST as above */
   int64_t unary_base;
   int64_t q_base;
 } fg_varclass_t;

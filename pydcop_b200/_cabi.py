@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libp
 class FgClass(C.Structure):
     _fields_ = [("arity", C.c_int32), ("dom", C.c_int32 * FG_MAX_ARITY),
                 ("row_off", C.c_int32 * FG_MAX_ARITY), ("row_total", C.c_int32),
-                ("n_factors", C.c_int32), ("first_factor", C.c_int32), ("first_edge", C.c_int32),
+                ("n_factors", C.c_int32), ("flags", C.c_int32), ("first_factor", C.c_int32),
+                ("first_edge", C.c_int32),
                 ("table_size", C.c_int64), ("table_base", C.c_int64), ("msg_base", C.c_int64)]
 
 
@@ -29,6 +30,7 @@ P = C.c_void_p
 class FgVarClass(C.Structure):
     _fields_ = [("dom", C.c_int32), ("degree", C.c_int32), ("n_vars", C.c_int32),
                 ("first_var", C.c_int32), ("first_slot", C.c_int32), ("n_slots", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32),
                 ("unary_base", C.c_int64), ("q_base", C.c_int64)]
 
 

@@ -57,10 +57,10 @@ static int check_class(const fg_class_t &c, char *err, size_t n) {
   int64_t ts = 1; int rt = 0;
   for (int i = 0; i < c.arity; ++i) {
     if (c.dom[i] < 1 || c.dom[i] > FG_MAX_DOM) { snprintf(err, n, "domain size %d out of range", c.dom[i]); return FG_ERR_ARG; }
-    if (c.row_off[i] != rt) { snprintf(err, n, "row_off mismatch"); return FG_ERR_ARG; }
-    ts *= c.dom[i]; rt += c.dom[i];
+    if (c.row_off[i] < rt) { snprintf(err, n, "row_off overlaps the previous row"); return FG_ERR_ARG; }
+    ts *= c.dom[i]; rt = c.row_off[i] + c.dom[i];
   }
-  if (ts != c.table_size || rt != c.row_total) { snprintf(err, n, "class size mismatch"); return FG_ERR_ARG; }
+  if (ts != c.table_size || rt > c.row_total) { snprintf(err, n, "class size mismatch"); return FG_ERR_ARG; }
   return FG_OK;
 }
 
@@ -136,7 +136,7 @@ static int maxsum_init_t(fg_maxsum *h, cudaStream_t st) {
   }
   for (const fg_class_t &c : h->classes) {
     bool posts = (c.arity == 1 && d.start_messages <= FG_START_LEAFS_VARS) || d.start_messages == FG_START_ALL;
-    if (!posts || c.n_factors == 0) continue;
+    if (!posts || c.n_factors == 0 || (c.flags & FG_CLASS_GHOST)) continue;
     k_f2v_start<T><<<blocks_for((int64_t)c.n_factors * c.arity, 128), 128, 0, st>>>(
         c, (const T *)d.dev_tables, (T *)d.dev_r[0], d.dev_r_valid, d.dev_r_sent, d.mode_max);
     ++h->launches;
@@ -171,7 +171,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
   // factor -> variable
   for (size_t ci = 0; ci < h->classes.size(); ++ci) {
     const fg_class_t &c = h->classes[ci];
-    if (c.n_factors == 0) continue;
+    if (c.n_factors == 0 || (c.flags & FG_CLASS_GHOST)) continue;
     if (!first && maxsum_fast_f2v<T>(h->fast, (int)ci, c, d, q_cur, r_cur, r_next, p, st, h->launches)) continue;
     const int64_t n = (int64_t)c.n_factors * c.arity;
     if (first)
@@ -189,10 +189,13 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
   if (d.n_edges) {
     VarSide g{d.dev_dom_size, d.dev_unary_off, d.dev_var_ptr, d.dev_var_qbase, d.dev_slot_roff, d.dev_slot_edge, d.dev_slot_var};
     if (first) {
-      k_v2f_generic<T, 1><<<blocks_for(d.n_edges, 128), 128, 0, st>>>(
-          g, 0, d.n_edges, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
-          d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
-      ++h->launches;
+      for (const fg_varclass_t &vc : h->varclasses) {
+        if (vc.n_slots == 0 || (vc.flags & FG_CLASS_GHOST)) continue;
+        k_v2f_generic<T, 1><<<blocks_for(vc.n_slots, 128), 128, 0, st>>>(
+            g, vc.first_slot, vc.n_slots, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
+            d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+        ++h->launches;
+      }
     } else {
       for (size_t li = 0; li < h->fast.v2f.size(); ++li) {
         if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;

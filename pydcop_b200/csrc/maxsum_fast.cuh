@@ -973,11 +973,15 @@ inline void maxsum_fast_plan(const fg_maxsum_desc_t &d, const std::vector<fg_cla
   const size_t elem = d.precision == FG_F64 ? 8 : 4;
   std::vector<uint8_t> taken(vcs.size(), 0);
   for (size_t i = 0; fast && i < vcs.size(); ++i) {
+    if (vcs[i].flags & FG_CLASS_GHOST) { taken[i] = 1; continue; }
     if (taken[i] || vcs[i].degree < 1 || !fg_fast_dom(vcs[i].dom)) continue;
     const int D = vcs[i].dom;
     std::vector<fg_varclass_t> same;
     for (size_t j = i; j < vcs.size(); ++j)
-      if (!taken[j] && vcs[j].dom == D && vcs[j].degree >= 1) { same.push_back(vcs[j]); taken[j] = 1; }
+      if (!taken[j] && !(vcs[j].flags & FG_CLASS_GHOST) && vcs[j].dom == D && vcs[j].degree >= 1) {
+        same.push_back(vcs[j]);
+        taken[j] = 1;
+      }
     std::vector<V2FLaunch> ls;
     v2f_build_launches(same, D, elem, ls);
     for (auto &l : ls) { plan.v2f.push_back(l); plan.v2f_dom.push_back(D); }

@@ -41,6 +41,7 @@ def _class_array(layout: FactorGraphLayout):
             fc.row_off[j] = c.row_off[j]
         fc.row_total = c.row_total
         fc.n_factors, fc.first_factor, fc.first_edge = c.n_factors, c.first_factor, c.first_edge
+        fc.flags = 1 if c.tag else 0
         fc.table_size, fc.table_base, fc.msg_base = c.table_size, c.table_base, c.msg_base
     return arr
 
@@ -52,6 +53,7 @@ def _varclass_array(layout: FactorGraphLayout):
         vc.dom, vc.degree, vc.n_vars = c.dom, c.degree, c.n_vars
         vc.first_var, vc.first_slot, vc.n_slots = c.first_var, c.first_slot, c.n_slots
         vc.unary_base, vc.q_base = c.unary_base, c.q_base
+        vc.flags = 1 if c.tag else 0
     return arr
 
 

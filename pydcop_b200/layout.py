@@ -38,18 +38,28 @@ class FactorClass:
     table_size: int
     table_base: int
     msg_base: int
+    tag: int = 0
 
     @property
-    def row_total(self):
-        return int(sum(self.dom))
+    def uniform(self):
+        return all(d == self.dom[0] for d in self.dom)
 
     @property
     def row_off(self):
+        """Offset of each scope position's message row inside the factor's row block.  Classes
+        whose positions have different domain sizes start every row on a 4-element boundary so
+        that a row of a D-valued variable is always aligned to gcd(16 bytes, D*sizeof(T))."""
         out, s = [], 0
         for d in self.dom:
             out.append(s)
-            s += d
+            s += d if self.uniform else (d + 3) // 4 * 4
         return tuple(out)
+
+    @property
+    def row_total(self):
+        if self.uniform:
+            return int(sum(self.dom))
+        return int(sum((d + 3) // 4 * 4 for d in self.dom))
 
 
 @dataclass
@@ -64,6 +74,7 @@ class VarClass:
     unary_base: int
     q_base: int
     n_slots: int = 0
+    tag: int = 0
 
 
 @dataclass
@@ -161,7 +172,10 @@ def default_var_csr(n_vars, edge_var):
 
 
 def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=None,
-                 var_ptr=None, var_edge=None, init_value=None) -> FactorGraphLayout:
+                 var_ptr=None, var_edge=None, init_value=None, factor_tag=None,
+                 var_tag=None) -> FactorGraphLayout:
+    """factor_tag / var_tag (optional small ints): factors / variables with different tags never
+    share a class.  The multi-GPU shards tag their ghost stubs so the engine can skip them."""
     dom_size = _as(dom_size, np.int32)
     factor_ptr = _as(factor_ptr, np.int64)
     edge_var = _as(edge_var, np.int32)
@@ -179,12 +193,15 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     edge_dom = dom_size[edge_var] if E else np.zeros(0, np.int32)
 
     # shape key per factor: domain sizes padded with zeros
-    key = np.zeros((F, MAX_ARITY), dtype=np.int32)
+    key = np.zeros((F, MAX_ARITY + 1), dtype=np.int32)
     if E:
         efac = np.repeat(np.arange(F, dtype=np.int64), arity)
         epos = np.arange(E, dtype=np.int64) - factor_ptr[:-1][efac]
         key[efac, epos] = edge_dom
-    tsize = np.where(key > 0, key, 1).astype(np.int64).prod(axis=1) if F else np.zeros(0, np.int64)
+    tsize = (np.where(key[:, :MAX_ARITY] > 0, key[:, :MAX_ARITY], 1).astype(np.int64).prod(axis=1)
+             if F else np.zeros(0, np.int64))
+    if factor_tag is not None and F:
+        key[:, MAX_ARITY] = _as(factor_tag, np.int32)
     if table_off is None:
         table_off = np.zeros(F + 1, dtype=np.int64)
         np.cumsum(tsize, out=table_off[1:])
@@ -198,7 +215,7 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
         uniq, cls_of_factor = np.unique(key, axis=0, return_inverse=True)
         cls_of_factor = cls_of_factor.reshape(-1)
     else:
-        uniq, cls_of_factor = np.zeros((0, MAX_ARITY), np.int32), np.zeros(0, np.int64)
+        uniq, cls_of_factor = np.zeros((0, MAX_ARITY + 1), np.int32), np.zeros(0, np.int64)
     order = np.argsort(cls_of_factor, kind="stable")          # internal factor -> canonical factor
     factor_perm = np.empty(F, dtype=np.int32)
     factor_perm[order] = np.arange(F, dtype=np.int32)          # canonical -> internal
@@ -212,10 +229,12 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     tab_parts = []
     first_factor = first_edge = table_base = msg_base = 0
     for ci in range(len(uniq)):
-        dom = tuple(int(x) for x in uniq[ci] if x > 0)
+        dom = tuple(int(x) for x in uniq[ci][:MAX_ARITY] if x > 0)
         a, n = len(dom), int(counts[ci])
-        S, R = int(np.prod(dom, dtype=np.int64)), int(sum(dom))
-        fc = FactorClass(a, dom, n, first_factor, first_edge, S, table_base, msg_base)
+        S = int(np.prod(dom, dtype=np.int64))
+        fc = FactorClass(a, dom, n, first_factor, first_edge, S, table_base, msg_base,
+                         tag=int(uniq[ci][MAX_ARITY]))
+        R = fc.row_total
         classes.append(fc)
         fs = order[first_factor:first_factor + n]               # canonical factor ids, in order
         # tables
@@ -267,6 +286,8 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     # class key: (domain size, degree), degrees above MAX_CLASS_DEGREE share one irregular class
     kdeg = np.where(c_deg <= MAX_CLASS_DEGREE, c_deg, MAX_CLASS_DEGREE + 1)
     vkey = dom_size.astype(np.int64) * (MAX_CLASS_DEGREE + 2) + kdeg
+    vtag = np.zeros(V, dtype=np.int64) if var_tag is None else _as(var_tag, np.int64)
+    vkey = vkey + vtag * ((MAX_DOM + 1) * (MAX_CLASS_DEGREE + 2))
     var_order = np.argsort(vkey, kind="stable").astype(np.int32)   # internal -> canonical
     var_perm = np.empty(V, dtype=np.int32)
     var_perm[var_order] = np.arange(V, dtype=np.int32)              # canonical -> internal
@@ -295,7 +316,7 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
         K = int(k % (MAX_CLASS_DEGREE + 2))
         regular = K <= MAX_CLASS_DEGREE
         vc = VarClass(D, K if regular else -1, n, st, int(i_var_ptr[st]), unary_base, q_base,
-                      int(i_deg[st:st + n].sum()))
+                      int(i_deg[st:st + n].sum()), tag=int(k // ((MAX_DOM + 1) * (MAX_CLASS_DEGREE + 2))))
         var_classes.append(vc)
         i_unary_off[st:st + n] = unary_base + np.arange(n, dtype=np.int64) * D
         slots_before = (i_var_ptr[st:st + n].astype(np.int64) - int(i_var_ptr[st]))

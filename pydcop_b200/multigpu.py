@@ -1,0 +1,352 @@
+"""Multi-GPU MaxSum: the factor graph partitioned by VARIABLE CUT over the GPUs of one box, one
+process per GPU, one halo exchange of boundary messages per cycle.
+
+Partition: variables are split into `world` contiguous blocks (row strips for a raster-ordered
+grid); a factor lives with its first scope variable.  For a CUT edge (factor F on rank B, variable v
+on rank A != B) the message r_{F->v} is produced on B and consumed on A, q_{v->F} the other way.
+
+Each rank builds a CLOSED local graph so the single-GPU engine runs unchanged:
+  * its own factors and its own variables;
+  * a GHOST VARIABLE for every remote variable in the scope of an own factor — its slots are
+    exactly the q rows that arrive from the owner;
+  * a unary GHOST STUB FACTOR on the own variable for every remote factor touching it — its r row
+    is exactly the row that arrives from the factor's owner, and it keeps the variable's true
+    degree and `links` order (maxsum.py:466), so sums are bit-identical to the single-GPU run.
+Ghost classes carry FG_CLASS_GHOST: their rows exist but are never computed, only filled by the
+exchange.  Per cycle: compute (writes the `next` buffers) -> pack boundary rows (CUDA kernel,
+fg_halo_pack) -> ONE all_to_all per direction over NCCL/NVLink -> unpack into `next` -> commit.
+This replaces Messaging.post_msg for cut edges (pydcop/infrastructure/communication.py:588-698).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .layout import FactorGraphLayout, build_layout, default_var_csr
+
+
+def variable_owner(n_vars: int, world: int) -> np.ndarray:
+    """Contiguous blocks of ceil(V / world) variables."""
+    per = -(-n_vars // world) if world > 0 else n_vars
+    return (np.arange(n_vars, dtype=np.int64) // max(per, 1)).astype(np.int32)
+
+
+@dataclass
+class ShardPlan:
+    """Everything rank `rank` needs: the closed local instance and the halo index lists."""
+    rank: int
+    world: int
+    layout: FactorGraphLayout
+    own_vars: np.ndarray            # global ids of the variables this rank owns (ascending)
+    n_own_vars: int
+    # halo, one entry per cut edge touching this rank, grouped by peer in ascending global edge id
+    send_r_off: np.ndarray          # int64 element offsets into r (rows this rank produces)
+    send_q_off: np.ndarray          # int64 element offsets into q
+    recv_r_off: np.ndarray          # where arriving r rows go (ghost stub rows)
+    recv_q_off: np.ndarray          # where arriving q rows go (ghost variable slots)
+    send_r_len: np.ndarray          # int32 row lengths
+    send_q_len: np.ndarray
+    recv_r_len: np.ndarray
+    recv_q_len: np.ndarray
+    send_r_edge: np.ndarray         # internal edge ids (for the validity flags exchanged at init)
+    send_q_edge: np.ndarray
+    recv_r_edge: np.ndarray
+    recv_q_edge: np.ndarray
+    send_r_split: List[int]         # elements per peer
+    send_q_split: List[int]
+    recv_r_split: List[int]
+    recv_q_split: List[int]
+    send_r_rows: List[int]          # rows per peer
+    send_q_rows: List[int]
+    recv_r_rows: List[int]
+    recv_q_rows: List[int]
+    n_cut_edges: int
+    own_factor_edges: Optional[np.ndarray] = None   # global edge ids of the local real edges
+    stub_edges: Optional[np.ndarray] = None         # global edge ids behind the local stub factors
+
+
+def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan:
+    dom_size = np.asarray(inst["dom_size"], dtype=np.int32)
+    factor_ptr = np.asarray(inst["factor_ptr"], dtype=np.int64)
+    edge_var = np.asarray(inst["edge_var"], dtype=np.int64)
+    tables = np.asarray(inst["tables"])
+    V, F, E = len(dom_size), len(factor_ptr) - 1, len(edge_var)
+    arity = np.diff(factor_ptr)
+    tsize = np.ones(F, dtype=np.int64)
+    efac = np.repeat(np.arange(F, dtype=np.int64), arity)
+    np.multiply.at(tsize, efac, dom_size[edge_var].astype(np.int64))
+    table_off = np.zeros(F + 1, dtype=np.int64)
+    np.cumsum(tsize, out=table_off[1:])
+    unary = np.asarray(inst["unary"], dtype=np.float64) if "unary" in inst and inst["unary"] is not None \
+        else np.zeros(int(dom_size.sum()))
+    unary_off = np.zeros(V + 1, dtype=np.int64)
+    np.cumsum(dom_size, out=unary_off[1:])
+    if "var_ptr" in inst and inst.get("var_edge") is not None:
+        g_var_ptr = np.asarray(inst["var_ptr"], dtype=np.int64)
+        g_var_edge = np.asarray(inst["var_edge"], dtype=np.int64)
+    else:
+        vp, ve = default_var_csr(V, edge_var)
+        g_var_ptr, g_var_edge = vp.astype(np.int64), ve.astype(np.int64)
+
+    owner_v = variable_owner(V, world)
+    fac_owner = owner_v[edge_var[factor_ptr[:-1]]] if F else np.zeros(0, np.int32)
+    e_fowner = fac_owner[efac]
+    e_vowner = owner_v[edge_var]
+    cut = e_fowner != e_vowner
+
+    own_f = np.nonzero(fac_owner == rank)[0]
+    own_v = np.nonzero(owner_v == rank)[0]
+    # edges of own factors, in factor order
+    own_f_edges = _ranges(factor_ptr[own_f], arity[own_f])
+    ghost_vars = np.unique(edge_var[own_f_edges][e_vowner[own_f_edges] != rank]) if len(own_f_edges) \
+        else np.zeros(0, np.int64)
+    # remote-factor edges of own variables (-> stub factors), ascending global edge id
+    stub_edges = np.nonzero((e_vowner == rank) & (e_fowner != rank))[0]
+
+    # local variable ids: own (ascending global id) then ghosts
+    n_own, n_ghost = len(own_v), len(ghost_vars)
+    g2l_var = np.full(V, -1, dtype=np.int64)
+    g2l_var[own_v] = np.arange(n_own)
+    g2l_var[ghost_vars] = n_own + np.arange(n_ghost)
+    l_dom = np.concatenate([dom_size[own_v], dom_size[ghost_vars]]).astype(np.int32)
+    l_var_tag = np.concatenate([np.zeros(n_own, np.int32), np.ones(n_ghost, np.int32)])
+
+    # local factors: own factors then one unary stub per remote-factor edge
+    n_real, n_stub = len(own_f), len(stub_edges)
+    real_ar = arity[own_f]
+    l_factor_ptr = np.zeros(n_real + n_stub + 1, dtype=np.int64)
+    np.cumsum(np.concatenate([real_ar, np.ones(n_stub, np.int64)]), out=l_factor_ptr[1:])
+    l_edge_var = np.concatenate([g2l_var[edge_var[own_f_edges]], g2l_var[edge_var[stub_edges]]])
+    l_factor_tag = np.concatenate([np.zeros(n_real, np.int32), np.ones(n_stub, np.int32)])
+    real_tab = tables[_ranges(table_off[own_f], tsize[own_f])] if n_real else np.zeros(0)
+    l_tables = np.concatenate([real_tab, np.zeros(int(dom_size[edge_var[stub_edges]].sum()))])
+    # global edge id -> local (canonical) edge id
+    g2l_edge = np.full(E, -1, dtype=np.int64)
+    g2l_edge[own_f_edges] = np.arange(len(own_f_edges))
+    g2l_edge[stub_edges] = len(own_f_edges) + np.arange(n_stub)
+
+    # variable CSR: own variables keep the global `links` order; ghosts list their local edges
+    own_deg = (g_var_ptr[own_v + 1] - g_var_ptr[own_v]) if n_own else np.zeros(0, np.int64)
+    own_slots_g = _ranges(g_var_ptr[own_v], own_deg) if n_own else np.zeros(0, np.int64)
+    own_var_edge = g2l_edge[g_var_edge[own_slots_g]] if len(own_slots_g) else np.zeros(0, np.int64)
+    assert (own_var_edge >= 0).all()
+    ghost_edge_l = np.nonzero(l_edge_var[:len(own_f_edges)] >= n_own)[0]
+    order = np.argsort(l_edge_var[ghost_edge_l], kind="stable")
+    ghost_var_edge = ghost_edge_l[order]
+    ghost_deg = np.bincount(l_edge_var[ghost_edge_l] - n_own, minlength=n_ghost) if n_ghost \
+        else np.zeros(0, np.int64)
+    l_var_ptr = np.zeros(n_own + n_ghost + 1, dtype=np.int64)
+    np.cumsum(np.concatenate([own_deg, ghost_deg]), out=l_var_ptr[1:])
+    l_var_edge = np.concatenate([own_var_edge, ghost_var_edge])
+    l_unary = np.concatenate([unary[_ranges(unary_off[own_v], dom_size[own_v].astype(np.int64))]
+                              if n_own else np.zeros(0),
+                              np.zeros(int(dom_size[ghost_vars].sum()))])
+    init = inst.get("init_value") if hasattr(inst, "get") else None
+    l_init = None
+    if init is not None:
+        init = np.asarray(init, dtype=np.int32)
+        l_init = np.concatenate([init[own_v], np.full(n_ghost, -1, np.int32)])
+
+    L = build_layout(l_dom, l_factor_ptr, l_edge_var, l_tables, None, l_unary, l_var_ptr, l_var_edge,
+                     l_init, factor_tag=l_factor_tag, var_tag=l_var_tag)
+
+    # ---- halo lists: every cut edge touching this rank, grouped by peer, ascending global id ----
+    def rows(global_edges):
+        ie = L.edge_perm[g2l_edge[global_edges]]
+        return (L.edge_msg_off[ie], L.edge_qoff[ie], dom_size[edge_var[global_edges]].astype(np.int32),
+                ie.astype(np.int32))
+
+    cut_e = np.nonzero(cut)[0]
+    mine_f = cut_e[e_fowner[cut_e] == rank]     # I own the factor: I send r, receive q
+    mine_v = cut_e[e_vowner[cut_e] == rank]     # I own the variable: I send q, receive r
+    mine_f = mine_f[np.argsort(e_vowner[mine_f], kind="stable")]   # grouped by peer (variable owner)
+    mine_v = mine_v[np.argsort(e_fowner[mine_v], kind="stable")]   # grouped by peer (factor owner)
+    fr, fq, fl, fe = rows(mine_f)
+    vr, vq, vl, ve = rows(mine_v)
+
+    def per_peer(peers, lens):
+        el = np.bincount(peers, weights=lens, minlength=world).astype(np.int64)
+        rw = np.bincount(peers, minlength=world).astype(np.int64)
+        return [int(x) for x in el], [int(x) for x in rw]
+
+    sr_split, sr_rows = per_peer(e_vowner[mine_f], fl)
+    rq_split, rq_rows = sr_split, sr_rows           # q rows come back along the same edges
+    sq_split, sq_rows = per_peer(e_fowner[mine_v], vl)
+    rr_split, rr_rows = sq_split, sq_rows
+    return ShardPlan(
+        rank=rank, world=world, layout=L, own_vars=own_v.astype(np.int64), n_own_vars=n_own,
+        send_r_off=fr, send_q_off=vq, recv_r_off=vr, recv_q_off=fq,
+        send_r_len=fl, send_q_len=vl, recv_r_len=vl, recv_q_len=fl,
+        send_r_edge=fe, send_q_edge=ve, recv_r_edge=ve, recv_q_edge=fe,
+        send_r_split=sr_split, send_q_split=sq_split, recv_r_split=rr_split, recv_q_split=rq_split,
+        send_r_rows=sr_rows, send_q_rows=sq_rows, recv_r_rows=rr_rows, recv_q_rows=rq_rows,
+        n_cut_edges=int(cut.sum()), own_factor_edges=own_f_edges, stub_edges=stub_edges)
+
+
+def _ranges(starts, lengths):
+    """Concatenation of arange(s, s + l) for every (s, l), vectorised."""
+    starts = np.asarray(starts, dtype=np.int64)
+    lengths = np.asarray(lengths, dtype=np.int64)
+    total = int(lengths.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.int64)
+    rep = np.repeat(starts - np.concatenate([[0], np.cumsum(lengths)[:-1]]), lengths)
+    return rep + np.arange(total, dtype=np.int64)
+
+
+class HaloExchange:
+    """Packs boundary rows, exchanges them with one all_to_all per direction, unpacks them.
+
+    `pack(src, packed, row_off, packed_off, row_len)` / `unpack(dst, packed, ...)` are injected:
+    the product passes the CUDA kernels behind fg_halo_pack / fg_halo_unpack; the CPU (gloo) tests
+    pass index-based stand-ins to exercise the plumbing without a GPU."""
+
+    def __init__(self, plan: ShardPlan, torch_dtype, device, pack, unpack, group=None):
+        import torch
+        self.torch, self.plan, self.pack, self.unpack, self.group = torch, plan, pack, unpack, group
+        dev = device
+
+        def dv(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+
+        def poff(lens):
+            o = np.zeros(len(lens), dtype=np.int64)
+            if len(lens):
+                np.cumsum(lens[:-1], out=o[1:])
+            return o
+
+        p = plan
+        self.sr = (dv(p.send_r_off, torch.int64), dv(poff(p.send_r_len), torch.int64), dv(p.send_r_len, torch.int32))
+        self.sq = (dv(p.send_q_off, torch.int64), dv(poff(p.send_q_len), torch.int64), dv(p.send_q_len, torch.int32))
+        self.rr = (dv(p.recv_r_off, torch.int64), dv(poff(p.recv_r_len), torch.int64), dv(p.recv_r_len, torch.int32))
+        self.rq = (dv(p.recv_q_off, torch.int64), dv(poff(p.recv_q_len), torch.int64), dv(p.recv_q_len, torch.int32))
+        z = lambda n: torch.zeros(max(int(n), 1), dtype=torch_dtype, device=dev)  # noqa: E731
+        self.buf_sr, self.buf_sq = z(sum(p.send_r_split)), z(sum(p.send_q_split))
+        self.buf_rr, self.buf_rq = z(sum(p.recv_r_split)), z(sum(p.recv_q_split))
+        self.launches = 0
+
+    def pack_rows(self, q, r):
+        p = self.plan
+        n_sr, n_sq = len(p.send_r_len), len(p.send_q_len)
+        if n_sr:
+            self.pack(r, self.buf_sr, *self.sr, n_sr)
+        if n_sq:
+            self.pack(q, self.buf_sq, *self.sq, n_sq)
+        self.launches += int(n_sr > 0) + int(n_sq > 0)
+
+    def unpack_rows(self, q, r):
+        p = self.plan
+        n_rr, n_rq = len(p.recv_r_len), len(p.recv_q_len)
+        if n_rr:
+            self.unpack(r, self.buf_rr, *self.rr, n_rr)
+        if n_rq:
+            self.unpack(q, self.buf_rq, *self.rq, n_rq)
+        self.launches += int(n_rr > 0) + int(n_rq > 0)
+
+    def exchange(self, q, r):
+        """Boundary rows of the given q / r buffers -> the peers' ghost rows (in place)."""
+        import torch.distributed as dist
+        p = self.plan
+        self.pack_rows(q, r)
+        tr, ts = sum(p.recv_r_split), sum(p.send_r_split)
+        dist.all_to_all_single(self.buf_rr[:tr], self.buf_sr[:ts], p.recv_r_split, p.send_r_split,
+                               group=self.group)
+        tq, tsq = sum(p.recv_q_split), sum(p.send_q_split)
+        dist.all_to_all_single(self.buf_rq[:tq], self.buf_sq[:tsq], p.recv_q_split, p.send_q_split,
+                               group=self.group)
+        self.unpack_rows(q, r)
+
+    def exchange_flags(self, q_valid, r_valid):
+        """Validity bytes of the cycle-0 (on_start) messages along the cut edges."""
+        import torch.distributed as dist
+        torch, p = self.torch, self.plan
+        dev = q_valid.device
+
+        def idx(a):
+            return torch.from_numpy(np.ascontiguousarray(a).astype(np.int64)).to(dev)
+
+        for flags, send_e, recv_e, s_rows, r_rows in (
+                (r_valid, p.send_r_edge, p.recv_r_edge, p.send_r_rows, p.recv_r_rows),
+                (q_valid, p.send_q_edge, p.recv_q_edge, p.send_q_rows, p.recv_q_rows)):
+            out = flags[idx(send_e)].contiguous() if len(send_e) else flags[:0].clone()
+            inn = torch.zeros(int(sum(r_rows)), dtype=flags.dtype, device=dev)
+            dist.all_to_all_single(inn, out, list(r_rows), list(s_rows), group=self.group)
+            if len(recv_e):
+                flags[idx(recv_e)] = inn
+
+
+class ShardedMaxSum:
+    """One rank of the partitioned MaxSum: same driving API as MaxSumEngine (init / step / values)."""
+
+    def __init__(self, inst, rank, world, device, precision="f32", group=None, **params):
+        import torch
+        from . import _cabi
+        from .engine import MaxSumEngine, PRECISIONS
+        self.torch = torch
+        self.plan = build_shard(inst, rank, world)
+        self.rank, self.world = rank, world
+        self.engine = MaxSumEngine(self.plan.layout, device=device, precision=precision, **params)
+        self.device = self.engine.device
+        prec, tdt, _ = PRECISIONS[precision]
+        lib = self.engine.lib
+
+        def stream():
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+        def pack(src, packed, row_off, packed_off, row_len, n):
+            rc = lib.fg_halo_pack(prec, C.c_void_p(src.data_ptr()), C.c_void_p(packed.data_ptr()),
+                                  C.c_void_p(row_off.data_ptr()), C.c_void_p(packed_off.data_ptr()),
+                                  C.c_void_p(row_len.data_ptr()), n, stream())
+            if rc != _cabi.FG_OK:
+                raise _cabi.EngineError(f"fg_halo_pack failed rc={rc}")
+
+        def unpack(dst, packed, row_off, packed_off, row_len, n):
+            rc = lib.fg_halo_unpack(prec, C.c_void_p(dst.data_ptr()), C.c_void_p(packed.data_ptr()),
+                                    C.c_void_p(row_off.data_ptr()), C.c_void_p(packed_off.data_ptr()),
+                                    C.c_void_p(row_len.data_ptr()), n, stream())
+            if rc != _cabi.FG_OK:
+                raise _cabi.EngineError(f"fg_halo_unpack failed rc={rc}")
+
+        self.halo = HaloExchange(self.plan, tdt, self.device, pack, unpack, group)
+        self.global_n_edges = int(len(np.asarray(inst["edge_var"])))
+        self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
+
+    @property
+    def layout(self):
+        return self.plan.layout
+
+    def init(self):
+        e = self.engine
+        e.init()
+        self.halo.exchange(e.q[0], e.r[0])
+        self.halo.exchange_flags(e.q_valid, e.r_valid)
+        return self
+
+    def step(self, n_cycles=1):
+        e = self.engine
+        for _ in range(int(n_cycles)):
+            e.cycle_compute()
+            nxt = e.cur ^ 1
+            self.halo.exchange(e.q[nxt], e.r[nxt])
+            e.cycle_commit()
+        return self
+
+    @property
+    def launch_count(self):
+        return self.engine.launch_count + self.halo.launches
+
+    def local_values(self):
+        """(global variable ids, value indices) of the variables this rank owns."""
+        val, _ = self.engine.values()
+        return self.plan.own_vars, val[:self.plan.n_own_vars]
+
+    def values(self):
+        """All-gathered assignment (every rank gets the full vector)."""
+        import torch.distributed as dist
+        torch = self.torch
+        ids, val = self.local_values()
+        out = torch.zeros(self.global_n_vars, dtype=torch.int32, device=self.device)
+        out[torch.from_numpy(ids).to(self.device)] = torch.from_numpy(val.astype(np.int32)).to(self.device)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.halo.group)
+        return out.cpu().numpy()
