@@ -189,16 +189,20 @@ def main():
     from pydcop_b200.engine import MaxSumEngine
 
     inst = config_c2(seed=0, n_vars=n_vars)
+    from pydcop_b200.generators import algorithmic_bytes_per_cycle_inst
+    vb = 4 if args.precision == "f32" else 8
+    n_edges_global = int(len(inst["edge_var"]))
     if world > 1:
         from pydcop_b200.multigpu import ShardedMaxSum
         runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision)
-        L = runner.global_layout
+        L = None
+        config["cut_edges"] = runner.plan.n_cut_edges
+        config["halo"] = "pack kernel + one NCCL all_to_all per direction (q, r) per cycle + unpack kernel"
     else:
         L = build_layout(**inst)
         runner = MaxSumEngine(L, device=dev, precision=args.precision, record_sent=True)
-    vb = 4 if args.precision == "f32" else 8
-    alg_bytes = algorithmic_bytes_per_cycle(L, vb)
-    updates_per_step = 2 * L.n_edges
+    alg_bytes = algorithmic_bytes_per_cycle_inst(inst, vb)
+    updates_per_step = 2 * n_edges_global
 
     if args.profile:
         runner.init()

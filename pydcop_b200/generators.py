@@ -94,3 +94,21 @@ def algorithmic_bytes_per_cycle(layout, value_bytes=4):
     d = layout.dom_size.astype(np.int64)
     b += int((w * d + deg * (3 * w * d + 6) + 12).sum())
     return int(b)
+
+
+def algorithmic_bytes_per_cycle_inst(inst, value_bytes=4):
+    """Same figure as algorithmic_bytes_per_cycle, straight from the instance arrays (no layout):
+    used by the multi-GPU bench where no rank builds the global layout."""
+    w = value_bytes
+    dom = np.asarray(inst["dom_size"], dtype=np.int64)
+    fp = np.asarray(inst["factor_ptr"], dtype=np.int64)
+    ev = np.asarray(inst["edge_var"], dtype=np.int64)
+    ed = dom[ev]
+    arity = np.diff(fp)
+    efac = np.repeat(np.arange(len(arity)), arity)
+    tsize = np.ones(len(arity), dtype=np.int64)
+    np.multiply.at(tsize, efac, ed)
+    b = int((w * tsize).sum() + (3 * w * ed + 6).sum())
+    deg = np.bincount(ev, minlength=len(dom)).astype(np.int64)
+    b += int((w * dom + deg * (3 * w * dom + 6) + 12).sum())
+    return b
