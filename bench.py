@@ -197,7 +197,7 @@ def main():
         runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision)
         L = None
         config["cut_edges"] = runner.plan.n_cut_edges
-        config["halo"] = "pack kernel + one NCCL all_to_all per direction (q, r) per cycle + unpack kernel"
+        config["halo"] = "pack kernels + ONE NCCL all_to_all (q and r rows together) per cycle + unpack kernels"
     else:
         L = build_layout(**inst)
         runner = MaxSumEngine(L, device=dev, precision=args.precision, record_sent=True)
@@ -277,6 +277,9 @@ def main():
                "solve": f"upload tables+unary+CSR from pinned host, init + {E2E_CYCLES} cycles, "
                         f"assignment back to host; {e2e_ms:.3f} ms per solve"}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks, peak_kind = load_peaks()

@@ -56,7 +56,14 @@ class _Graph:
         self.dom_size = c(inst["dom_size"], dtype=np.int32)
         self.factor_ptr = c(inst["factor_ptr"], dtype=np.int32)
         self.edge_var = c(inst["edge_var"], dtype=np.int32)
-        self.table_off = c(inst["table_off"], dtype=np.int64)
+        if "table_off" in inst and inst["table_off"] is not None:
+            self.table_off = c(inst["table_off"], dtype=np.int64)
+        else:  # dense tables back to back, sizes from the scopes' domain sizes
+            ar = np.diff(self.factor_ptr)
+            ts = np.ones(len(ar), dtype=np.int64)
+            np.multiply.at(ts, np.repeat(np.arange(len(ar)), ar),
+                           self.dom_size[self.edge_var].astype(np.int64))
+            self.table_off = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
         self.var_ptr = c(inst["var_ptr"], dtype=np.int32)
         self.var_edge = c(inst["var_edge"], dtype=np.int32)
         self.tables = c(inst["tables"], dtype=self.dtype)

@@ -210,50 +210,68 @@ class HaloExchange:
         def dv(a, dt):
             return torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
 
-        def poff(lens):
-            o = np.zeros(len(lens), dtype=np.int64)
-            if len(lens):
-                np.cumsum(lens[:-1], out=o[1:])
-            return o
-
         p = plan
-        self.sr = (dv(p.send_r_off, torch.int64), dv(poff(p.send_r_len), torch.int64), dv(p.send_r_len, torch.int32))
-        self.sq = (dv(p.send_q_off, torch.int64), dv(poff(p.send_q_len), torch.int64), dv(p.send_q_len, torch.int32))
-        self.rr = (dv(p.recv_r_off, torch.int64), dv(poff(p.recv_r_len), torch.int64), dv(p.recv_r_len, torch.int32))
-        self.rq = (dv(p.recv_q_off, torch.int64), dv(poff(p.recv_q_len), torch.int64), dv(p.recv_q_len, torch.int32))
+        # ONE exchange per cycle: the block for peer b is [r rows for b | q rows for b]
+        W = p.world
+        sr_rows, sq_rows = np.asarray(p.send_r_rows), np.asarray(p.send_q_rows)
+        rr_rows, rq_rows = np.asarray(p.recv_r_rows), np.asarray(p.recv_q_rows)
+        sr_el, sq_el = np.asarray(p.send_r_split, np.int64), np.asarray(p.send_q_split, np.int64)
+        rr_el, rq_el = np.asarray(p.recv_r_split, np.int64), np.asarray(p.recv_q_split, np.int64)
+        self.send_split = [int(a + b) for a, b in zip(sr_el, sq_el)]
+        self.recv_split = [int(a + b) for a, b in zip(rr_el, rq_el)]
+        s_base = np.concatenate([[0], np.cumsum(sr_el + sq_el)])[:-1]
+        r_base = np.concatenate([[0], np.cumsum(rr_el + rq_el)])[:-1]
+
+        def packed_offsets(lens, rows_per_peer, base, shift):
+            """offset of every row inside the combined buffer: rows are grouped by peer"""
+            out = np.zeros(len(lens), dtype=np.int64)
+            pos = 0
+            for b in range(W):
+                n = int(rows_per_peer[b])
+                if n:
+                    ln = np.asarray(lens[pos:pos + n], dtype=np.int64)
+                    out[pos:pos + n] = base[b] + shift[b] + np.concatenate([[0], np.cumsum(ln)[:-1]])
+                pos += n
+            return out
+
+        zero = np.zeros(W, dtype=np.int64)
+        self.sr = (dv(p.send_r_off, torch.int64), dv(packed_offsets(p.send_r_len, sr_rows, s_base, zero), torch.int64),
+                   dv(p.send_r_len, torch.int32))
+        self.sq = (dv(p.send_q_off, torch.int64), dv(packed_offsets(p.send_q_len, sq_rows, s_base, sr_el), torch.int64),
+                   dv(p.send_q_len, torch.int32))
+        self.rr = (dv(p.recv_r_off, torch.int64), dv(packed_offsets(p.recv_r_len, rr_rows, r_base, zero), torch.int64),
+                   dv(p.recv_r_len, torch.int32))
+        self.rq = (dv(p.recv_q_off, torch.int64), dv(packed_offsets(p.recv_q_len, rq_rows, r_base, rr_el), torch.int64),
+                   dv(p.recv_q_len, torch.int32))
         z = lambda n: torch.zeros(max(int(n), 1), dtype=torch_dtype, device=dev)  # noqa: E731
-        self.buf_sr, self.buf_sq = z(sum(p.send_r_split)), z(sum(p.send_q_split))
-        self.buf_rr, self.buf_rq = z(sum(p.recv_r_split)), z(sum(p.recv_q_split))
+        self.buf_send, self.buf_recv = z(sum(self.send_split)), z(sum(self.recv_split))
         self.launches = 0
 
     def pack_rows(self, q, r):
         p = self.plan
         n_sr, n_sq = len(p.send_r_len), len(p.send_q_len)
         if n_sr:
-            self.pack(r, self.buf_sr, *self.sr, n_sr)
+            self.pack(r, self.buf_send, *self.sr, n_sr)
         if n_sq:
-            self.pack(q, self.buf_sq, *self.sq, n_sq)
+            self.pack(q, self.buf_send, *self.sq, n_sq)
         self.launches += int(n_sr > 0) + int(n_sq > 0)
 
     def unpack_rows(self, q, r):
         p = self.plan
         n_rr, n_rq = len(p.recv_r_len), len(p.recv_q_len)
         if n_rr:
-            self.unpack(r, self.buf_rr, *self.rr, n_rr)
+            self.unpack(r, self.buf_recv, *self.rr, n_rr)
         if n_rq:
-            self.unpack(q, self.buf_rq, *self.rq, n_rq)
+            self.unpack(q, self.buf_recv, *self.rq, n_rq)
         self.launches += int(n_rr > 0) + int(n_rq > 0)
 
     def exchange(self, q, r):
-        """Boundary rows of the given q / r buffers -> the peers' ghost rows (in place)."""
+        """Boundary rows of the given q / r buffers -> the peers' ghost rows: pack, ONE
+        all_to_all (NCCL grouped send/recv over NVLink), unpack."""
         import torch.distributed as dist
-        p = self.plan
         self.pack_rows(q, r)
-        tr, ts = sum(p.recv_r_split), sum(p.send_r_split)
-        dist.all_to_all_single(self.buf_rr[:tr], self.buf_sr[:ts], p.recv_r_split, p.send_r_split,
-                               group=self.group)
-        tq, tsq = sum(p.recv_q_split), sum(p.send_q_split)
-        dist.all_to_all_single(self.buf_rq[:tq], self.buf_sq[:tsq], p.recv_q_split, p.send_q_split,
+        ts, tr = sum(self.send_split), sum(self.recv_split)
+        dist.all_to_all_single(self.buf_recv[:tr], self.buf_send[:ts], self.recv_split, self.send_split,
                                group=self.group)
         self.unpack_rows(q, r)
 

@@ -19,17 +19,14 @@ class _LocalFabric:
         self.shards = shards
 
     def exchange(self, which):
-        import torch
-        for name_s, name_r, split_s, split_r in (("buf_sr", "buf_rr", "send_r_split", "recv_r_split"),
-                                                ("buf_sq", "buf_rq", "send_q_split", "recv_q_split")):
-            for a, sa in enumerate(self.shards):
-                so = np.concatenate([[0], np.cumsum(getattr(sa.plan, split_s))]).astype(int)
-                for b, sb in enumerate(self.shards):
-                    ro = np.concatenate([[0], np.cumsum(getattr(sb.plan, split_r))]).astype(int)
-                    n = so[b + 1] - so[b]
-                    assert n == ro[a + 1] - ro[a]
-                    if n:
-                        getattr(sb.halo, name_r)[ro[a]:ro[a + 1]] = getattr(sa.halo, name_s)[so[b]:so[b + 1]]
+        for a, sa in enumerate(self.shards):
+            so = np.concatenate([[0], np.cumsum(sa.halo.send_split)]).astype(int)
+            for b, sb in enumerate(self.shards):
+                ro = np.concatenate([[0], np.cumsum(sb.halo.recv_split)]).astype(int)
+                n = so[b + 1] - so[b]
+                assert n == ro[a + 1] - ro[a]
+                if n:
+                    sb.halo.buf_recv[ro[a]:ro[a + 1]] = sa.halo.buf_send[so[b]:so[b + 1]]
 
     def exchange_flags(self, attr_send, attr_recv, rows_s, rows_r, arr):
         pass

@@ -1,0 +1,186 @@
+"""The pyDcop drop-in boundary, exercised with the UNMODIFIED reference in thread mode (build
+container only: needs /root/reference).  There is no GPU here, so the end-to-end runs put the CPU
+oracle behind the session's engine seam — that checks the plugin plumbing (registration, closure
+detection, value reporting, cycle counting, FINISHED status), not the kernels; without the seam
+the product path must fail loudly instead of falling back."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(),
+                                reason="reference tree not present (GPU box)")
+
+INSTANCES = os.path.join(ref_shim.REFERENCE_ROOT, "tests", "instances")
+
+
+@pytest.fixture(scope="module")
+def pydcop_ready():
+    ref_shim.install()
+    import logging
+    logging.disable(logging.CRITICAL)
+    from pydcop_b200 import launcher
+    launcher.install()
+    yield
+    logging.disable(logging.NOTSET)
+
+
+class _OracleEngine:
+    """Test double with the MaxSumEngine / DsaEngine driving API, backed by the CPU oracle."""
+
+    def __init__(self, kind, layout, inst, params):
+        self.kind = kind
+        if kind == "maxsum":
+            self.o = orc.MaxSumOracle(inst, np.float64, mode=params["mode"],
+                                      **{k: params[k] for k in ("damping", "damping_nodes", "stability",
+                                                                "start_messages") if k in params})
+        else:
+            inst = dict(inst)
+            self.o = orc.DsaOracle(inst, np.float64, mode=params["mode"],
+                                   **{k: params[k] for k in ("probability", "p_mode", "variant",
+                                                             "stop_cycle", "seed") if k in params})
+
+    def init(self):
+        self.o.init()
+        if self.kind == "dsa":
+            pass
+        return self
+
+    def step(self, n):
+        self.o.step(n)
+        return self
+
+    def values(self):
+        if self.kind == "maxsum":
+            return self.o.value.copy(), self.o.value_cost.copy()
+        return self.o.val.copy()
+
+
+@pytest.fixture
+def oracle_seam(pydcop_ready):
+    from pydcop_b200.algorithms._session import GpuSession
+    GpuSession.reset()
+    GpuSession.engine_factory = _OracleEngine
+    yield GpuSession
+    GpuSession.engine_factory = None
+    GpuSession.reset()
+
+
+def test_modules_are_discovered_and_loaded(pydcop_ready):
+    from pydcop.algorithms import list_available_algorithms, load_algorithm_module
+    names = list_available_algorithms()
+    assert "maxsum_gpu" in names and "dsa_gpu" in names and "maxsum" in names
+    ref, gpu = load_algorithm_module("maxsum"), load_algorithm_module("maxsum_gpu")
+    assert gpu.GRAPH_TYPE == ref.GRAPH_TYPE == "factor_graph"
+    ref_params = {p.name: p for p in ref.algo_params}
+    gpu_params = {p.name: p for p in gpu.algo_params}
+    for n, p in ref_params.items():   # every reference parameter, same type / values / default
+        assert gpu_params[n] == p
+    assert {"stop_cycle", "precision", "seed", "session"} <= set(gpu_params)
+    refd, gpud = load_algorithm_module("dsa"), load_algorithm_module("dsa_gpu")
+    assert gpud.GRAPH_TYPE == refd.GRAPH_TYPE == "constraints_hypergraph"
+    for p in refd.algo_params:
+        assert {q.name: q for q in gpud.algo_params}[p.name] == p
+
+
+def test_memory_and_load_models_match_reference(pydcop_ready):
+    from pydcop.algorithms import load_algorithm_module
+    from pydcop.computations_graph import constraints_hypergraph, factor_graph
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "secp_simple1.yaml")])
+    fg = factor_graph.build_computation_graph(dcop)
+    ref, gpu = load_algorithm_module("maxsum"), load_algorithm_module("maxsum_gpu")
+    for node in fg.nodes:
+        assert gpu.computation_memory(node) == ref.computation_memory(node)
+        for nb in node.neighbors:
+            assert gpu.communication_load(node, nb) == ref.communication_load(node, nb)
+    hg = constraints_hypergraph.build_computation_graph(dcop)
+    refd, gpud = load_algorithm_module("dsa"), load_algorithm_module("dsa_gpu")
+    for node in hg.nodes:
+        assert gpud.computation_memory(node) == refd.computation_memory(node)
+        for nb in node.neighbors:
+            assert gpud.communication_load(node, nb) == refd.communication_load(node, nb)
+
+
+def test_solve_api_maxsum_gpu_known_answer(oracle_seam):
+    """tests/api/test_api_solve.py:35-60 of the reference, with --algo maxsum_gpu."""
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    assignment = solve(dcop, "maxsum_gpu", "adhoc", timeout=3)
+    assert assignment == {"v1": "R", "v2": "G", "v3": "R"}
+
+
+def test_run_finishes_with_stop_cycle_and_counts_cycles(oracle_seam):
+    from pydcop.algorithms import AlgorithmDef, load_algorithm_module
+    from pydcop.computations_graph import factor_graph
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.distribution import adhoc
+    from pydcop.infrastructure.run import run_local_thread_dcop
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring_10_4_15_0.1.yml")])
+    algo_module = load_algorithm_module("maxsum_gpu")
+    algo = AlgorithmDef.build_with_default_param("maxsum_gpu", {"stop_cycle": 30, "seed": 1},
+                                                 mode=dcop.objective)
+    cg = factor_graph.build_computation_graph(dcop)
+    dist = adhoc.distribute(cg, dcop.agents.values(), computation_memory=algo_module.computation_memory,
+                            communication_load=algo_module.communication_load)
+    orchestrator = run_local_thread_dcop(algo, cg, dist, dcop, 1e9)
+    try:
+        orchestrator.deploy_computations()
+        t0 = time.time()
+        orchestrator.run(timeout=20)
+        elapsed = time.time() - t0
+        metrics = orchestrator.end_metrics()
+        status = orchestrator.status
+    finally:
+        orchestrator.stop_agents(5)
+        orchestrator.stop()
+    # `pydcop solve` prints FINISHED exactly when the run ended before the timeout because every
+    # computation called finished() (commands/solve.py:547-553, orchestrator.py:898-913)
+    assert status not in ("TIMEOUT", "STOPPED") and elapsed < 15
+    assert metrics["cost"] == 0 and metrics["violation"] == 0      # a proper 3-colouring
+    assert metrics["cycle"] == 30
+    assert set(metrics["assignment"]) == {f"v{i}" for i in range(10)}
+
+
+def test_solve_api_dsa_gpu(oracle_seam):
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    assignment = solve(dcop, "dsa_gpu", "oneagent", timeout=3)
+    assert assignment in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
+
+
+def test_no_gpu_means_loud_failure_not_fallback(pydcop_ready):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pydcop_b200.algorithms._session import GpuSession
+    from pydcop_b200.engine import EngineError
+    from pydcop.algorithms import AlgorithmDef, ComputationDef, load_algorithm_module
+    from pydcop.computations_graph import factor_graph
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    GpuSession.reset()
+    GpuSession.engine_factory = None
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    algo = AlgorithmDef.build_with_default_param("maxsum_gpu", {"session": "nogpu"}, mode="min")
+    module = load_algorithm_module("maxsum_gpu")
+    comps = []
+    for node in factor_graph.build_computation_graph(dcop).nodes:
+        c = module.build_computation(ComputationDef(node, algo))
+        c.message_sender = lambda *a, **k: None
+        c.periodic_action_handler = type("H", (), {"set_periodic_action": lambda s, p, cb: cb,
+                                                   "remove_periodic_action": lambda s, h: None})()
+        comps.append(c)
+    for c in comps:
+        c.start()
+    s = GpuSession.get("maxsum:nogpu", "maxsum")
+    s.thread.join(timeout=30)
+    assert isinstance(s.error, EngineError)
+    with pytest.raises(EngineError):
+        comps[0]._poll()
+    GpuSession.reset()
