@@ -132,7 +132,7 @@ def test_run_finishes_with_stop_cycle_and_counts_cycles(oracle_seam):
     try:
         orchestrator.deploy_computations()
         t0 = time.time()
-        orchestrator.run(timeout=20)
+        orchestrator.run(timeout=60)
         elapsed = time.time() - t0
         metrics = orchestrator.end_metrics()
         status = orchestrator.status
@@ -141,7 +141,7 @@ def test_run_finishes_with_stop_cycle_and_counts_cycles(oracle_seam):
         orchestrator.stop()
     # `pydcop solve` prints FINISHED exactly when the run ended before the timeout because every
     # computation called finished() (commands/solve.py:547-553, orchestrator.py:898-913)
-    assert status not in ("TIMEOUT", "STOPPED") and elapsed < 15
+    assert status not in ("TIMEOUT", "STOPPED") and elapsed < 55, (status, elapsed)
     assert metrics["cost"] == 0 and metrics["violation"] == 0      # a proper 3-colouring
     assert metrics["cycle"] == 30
     assert set(metrics["assignment"]) == {f"v{i}" for i in range(10)}
