@@ -122,6 +122,53 @@ def cpu_baseline(inst, L, seconds=12.0, dtype=np.float32):
                       f"{'f32' if dtype == np.float32 else 'f64'}, OpenMP {cores} threads, {dt:.1f}s"}
 
 
+def side_workload(args, dev):
+    """Other BASELINE configs on one GPU (not the driver's line): same timing rules."""
+    import torch
+    from pydcop_b200 import build_layout
+    from pydcop_b200 import generators as G
+    from pydcop_b200.engine import DsaEngine, MaxSumEngine
+    w = args.workload
+    inst = {"c3": G.config_c3, "c5": G.config_c5, "target": G.config_target, "c4": G.config_c4}[w]()
+    L = build_layout(**inst)
+    vb = 4 if args.precision == "f32" else 8
+    if w == "c4":
+        eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
+        units, metric = L.n_vars, "dsa_variable_updates_per_s"
+        d, k = 20, 6
+        alg = L.n_vars * (k * (vb * d + 4 + 8 + vb) + 8)   # SURVEY 8d: ~584 B per variable update
+    else:
+        eng = MaxSumEngine(L, device=dev, precision=args.precision)
+        units, metric = 2 * L.n_edges, METRIC
+        alg = G.algorithmic_bytes_per_cycle_inst(inst, vb)
+    eng.init()
+    if args.profile:
+        eng.step(max(3, args.warmup) + args.steps)
+        torch.cuda.synchronize(dev)
+        return
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    eng.step(max(3, args.warmup))
+    torch.cuda.synchronize(dev)
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.step(1)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    peaks, kind = load_peaks()
+    ach = alg / (ms * 1e-3) / 1e9
+    print(json.dumps({"metric": metric, "value": units / (ms * 1e-3), "unit": "updates/s", "n_gpus": 1,
+                      "steps": args.steps, "ms_per_step": ms, "dtype": args.precision,
+                      "config": {"workload": w, "n_vars": L.n_vars, "n_factors": L.n_factors,
+                                 "n_edges": L.n_edges},
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_step": int(alg)}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,6 +178,9 @@ def main():
     ap.add_argument("--vars-per-gpu", type=int, default=100_000)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "target", "c4"],
+                    help="c2 (default, the driver's line) | c3 Ising 1024^2 | c5 arity-3 | target 1M vars "
+                         "| c4 DSA 1M vars d=20 (variable updates/s)")
     ap.add_argument("--profile", action="store_true",
                     help="lean run for ncu: init + warmup + steps back to back, no flush/e2e/JSON")
     args = ap.parse_args()
@@ -188,6 +238,8 @@ def main():
 
     from pydcop_b200.engine import MaxSumEngine
 
+    if args.workload != "c2":
+        return side_workload(args, dev)
     inst = config_c2(seed=0, n_vars=n_vars)
     from pydcop_b200.generators import algorithmic_bytes_per_cycle_inst
     vb = 4 if args.precision == "f32" else 8

@@ -186,6 +186,15 @@ typedef struct {
   const uint8_t *dev_has_nbr;    /* [n_vars] variable has >= 1 neighbour (dsa.py:278) */
   const double *dev_prob;        /* [n_vars] change threshold (p_mode fixed|arity, dsa.py:252-263) */
   void *dev_con_opt;             /* T[n_factors] per-constraint optimum, filled by fg_dsa_init */
+  /* optional fast path: every constraint binary over one domain size `fast_dom` (else NULL / 0).
+   * Per slot (variable v, incident constraint c, neighbour u): the table of c ORIENTED so that
+   * row y = value of u is contiguous over v's values (position-0 slots read a transposed copy):
+   *   cost_v[x] += dev_tables_or[slot_tab[s] + y * fast_dom + x] */
+  const void *dev_tables_or;     /* T[...] original tables followed by the transposed copies */
+  const int32_t *dev_slot_nbr;   /* [n_edges] neighbour variable of slot s */
+  const int64_t *dev_slot_tab;   /* [n_edges] element offset of the oriented table of slot s */
+  const void *dev_slot_opt;      /* T[n_edges] optimum of the slot's constraint (variant B) */
+  int32_t fast_dom, reserved1;
   int32_t *dev_value[2];         /* [n_vars] current / next value index (double buffer) */
   void *dev_value_cost;          /* T[n_vars] cost reported with the last selection */
   int32_t mode_max, variant;     /* FG_DSA_* */

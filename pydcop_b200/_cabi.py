@@ -61,7 +61,9 @@ class FgDsaDesc(C.Structure):
                 ("dev_tables", P), ("dev_dom_size", P), ("dev_var_id", P), ("dev_edge_var", P),
                 ("dev_edge_class", P),
                 ("dev_var_ptr", P), ("dev_slot_edge", P), ("dev_has_nbr", P), ("dev_prob", P),
-                ("dev_con_opt", P), ("dev_value", P * 2), ("dev_value_cost", P),
+                ("dev_con_opt", P), ("dev_tables_or", P), ("dev_slot_nbr", P), ("dev_slot_tab", P),
+                ("dev_slot_opt", P), ("fast_dom", C.c_int32), ("reserved1", C.c_int32),
+                ("dev_value", P * 2), ("dev_value_cost", P),
                 ("mode_max", C.c_int32), ("variant", C.c_int32), ("stop_cycle", C.c_int32),
                 ("seed", C.c_uint64)]
 

@@ -287,6 +287,31 @@ class DsaEngine(_EngineBase):
             self.value = [self._dev(isolated_value, torch.int32) if L.n_vars else z(1, torch.int32),
                           z(L.n_vars, torch.int32)]
             self.value_cost = z(L.n_vars, tdt)
+        # fast path: every constraint binary over ONE domain size -> oriented tables, one contiguous
+        # row per incidence (transposed copy for scope position 0)
+        self.tables_or = self.slot_nbr = self.slot_tab = self.slot_opt = None
+        fast_dom = 0
+        if (len(L.classes) == 1 and L.classes[0].arity == 2 and L.classes[0].dom[0] == L.classes[0].dom[1]
+                and L.n_edges and not L.classes[0].tag):
+            c0 = L.classes[0]
+            D = c0.dom[0]
+            S = D * D
+            nF = c0.n_factors
+            with torch.cuda.device(self.device):
+                t = self.tables[c0.table_base:c0.table_base + nF * S].view(nF, D, D)
+                self.tables_or = torch.cat([t.reshape(-1), t.transpose(1, 2).contiguous().reshape(-1)])
+                opt = (t.reshape(nF, S).max(dim=1).values if mode == "max"
+                       else t.reshape(nF, S).min(dim=1).values)
+            e = L.slot_edge.astype(np.int64) - c0.first_edge
+            f, j = e // 2, e % 2
+            # position 1 (me second): T[y][x] is already row-contiguous; position 0: transposed copy
+            slot_tab = np.where(j == 1, f * S, nF * S + f * S).astype(np.int64)
+            slot_nbr = L.edge_var[c0.first_edge + f * 2 + (1 - j)].astype(np.int32)
+            with torch.cuda.device(self.device):
+                self.slot_tab = self._dev(slot_tab, torch.int64)
+                self.slot_nbr = self._dev(slot_nbr, torch.int32)
+                self.slot_opt = opt[torch.from_numpy(f).to(self.device)].contiguous()
+            fast_dom = D
         self._classes = _class_array(L)
         d = FgDsaDesc()
         d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
@@ -299,6 +324,9 @@ class DsaEngine(_EngineBase):
         d.dev_has_nbr, d.dev_prob, d.dev_con_opt = _ptr(self.has_nbr), _ptr(self.prob), _ptr(self.con_opt)
         d.dev_value[0], d.dev_value[1] = self.value[0].data_ptr(), self.value[1].data_ptr()
         d.dev_value_cost = _ptr(self.value_cost)
+        d.dev_tables_or, d.dev_slot_nbr = _ptr(self.tables_or), _ptr(self.slot_nbr)
+        d.dev_slot_tab, d.dev_slot_opt = _ptr(self.slot_tab), _ptr(self.slot_opt)
+        d.fast_dom = fast_dom
         d.mode_max, d.variant = int(mode == "max"), _cabi.DSA_VARIANTS[variant]
         d.stop_cycle, d.seed = int(stop_cycle), int(seed) & (2 ** 64 - 1)
         self._desc = d

@@ -123,3 +123,25 @@ def test_division_free_approx_match_is_exact(precision):
     assert torch.equal(of, oe)
     frac = float(oe.float().mean())
     assert 0.2 < frac < 0.8, frac   # the inputs really straddle the threshold
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("variant,mode,d", [("B", "min", 20), ("A", "min", 10), ("C", "max", 5), ("B", "max", 8)])
+def test_dsa_binary_fast_path_vs_oracle(variant, mode, d, precision):
+    """oriented-table DSA kernel (all constraints binary, one domain size) against the oracle;
+    few distinct integer costs -> many ties -> the delta == 0 branches are exercised."""
+    from pydcop_b200 import DsaEngine, build_layout
+    rng = np.random.default_rng(7)
+    inst = random_factor_graph(2500, d, 7000, 2, seed=11 + d, noise=0.0)
+    inst["tables"] = rng.integers(0, 3, len(inst["tables"])).astype(np.float32)
+    L = build_layout(**inst)
+    npdt = np.float64 if precision == "f64" else np.float32
+    o = orc.DsaOracle(oracle_instance(inst, L), npdt, mode=mode, variant=variant, seed=31).init()
+    eng = DsaEngine(L, precision=precision, mode=mode, variant=variant, seed=31).init()
+    assert eng.tables_or is not None          # the fast path is really the one running
+    assert np.array_equal(eng.values(), o.val)
+    for k in range(12):
+        o.step()
+        eng.step()
+        assert np.array_equal(eng.values(), o.val), k
+    assert eng.launch_count > 0
