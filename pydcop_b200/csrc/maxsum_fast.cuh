@@ -474,8 +474,8 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 // variable -> factor: one thread per variable, variables grouped in (domain, degree) classes
 // ------------------------------------------------------------------------------------------------
 #define FG_V2F_MAX_ENTRIES 24
-#define FG_V2F_NT 128
-#define FG_V2F_ROUNDS 2   // a thread finishes at most this many slots per tile
+#define FG_V2F_NT 256
+#define FG_V2F_ROUNDS 1   // a thread finishes at most this many slots per tile
 
 struct V2FEntry {
   fg_varclass_t vc;
@@ -529,13 +529,17 @@ __device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D, i
 
 // costs_for_factor (maxsum.py:623-676) for slot f of a variable whose K gathered r rows are at
 // col[g*D + x]: value-major, then factor order; the own factor contributes +0 (exact).
-// K > 0: compile-time degree (fully unrolled); K == 0: run-time degree `k_rt`.
+// K > 0: compile-time degree (inner loop unrolled); K == 0: run-time degree `k_rt`.  The loop over
+// the values is a run-time loop on purpose: it keeps every degree variant a few dozen
+// instructions, so the whole kernel stays resident in the instruction cache.  Raw sums go to
+// `out` (shared memory); returns the normalisation term sum_cost / D.
 template <typename T, int D, int K>
-__device__ __forceinline__ void v2f_slot_msg(const T *__restrict__ col, int f, int k_rt, T (&cand)[D]) {
+__device__ __forceinline__ T v2f_slot_msg(const T *__restrict__ col, const T *__restrict__ ur, int f, int k_rt,
+                                          T *__restrict__ out) {
   T sum_cost = (T)0;
-#pragma unroll
+#pragma unroll 1
   for (int x = 0; x < D; ++x) {
-    T m = cand[x];  // in: the variable's own cost
+    T m = ur[x];
     if constexpr (K > 0) {
 #pragma unroll
       for (int g = 0; g < K; ++g) {
@@ -550,11 +554,9 @@ __device__ __forceinline__ void v2f_slot_msg(const T *__restrict__ col, int f, i
         m += cst;
       }
     }
-    cand[x] = m;
+    out[x] = m;
   }
-  const T avg_c = sum_cost / (T)D;
-#pragma unroll
-  for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg_c;
+  return sum_cost / (T)D;
 }
 
 // select_value (maxsum.py:584-620): costs summed in `links` order, first optimum wins
@@ -563,7 +565,7 @@ __device__ __forceinline__ void v2f_select(const T *__restrict__ col, const T *_
                                            int32_t *value_out, T *cost_out) {
   int best = 0;
   T best_c = (T)0;
-#pragma unroll
+#pragma unroll 1
   for (int x = 0; x < D; ++x) {
     T tot = ur[x];
     if constexpr (K > 0) {
@@ -717,8 +719,11 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
         const int i = sl / K, f = sl - i * K;
         const T *col = rrow + i * t.VS;
         T cand[D], prev[D];
-        ld_row<T, D, C::VR>(un + i * D, cand);
-        FG_V2F_K_SWITCH(K, (v2f_slot_msg<T, D, KK>(col, f, K, cand)))
+        T avg_c;
+        FG_V2F_K_SWITCH(K, (avg_c = v2f_slot_msg<T, D, KK>(col, un + i * D, f, K, qout + sl * D)))
+        ld_row<T, D, C::VR>(qout + sl * D, cand);
+#pragma unroll
+        for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg_c;
         ld_row<T, D, C::VR>(qio + sl * D, prev);
         uint8_t c8 = cnt[u];
         const bool sent = damp_gate_row<T, D>(cand, prev, c8, p.damp_vars != 0, lam, oml, stab);
