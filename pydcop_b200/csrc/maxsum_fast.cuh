@@ -800,7 +800,7 @@ inline void launch_f2v_tile(const fg_class_t &c, const fg_maxsum_desc_t &d, cons
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::NT, PP::SMEM);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // the two sides of a cycle run concurrently on two streams: leave room for the other kernel
-    const int cap = fg_env_int("PYDCOP_B200_F2V_CPS", 3);
+    const int cap = fg_env_int("PYDCOP_B200_F2V_CPS", 2);
     if (ctas_per_sm > cap) ctas_per_sm = cap;
   }
   const int n_tiles = (c.n_factors + C::NF - 1) / C::NF;
@@ -890,7 +890,7 @@ inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, siz
     const int VR = fg_gcd(16, D * (int)elem) / (int)elem;
     const int VS = v2f_vstride(K, D, VR);
     const size_t per_var = (size_t)(VS + K * D + D) * elem;  // stage bytes per variable
-    static const int stage_kb = fg_env_int("PYDCOP_B200_V2F_STAGE_KB", 10);
+    static const int stage_kb = fg_env_int("PYDCOP_B200_V2F_STAGE_KB", 14);
     int nv = (int)((size_t)(stage_kb * 1024) / per_var);
     const int cap = (FG_V2F_ROUNDS * FG_V2F_NT) / K;        // slots per tile <= ROUNDS * NT
     if (nv > cap) nv = cap;
@@ -930,7 +930,7 @@ inline void launch_v2f_classes(const V2FLaunch &L, const fg_maxsum_desc_t &d, co
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2F_NT, L.smem);
   if (per_sm < 1) per_sm = 1;
-  static const int cap = fg_env_int("PYDCOP_B200_V2F_CPS", 4);
+  static const int cap = fg_env_int("PYDCOP_B200_V2F_CPS", 3);
   if (per_sm > cap) per_sm = cap;
   const unsigned blocks = (unsigned)std::min(L.tab.total_tiles, n_sm * per_sm);
   kern<<<blocks, FG_V2F_NT, L.smem, st>>>(L.tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,

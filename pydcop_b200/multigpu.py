@@ -350,6 +350,30 @@ class ShardedMaxSum:
             e.cycle_commit()
         return self
 
+    def timed_breakdown(self, n_cycles=50):
+        """Device time (ms per cycle) of compute / pack / all_to_all / unpack, for tuning."""
+        import torch.distributed as dist
+        torch, e, h = self.torch, self.engine, self.halo
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        acc = np.zeros(4)
+        for _ in range(n_cycles):
+            t = [ev() for _ in range(5)]
+            t[0].record()
+            e.cycle_compute()
+            t[1].record()
+            nxt = e.cur ^ 1
+            h.pack_rows(e.q[nxt], e.r[nxt])
+            t[2].record()
+            ts, tr = sum(h.send_split), sum(h.recv_split)
+            dist.all_to_all_single(h.buf_recv[:tr], h.buf_send[:ts], h.recv_split, h.send_split, group=h.group)
+            t[3].record()
+            h.unpack_rows(e.q[nxt], e.r[nxt])
+            t[4].record()
+            e.cycle_commit()
+            torch.cuda.synchronize(self.device)
+            acc += [t[i].elapsed_time(t[i + 1]) for i in range(4)]
+        return dict(zip(("compute", "pack", "all_to_all", "unpack"), (acc / n_cycles).tolist()))
+
     @property
     def launch_count(self):
         return self.engine.launch_count + self.halo.launches
