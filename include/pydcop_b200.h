@@ -164,6 +164,16 @@ int fg_halo_unpack(int32_t precision, void *dev_dst, const void *dev_packed,
                    const int64_t *dev_row_off, const int64_t *dev_packed_off,
                    const int32_t *dev_row_len, int64_t n_rows, void *stream);
 
+/* Uniform-domain fast form of the two calls above, r and q rows in ONE launch.  The packed
+ * buffer is the all_to_all buffer: for peer p the block [r rows for p | q rows for p] starts at
+ * element peer_base[p]; rows of the r list [peer_r_start[p], peer_r_start[p+1]) and of the q list
+ * [peer_q_start[p], peer_q_start[p+1]) belong to peer p (HOST arrays of n_peers+1 / n_peers
+ * entries, n_peers <= 16).  pack != 0: arrays -> packed; pack == 0: packed -> arrays. */
+int fg_halo_rows_uniform(int32_t precision, int32_t pack, void *dev_r, void *dev_q, void *dev_packed,
+                         const int64_t *dev_row_off_r, const int64_t *dev_row_off_q, int64_t n_r,
+                         int64_t n_q, int32_t dom, int32_t n_peers, const int64_t *peer_r_start,
+                         const int64_t *peer_q_start, const int64_t *peer_base, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * DSA  (replaces DsaComputation.on_start dsa.py:277-299 and evaluate_cycle :320-357 with
  * find_optimal relations.py:1594-1638, assignment_cost :1479-1532, variant_a/b/c dsa.py:359-405,

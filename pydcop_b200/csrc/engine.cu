@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -293,6 +294,63 @@ extern "C" int fg_halo_pack(int32_t precision, const void *dev_src, void *dev_pa
 extern "C" int fg_halo_unpack(int32_t precision, void *dev_dst, const void *dev_packed, const int64_t *dev_row_off,
                               const int64_t *dev_packed_off, const int32_t *dev_row_len, int64_t n_rows, void *stream) {
   return halo_rows<false>(precision, dev_dst, const_cast<void *>(dev_packed), dev_row_off, dev_packed_off, dev_row_len, n_rows, stream);
+}
+
+struct HaloPeers {
+  int n;
+  int64_t r_start[17], q_start[17], base[16];
+};
+
+// one thread per (row, 4/8/16-byte piece): r rows first, then q rows
+template <int PB, bool PACK>
+__global__ void __launch_bounds__(256)
+k_halo_rows_uniform(unsigned char *__restrict__ arr_r, unsigned char *__restrict__ arr_q,
+                    unsigned char *__restrict__ packed, const int64_t *__restrict__ off_r,
+                    const int64_t *__restrict__ off_q, int64_t n_r, int64_t n_q, int row_bytes, int elem,
+                    HaloPeers hp) {
+  const int ppr = row_bytes / PB;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = t / ppr;
+  const int piece = (int)(t - row * ppr);
+  if (row >= n_r + n_q) return;
+  const bool is_q = row >= n_r;
+  const int64_t i = is_q ? row - n_r : row;
+  const int64_t *start = is_q ? hp.q_start : hp.r_start;
+  int p = 0;
+#pragma unroll 1
+  while (p + 1 < hp.n && i >= start[p + 1]) ++p;
+  int64_t pk = hp.base[p] * elem + (i - start[p]) * row_bytes;            // byte offset in the packed buffer
+  if (is_q) pk += (hp.r_start[p + 1] - hp.r_start[p]) * (int64_t)row_bytes;  // after the peer's r rows
+  unsigned char *a = (is_q ? arr_q : arr_r) + (is_q ? off_q[i] : off_r[i]) * elem + piece * PB;
+  unsigned char *b = packed + pk + piece * PB;
+  using V = typename std::conditional<PB == 16, uint4, typename std::conditional<PB == 8, uint2, uint32_t>::type>::type;
+  if (PACK) *reinterpret_cast<V *>(b) = *reinterpret_cast<const V *>(a);
+  else *reinterpret_cast<V *>(a) = *reinterpret_cast<const V *>(b);
+}
+
+extern "C" int fg_halo_rows_uniform(int32_t precision, int32_t pack, void *dev_r, void *dev_q, void *dev_packed,
+                                    const int64_t *dev_row_off_r, const int64_t *dev_row_off_q, int64_t n_r, int64_t n_q,
+                                    int32_t dom, int32_t n_peers, const int64_t *peer_r_start, const int64_t *peer_q_start,
+                                    const int64_t *peer_base, void *stream) {
+  if (n_r + n_q <= 0) return FG_OK;
+  if (n_peers < 1 || n_peers > 16 || dom < 1) return FG_ERR_ARG;
+  HaloPeers hp;
+  hp.n = n_peers;
+  for (int i = 0; i <= n_peers; ++i) { hp.r_start[i] = peer_r_start[i]; hp.q_start[i] = peer_q_start[i]; }
+  for (int i = 0; i < n_peers; ++i) hp.base[i] = peer_base[i];
+  const int elem = precision == FG_F64 ? 8 : 4;
+  const int row_bytes = dom * elem;
+  const int pb = (row_bytes % 16 == 0) ? 16 : ((row_bytes % 8 == 0) ? 8 : 4);
+  const int64_t threads = (n_r + n_q) * (row_bytes / pb);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *r = (unsigned char *)dev_r, *q = (unsigned char *)dev_q, *pk = (unsigned char *)dev_packed;
+  const unsigned blocks = blocks_for(threads, 256);
+#define FG_HALO_LAUNCH(PB_)                                                                                                    \
+  if (pack) k_halo_rows_uniform<PB_, true><<<blocks, 256, 0, st>>>(r, q, pk, dev_row_off_r, dev_row_off_q, n_r, n_q, row_bytes, elem, hp); \
+  else k_halo_rows_uniform<PB_, false><<<blocks, 256, 0, st>>>(r, q, pk, dev_row_off_r, dev_row_off_q, n_r, n_q, row_bytes, elem, hp);
+  if (pb == 16) { FG_HALO_LAUNCH(16) } else if (pb == 8) { FG_HALO_LAUNCH(8) } else { FG_HALO_LAUNCH(4) }
+#undef FG_HALO_LAUNCH
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------

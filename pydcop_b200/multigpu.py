@@ -246,10 +246,22 @@ class HaloExchange:
         z = lambda n: torch.zeros(max(int(n), 1), dtype=torch_dtype, device=dev)  # noqa: E731
         self.buf_send, self.buf_recv = z(sum(self.send_split)), z(sum(self.recv_split))
         self.launches = 0
+        # uniform-domain fast form: one launch moves the r and the q rows (fg_halo_rows_uniform)
+        self.fused = None
+        self.uniform_dom = int(p.layout.uniform_dom)
+        c64 = lambda a: (C.c_int64 * len(a))(*[int(x) for x in a])  # noqa: E731
+        cs = lambda a: np.concatenate([[0], np.cumsum(a)])  # noqa: E731
+        self.peers_send = (c64(cs(sr_rows)), c64(cs(sq_rows)), c64(s_base))
+        self.peers_recv = (c64(cs(rr_rows)), c64(cs(rq_rows)), c64(r_base))
 
     def pack_rows(self, q, r):
         p = self.plan
         n_sr, n_sq = len(p.send_r_len), len(p.send_q_len)
+        if self.fused is not None and self.uniform_dom and (n_sr + n_sq):
+            self.fused(1, r, q, self.buf_send, self.sr[0], self.sq[0], n_sr, n_sq, self.uniform_dom,
+                       p.world, *self.peers_send)
+            self.launches += 1
+            return
         if n_sr:
             self.pack(r, self.buf_send, *self.sr, n_sr)
         if n_sq:
@@ -259,6 +271,11 @@ class HaloExchange:
     def unpack_rows(self, q, r):
         p = self.plan
         n_rr, n_rq = len(p.recv_r_len), len(p.recv_q_len)
+        if self.fused is not None and self.uniform_dom and (n_rr + n_rq):
+            self.fused(0, r, q, self.buf_recv, self.rr[0], self.rq[0], n_rr, n_rq, self.uniform_dom,
+                       p.world, *self.peers_recv)
+            self.launches += 1
+            return
         if n_rr:
             self.unpack(r, self.buf_recv, *self.rr, n_rr)
         if n_rq:
@@ -327,6 +344,18 @@ class ShardedMaxSum:
                 raise _cabi.EngineError(f"fg_halo_unpack failed rc={rc}")
 
         self.halo = HaloExchange(self.plan, tdt, self.device, pack, unpack, group)
+
+        def fused(is_pack, r, q, packed, off_r, off_q, n_r, n_q, dom, n_peers, pr, pq, pb):
+            rc = lib.fg_halo_rows_uniform(prec, is_pack, C.c_void_p(r.data_ptr()), C.c_void_p(q.data_ptr()),
+                                          C.c_void_p(packed.data_ptr()), C.c_void_p(off_r.data_ptr()),
+                                          C.c_void_p(off_q.data_ptr()), n_r, n_q, dom, n_peers,
+                                          C.cast(pr, C.c_void_p), C.cast(pq, C.c_void_p),
+                                          C.cast(pb, C.c_void_p), stream())
+            if rc != _cabi.FG_OK:
+                raise _cabi.EngineError(f"fg_halo_rows_uniform failed rc={rc}")
+
+        if self.plan.layout.uniform_dom:
+            self.halo.fused = fused
         self.global_n_edges = int(len(np.asarray(inst["edge_var"])))
         self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
 
