@@ -104,41 +104,45 @@ __device__ __forceinline__ bool approx_match_fast(T c, T prev_c, T stab) {
   return (prev_c == c) || res;
 }
 
-// damping + approx_match + gate for one message row held in registers.
-// cand: fresh message (in) / message to store (out).  Returns `sent`.
-// The match predicate is evaluated division-free for the whole row (straight-line code); only if
-// some element sits within a few ulps of the threshold (or in the denormal / overflow range) the
-// literal form with the IEEE division is evaluated for that element.
+// damping + approx_match for (a part of) one message row held in registers.
+// cand: fresh values in, damped values out.  Returns whether every element matches `prev`.
+// The predicate is evaluated division-free for the whole row (straight-line code); only if some
+// element sits within a few ulps of the threshold (or in the denormal / overflow range) the
+// literal form with the IEEE division is evaluated.
+template <typename T, int N>
+__device__ __forceinline__ bool damp_match_row(T (&cand)[N], const T (&prev)[N], bool has_prev, bool damp_side,
+                                               T lam, T oml, T stab) {
+  if (!has_prev) return false;
+  bool all_ok = true, unsure = false;
+#pragma unroll
+  for (int x = 0; x < N; ++x) {
+    T c = cand[x];
+    if (damp_side) c = lam * prev[x] + oml * c;
+    cand[x] = c;
+    const T s = prev[x] + c;
+    const T d2 = (T)2 * fg_abs<T>(prev[x] - c);
+    const T rhs = stab * fg_abs<T>(s);
+    const bool safe = (rhs > MatchEps<T>::tiny()) && (rhs < Inf<T>::pos());
+    const bool lt = d2 < rhs * MatchEps<T>::lo();
+    const bool gt = d2 > rhs * MatchEps<T>::hi();
+    const bool eq = prev[x] == c;
+    unsure = unsure || (!eq && !(safe && (lt || gt)));
+    all_ok = all_ok && (eq || lt);
+  }
+  if (unsure) {  // rare
+    all_ok = true;
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+      if (!approx_match1<T>(cand[x], prev[x], stab)) all_ok = false;
+  }
+  return all_ok;
+}
+
+// whole row: damping, match, send gate.  Returns `sent`; cand holds the row to store.
 template <typename T, int D>
 __device__ __forceinline__ bool damp_gate_row(T (&cand)[D], const T (&prev)[D], uint8_t &cnt, bool damp_side,
                                               T lam, T oml, T stab) {
-  const bool has_prev = cnt & 1;
-  bool match = has_prev;
-  if (has_prev) {
-    bool all_ok = true, unsure = false;
-#pragma unroll
-    for (int x = 0; x < D; ++x) {
-      T c = cand[x];
-      if (damp_side) c = lam * prev[x] + oml * c;
-      cand[x] = c;
-      const T s = prev[x] + c;
-      const T d2 = (T)2 * fg_abs<T>(prev[x] - c);
-      const T rhs = stab * fg_abs<T>(s);
-      const bool safe = (rhs > MatchEps<T>::tiny()) && (rhs < Inf<T>::pos());
-      const bool lt = d2 < rhs * MatchEps<T>::lo();
-      const bool gt = d2 > rhs * MatchEps<T>::hi();
-      const bool eq = prev[x] == c;
-      unsure = unsure || (!eq && !(safe && (lt || gt)));
-      all_ok = all_ok && (eq || lt);
-    }
-    match = all_ok;
-    if (unsure) {  // rare
-      match = true;
-#pragma unroll
-      for (int x = 0; x < D; ++x)
-        if (!approx_match1<T>(cand[x], prev[x], stab)) match = false;
-    }
-  }
+  const bool match = damp_match_row<T, D>(cand, prev, (cnt & 1) != 0, damp_side, lam, oml, stab);
   const bool sent = gate_decide(match, cnt);
   if (!sent) {
 #pragma unroll
@@ -166,7 +170,13 @@ struct F2VCfg {
   static constexpr int SP = S + PAD;
   static constexpr int PER_FACTOR = (SP + 3 * R) * (int)sizeof(T);
   static constexpr int NF = fg_clamp(((20 * 1024) / PER_FACTOR) / 32 * 32, 32, 512);
-  static constexpr int NT = fg_clamp(NF * A, 64, 256);
+  // two threads per directed edge (each owns half of the D outputs) when D is even: twice the
+  // warps per tile for the same shared memory
+  static constexpr int SPLIT = (A >= 2 && D % 2 == 0 && D >= 4) ? 2 : 1;
+  static constexpr int HD = D / SPLIT;
+  static constexpr int NT = fg_clamp(NF * A * SPLIT, 64, 256);
+  static constexpr int VH_BYTES = fg_gcd(16, HD * (int)sizeof(T));
+  static constexpr int VH = VH_BYTES / (int)sizeof(T);
   // vector width (elements) for table rows (D contiguous elements at multiples of D inside a
   // factor whose stride is SP) and for message rows
   static constexpr int VT_BYTES = fg_gcd(16, fg_gcd(D * (int)sizeof(T), SP * (int)sizeof(T)));
@@ -192,108 +202,140 @@ __device__ __forceinline__ T opt_tree(const T (&v)[N], bool mx) {
 
 // All edges of one staged tile: min-marginal (factor_costs_for_var, maxsum.py:382-447), damping,
 // send gate; results into `ot` (same [f][j][x] layout as the class-major r array).
-template <typename T, int A, int D, int EPT>
+// Work item w -> (position j, factor f, half h): lanes of a warp share j, the two halves of an edge
+// sit in adjacent lanes (h = lane & 1) and combine their match flags with one shuffle.
+template <typename T, int A, int D, int WPT>
 __device__ __forceinline__ void f2v_compute_tile(const T *__restrict__ tab, const T *__restrict__ qt,
                                                  const T *__restrict__ rt, T *__restrict__ ot, int nf, int e_base,
-                                                 const uint8_t (&cnt_in)[EPT], uint8_t *__restrict__ r_cnt,
+                                                 const uint8_t (&cnt_in)[WPT], uint8_t *__restrict__ r_cnt,
                                                  uint8_t *__restrict__ r_sent, const MaxSumParams &p, int tid) {
   using C = F2VCfg<T, A, D>;
-  constexpr int R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, INNER = C::INNER;
+  constexpr int R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, INNER = C::INNER, SPLIT = C::SPLIT, HD = C::HD;
   const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
   const T init = mx ? -Inf<T>::pos() : Inf<T>::pos();
 #pragma unroll
-  for (int u = 0; u < EPT; ++u) {
-    const int le = tid + u * NT;
-    if (le >= NF * A) break;
-    const int j = le / NF, f = le - j * NF;  // warp-uniform j (NF % 32 == 0)
-    if (f >= nf) continue;
-    const T *tf = tab + f * SP;
-    const T *qf = qt + f * R;
-    T *of = ot + f * R + j * D;
-    T cand[D];
-    if (A == 1) {
-      ld_row<T, D, C::VT>(tf, cand);
-    } else if (A == 2) {
-      if (j == 0) {
-        T qo[D];
-        ld_row<T, D, C::VR>(qf + D, qo);
+  for (int u = 0; u < WPT; ++u) {
+    const int w = tid + u * NT;
+    const bool in_range = w < NF * A * SPLIT;
+    const int j = w / (NF * SPLIT), rem = w - j * (NF * SPLIT);  // warp-uniform j
+    const int f = rem / SPLIT, h = rem - f * SPLIT;
+    const bool active = in_range && f < nf;
+    const int x_lo = h * HD;  // this thread's outputs are x_lo .. x_lo + HD - 1
+    T cand[HD];
+    bool match = false;
+    uint8_t cnt = cnt_in[u];
+    T prev[HD];
+    T *of = ot + f * R + j * D + x_lo;
+    if (active) {
+      const T *tf = tab + f * SP;
+      const T *qf = qt + f * R;
+      if (A == 1) {
+        ld_row<T, HD, C::VH>(tf + x_lo, cand);
+      } else if (A == 2) {
+        if (j == 0) {
+          T qo[D];
+          ld_row<T, D, C::VR>(qf + D, qo);
 #pragma unroll
-        for (int x0 = 0; x0 < D; ++x0) {
-          T row[D];
-          ld_row<T, D, C::VT>(tf + x0 * D, row);
-#pragma unroll
-          for (int x1 = 0; x1 < D; ++x1) row[x1] = row[x1] + qo[x1];
-          cand[x0] = opt_tree<T, D>(row, mx);
-        }
-      } else {
-#pragma unroll
-        for (int x1 = 0; x1 < D; ++x1) cand[x1] = init;
-        T q0r[D];
-        ld_row<T, D, C::VR>(qf, q0r);
-#pragma unroll
-        for (int x0 = 0; x0 < D; ++x0) {
-          T row[D];
-          ld_row<T, D, C::VT>(tf + x0 * D, row);
-#pragma unroll
-          for (int x1 = 0; x1 < D; ++x1) cand[x1] = fg_opt<T>(cand[x1], row[x1] + q0r[x0], mx);
-        }
-      }
-    } else {  // A == 3, table[x0][x1][x2]; sum of the two other rows in position order
-      if (j == 0) {
-        T q1[D], q2[D];
-        ld_row<T, D, C::VR>(qf + D, q1);
-        ld_row<T, D, C::VR>(qf + 2 * D, q2);
-#pragma unroll 1
-        for (int x0 = 0; x0 < D; ++x0) {
-          T part[D];
-#pragma unroll
-          for (int x1 = 0; x1 < D; ++x1) {
+          for (int i = 0; i < HD; ++i) {
             T row[D];
-            ld_row<T, D, C::VT>(tf + x0 * INNER + x1 * D, row);
+            ld_row<T, D, C::VT>(tf + (x_lo + i) * D, row);
 #pragma unroll
-            for (int x2 = 0; x2 < D; ++x2) row[x2] = row[x2] + (q1[x1] + q2[x2]);
-            part[x1] = opt_tree<T, D>(row, mx);
+            for (int x1 = 0; x1 < D; ++x1) row[x1] = row[x1] + qo[x1];
+            cand[i] = opt_tree<T, D>(row, mx);
           }
-          of[x0] = opt_tree<T, D>(part, mx);
+        } else {
+#pragma unroll
+          for (int i = 0; i < HD; ++i) cand[i] = init;
+          T q0r[D];
+          ld_row<T, D, C::VR>(qf, q0r);
+#pragma unroll
+          for (int x0 = 0; x0 < D; ++x0) {
+            T row[HD];
+            ld_row<T, HD, C::VH>(tf + x0 * D + x_lo, row);
+#pragma unroll
+            for (int i = 0; i < HD; ++i) cand[i] = fg_opt<T>(cand[i], row[i] + q0r[x0], mx);
+          }
         }
-        ld_row<T, D, C::VR>(of, cand);
-      } else {
-#pragma unroll
-        for (int x = 0; x < D; ++x) cand[x] = init;
-        T qk[D];  // the other non-leading row: position 2 when j == 1, position 1 when j == 2
-        ld_row<T, D, C::VR>(qf + (j == 1 ? 2 * D : D), qk);
+      } else {  // A == 3, table[x0][x1][x2]; sum of the two other rows in position order
+        if (j == 0) {
+          T q1[D], q2[D];
+          ld_row<T, D, C::VR>(qf + D, q1);
+          ld_row<T, D, C::VR>(qf + 2 * D, q2);
 #pragma unroll 1
-        for (int x0 = 0; x0 < D; ++x0) {
-          const T q0 = qf[x0];
-          T s[D];
+          for (int i = 0; i < HD; ++i) {
+            T part[D];
 #pragma unroll
-          for (int x = 0; x < D; ++x) s[x] = q0 + qk[x];
+            for (int x1 = 0; x1 < D; ++x1) {
+              T row[D];
+              ld_row<T, D, C::VT>(tf + (x_lo + i) * INNER + x1 * D, row);
 #pragma unroll
-          for (int x1 = 0; x1 < D; ++x1) {
-            T row[D];
-            ld_row<T, D, C::VT>(tf + x0 * INNER + x1 * D, row);
-            if (j == 1) {
+              for (int x2 = 0; x2 < D; ++x2) row[x2] = row[x2] + (q1[x1] + q2[x2]);
+              part[x1] = opt_tree<T, D>(row, mx);
+            }
+            of[i] = opt_tree<T, D>(part, mx);
+          }
+          ld_row<T, HD, C::VH>(of, cand);
+        } else if (j == 1) {
+#pragma unroll
+          for (int i = 0; i < HD; ++i) cand[i] = init;
+          T q2[D];
+          ld_row<T, D, C::VR>(qf + 2 * D, q2);
+#pragma unroll 1
+          for (int x0 = 0; x0 < D; ++x0) {
+            const T q0 = qf[x0];
+            T s[D];
+#pragma unroll
+            for (int x = 0; x < D; ++x) s[x] = q0 + q2[x];
+#pragma unroll
+            for (int i = 0; i < HD; ++i) {
+              T row[D];
+              ld_row<T, D, C::VT>(tf + x0 * INNER + (x_lo + i) * D, row);
 #pragma unroll
               for (int x2 = 0; x2 < D; ++x2) row[x2] = row[x2] + s[x2];
-              cand[x1] = fg_opt<T>(cand[x1], opt_tree<T, D>(row, mx), mx);
-            } else {
+              cand[i] = fg_opt<T>(cand[i], opt_tree<T, D>(row, mx), mx);
+            }
+          }
+        } else {
 #pragma unroll
-              for (int x2 = 0; x2 < D; ++x2) cand[x2] = fg_opt<T>(cand[x2], row[x2] + s[x1], mx);
+          for (int i = 0; i < HD; ++i) cand[i] = init;
+          T q1[D];
+          ld_row<T, D, C::VR>(qf + D, q1);
+#pragma unroll 1
+          for (int x0 = 0; x0 < D; ++x0) {
+            const T q0 = qf[x0];
+#pragma unroll
+            for (int x1 = 0; x1 < D; ++x1) {
+              const T s = q0 + q1[x1];
+              T row[HD];
+              ld_row<T, HD, C::VH>(tf + x0 * INNER + x1 * D + x_lo, row);
+#pragma unroll
+              for (int i = 0; i < HD; ++i) cand[i] = fg_opt<T>(cand[i], row[i] + s, mx);
             }
           }
         }
       }
+      // damping and match of this thread's part of the row
+      ld_row<T, HD, C::VH>(rt + f * R + j * D + x_lo, prev);
+      match = damp_match_row<T, HD>(cand, prev, (cnt & 1) != 0, p.damp_factors != 0, lam, oml, stab);
     }
-    // damping, send gate, state update
-    T prev[D];
-    ld_row<T, D, C::VR>(rt + f * R + j * D, prev);
-    const int e = e_base + f * A + j;
-    uint8_t cnt = cnt_in[u];  // prefetched one tile ahead (a global load here would stall the tile)
-    const bool sent = damp_gate_row<T, D>(cand, prev, cnt, p.damp_factors != 0, lam, oml, stab);
-    st_row<T, D, C::VR>(of, cand);
-    r_cnt[e] = cnt;
-    if (r_sent) r_sent[e] = sent ? 1 : 0;
+    if (SPLIT == 2) {  // both halves must match; partner = adjacent lane (same warp, same activity)
+      const bool other = __shfl_xor_sync(0xffffffffu, match ? 1 : 0, 1) != 0;
+      match = match && other;
+    }
+    if (active) {
+      const bool sent = gate_decide(match, cnt);
+      if (!sent) {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) cand[i] = prev[i];
+      }
+      st_row<T, HD, C::VH>(of, cand);
+      if (h == 0) {
+        const int e = e_base + f * A + j;
+        r_cnt[e] = cnt;
+        if (r_sent) r_sent[e] = sent ? 1 : 0;
+      }
+    }
   }
 }
 
@@ -309,7 +351,8 @@ template <typename T, int A, int D>
 struct F2VPipe {
   using C = F2VCfg<T, A, D>;
   static constexpr int STAGE = C::NF * C::SP + 2 * C::NF * C::R;  // tab | qt | rt (elements)
-  static constexpr int EPT = (C::NF * A + C::NT - 1) / C::NT;     // edges per thread per tile
+  static constexpr int EPT = (C::NF * A + C::NT - 1) / C::NT;     // gathered edges per thread per tile
+  static constexpr int WPT = (C::NF * A * C::SPLIT + C::NT - 1) / C::NT;  // compute items per thread
   static constexpr size_t smem_for(int ns) { return (size_t)(ns * STAGE + 2 * C::NF * C::R) * sizeof(T) + 64; }
   static constexpr int NS = FG_F2V_NS <= 2 ? 2 : (smem_for(FG_F2V_NS) <= FG_SMEM_LIMIT ? FG_F2V_NS : 2);
   static constexpr bool FITS = smem_for(2) <= FG_SMEM_LIMIT;
@@ -323,7 +366,8 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
            uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
   using C = F2VCfg<T, A, D>;
   using P = F2VPipe<T, A, D>;
-  constexpr int S = C::S, R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, NS = P::NS, EPT = P::EPT;
+  constexpr int S = C::S, R = C::R, SP = C::SP, NF = C::NF, NT = C::NT, NS = P::NS, EPT = P::EPT, WPT = P::WPT;
+  constexpr int SPLIT = C::SPLIT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T *stage0 = reinterpret_cast<T *>(smem_raw);
   T *ot0 = stage0 + NS * P::STAGE;  // two output buffers: the bulk store of tile k-1 may still be reading
@@ -403,23 +447,23 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
   };
 
   // send-gate counters of my k-th tile -> registers, in the compute mapping (le -> (j, f))
-  auto load_cnt = [&](int k, uint8_t (&cn)[EPT]) {
+  auto load_cnt = [&](int k, uint8_t (&cn)[WPT]) {
     if (k < n_my) {
       const int tile = (int)blockIdx.x + k * (int)gridDim.x;
       const int f0 = tile * NF;
       const int nf = min(NF, c.n_factors - f0);
       const int e_base = c.first_edge + f0 * A;
 #pragma unroll
-      for (int u = 0; u < EPT; ++u) {
-        const int le = tid + u * NT;
-        const int j = le / NF, f = le - j * NF;
-        cn[u] = (le < NF * A && f < nf) ? r_cnt[e_base + f * A + j] : (uint8_t)0;
+      for (int u = 0; u < WPT; ++u) {
+        const int w = tid + u * NT;
+        const int j = w / (NF * SPLIT), f = (w - j * (NF * SPLIT)) / SPLIT;
+        cn[u] = (w < NF * A * SPLIT && f < nf) ? r_cnt[e_base + f * A + j] : (uint8_t)0;
       }
     }
   };
 
   OffT idx[EPT];
-  uint8_t cnt[EPT];
+  uint8_t cnt[WPT];
   // prologue: tiles 0 .. NS-2 in flight, indices of tile NS-1 on their way
 #pragma unroll 1
   for (int k = 0; k < NS - 1; ++k) {
@@ -432,7 +476,7 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 #pragma unroll 1
   for (int k = 0; k < n_my; ++k) {
     OffT idx_next[EPT];
-    uint8_t cnt_next[EPT];
+    uint8_t cnt_next[WPT];
     load_idx(k + NS, idx_next);
     load_cnt(k + 1, cnt_next);
     issue(k + NS - 1, idx);  // into the stage tile k-1 has just vacated
@@ -448,10 +492,10 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     const int nf = min(NF, c.n_factors - f0);
     const T *tab = stage0 + (k % NS) * P::STAGE;
     T *ot = ot0 + (k & 1) * NF * R;
-    f2v_compute_tile<T, A, D, EPT>(tab, tab + NF * SP, tab + NF * SP + NF * R, ot, nf, c.first_edge + f0 * A, cnt,
+    f2v_compute_tile<T, A, D, WPT>(tab, tab + NF * SP, tab + NF * SP + NF * R, ot, nf, c.first_edge + f0 * A, cnt,
                                    r_cnt, r_sent, p, tid);
 #pragma unroll
-    for (int u = 0; u < EPT; ++u) cnt[u] = cnt_next[u];
+    for (int u = 0; u < WPT; ++u) cnt[u] = cnt_next[u];
     const int64_t rbase = c.msg_base + (int64_t)f0 * R;
     if (nf == NF && ((NF * R * (int)sizeof(T)) % 16 == 0)) {
       fence_proxy_async_smem();
