@@ -296,40 +296,45 @@ def main():
         config["breakdown_ms_rank0"] = runner.timed_breakdown(50)
 
     # end to end through the public API: pinned host arrays -> device, E2E_CYCLES cycles, values back
-    e2e = None
-    if world == 1:
-        host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
-                (("tables", L.tables.astype(np.float32 if vb == 4 else np.float64)),
-                 ("unary", L.unary.astype(np.float32 if vb == 4 else np.float64)),
-                 ("slot_roff", L.slot_roff), ("edge_qoff", L.edge_qoff),
-                 ("slot_edge", L.slot_edge), ("slot_var", L.slot_var), ("var_ptr", L.var_ptr))}
-        out_host = torch.empty(L.n_vars, dtype=torch.int32).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in host.values())
-        d2h = out_host.numel() * 4
-        times = []
-        for it in range(3 + 5):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            runner.tables.copy_(host["tables"], non_blocking=True)
-            runner.unary.copy_(host["unary"], non_blocking=True)
-            runner.slot_roff.copy_(host["slot_roff"], non_blocking=True)
-            runner.edge_qoff.copy_(host["edge_qoff"], non_blocking=True)
-            runner.slot_edge.copy_(host["slot_edge"], non_blocking=True)
-            runner.slot_var.copy_(host["slot_var"], non_blocking=True)
-            runner.var_ptr.copy_(host["var_ptr"], non_blocking=True)
-            runner.init()
-            runner.step(E2E_CYCLES)
-            out_host.copy_(runner.value[:L.n_vars], non_blocking=True)
-            b.record()
-            torch.cuda.synchronize(dev)
-            if it >= 3:
-                times.append(a.elapsed_time(b))
-        e2e_ms = float(np.mean(times))
-        e2e = {"value": updates_per_step * E2E_CYCLES / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "solve": f"upload tables+unary+CSR from pinned host, init + {E2E_CYCLES} cycles, "
-                        f"assignment back to host; {e2e_ms:.3f} ms per solve"}
+    # (N > 1: every rank uploads its own shard; time = max over ranks)
+    eng = runner.engine if world > 1 else runner
+    Ls = eng.layout
+    npdt = np.float32 if vb == 4 else np.float64
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
+            (("tables", Ls.tables.astype(npdt)), ("unary", Ls.unary.astype(npdt)),
+             ("slot_roff", Ls.slot_roff), ("edge_qoff", Ls.edge_qoff),
+             ("slot_edge", Ls.slot_edge), ("slot_var", Ls.slot_var), ("var_ptr", Ls.var_ptr))}
+    out_host = torch.empty(Ls.n_vars, dtype=torch.int32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = out_host.numel() * 4
+    times = []
+    for it in range(3 + 5):
+        flush.zero_()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k, t in host.items():
+            getattr(eng, k).copy_(t, non_blocking=True)
+        runner.init()
+        runner.step(E2E_CYCLES)
+        out_host.copy_(eng.value[:Ls.n_vars], non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(dev)
+        if it >= 3:
+            times.append(a.elapsed_time(b))
+    e2e_ms = float(np.mean(times))
+    if world > 1:
+        t = torch.tensor([e2e_ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_ms, h2d, d2h = float(tm[0].item()), int(t[1].item()), int(t[2].item())
+    e2e = {"value": updates_per_step * E2E_CYCLES / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "solve": f"upload tables+unary+CSR from pinned host, init + {E2E_CYCLES} cycles, "
+                    f"assignment back to host; {e2e_ms:.3f} ms per solve"
+                    + (" (max over ranks; bytes summed over ranks)" if world > 1 else "")}
 
     if world > 1:
         dist.barrier()
