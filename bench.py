@@ -246,10 +246,10 @@ def main():
     n_edges_global = int(len(inst["edge_var"]))
     if world > 1:
         from pydcop_b200.multigpu import ShardedMaxSum
-        runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision)
+        runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision,
+                               halo=os.environ.get("PYDCOP_B200_HALO", "auto"))
         L = None
         config["cut_edges"] = runner.plan.n_cut_edges
-        config["halo"] = "pack kernels + ONE NCCL all_to_all (q and r rows together) per cycle + unpack kernels"
     else:
         L = build_layout(**inst)
         runner = MaxSumEngine(L, device=dev, precision=args.precision, record_sent=True)
@@ -263,6 +263,10 @@ def main():
         return
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     runner.init()
+    if world > 1:
+        config["halo"] = ("ONE push kernel storing boundary rows straight into the peers' buffers over "
+                          "NVLink (CUDA IPC) + barrier per cycle" if runner.peer is not None else
+                          "pack kernel + ONE NCCL all_to_all (q and r rows together) + unpack kernel per cycle")
     for _ in range(max(3, args.warmup)):
         runner.step(1)
     torch.cuda.synchronize(dev)

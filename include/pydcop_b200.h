@@ -174,6 +174,15 @@ int fg_halo_rows_uniform(int32_t precision, int32_t pack, void *dev_r, void *dev
                          int64_t n_q, int32_t dom, int32_t n_peers, const int64_t *peer_r_start,
                          const int64_t *peer_q_start, const int64_t *peer_base, void *stream);
 
+/* Direct halo push over NVLink peer memory (uniform domain): row i of the r list
+ * (dev_r + row_off_r[i], `dom` elements) is stored at the ABSOLUTE device address dst_r[i] — a
+ * location inside the consuming rank's `next` buffer, mapped into this process through CUDA IPC —
+ * and likewise for the q list.  One launch replaces pack -> NCCL all_to_all -> unpack; the caller
+ * closes the cycle with a barrier. */
+int fg_halo_push(int32_t precision, const void *dev_r, const void *dev_q, const int64_t *dev_row_off_r,
+                 const int64_t *dev_row_off_q, const int64_t *dev_dst_r, const int64_t *dev_dst_q,
+                 int64_t n_r, int64_t n_q, int32_t dom, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * DSA  (replaces DsaComputation.on_start dsa.py:277-299 and evaluate_cycle :320-357 with
  * find_optimal relations.py:1594-1638, assignment_cost :1479-1532, variant_a/b/c dsa.py:359-405,

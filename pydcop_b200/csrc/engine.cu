@@ -353,6 +353,44 @@ extern "C" int fg_halo_rows_uniform(int32_t precision, int32_t pack, void *dev_r
   return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }
 
+// rows -> absolute (peer) addresses: stores travel over NVLink
+template <int PB>
+__global__ void __launch_bounds__(256)
+k_halo_push(const unsigned char *__restrict__ arr_r, const unsigned char *__restrict__ arr_q,
+            const int64_t *__restrict__ off_r, const int64_t *__restrict__ off_q,
+            const int64_t *__restrict__ dst_r, const int64_t *__restrict__ dst_q, int64_t n_r, int64_t n_q,
+            int row_bytes, int elem) {
+  const int ppr = row_bytes / PB;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = t / ppr;
+  const int piece = (int)(t - row * ppr);
+  if (row >= n_r + n_q) return;
+  const bool is_q = row >= n_r;
+  const int64_t i = is_q ? row - n_r : row;
+  const unsigned char *a = (is_q ? arr_q : arr_r) + (is_q ? off_q[i] : off_r[i]) * elem + piece * PB;
+  unsigned char *b = reinterpret_cast<unsigned char *>(is_q ? dst_q[i] : dst_r[i]) + piece * PB;
+  using V = typename std::conditional<PB == 16, uint4, typename std::conditional<PB == 8, uint2, uint32_t>::type>::type;
+  *reinterpret_cast<V *>(b) = *reinterpret_cast<const V *>(a);
+}
+
+extern "C" int fg_halo_push(int32_t precision, const void *dev_r, const void *dev_q, const int64_t *dev_row_off_r,
+                            const int64_t *dev_row_off_q, const int64_t *dev_dst_r, const int64_t *dev_dst_q, int64_t n_r,
+                            int64_t n_q, int32_t dom, void *stream) {
+  if (n_r + n_q <= 0) return FG_OK;
+  if (dom < 1) return FG_ERR_ARG;
+  const int elem = precision == FG_F64 ? 8 : 4;
+  const int row_bytes = dom * elem;
+  const int pb = (row_bytes % 16 == 0) ? 16 : ((row_bytes % 8 == 0) ? 8 : 4);
+  const int64_t threads = (n_r + n_q) * (row_bytes / pb);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned char *r = (const unsigned char *)dev_r, *q = (const unsigned char *)dev_q;
+  const unsigned blocks = blocks_for(threads, 256);
+  if (pb == 16) k_halo_push<16><<<blocks, 256, 0, st>>>(r, q, dev_row_off_r, dev_row_off_q, dev_dst_r, dev_dst_q, n_r, n_q, row_bytes, elem);
+  else if (pb == 8) k_halo_push<8><<<blocks, 256, 0, st>>>(r, q, dev_row_off_r, dev_row_off_q, dev_dst_r, dev_dst_q, n_r, n_q, row_bytes, elem);
+  else k_halo_push<4><<<blocks, 256, 0, st>>>(r, q, dev_row_off_r, dev_row_off_q, dev_dst_r, dev_dst_q, n_r, n_q, row_bytes, elem);
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
 // ---------------------------------------------------------------------------------------------
 // DSA
 // ---------------------------------------------------------------------------------------------

@@ -311,10 +311,80 @@ class HaloExchange:
                 flags[idx(recv_e)] = inn
 
 
+class PeerPush:
+    """Halo over NVLink peer memory: every rank maps the peers' message buffers (torch CUDA IPC) and
+    its push kernel stores each boundary row straight into the consumer's `next` buffer; a barrier
+    closes the cycle.  One kernel + one barrier instead of pack -> all_to_all -> unpack."""
+
+    def __init__(self, sharded, group=None):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.torch, self.dist, self.group = torch, dist, group
+        e, p, h = sharded.engine, sharded.plan, sharded.halo
+        self.engine, self.plan, self.sharded = e, p, sharded
+        dev = e.device
+        W, me = p.world, p.rank
+        if not p.layout.uniform_dom:
+            raise RuntimeError("peer push needs a uniform domain size")
+        # 1. share my four message buffers, map everybody else's
+        mine = [reduce_tensor(t) for t in (e.q[0], e.q[1], e.r[0], e.r[1])]
+        everyone = [None] * W
+        dist.all_gather_object(everyone, mine, group=group)
+        self._keep = []   # mapped peer tensors must stay alive
+        base = np.zeros((W, 4), dtype=np.int64)
+        for rnk in range(W):
+            if rnk == me:
+                ts = [e.q[0], e.q[1], e.r[0], e.r[1]]
+            else:
+                ts = [fn(*args) for fn, args in everyone[rnk]]
+                self._keep.append(ts)
+            base[rnk] = [t.data_ptr() for t in ts]
+        # 2. where do my rows land?  the consumer's recv offsets, in my send order
+        def peer_offsets(recv_off, recv_rows, send_rows):
+            out = torch.zeros(int(sum(send_rows)), dtype=torch.int64, device=dev)
+            inp = torch.from_numpy(np.ascontiguousarray(recv_off, dtype=np.int64)).to(dev)
+            dist.all_to_all_single(out, inp, list(send_rows), list(recv_rows), group=group)
+            return out.cpu().numpy()
+
+        dst_r_off = peer_offsets(p.recv_r_off, p.recv_r_rows, p.send_r_rows)   # offsets in the peer's r
+        dst_q_off = peer_offsets(p.recv_q_off, p.recv_q_rows, p.send_q_rows)
+        elem = e.q[0].element_size()
+        peer_of_r = np.repeat(np.arange(W), p.send_r_rows)
+        peer_of_q = np.repeat(np.arange(W), p.send_q_rows)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)  # noqa: E731
+        # absolute destination addresses for `next` buffer index b (0 / 1)
+        self.dst_r = [to(base[peer_of_r, 2 + b] + dst_r_off * elem) for b in range(2)]
+        self.dst_q = [to(base[peer_of_q, 0 + b] + dst_q_off * elem) for b in range(2)]
+        self.src_r_off, self.src_q_off = h.sr[0], h.sq[0]
+        self.n_r, self.n_q = len(p.send_r_len), len(p.send_q_len)
+        self.dom = int(p.layout.uniform_dom)
+        self.token = torch.zeros(1, device=dev)
+        self.launches = 0
+        from .engine import PRECISIONS
+        self.prec = PRECISIONS[e.precision][0]
+        dist.barrier(group=group)
+
+    def push(self, buf_index):
+        e, torch = self.engine, self.torch
+        if self.n_r + self.n_q:
+            rc = e.lib.fg_halo_push(self.prec, C.c_void_p(e.r[buf_index].data_ptr()),
+                                    C.c_void_p(e.q[buf_index].data_ptr()),
+                                    C.c_void_p(self.src_r_off.data_ptr()), C.c_void_p(self.src_q_off.data_ptr()),
+                                    C.c_void_p(self.dst_r[buf_index].data_ptr()),
+                                    C.c_void_p(self.dst_q[buf_index].data_ptr()), self.n_r, self.n_q, self.dom,
+                                    C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"fg_halo_push failed rc={rc}")
+            self.launches += 1
+        # every rank's stores are complete and visible once all ranks passed this point
+        self.dist.all_reduce(self.token, group=self.group)
+
+
 class ShardedMaxSum:
     """One rank of the partitioned MaxSum: same driving API as MaxSumEngine (init / step / values)."""
 
-    def __init__(self, inst, rank, world, device, precision="f32", group=None, **params):
+    def __init__(self, inst, rank, world, device, precision="f32", group=None, halo="nccl", **params):
         import torch
         from . import _cabi
         from .engine import MaxSumEngine, PRECISIONS
@@ -356,6 +426,8 @@ class ShardedMaxSum:
 
         if self.plan.layout.uniform_dom:
             self.halo.fused = fused
+        self.halo_mode = halo
+        self.peer = None
         self.global_n_edges = int(len(np.asarray(inst["edge_var"])))
         self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
 
@@ -368,6 +440,13 @@ class ShardedMaxSum:
         e.init()
         self.halo.exchange(e.q[0], e.r[0])
         self.halo.exchange_flags(e.q_valid, e.r_valid)
+        if self.halo_mode in ("p2p", "auto") and self.peer is None and self.world > 1:
+            try:
+                self.peer = PeerPush(self, self.halo.group)
+            except Exception as ex:  # noqa: BLE001 — no peer mapping: keep the NCCL exchange
+                if self.halo_mode == "p2p":
+                    raise
+                self.peer_error = repr(ex)
         return self
 
     def step(self, n_cycles=1):
@@ -375,7 +454,10 @@ class ShardedMaxSum:
         for _ in range(int(n_cycles)):
             e.cycle_compute()
             nxt = e.cur ^ 1
-            self.halo.exchange(e.q[nxt], e.r[nxt])
+            if self.peer is not None:
+                self.peer.push(nxt)
+            else:
+                self.halo.exchange(e.q[nxt], e.r[nxt])
             e.cycle_commit()
         return self
 
@@ -405,7 +487,7 @@ class ShardedMaxSum:
 
     @property
     def launch_count(self):
-        return self.engine.launch_count + self.halo.launches
+        return self.engine.launch_count + self.halo.launches + (self.peer.launches if self.peer else 0)
 
     def local_values(self):
         """(global variable ids, value indices) of the variables this rank owns."""
