@@ -179,6 +179,9 @@ int fg_halo_rows_uniform(int32_t precision, int32_t pack, void *dev_r, void *dev
  * location inside the consuming rank's `next` buffer, mapped into this process through CUDA IPC —
  * and likewise for the q list.  One launch replaces pack -> NCCL all_to_all -> unpack; the caller
  * closes the cycle with a barrier. */
+/* Enable stores from the CURRENT device into `peer_device`'s memory (cudaDeviceEnablePeerAccess);
+ * returns FG_ERR_UNSUPPORTED when the pair has no peer path. */
+int fg_enable_peer_access(int32_t peer_device);
 int fg_halo_push(int32_t precision, const void *dev_r, const void *dev_q, const int64_t *dev_row_off_r,
                  const int64_t *dev_row_off_q, const int64_t *dev_dst_r, const int64_t *dev_dst_q,
                  int64_t n_r, int64_t n_q, int32_t dom, void *stream);

@@ -85,6 +85,7 @@ SYMBOLS = {
     "fg_halo_unpack": (C.c_int, [C.c_int32, P, P, P, P, P, C.c_int64, P]),
     "fg_halo_rows_uniform": (C.c_int, [C.c_int32, C.c_int32, P, P, P, P, P, C.c_int64, C.c_int64,
                                        C.c_int32, C.c_int32, P, P, P, P]),
+    "fg_enable_peer_access": (C.c_int, [C.c_int32]),
     "fg_halo_push": (C.c_int, [C.c_int32, P, P, P, P, P, P, C.c_int64, C.c_int64, C.c_int32, P]),
     "fg_dsa_create": (C.c_int, [C.POINTER(FgDsaDesc), C.POINTER(P)]),
     "fg_dsa_destroy": (C.c_int, [P]),

@@ -373,6 +373,16 @@ k_halo_push(const unsigned char *__restrict__ arr_r, const unsigned char *__rest
   *reinterpret_cast<V *>(b) = *reinterpret_cast<const V *>(a);
 }
 
+extern "C" int fg_enable_peer_access(int32_t peer_device) {
+  int cur = 0, can = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) return FG_ERR_CUDA;
+  if (cur == peer_device) return FG_OK;
+  if (cudaDeviceCanAccessPeer(&can, cur, peer_device) != cudaSuccess || !can) { cudaGetLastError(); return FG_ERR_UNSUPPORTED; }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return FG_OK; }
+  return e == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
 extern "C" int fg_halo_push(int32_t precision, const void *dev_r, const void *dev_q, const int64_t *dev_row_off_r,
                             const int64_t *dev_row_off_q, const int64_t *dev_dst_r, const int64_t *dev_dst_q, int64_t n_r,
                             int64_t n_q, int32_t dom, void *stream) {

@@ -333,13 +333,22 @@ class PeerPush:
         dist.all_gather_object(everyone, mine, group=group)
         self._keep = []   # mapped peer tensors must stay alive
         base = np.zeros((W, 4), dtype=np.int64)
-        for rnk in range(W):
-            if rnk == me:
-                ts = [e.q[0], e.q[1], e.r[0], e.r[1]]
-            else:
-                ts = [fn(*args) for fn, args in everyone[rnk]]
-                self._keep.append(ts)
-            base[rnk] = [t.data_ptr() for t in ts]
+        with torch.cuda.device(dev):
+            for rnk in range(W):
+                if rnk == me:
+                    ts = [e.q[0], e.q[1], e.r[0], e.r[1]]
+                else:
+                    ts = [fn(*args) for fn, args in everyone[rnk]]
+                    self._keep.append(ts)
+                    # torch opens the IPC handle with the PEER as current device, which does not
+                    # enable access from MY device: do it explicitly, then prove it with a copy
+                    rc = e.lib.fg_enable_peer_access(int(ts[0].device.index))
+                    if rc != 0:
+                        raise RuntimeError(f"no peer access from {dev} to {ts[0].device} (rc={rc})")
+                    probe = ts[0][:1].to(dev)
+                    torch.cuda.synchronize(dev)
+                    del probe
+                base[rnk] = [t.data_ptr() for t in ts]
         # 2. where do my rows land?  the consumer's recv offsets, in my send order
         def peer_offsets(recv_off, recv_rows, send_rows):
             out = torch.zeros(int(sum(send_rows)), dtype=torch.int64, device=dev)
