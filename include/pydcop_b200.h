@@ -182,6 +182,12 @@ int fg_halo_rows_uniform(int32_t precision, int32_t pack, void *dev_r, void *dev
 /* Enable stores from the CURRENT device into `peer_device`'s memory (cudaDeviceEnablePeerAccess);
  * returns FG_ERR_UNSUPPORTED when the pair has no peer path. */
 int fg_enable_peer_access(int32_t peer_device);
+/* CUDA IPC for the peer push: export = IPC handle (64 bytes) of the allocation containing dev_ptr
+ * and dev_ptr's byte offset inside it; import = map a peer's allocation into THIS process with the
+ * current device as accessor (cudaIpcMemLazyEnablePeerAccess), returning its base address. */
+int fg_ipc_export(const void *dev_ptr, unsigned char handle_out[64], int64_t *offset_out);
+int fg_ipc_import(const unsigned char handle[64], void **base_out);
+int fg_ipc_close(void *base);
 int fg_halo_push(int32_t precision, const void *dev_r, const void *dev_q, const int64_t *dev_row_off_r,
                  const int64_t *dev_row_off_q, const int64_t *dev_dst_r, const int64_t *dev_dst_q,
                  int64_t n_r, int64_t n_q, int32_t dom, void *stream);

@@ -86,6 +86,9 @@ SYMBOLS = {
     "fg_halo_rows_uniform": (C.c_int, [C.c_int32, C.c_int32, P, P, P, P, P, C.c_int64, C.c_int64,
                                        C.c_int32, C.c_int32, P, P, P, P]),
     "fg_enable_peer_access": (C.c_int, [C.c_int32]),
+    "fg_ipc_export": (C.c_int, [P, P, C.POINTER(C.c_int64)]),
+    "fg_ipc_import": (C.c_int, [P, C.POINTER(P)]),
+    "fg_ipc_close": (C.c_int, [P]),
     "fg_halo_push": (C.c_int, [C.c_int32, P, P, P, P, P, P, C.c_int64, C.c_int64, C.c_int32, P]),
     "fg_dsa_create": (C.c_int, [C.POINTER(FgDsaDesc), C.POINTER(P)]),
     "fg_dsa_destroy": (C.c_int, [P]),

@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libpydcop_b200.so")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "engine.cu"), "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -383,6 +383,41 @@ extern "C" int fg_enable_peer_access(int32_t peer_device) {
   return e == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }
 
+// cuMemGetAddressRange through dlopen: the library must load on boxes without a driver
+#include <dlfcn.h>
+extern "C" int fg_ipc_export(const void *dev_ptr, unsigned char handle_out[64], int64_t *offset_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+  static range_fn get_range = nullptr;
+  if (!get_range) {
+    void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return FG_ERR_UNSUPPORTED;
+    get_range = (range_fn)dlsym(lib, "cuMemGetAddressRange_v2");
+    if (!get_range) return FG_ERR_UNSUPPORTED;
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (unsigned long long)dev_ptr) != 0) return FG_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, (void *)base) != cudaSuccess) { cudaGetLastError(); return FG_ERR_CUDA; }
+  memcpy(handle_out, &h, 64);
+  *offset_out = (int64_t)((unsigned long long)dev_ptr - base);
+  return FG_OK;
+}
+
+extern "C" int fg_ipc_import(const unsigned char handle[64], void **base_out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void *p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return FG_ERR_CUDA; }
+  *base_out = p;
+  return FG_OK;
+}
+
+extern "C" int fg_ipc_close(void *base) {
+  return cudaIpcCloseMemHandle(base) == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
 extern "C" int fg_halo_push(int32_t precision, const void *dev_r, const void *dev_q, const int64_t *dev_row_off_r,
                             const int64_t *dev_row_off_q, const int64_t *dev_dst_r, const int64_t *dev_dst_q, int64_t n_r,
                             int64_t n_q, int32_t dom, void *stream) {

@@ -319,7 +319,6 @@ class PeerPush:
     def __init__(self, sharded, group=None):
         import torch
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
         self.torch, self.dist, self.group = torch, dist, group
         e, p, h = sharded.engine, sharded.plan, sharded.halo
         self.engine, self.plan, self.sharded = e, p, sharded
@@ -327,28 +326,36 @@ class PeerPush:
         W, me = p.world, p.rank
         if not p.layout.uniform_dom:
             raise RuntimeError("peer push needs a uniform domain size")
-        # 1. share my four message buffers, map everybody else's
-        mine = [reduce_tensor(t) for t in (e.q[0], e.q[1], e.r[0], e.r[1])]
+        # 1. share my four message buffers (CUDA IPC handle of the containing allocation + offset),
+        #    map everybody else's with MY device as the accessor
+        lib = e.lib
+        mine = []
+        for t in (e.q[0], e.q[1], e.r[0], e.r[1]):
+            hb = (C.c_ubyte * 64)()
+            off = C.c_int64()
+            rc = lib.fg_ipc_export(C.c_void_p(t.data_ptr()), C.cast(hb, C.c_void_p), C.byref(off))
+            if rc != 0:
+                raise RuntimeError(f"fg_ipc_export failed rc={rc}")
+            mine.append((bytes(hb), int(off.value)))
         everyone = [None] * W
         dist.all_gather_object(everyone, mine, group=group)
-        self._keep = []   # mapped peer tensors must stay alive
+        self._mapped = {}   # (rank, handle bytes) -> base address in this process
         base = np.zeros((W, 4), dtype=np.int64)
         with torch.cuda.device(dev):
             for rnk in range(W):
                 if rnk == me:
-                    ts = [e.q[0], e.q[1], e.r[0], e.r[1]]
-                else:
-                    ts = [fn(*args) for fn, args in everyone[rnk]]
-                    self._keep.append(ts)
-                    # torch opens the IPC handle with the PEER as current device, which does not
-                    # enable access from MY device: do it explicitly, then prove it with a copy
-                    rc = e.lib.fg_enable_peer_access(int(ts[0].device.index))
-                    if rc != 0:
-                        raise RuntimeError(f"no peer access from {dev} to {ts[0].device} (rc={rc})")
-                    probe = ts[0][:1].to(dev)
-                    torch.cuda.synchronize(dev)
-                    del probe
-                base[rnk] = [t.data_ptr() for t in ts]
+                    base[rnk] = [t.data_ptr() for t in (e.q[0], e.q[1], e.r[0], e.r[1])]
+                    continue
+                for i, (hbytes, off) in enumerate(everyone[rnk]):
+                    key = (rnk, hbytes)
+                    if key not in self._mapped:
+                        out = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(hbytes)
+                        rc = lib.fg_ipc_import(C.cast(buf, C.c_void_p), C.byref(out))
+                        if rc != 0:
+                            raise RuntimeError(f"fg_ipc_import failed rc={rc} (rank {rnk})")
+                        self._mapped[key] = int(out.value)
+                    base[rnk, i] = self._mapped[key] + off
         # 2. where do my rows land?  the consumer's recv offsets, in my send order
         def peer_offsets(recv_off, recv_rows, send_rows):
             out = torch.zeros(int(sum(send_rows)), dtype=torch.int64, device=dev)
