@@ -296,7 +296,7 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
-    if world > 1 and os.environ.get("PYDCOP_B200_BREAKDOWN"):
+    if world > 1 and os.environ.get("PYDCOP_B200_BREAKDOWN", "0") not in ("", "0") and runner.peer is None:
         config["breakdown_ms_rank0"] = runner.timed_breakdown(50)
 
     # end to end through the public API: pinned host arrays -> device, E2E_CYCLES cycles, values back
