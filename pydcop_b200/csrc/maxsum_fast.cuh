@@ -745,8 +745,9 @@ k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__re
     T *rrow = stage0 + (k % NS) * tab.stage_elems;
     const T *qio = rrow + t.nv_full * t.VS;
     const T *un = qio + t.nv_full * K * D;
-    {  // one thread per variable, variables spread over the warps
-      const int vi = (tid & 31) * (NT / 32) + (tid >> 5);
+    {  // one thread per variable, packed into the first warps (a spread mapping would make every
+       // warp issue the whole selection code for a handful of lanes)
+      const int vi = tid;
       if (vi < t.nv) {
         int32_t val;
         T cst;
