@@ -228,6 +228,23 @@ class MaxSumEngine(_EngineBase):
             out["r_sent"] = L.edges_to_canonical(self.r_sent.cpu().numpy()[:L.n_edges])
         return out
 
+    def solution_cost(self):
+        """(cost, violations) of the currently selected assignment, reduced on the device: sum of the
+        factors' table entries + the variables' own costs; factors at +/-inf count as violations
+        (pydcop/dcop/dcop.py:319-367 `solution_cost`)."""
+        L = self.layout
+        with torch.cuda.device(self.device):
+            if not hasattr(self, "_edge_var_dev"):
+                self._edge_var_dev = self._dev(L.edge_var, torch.int32)
+                self._cost_out = torch.zeros(2, dtype=torch.float64, device=self.device)
+            rc = self.lib.fg_solution_cost(
+                self._desc.precision, len(L.classes), C.cast(self._classes, C.POINTER(FgClass)),
+                _ptr(self.tables), _ptr(self._edge_var_dev), _ptr(self.value), _ptr(self.unary),
+                _ptr(self.unary_off), L.n_vars, _ptr(self._cost_out), self._stream())
+            self._check(rc, "fg_solution_cost")
+            out = self._cost_out.cpu().numpy()
+        return float(out[0]), int(out[1])
+
     def values(self):
         """(value index, reported cost) per variable, in the caller's canonical variable order."""
         L = self.layout

@@ -76,3 +76,25 @@ def test_multi_cycle_step_equals_single_steps():
         assert np.array_equal(x, y)
     assert np.array_equal(a.values()[0], b.values()[0])
     assert a.launch_count == b.launch_count > 0
+
+
+@pytest.mark.parametrize("name", ["ms_rand_mixed", "ms_arity4_mixed", "ms_gc10_default"])
+def test_solution_cost_kernel(name):
+    """fg_solution_cost (dcop.py:319-367) against a numpy evaluation of the same assignment."""
+    from pydcop_b200 import MaxSumEngine, layout_from_instance
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    p = {k: v for k, v in meta["params"].items() if k != "noise"}
+    eng = MaxSumEngine(layout_from_instance(inst), precision="f64", mode=meta["mode"], **p).init().step(15)
+    val, _ = eng.values()
+    cost, viol = eng.solution_cost()
+    expect = 0.0
+    fp, ev, toff = inst["factor_ptr"], inst["edge_var"], inst["table_off"]
+    for f in range(len(fp) - 1):
+        scope = ev[fp[f]:fp[f + 1]]
+        shape = tuple(int(inst["dom_size"][v]) for v in scope)
+        t = np.asarray(inst["tables"][toff[f]:toff[f + 1]]).reshape(shape)
+        expect += float(t[tuple(int(val[v]) for v in scope)])
+    uoff = np.concatenate([[0], np.cumsum(inst["dom_size"])])
+    expect += float(sum(inst["unary"][uoff[v] + val[v]] for v in range(len(val))))
+    assert viol == 0
+    assert abs(cost - expect) <= 1e-9 * max(1.0, abs(expect))
