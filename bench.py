@@ -347,6 +347,10 @@ def main():
         return
     peaks, peak_kind = load_peaks()
     peak = float(peaks["hbm_gbs"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_c2_f32.json")
+    if world == 1 and args.precision == "f32" and args.vars_per_gpu == 100_000 and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["per_step_bytes"]   # from the committed ncu --set full capture
     per_gpu_bytes = alg_bytes / max(1, world)
     achieved = per_gpu_bytes / (ms_per_step * 1e-3) / 1e9
     line = {
@@ -355,7 +359,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": config, "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": traffic,
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                      "algorithmic_bytes_per_step": int(per_gpu_bytes),
                      "bytes_per_update": alg_bytes / updates_per_step,
