@@ -11,7 +11,8 @@
  * Conventions
  *   - plain C, opaque handles, int return codes (0 = FG_OK), no exceptions, no torch types;
  *   - every `dev_*` pointer is CALLER-OWNED DEVICE memory (the Python host passes
- *     torch.Tensor.data_ptr()); the library allocates no device memory of its own;
+ *     torch.Tensor.data_ptr()); the only device memory the library owns is the DSA handle's copy
+ *     of the class table (a few hundred bytes), and a MaxSum handle owns one side stream + 2 events;
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
  *   - all calls are asynchronous on `stream`; the caller synchronises;
  *   - value type T is float (precision = FG_F32) or double (FG_F64) for every cost/message array;
@@ -23,12 +24,17 @@
  *   table of f        = dev_tables + table_base + f * table_size          (row-major, axis i <->
  *                                                                           scope position i)
  *   message row (f,j) = msg_base + f * row_total + row_off[j], length dom[j]
+ *                       (rows of a class whose positions have DIFFERENT domain sizes start on
+ *                       4-element boundaries; uniform classes are dense: row_off[j] = j * dom)
  * (this is the layout of the factor->variable array r, written by the factor side).  The variable
  * side owns a CSR: variable v has slots [var_ptr[v], var_ptr[v+1]) in the reference's `links` order
  * (pydcop/algorithms/maxsum.py:466); the variable->factor array q is stored in SLOT order:
  *   q row of slot s   = var_qbase[v] + (s - var_ptr[v]) * dom_size[v]
  * so each side WRITES its own messages with perfectly coalesced stores and reads the other side's
  * through one gather index: edge_qoff[e] (factor side reads q), slot_roff[s] (variable side reads r).
+ * Variables are stored class-major too (classes of identical (domain size, degree), fg_varclass_t);
+ * dev_value / dev_value_cost are in that internal variable order (the Python host keeps the
+ * permutation, pydcop_b200/layout.py).
  */
 #ifndef PYDCOP_B200_H
 #define PYDCOP_B200_H
