@@ -97,10 +97,6 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
-  for (V2FLaunch &L : h->fast.v2f) {  // tile descriptors: a few KB the library owns on the device
-    CUDA_TRY(h, cudaMalloc(&L.dev_tiles, sizeof(V2FTile) * L.tiles.size()));
-    CUDA_TRY(h, cudaMemcpy(L.dev_tiles, L.tiles.data(), sizeof(V2FTile) * L.tiles.size(), cudaMemcpyHostToDevice));
-  }
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -111,8 +107,6 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
 
 extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
   if (h) {
-    for (V2FLaunch &L : h->fast.v2f)
-      if (L.dev_tiles) cudaFree(L.dev_tiles);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);

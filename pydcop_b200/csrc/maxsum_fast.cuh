@@ -517,8 +517,23 @@ k_f2v_pipe(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 // ------------------------------------------------------------------------------------------------
 // variable -> factor: one thread per variable, variables grouped in (domain, degree) classes
 // ------------------------------------------------------------------------------------------------
+#define FG_V2F_MAX_ENTRIES 24
 #define FG_V2F_NT 256
 #define FG_V2F_ROUNDS 1   // a thread finishes at most this many slots per tile
+
+struct V2FEntry {
+  fg_varclass_t vc;
+  int32_t tile_begin;  // first tile of this class in the launch
+  int32_t nv_tile;     // variables per tile
+};
+struct V2FTable {
+  int32_t n;
+  int32_t total_tiles;
+  int32_t stage_elems;  // elements of one stage buffer (max over the classes)
+  int32_t out_elems;    // elements of the output buffer
+  int32_t avg_elems;    // elements of the per-slot normalisation scratch
+  V2FEntry e[FG_V2F_MAX_ENTRIES];
+};
 
 template <typename T, int D>
 struct V2FCfg {
@@ -526,33 +541,35 @@ struct V2FCfg {
   static constexpr int VR = VR_BYTES / (int)sizeof(T);
 };
 
-// one tile of the launch, precomputed on the host (48 bytes, read through the read-only path)
-struct __align__(16) V2FTile {
-  int32_t K, VS, nv_full, nv;
-  int32_t nslots, slot0, var0, magic;   // magic = ceil(2^32 / K): sl / K == __umulhi(sl, magic) for sl < 2^16
+struct V2FTile {
+  int K, VS, nv_full, nv, nslots, slot0, var0, valid;
   int64_t qoff, uoff;
 };
 
 // variable stride (elements) of the gathered rows of one variable: K*D rounded up so that
-// the stride counted in row-vector units is odd -> per-variable reads hit distinct banks
+// the stride counted in row-vector units is odd -> one-thread-per-variable reads hit distinct banks
 __host__ __device__ inline int v2f_vstride(int K, int D, int VR) { return (((K * D) / VR) | 1) * VR; }
 
-__device__ __forceinline__ V2FTile v2f_load_tile(const V2FTile *__restrict__ tiles, int t, int total) {
+// tile t of the launch; `ci` is a cursor that only moves forward (tiles are visited in order)
+__device__ __forceinline__ V2FTile v2f_tile(const V2FTable &tab, int t, int D, int VR, int &ci) {
   V2FTile o;
-  if (t < total) {
-    const int4 *p = reinterpret_cast<const int4 *>(tiles + t);
-    const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    o.K = a.x; o.VS = a.y; o.nv_full = a.z; o.nv = a.w;
-    o.nslots = b.x; o.slot0 = b.y; o.var0 = b.z; o.magic = b.w;
-    o.qoff = ((int64_t)(uint32_t)c.x) | ((int64_t)c.y << 32);
-    o.uoff = ((int64_t)(uint32_t)c.z) | ((int64_t)c.w << 32);
-  } else {
-    o.K = 0; o.VS = 0; o.nv_full = o.nv = o.nslots = o.slot0 = o.var0 = 0; o.magic = 0; o.qoff = o.uoff = 0;
-  }
+  o.valid = t < tab.total_tiles;
+  if (!o.valid) { o.K = 1; o.VS = D; o.nv_full = o.nv = o.nslots = o.slot0 = o.var0 = 0; o.qoff = o.uoff = 0; return o; }
+#pragma unroll 1
+  while (ci + 1 < tab.n && t >= tab.e[ci + 1].tile_begin) ++ci;
+  const V2FEntry &en = tab.e[ci];
+  o.K = en.vc.degree;
+  o.VS = v2f_vstride(o.K, D, VR);
+  o.nv_full = en.nv_tile;
+  const int v0 = (t - en.tile_begin) * en.nv_tile;
+  o.nv = min(en.nv_tile, en.vc.n_vars - v0);
+  o.nslots = o.nv * o.K;
+  o.slot0 = en.vc.first_slot + v0 * o.K;
+  o.var0 = en.vc.first_var + v0;
+  o.qoff = en.vc.q_base + (int64_t)v0 * o.K * D;
+  o.uoff = en.vc.unary_base + (int64_t)v0 * D;
   return o;
 }
-#define FG_TILE_VALID(t) ((t).K > 0)
-#define FG_DIV_K(sl, t) ((t).K == 1 ? (int)(sl) : (int)__umulhi((unsigned)(sl), (unsigned)(t).magic))
 
 // costs_for_factor (maxsum.py:623-676) for slot f of a variable whose K gathered r rows are at
 // col[g*D + x]: value-major, then factor order; the own factor contributes +0 (exact).
@@ -628,8 +645,7 @@ __device__ __forceinline__ void v2f_select(const T *__restrict__ col, const T *_
 // (value selection).
 template <typename T, int D, typename OffT>
 __global__ void __launch_bounds__(FG_V2F_NT)
-k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, int out_elems, int avg_elems,
-           const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
+k_v2f_pipe(const V2FTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
            const T *__restrict__ r_cur, const T *__restrict__ q_cur, T *__restrict__ q_next,
            uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
            T *__restrict__ value_cost, MaxSumParams p) {
@@ -637,9 +653,9 @@ k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, 
   constexpr int NT = FG_V2F_NT, NS = 2, RND = FG_V2F_ROUNDS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T *stage0 = reinterpret_cast<T *>(smem_raw);  // per stage: rrow | qio | un
-  T *qout = stage0 + NS * stage_elems;          // output rows
-  T *avg = qout + out_elems;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(avg + avg_elems);
+  T *qout = stage0 + NS * tab.stage_elems;      // output rows; also the scratch of the run-time-K path
+  T *avg = qout + tab.out_elems;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(avg + tab.avg_elems);
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -649,24 +665,25 @@ k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, 
   }
   __syncthreads();
 
-  auto tile_at = [&](int k) { return v2f_load_tile(tiles, (int)blockIdx.x + k * (int)gridDim.x, total_tiles); };
+  int cursor = 0;
+  auto tile_at = [&](int k) { return v2f_tile(tab, (int)blockIdx.x + k * (int)gridDim.x, D, C::VR, cursor); };
   auto load_idx = [&](const V2FTile &t, OffT (&idx)[RND]) {
 #pragma unroll
     for (int u = 0; u < RND; ++u) {
       const int sl = tid + u * NT;
-      idx[u] = (sl < t.nslots) ? slot_roff[t.slot0 + sl] : (OffT)0;
+      idx[u] = (t.valid && sl < t.nslots) ? slot_roff[t.slot0 + sl] : (OffT)0;
     }
   };
   auto load_cnt = [&](const V2FTile &t, uint8_t (&cn)[RND]) {
 #pragma unroll
     for (int u = 0; u < RND; ++u) {
       const int sl = tid + u * NT;
-      cn[u] = (sl < t.nslots) ? q_cnt[t.slot0 + sl] : (uint8_t)0;
+      cn[u] = (t.valid && sl < t.nslots) ? q_cnt[t.slot0 + sl] : (uint8_t)0;
     }
   };
   auto issue = [&](int k, const V2FTile &t, const OffT (&idx)[RND]) {
-    if (FG_TILE_VALID(t)) {
-      T *rrow = stage0 + (k % NS) * stage_elems;
+    if (t.valid) {
+      T *rrow = stage0 + (k % NS) * tab.stage_elems;
       T *qio = rrow + t.nv_full * t.VS;
       T *un = qio + t.nv_full * t.K * D;
       const uint32_t qbytes = (uint32_t)(t.nslots * D) * (uint32_t)sizeof(T);
@@ -688,7 +705,7 @@ k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, 
       for (int u = 0; u < RND; ++u) {
         const int sl = tid + u * NT;
         if (sl < t.nslots) {
-          const int i = FG_DIV_K(sl, t), g = sl - i * t.K;
+          const int i = sl / t.K, g = sl - i * t.K;
           const T *src = r_cur + (int64_t)idx[u];
           T *dst = rrow + i * t.VS + g * D;
 #pragma unroll
@@ -710,7 +727,7 @@ k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, 
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
 
 #pragma unroll 1
-  for (int k = 0; FG_TILE_VALID(t_cur); ++k) {
+  for (int k = 0; t_cur.valid; ++k) {
     OffT idx_next[RND];
     uint8_t cnt_next[RND];
     load_idx(t_n2, idx_next);
@@ -725,7 +742,7 @@ k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, 
 
     const V2FTile t = t_cur;
     const int K = t.K;
-    T *rrow = stage0 + (k % NS) * stage_elems;
+    T *rrow = stage0 + (k % NS) * tab.stage_elems;
     const T *qio = rrow + t.nv_full * t.VS;
     const T *un = qio + t.nv_full * K * D;
     {  // one thread per variable, packed into the first warps (a spread mapping would make every
@@ -744,7 +761,7 @@ k_v2f_pipe(const V2FTile *__restrict__ tiles, int total_tiles, int stage_elems, 
     for (int u = 0; u < RND; ++u) {
       const int sl = tid + u * NT;
       if (sl < t.nslots) {
-        const int i = FG_DIV_K(sl, t), f = sl - i * K;
+        const int i = sl / K, f = sl - i * K;
         const T *col = rrow + i * t.VS;
         T cand[D], prev[D];
         T avg_c;
@@ -880,58 +897,64 @@ inline bool dispatch_f2v(bool probe, const fg_class_t &c, const fg_maxsum_desc_t
 }
 
 struct V2FLaunch {
-  std::vector<V2FTile> tiles;   // host copy, launch order (costly tiles first)
-  V2FTile *dev_tiles = nullptr; // device copy (owned by the engine handle)
-  int stage_elems = 0, out_elems = 0, avg_elems = 0;
+  V2FTable tab;
   size_t smem = 0;
 };
 
-// Tile list over the regular variable classes (degree 1..16) of one domain size D.
+// Split the regular variable classes (degree 1..16, one domain size D) into launches of at most
+// FG_V2F_MAX_ENTRIES classes each, choosing the tile size of every class.
 inline void v2f_build_launches(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<V2FLaunch> &out) {
   V2FLaunch cur;
+  auto reset = [&]() {
+    cur = V2FLaunch();
+    cur.tab.n = 0;
+    cur.tab.total_tiles = 0;
+    cur.tab.stage_elems = 0;
+    cur.tab.out_elems = 0;
+    cur.tab.avg_elems = 0;
+  };
+  auto flush = [&]() {
+    if (cur.tab.n) {
+      // 16-byte aligned section sizes
+      const int al = (int)(16 / elem);
+      cur.tab.stage_elems = (cur.tab.stage_elems + al - 1) / al * al;
+      cur.tab.out_elems = (cur.tab.out_elems + al - 1) / al * al;
+      cur.tab.avg_elems = (cur.tab.avg_elems + al - 1) / al * al;
+      cur.smem = (size_t)(2 * cur.tab.stage_elems + cur.tab.out_elems + cur.tab.avg_elems) * elem + 64;
+      out.push_back(cur);
+    }
+    reset();
+  };
+  reset();
   std::vector<fg_varclass_t> order(vcs);
   std::stable_sort(order.begin(), order.end(),
                    [](const fg_varclass_t &a, const fg_varclass_t &b) { return a.degree > b.degree; });  // costly tiles first
-  static const int stage_kb = fg_env_int("PYDCOP_B200_V2F_STAGE_KB", 14);
-  const int VR = fg_gcd(16, D * (int)elem) / (int)elem;
   for (const fg_varclass_t &vc : order) {
     if (vc.dom != D || vc.degree < 1 || vc.n_vars == 0) continue;
     const int K = vc.degree;
+    const int VR = fg_gcd(16, D * (int)elem) / (int)elem;
     const int VS = v2f_vstride(K, D, VR);
     const size_t per_var = (size_t)(VS + K * D + D) * elem;  // stage bytes per variable
+    static const int stage_kb = fg_env_int("PYDCOP_B200_V2F_STAGE_KB", 14);
     int nv = (int)((size_t)(stage_kb * 1024) / per_var);
     const int cap = (FG_V2F_ROUNDS * FG_V2F_NT) / K;        // slots per tile <= ROUNDS * NT
     if (nv > cap) nv = cap;
-    if (nv > FG_V2F_NT) nv = FG_V2F_NT;                      // one selection thread per variable
     nv = nv / 8 * 8;
     if (nv < 8) nv = 8;
-    const int n_tiles = (vc.n_vars + nv - 1) / nv;
-    for (int t = 0; t < n_tiles; ++t) {
-      V2FTile d;
-      const int v0 = t * nv;
-      d.K = K; d.VS = VS; d.nv_full = nv;
-      d.nv = std::min(nv, vc.n_vars - v0);
-      d.nslots = d.nv * K;
-      d.slot0 = vc.first_slot + v0 * K;
-      d.var0 = vc.first_var + v0;
-      d.magic = K == 1 ? 0 : (int32_t)(uint32_t)((0x100000000ULL + (unsigned)K - 1) / (unsigned)K);
-      d.qoff = vc.q_base + (int64_t)v0 * K * D;
-      d.uoff = vc.unary_base + (int64_t)v0 * D;
-      cur.tiles.push_back(d);
-    }
+    if (nv > FG_V2F_NT) nv = FG_V2F_NT;
+    V2FEntry e;
+    e.vc = vc;
+    e.tile_begin = cur.tab.total_tiles;
+    e.nv_tile = nv;
+    cur.tab.e[cur.tab.n++] = e;
+    cur.tab.total_tiles += (vc.n_vars + nv - 1) / nv;
     const int st = nv * (VS + K * D + D), ot = nv * K * D;
-    if (st > cur.stage_elems) cur.stage_elems = st;
-    if (ot > cur.out_elems) cur.out_elems = ot;
-    if (ot / D > cur.avg_elems) cur.avg_elems = ot / D;
+    if (st > cur.tab.stage_elems) cur.tab.stage_elems = st;
+    if (ot > cur.tab.out_elems) cur.tab.out_elems = ot;
+    if (ot / D > cur.tab.avg_elems) cur.tab.avg_elems = ot / D;
+    if (cur.tab.n == FG_V2F_MAX_ENTRIES) flush();
   }
-  if (!cur.tiles.empty()) {
-    const int al = (int)(16 / elem);
-    cur.stage_elems = (cur.stage_elems + al - 1) / al * al;
-    cur.out_elems = (cur.out_elems + al - 1) / al * al;
-    cur.avg_elems = (cur.avg_elems + al - 1) / al * al;
-    cur.smem = (size_t)(2 * cur.stage_elems + cur.out_elems + cur.avg_elems) * elem + 64;
-    out.push_back(cur);
-  }
+  flush();
 }
 
 template <typename T, int D>
@@ -954,11 +977,9 @@ inline void launch_v2f_classes(const V2FLaunch &L, const fg_maxsum_desc_t &d, co
   if (per_sm < 1) per_sm = 1;
   static const int cap = fg_env_int("PYDCOP_B200_V2F_CPS", 3);
   if (per_sm > cap) per_sm = cap;
-  const int total = (int)L.tiles.size();
-  const unsigned blocks = (unsigned)std::min(total, n_sm * per_sm);
-  kern<<<blocks, FG_V2F_NT, L.smem, st>>>(L.dev_tiles, total, L.stage_elems, L.out_elems, L.avg_elems, d.dev_slot_roff32,
-                                          (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_q_cnt, d.dev_q_sent,
-                                          d.dev_value, (T *)d.dev_value_cost, p);
+  const unsigned blocks = (unsigned)std::min(L.tab.total_tiles, n_sm * per_sm);
+  kern<<<blocks, FG_V2F_NT, L.smem, st>>>(L.tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
+                                          d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
 }
 
 template <typename T>
