@@ -237,6 +237,11 @@ class GpuSession:
                 time.sleep(0)  # let the agent threads poll
         except BaseException as e:  # noqa: BLE001 — surfaced to every proxy (fail loudly)
             self.error = e
+            import logging
+            import sys
+            msg = f"pydcop_b200: {self.kind}_gpu session '{self.key}' failed: {e!r} (no CPU fallback)"
+            logging.getLogger("pydcop_b200").critical(msg)
+            print(msg, file=sys.stderr, flush=True)
 
     def _publish(self, engine, cycle, finished):
         out = engine.values()

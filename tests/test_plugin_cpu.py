@@ -184,3 +184,27 @@ def test_no_gpu_means_loud_failure_not_fallback(pydcop_ready):
     with pytest.raises(EngineError):
         comps[0]._poll()
     GpuSession.reset()
+
+
+def test_cli_drop_in_without_gpu_reports_the_engine_error(pydcop_ready, tmp_path):
+    """`pydcop solve --algo maxsum_gpu` through the unmodified CLI: the algorithm is accepted by the
+    reference's argparse (choices come from list_available_algorithms) and, with no GPU in this
+    container, the failure is printed — not silently replaced by a CPU computation."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import ref_shim; ref_shim.install()\n"
+        "from pydcop_b200 import launcher\n"
+        "launcher.main(['-t', '3', 'solve', '--algo', 'maxsum_gpu', '--algo_params', 'stop_cycle:5',"
+        " '-d', 'adhoc', %r])\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+         os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
+         os.path.join(INSTANCES, "graph_coloring1.yaml"))
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True,
+                       timeout=120, cwd=str(tmp_path))
+    assert "EngineError" in r.stderr and "no CPU fallback" in r.stderr, r.stderr[-2000:]
+    assert '"assignment": {}' in r.stdout            # nothing was computed on the CPU instead
