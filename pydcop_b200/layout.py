@@ -179,7 +179,9 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     dom_size = _as(dom_size, np.int32)
     factor_ptr = _as(factor_ptr, np.int64)
     edge_var = _as(edge_var, np.int32)
-    tables = _as(tables, np.float64).reshape(-1)
+    tables = np.ascontiguousarray(np.asarray(tables)).reshape(-1)
+    if tables.dtype != np.float32:      # float32 tables are kept as they are (half the host memory)
+        tables = tables.astype(np.float64, copy=False)
     V, F, E = len(dom_size), len(factor_ptr) - 1, len(edge_var)
     if F < 0 or factor_ptr[0] != 0 or factor_ptr[-1] != E:
         raise ValueError("factor_ptr must start at 0 and end at len(edge_var)")
@@ -243,7 +245,7 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
         pad = (-t.size) % ALIGN
         tab_parts.append(t)
         if pad:
-            tab_parts.append(np.zeros(pad))
+            tab_parts.append(np.zeros(pad, dtype=tables.dtype))
         # edges
         ce = (factor_ptr[fs][:, None] + np.arange(a, dtype=np.int64)[None, :]).reshape(-1)
         ie = first_edge + np.arange(n * a, dtype=np.int64)
@@ -259,7 +261,7 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
         msg_base += n * R
         msg_base += (-msg_base) % ALIGN
     n_msg = msg_base
-    tables_int = np.concatenate(tab_parts) if tab_parts else np.zeros(0)
+    tables_int = np.concatenate(tab_parts) if tab_parts else np.zeros(0, dtype=tables.dtype)
 
     canon_msg_off = np.zeros(E + 1, dtype=np.int64)
     np.cumsum(edge_dom, out=canon_msg_off[1:])
