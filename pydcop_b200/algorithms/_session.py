@@ -148,11 +148,13 @@ class GpuSession:
 
     # -- packing ----------------------------------------------------------------------------
     def build_instance(self):
-        """Flat arrays of the registered graph, in registration-independent (name) order for
-        constraints = the order pyDcop lists them in (`links`)."""
-        var_names = list(self.variables)
+        """Flat arrays of the registered graph.  Variables and constraints are taken in NAME order,
+        not in the (thread-dependent) order the proxies registered in, so the instance — and with
+        a `seed` the noise / random draws — is identical from run to run; every variable keeps the
+        `links` order pyDcop gave it."""
+        var_names = sorted(self.variables)
         vidx = {n: i for i, n in enumerate(var_names)}
-        cons_names = list(self.constraints)
+        cons_names = sorted(self.constraints)
         cidx = {n: i for i, n in enumerate(cons_names)}
         dom_size = np.array([len(self.variables[n].domain) for n in var_names], dtype=np.int32)
         factor_ptr, edge_var, tables, edge_of = [0], [], [], {}
