@@ -110,8 +110,12 @@ def test_solve_api_maxsum_gpu_known_answer(oracle_seam):
     """tests/api/test_api_solve.py:35-60 of the reference, with --algo maxsum_gpu."""
     from pydcop.dcop.yamldcop import load_dcop_from_file
     from pydcop.infrastructure.run import solve
+    from pydcop.algorithms import AlgorithmDef
     dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
-    assignment = solve(dcop, "maxsum_gpu", "adhoc", timeout=3)
+    # stop_cycle fixes the number of cycles, so the answer does not depend on how many cycles fit
+    # in the wall-clock budget (the reference's solve() always waits for its timeout, run.py:130-133)
+    algo = AlgorithmDef.build_with_default_param("maxsum_gpu", {"stop_cycle": 40}, mode=dcop.objective)
+    assignment = solve(dcop, algo, "adhoc", timeout=8)
     assert assignment == {"v1": "R", "v2": "G", "v3": "R"}
 
 
@@ -159,8 +163,10 @@ def test_run_finishes_with_stop_cycle_and_counts_cycles(oracle_seam):
 def test_solve_api_dsa_gpu(oracle_seam):
     from pydcop.dcop.yamldcop import load_dcop_from_file
     from pydcop.infrastructure.run import solve
+    from pydcop.algorithms import AlgorithmDef
     dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
-    assignment = solve(dcop, "dsa_gpu", "oneagent", timeout=3)
+    algo = AlgorithmDef.build_with_default_param("dsa_gpu", {"stop_cycle": 40, "seed": 3}, mode=dcop.objective)
+    assignment = solve(dcop, algo, "oneagent", timeout=8)
     assert assignment in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
 
 
