@@ -146,3 +146,16 @@ def test_halo_exchange_over_gloo(kind, world):
     for p in procs:
         p.join(timeout=30)
     assert all(r[1] == "ok" for r in results), results
+
+
+def test_more_ranks_than_variables():
+    """Ranks that own nothing get an empty (but valid) shard and empty halo lists."""
+    inst = random_factor_graph(5, 3, 6, 2, seed=1)
+    plans = [build_shard(inst, r, 8) for r in range(8)]
+    assert sum(p.n_own_vars for p in plans) == 5
+    assert sorted(np.concatenate([p.own_factor_edges for p in plans]).tolist()) == list(range(12))
+    for p in plans[5:]:
+        assert p.n_own_vars == 0 and p.layout.n_edges == 0 and sum(p.send_r_split) == 0
+    for a in range(8):
+        for b in range(8):
+            assert plans[a].send_r_split[b] == plans[b].recv_r_split[a]
