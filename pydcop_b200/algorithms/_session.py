@@ -14,7 +14,6 @@ Everything here is duck-typed on the reference's node / constraint / variable ob
 (`.name`, `.dimensions`, `.domain`, `__call__`, `.cost_for_val`, `.initial_value`): no pydcop
 import is needed, which keeps this module testable without the reference.
 """
-import itertools
 import random
 import threading
 import time
@@ -27,19 +26,14 @@ def domain_values(variable) -> list:
     return list(variable.domain)
 
 
-def tabulate(constraint) -> np.ndarray:
+def tabulate(constraint, cache=None) -> np.ndarray:
     """Dense row-major cost table, axis i <-> constraint.dimensions[i]
-    (layout of NAryMatrixRelation._m, pydcop/dcop/relations.py:716-733)."""
-    dims = list(constraint.dimensions)
-    shape = tuple(len(v.domain) for v in dims)
-    m = getattr(constraint, "_m", None)
-    if m is not None and tuple(np.shape(m)) == shape:
-        return np.asarray(m, dtype=np.float64)
-    doms = [domain_values(v) for v in dims]
-    t = np.zeros(shape, dtype=np.float64)
-    for idx in itertools.product(*(range(s) for s in shape)):
-        t[idx] = constraint(**{v.name: doms[k][i] for k, (v, i) in enumerate(zip(dims, idx))})
-    return t
+    (layout of NAryMatrixRelation._m, pydcop/dcop/relations.py:716-733).  Expression constraints
+    are evaluated on broadcast numpy axes and shared between identical functions
+    (pydcop_b200.ingest.tabulate_constraint)."""
+    from ..ingest import tabulate_constraint
+    shape = tuple(len(v.domain) for v in constraint.dimensions)
+    return tabulate_constraint(constraint, cache).reshape(shape)
 
 
 class Snapshot:
@@ -158,13 +152,15 @@ class GpuSession:
         cidx = {n: i for i, n in enumerate(cons_names)}
         dom_size = np.array([len(self.variables[n].domain) for n in var_names], dtype=np.int32)
         factor_ptr, edge_var, tables, edge_of = [0], [], [], {}
+        from ..ingest import TableCache
+        cache = TableCache()
         for cn in cons_names:
             c = self.constraints[cn]
             for v in c.dimensions:
                 edge_of[(cn, v.name)] = len(edge_var)
                 edge_var.append(vidx[v.name])
             factor_ptr.append(len(edge_var))
-            tables.append(tabulate(c).reshape(-1))
+            tables.append(tabulate(c, cache).reshape(-1))
         var_ptr, var_edge = [0], []
         for n in var_names:
             for cn in self.var_links[n]:
