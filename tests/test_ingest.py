@@ -276,12 +276,7 @@ def test_from_dcop_objects():
 
 # ---- the reference's own instances (only where /root/reference exists) --------------------------
 def _reference():
-    try:
-        from oracle import ref_shim
-    except ImportError:
-        import sys
-        sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
-        import ref_shim
+    import ref_shim
     if not ref_shim.reference_available():
         pytest.skip("reference not available")
     ref_shim.install()
