@@ -37,6 +37,7 @@ import itertools
 import json
 import os
 import random
+import re
 import struct
 from dataclasses import dataclass, field
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple, Union
@@ -177,8 +178,7 @@ class Expression:
         v.visit(tree)
         self.variable_names = v.free()
         self.has_return = v.has_return
-        canon = _Rename({n: f"_a{i}" for i, n in enumerate(self.variable_names)}).visit(
-            ast.parse(self.text))
+        canon = _Rename({n: f"_a{i}" for i, n in enumerate(self.variable_names)}).visit(tree)
         #: identical for expressions that differ only by the names of their variables
         self.canonical_key = (ast.dump(canon), self.source_file)
         if self.has_return:
@@ -301,17 +301,27 @@ def _domain_values(spec) -> list:
     return list(values)
 
 
-def _value_index(dom_vals: list, token: str, dom_name: str) -> int:
-    """Domain.to_domain_value (objects.py:137-165): first value whose str() equals the token."""
+def _value_lookup(dom_vals: list) -> Dict[str, int]:
+    """Domain.to_domain_value (objects.py:137-165) as a table: str(value) -> index of the FIRST
+    value with that representation."""
+    lut: Dict[str, int] = {}
     for i, v in enumerate(dom_vals):
-        if str(v) == token:
-            return i
-    raise DcopFormatError(f"{token} is not in the domain {dom_name}")
+        lut.setdefault(str(v), i)
+    return lut
+
+
+_IDENT = re.compile(r"(?<![\w.])[A-Za-z_]\w*")
 
 
 class TableCache:
     """Tables of intentional constraints, shared between constraints that are the same function
-    of same-domain variables up to renaming (graph colouring: |C| constraints, 1 table)."""
+    of same-domain variables up to renaming (graph colouring: |C| constraints, 1 table).
+
+    Two levels.  `canonical()` renames the known variable names in the expression TEXT to
+    positional placeholders with one regex pass, so that all constraints of one form share one
+    parsed + compiled `Expression` (parsing and compiling dominate the load time otherwise);
+    texts with string literals, where a textual rename could touch a literal, skip this level and
+    are compared through their renamed AST instead (`Expression.canonical_key`)."""
 
     def __init__(self):
         self.tables: Dict[Any, np.ndarray] = {}
@@ -325,17 +335,37 @@ class TableCache:
             e = self.expressions[key] = Expression(text, source_file)
         return e
 
-    def get(self, expr: Expression, doms: List[Tuple[str, list]]):
-        try:
-            key = (expr.canonical_key, tuple(d[0] for d in doms))
-            t = self.tables.get(key)
-        except TypeError:  # pragma: no cover — unhashable key parts
-            key, t = None, None
+    def canonical(self, text: str, known, source_file=None):
+        """(shared Expression over placeholders _a0.., real variable names in placeholder order),
+        or None when the text cannot be renamed safely."""
+        if "'" in text or '"' in text:
+            return None
+        order: Dict[str, str] = {}
+        clash = []
+
+        def repl(m):
+            n = m.group(0)
+            if n.startswith("_a"):  # would be mistaken for a placeholder
+                clash.append(n)
+            if n not in known or n in _BUILTIN_NAMES or n.startswith("source"):
+                return n
+            ph = order.get(n)
+            if ph is None:
+                ph = order[n] = f"_a{len(order)}"
+            return ph
+
+        canon = _IDENT.sub(repl, text)
+        if clash:
+            return None
+        return self.expression(canon, source_file), list(order)
+
+    def get(self, expr: Expression, doms: List[Tuple[str, list]], names=None):
+        key = (expr.canonical_key, tuple(d[0] for d in doms))
+        t = self.tables.get(key)
         if t is None:
-            t = tabulate_expression(expr.func, expr.variable_names, [d[1] for d in doms],
+            t = tabulate_expression(expr.func, names or expr.variable_names, [d[1] for d in doms],
                                     stats=self.stats).reshape(-1)
-            if key is not None:
-                self.tables[key] = t
+            self.tables[key] = t
         else:
             self.stats["shared"] += 1
         return t
@@ -386,19 +416,32 @@ def loads_yaml(text: str, main_dir: Optional[str] = None, seed: Optional[int] = 
     dom_size = np.array([len(domain_values[d]) for d in var_domain], dtype=np.int32)
 
     con_names, factor_ptr, edge_var, tables = [], [0], [], []
-    cache = TableCache()
+    cache, luts = TableCache(), {}
     for c_name, c in (loaded.get("constraints") or {}).items():
         ctype = (c or {}).get("type")
         if ctype == "intention":
             src = c.get("source")
             if src is not None and not os.path.isabs(src):
                 src = os.path.join(str(main_dir) if main_dir is not None else ".", src)
-            e = cache.expression(str(c["function"]), src)
-            for n in e.variable_names:
-                if n not in vidx:  # relations.py:1301-1305
-                    raise DcopFormatError(f'Missing variable {n} for string-based function '
-                                          f'"{e.text}"')
-            scope = [vidx[n] for n in e.variable_names]
+            text = str(c["function"])
+            shared = cache.canonical(text, vidx, src)
+            if shared is not None:
+                e, real = shared
+                # placeholders the expression really depends on, in order of first appearance
+                try:
+                    scope_names = [real[int(n[2:])] if n.startswith("_a") else None
+                                   for n in e.variable_names]
+                except (ValueError, IndexError):
+                    scope_names = [None]
+                missing = [n for n, r in zip(e.variable_names, scope_names) if r is None]
+            else:
+                e = cache.expression(text, src)
+                scope_names = list(e.variable_names)
+                missing = [n for n in scope_names if n not in vidx]
+            if missing:  # relations.py:1301-1305
+                raise DcopFormatError(f'Missing variable {missing[0]} for string-based function '
+                                      f'"{text.lstrip()}"')
+            scope = [vidx[n] for n in scope_names]
             doms = [(var_domain[i], domain_values[var_domain[i]]) for i in scope]
             table = cache.get(e, doms)
         elif ctype == "extensional":
@@ -409,7 +452,7 @@ def loads_yaml(text: str, main_dir: Optional[str] = None, seed: Optional[int] = 
                 if n not in vidx:
                     raise DcopFormatError(f"unknown variable {n} in constraint {c_name}")
             scope = [vidx[n] for n in scope_names]
-            table = _extensional_table(c_name, c, scope, var_domain, domain_values)
+            table = _extensional_table(c_name, c, scope, var_domain, domain_values, luts)
         else:
             raise DcopFormatError(f"Error in constraint {c_name} definition: type is mandatory "
                                   'and must be "intention" or "extensional"')
@@ -426,34 +469,49 @@ def loads_yaml(text: str, main_dir: Optional[str] = None, seed: Optional[int] = 
                             "tabulation": dict(cache.stats)})
 
 
-def _extensional_table(c_name, c, scope, var_domain, domain_values):
+def _extensional_table(c_name, c, scope, var_domain, domain_values, luts):
     """yamldcop.py:227-277: {cost: "v1 v2 | v1 v2 …"} (or {cost: value} for one variable), cells
-    not listed take `default`."""
+    not listed take `default`; a cell listed twice keeps the LAST cost, as in the reference."""
     doms = [domain_values[var_domain[i]] for i in scope]
     shape = tuple(len(d) for d in doms)
+    arity = len(scope)
+    strides = [int(np.prod(shape[k + 1:])) for k in range(arity)]
     default = c.get("default")
-    t = np.full(shape, np.nan if default is None else float(default), dtype=np.float64)
-    covered = np.zeros(shape, dtype=bool) if default is None else None
+    t = np.full(int(np.prod(shape)), np.nan if default is None else float(default), dtype=np.float64)
+    covered = np.zeros(len(t), dtype=bool) if default is None else None
+    lut = []
+    for i in scope:
+        d = var_domain[i]
+        if d not in luts:
+            luts[d] = _value_lookup(domain_values[d])
+        lut.append(luts[d])
     for value, assignments in (c.get("values") or {}).items():
-        if len(scope) == 1 and not isinstance(assignments, str):
-            idx = (doms[0].index(assignments),)
-            t[idx] = value
-            if covered is not None:
-                covered[idx] = True
-            continue
-        for ass in str(assignments).split("|"):
-            toks = ass.split()
-            if len(toks) != len(scope):
-                raise DcopFormatError(f"constraint {c_name}: assignment '{ass.strip()}' does not "
-                                      f"list {len(scope)} values")
-            idx = tuple(_value_index(doms[k], tok.strip(), var_domain[scope[k]])
-                        for k, tok in enumerate(toks))
-            t[idx] = value
-            if covered is not None:
-                covered[idx] = True
+        if arity == 1 and not isinstance(assignments, str):
+            try:
+                lin = [doms[0].index(assignments)]
+            except ValueError:
+                raise DcopFormatError(f"{assignments} is not in the domain {var_domain[scope[0]]}") from None
+        else:
+            toks = [p.split() for p in str(assignments).split("|")]
+            for tk in toks:
+                if len(tk) != arity:
+                    raise DcopFormatError(f"constraint {c_name}: assignment '{' '.join(tk)}' does "
+                                          f"not list {arity} values")
+            flat = list(itertools.chain.from_iterable(toks))
+            lin = np.zeros(len(toks), dtype=np.int64)
+            for k in range(arity):
+                try:
+                    lin += np.fromiter((lut[k][tok] for tok in flat[k::arity]), dtype=np.int64,
+                                       count=len(toks)) * strides[k]
+                except KeyError as e:
+                    raise DcopFormatError(f"{e.args[0]} is not in the domain "
+                                          f"{var_domain[scope[k]]}") from None
+        t[lin] = value
+        if covered is not None:
+            covered[lin] = True
     if covered is not None and not covered.all():
         raise DcopFormatError(f"constraint {c_name}: assignments without a cost and no default")
-    return t.reshape(-1)
+    return t
 
 
 def _assemble(dom_size, factor_ptr, edge_var, tables, unary, init_value):

@@ -312,3 +312,36 @@ def test_reference_test_instances_load_identically():
             hasattr(v, "noise_level") for v in ref.variables.values())
         n += 1
     assert n >= 10
+
+
+def test_text_level_sharing_is_safe():
+    """Constraints of one form share one compiled expression; string literals, placeholder-like
+    names, builtins used as names and locally assigned names do not get confused."""
+    text = ("name: s\nobjective: min\ndomains:\n  d: {values: [0, 1, 2]}\n  s: {values: [v1, v2, x]}\n"
+            "variables:\n  v1: {domain: d}\n  v2: {domain: d}\n  v3: {domain: d}\n  _a0: {domain: d}\n"
+            "  p: {domain: s}\n  q: {domain: s}\n"
+            "constraints:\n"
+            "  c12: {type: intention, function: 3 * v1 - v2}\n"
+            "  c23: {type: intention, function: 3 * v2 - v3}\n"
+            "  c31: {type: intention, function: 3 * v3 - v1}\n"
+            '  lit1: {type: intention, function: "1 if p == \'v1\' else 0"}\n'
+            '  lit2: {type: intention, function: "1 if q == \'v2\' else 0"}\n'
+            "  ph: {type: intention, function: _a0 * 2 + v1}\n"
+            "  loc:\n    type: intention\n    function: |\n      v3 = v1 * 2\n      return v3 + v2\n")
+    d = ingest.loads_yaml(text)
+    a = d.arrays
+
+    def table(name):
+        ci = d.con_names.index(name)
+        scope = [d.var_names[i] for i in a["edge_var"][a["factor_ptr"][ci]:a["factor_ptr"][ci + 1]]]
+        return scope, a["tables"][a["table_off"][ci]:a["table_off"][ci + 1]].tolist()
+
+    want = [3.0 * x - y for x in range(3) for y in range(3)]
+    assert table("c12") == (["v1", "v2"], want)
+    assert table("c23") == (["v2", "v3"], want)
+    assert table("c31") == (["v3", "v1"], want)
+    assert table("lit1") == (["p"], [1.0, 0.0, 0.0])
+    assert table("lit2") == (["q"], [0.0, 1.0, 0.0])
+    assert table("ph") == (["_a0", "v1"], [2.0 * x + y for x in range(3) for y in range(3)])
+    assert table("loc") == (["v1", "v2"], [2.0 * x + y for x in range(3) for y in range(3)])
+    assert d.meta["tabulation"]["shared"] == 2
