@@ -79,7 +79,7 @@ class MaxSumEngine(_EngineBase):
     """All-edges-at-once synchronous MaxSum.
 
     Parameters mirror the reference's algo_params (pydcop/algorithms/maxsum.py:212-220); `noise`
-    is applied by the caller to `layout.unary` (see pydcop_b200.noise.add_noise).
+    is applied by the caller to the instance's `unary` before packing (pydcop_b200.ingest.add_noise).
     State after `init()` is the reference's cycle 0 (on_start); each `step()` cycle is one
     synchronous round of every factor's and every variable's on_new_cycle.
     """

@@ -59,3 +59,47 @@ def test_no_cpu_fallback_without_gpu():
         MaxSumEngine(L)
     with pytest.raises(EngineError):
         DsaEngine(L)
+
+
+def test_create_validates_its_descriptor_before_touching_the_device():
+    """fg_maxsum_create / fg_dsa_create reject malformed descriptors with FG_ERR_ARG and a
+    message, and report FG_ERR_CUDA (never a silent CPU path) when no device is visible."""
+    import ctypes as C
+    import torch
+    from pydcop_b200 import _cabi
+    lib = _cabi.load()
+    h = C.c_void_p()
+    assert lib.fg_maxsum_create(None, C.byref(h)) == _cabi.FG_ERR_ARG
+    assert lib.fg_dsa_create(None, C.byref(h)) == _cabi.FG_ERR_ARG
+
+    d = _cabi.FgMaxSumDesc()
+    d.abi_version, d.precision = _cabi.FG_ABI_VERSION + 1, _cabi.FG_F32
+    assert lib.fg_maxsum_create(C.byref(d), C.byref(h)) == _cabi.FG_ERR_ARG and not h.value
+    d.abi_version, d.precision = _cabi.FG_ABI_VERSION, 7
+    assert lib.fg_maxsum_create(C.byref(d), C.byref(h)) == _cabi.FG_ERR_ARG and not h.value
+
+    # one binary class whose table_size disagrees with its domain sizes
+    cls = (_cabi.FgClass * 1)()
+    cls[0].arity, cls[0].n_factors, cls[0].table_size, cls[0].row_total = 2, 1, 5, 4
+    cls[0].dom[0], cls[0].dom[1] = 2, 2
+    cls[0].row_off[0], cls[0].row_off[1] = 0, 2
+    d.precision, d.n_classes, d.n_edges, d.n_factors, d.n_vars = _cabi.FG_F32, 1, 2, 1, 2
+    d.classes = C.cast(cls, C.POINTER(_cabi.FgClass))
+    assert lib.fg_maxsum_create(C.byref(d), C.byref(h)) == _cabi.FG_ERR_ARG
+    assert b"class size mismatch" in lib.fg_maxsum_last_error(h)
+    lib.fg_maxsum_destroy(h)
+
+    # consistent class, but the variable classes do not cover the edges
+    cls[0].table_size = 4
+    assert lib.fg_maxsum_create(C.byref(d), C.byref(h)) == _cabi.FG_ERR_ARG
+    assert b"variable classes cover 0 slots, expected 2" in lib.fg_maxsum_last_error(h)
+    lib.fg_maxsum_destroy(h)
+
+    if not torch.cuda.is_available():
+        vcs = (_cabi.FgVarClass * 1)()
+        vcs[0].dom, vcs[0].degree, vcs[0].n_vars, vcs[0].n_slots = 2, 1, 2, 2
+        d.n_varclasses, d.varclasses = 1, C.cast(vcs, C.POINTER(_cabi.FgVarClass))
+        assert lib.fg_maxsum_create(C.byref(d), C.byref(h)) == _cabi.FG_ERR_CUDA
+        assert b"no CPU fallback" in lib.fg_maxsum_last_error(h)
+        lib.fg_maxsum_destroy(h)
+        assert lib.fg_device_count() <= 0
