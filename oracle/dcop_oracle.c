@@ -63,6 +63,32 @@ void dsa_oracle_init(const fg_t *g, const double *unary, const uint8_t *has_nbr,
   }
 }
 
+/* MGM on_start (mgm.py:283-310): a variable without neighbours takes argopt of (own cost, value)
+ * (optimal_cost_value, relations.py:1641-1669) and is done; the others take their initial_value or an
+ * injected random.choice(domain) (draw keyed cycle = 0xffffffff). */
+void mgm_oracle_init(const fg_t *g, const double *unary, const uint8_t *has_nbr,
+                     const int32_t *init_value, int mode_max, uint64_t seed, int32_t *val) {
+  for (int v = 0; v < g->V; ++v) {
+    int d = g->dom_size[v];
+    if (has_nbr[v]) {
+      if (init_value && init_value[v] >= 0) {
+        val[v] = init_value[v];
+      } else {
+        uint32_t b[4];
+        philox4x32_10((uint32_t)v, 0xFFFFFFFFu, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+        val[v] = (int32_t)(((uint64_t)b[2] * (uint64_t)d) >> 32);
+      }
+    } else {
+      int best = 0;
+      for (int x = 1; x < d; ++x) {
+        double c = unary[g->unary_off[v] + x], bc = unary[g->unary_off[v] + best];
+        if (mode_max ? (c >= bc) : (c < bc)) best = x;
+      }
+      val[v] = best;
+    }
+  }
+}
+
 #define REAL double
 #define SUFFIX _f64
 #define FABS fabs

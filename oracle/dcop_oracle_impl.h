@@ -333,6 +333,112 @@ void FN(dsa_oracle_step)(const fg_t *g, const REAL *tables, const int32_t *edge_
   }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * MGM (pydcop/algorithms/mgm.py).  One cycle = mgm_oracle_gain (every variable's best local gain,
+ * :343-397,434-455) then mgm_oracle_decide (who moves, :497-537,574-591).
+ *   nbr_ptr / nbr_idx   distinct neighbours of each variable (mgm.py:245-252)
+ *   var_rank            position of the variable's name in sorted order (lexic tie break)
+ *   cost / has_cost     current_cost, None until the first round (:349)
+ * Quirks kept on purpose: the variable's own cost enters at its CURRENT value, not at the
+ * candidate (:449); current_cost is computed once and afterwards only updated by the variable's
+ * own moves (:349,518), so it goes stale when neighbours move; in max mode the comparison of gains
+ * is the same `>` as in min mode (:516) although improving gains are negative; break_mode
+ * 'random' is dead code (`self.break_mode == random` compares with the module, :541).
+ * The reference adds the concerned variables' costs in the iteration order of a Python set
+ * (:360-366,446-452); here: own cost first, then the neighbours in nbr order. */
+void FN(mgm_oracle_gain)(const fg_t *g, const REAL *tables, const REAL *unary,
+                         const int32_t *edge_fac, const uint8_t *has_nbr, const int32_t *nbr_ptr,
+                         const int32_t *nbr_idx, int mode_max, uint64_t seed, uint32_t cycle,
+                         const int32_t *val, REAL *cost, uint8_t *has_cost, REAL *gain,
+                         int32_t *new_val) {
+#pragma omp parallel
+  {
+    int best[MAX_DOM];
+#pragma omp for schedule(static)
+    for (int v = 0; v < g->V; ++v) {
+      if (!has_nbr[v]) continue;
+      int d = g->dom_size[v], cur = val[v];
+      int s0 = g->var_ptr[v], s1 = g->var_ptr[v + 1];
+      /* costs of the concerned variables at their current values */
+      REAL others = unary[g->unary_off[v] + cur];
+      if (!has_cost[v]) { /* first round: current_cost, mgm.py:349-368 */
+        REAL c = (REAL)0;
+        for (int s = s0; s < s1; ++s) {
+          int e = g->var_edge[s], f = edge_fac[e];
+          REAL t = FN(con_value)(g, tables, val, f, e - g->factor_ptr[f], cur);
+          c = (s == s0) ? t : c + t;
+        }
+        c += unary[g->unary_off[v] + cur];
+        for (int i = nbr_ptr[v]; i < nbr_ptr[v + 1]; ++i) {
+          int u = nbr_idx[i];
+          c += unary[g->unary_off[u] + val[u]];
+        }
+        cost[v] = c;
+        has_cost[v] = 1;
+      }
+      /* find_arg_optimal, relations.py:1554-1591 */
+      REAL best_val = mode_max ? (REAL)-2147483648.0 : (REAL)2147483647.0;
+      int nbest = 0;
+      for (int x = 0; x < d; ++x) {
+        REAL c = (REAL)0;
+        for (int s = s0; s < s1; ++s) {
+          int e = g->var_edge[s], f = edge_fac[e];
+          REAL t = FN(con_value)(g, tables, val, f, e - g->factor_ptr[f], x);
+          c = (s == s0) ? t : c + t;
+        }
+        if (mode_max ? (best_val < c) : (best_val > c)) {
+          best_val = c;
+          nbest = 0;
+          best[nbest++] = x;
+        } else if (c == best_val) {
+          best[nbest++] = x;
+        }
+      }
+      REAL val_cost = best_val + others; /* own cost at the CURRENT value, mgm.py:449 */
+      for (int i = nbr_ptr[v]; i < nbr_ptr[v + 1]; ++i) {
+        int u = nbr_idx[i];
+        val_cost += unary[g->unary_off[u] + val[u]];
+      }
+      REAL gn = cost[v] - val_cost;
+      gain[v] = gn;
+      if (mode_max ? (gn < (REAL)0) : (gn > (REAL)0)) { /* mgm.py:382-385 */
+        uint32_t b[4];
+        philox4x32_10((uint32_t)v, cycle, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+        new_val[v] = best[(int)(((uint64_t)b[2] * (uint64_t)nbest) >> 32)];
+      } else {
+        new_val[v] = cur;
+      }
+    }
+  }
+}
+
+void FN(mgm_oracle_decide)(const fg_t *g, const uint8_t *has_nbr, const int32_t *nbr_ptr,
+                           const int32_t *nbr_idx, const int32_t *var_rank, const REAL *gain,
+                           const int32_t *new_val, int32_t *val, REAL *cost) {
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < g->V; ++v) {
+    if (!has_nbr[v]) continue;
+    REAL mx = gain[nbr_idx[nbr_ptr[v]]];
+    for (int i = nbr_ptr[v] + 1; i < nbr_ptr[v + 1]; ++i)
+      if (gain[nbr_idx[i]] > mx) mx = gain[nbr_idx[i]];
+    int move = 0;
+    if (gain[v] > mx) {
+      move = 1;
+    } else if (gain[v] == mx) { /* lexic order of the names, mgm.py:574-583 */
+      move = 1;
+      for (int i = nbr_ptr[v]; i < nbr_ptr[v + 1]; ++i) {
+        int u = nbr_idx[i];
+        if (gain[u] == mx && var_rank[u] < var_rank[v]) move = 0;
+      }
+    }
+    if (move) { /* value_selection(new_value, current_cost - gain), mgm.py:518 */
+      /* val is read by no other variable in this phase: in-place update is safe */
+      cost[v] = cost[v] - gain[v];
+    }
+    if (move) val[v] = new_val[v];
+  }
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

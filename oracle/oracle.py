@@ -181,6 +181,92 @@ class DsaOracle(_Graph):
         return self
 
 
+def distinct_neighbours(factor_ptr, edge_var, var_ptr, var_edge, edge_fac):
+    """CSR of each variable's distinct neighbours, in order of first appearance over its
+    constraints (set semantics of mgm.py:245-252; any fixed order is admissible)."""
+    V = len(var_ptr) - 1
+    ptr, idx = [0], []
+    for v in range(V):
+        seen = []
+        for s in range(var_ptr[v], var_ptr[v + 1]):
+            f = edge_fac[var_edge[s]]
+            for e in range(factor_ptr[f], factor_ptr[f + 1]):
+                u = int(edge_var[e])
+                if u != v and u not in seen:
+                    seen.append(u)
+        idx.extend(seen)
+        ptr.append(len(idx))
+    return np.array(ptr, dtype=np.int32), np.array(idx, dtype=np.int32)
+
+
+class MgmOracle(_Graph):
+    """Lock-step MGM with injected Philox draws.  State after `init()` == golden state 0, after
+    n `step()` == state n (one step = value phase + gain phase)."""
+
+    def __init__(self, inst, dtype=np.float64, mode="min", stop_cycle=0, seed=0, break_mode="lexic",
+                 **_ignored):
+        if "var_edge" not in inst:
+            inst = dict(inst)
+            inst["var_edge"] = var_con_to_edges(inst)
+        super().__init__(inst, dtype)
+        self.unary64 = np.ascontiguousarray(inst["unary"], dtype=np.float64)
+        self.unary = np.ascontiguousarray(inst["unary"], dtype=self.dtype)
+        iv = inst["init_value"] if "init_value" in inst else None
+        self.init_value = (np.ascontiguousarray(iv, dtype=np.int32) if iv is not None
+                           else np.full(self.V, -1, np.int32))
+        rank = inst["var_rank"] if "var_rank" in inst else None
+        self.var_rank = (np.ascontiguousarray(rank, dtype=np.int32) if rank is not None
+                         else np.arange(self.V, dtype=np.int32))
+        self.mode_max = int(mode == "max")
+        self.stop_cycle, self.seed = int(stop_cycle), int(seed)
+        arity = np.diff(self.factor_ptr)
+        self.edge_fac = np.repeat(np.arange(self.F, dtype=np.int32), arity).astype(np.int32)
+        self.nbr_ptr, self.nbr_idx = distinct_neighbours(self.factor_ptr, self.edge_var,
+                                                         self.var_ptr, self.var_edge, self.edge_fac)
+        if len(self.nbr_idx) == 0:
+            self.nbr_idx = np.zeros(1, np.int32)
+        self.has_nbr = (np.diff(self.nbr_ptr) > 0).astype(np.uint8)
+        self.val = np.zeros(self.V, np.int32)
+        self.cost = np.zeros(self.V, self.dtype)
+        self.has_cost = np.zeros(self.V, np.uint8)
+        self.gain = np.zeros(self.V, self.dtype)
+        self.new_val = np.zeros(self.V, np.int32)
+        self.cycle = 0
+
+    def init(self):
+        lib().mgm_oracle_init(C.byref(self.fg), _p(self.unary64), _p(self.has_nbr),
+                              _p(self.init_value), self.mode_max, C.c_uint64(self.seed),
+                              _p(self.val))
+        self.has_cost[:] = 0
+        self.cost[:] = 0
+        for v in np.nonzero(self.has_nbr == 0)[0]:  # value_selection(value, cost), mgm.py:292
+            self.cost[v] = self.unary[self.unary_off[v] + self.val[v]]
+            self.has_cost[v] = 1
+        self.cycle = 0
+        return self
+
+    @property
+    def finished(self):
+        """mgm.py:404-407: cycle_count (= rounds done + 1) reached stop_cycle."""
+        return bool(self.stop_cycle and self.cycle + 1 >= self.stop_cycle)
+
+    def step(self, n=1):
+        gain_fn = getattr(lib(), "mgm_oracle_gain" + self.sfx)
+        decide_fn = getattr(lib(), "mgm_oracle_decide" + self.sfx)
+        for _ in range(n):
+            if self.finished:
+                break
+            gain_fn(C.byref(self.fg), _p(self.tables), _p(self.unary), _p(self.edge_fac),
+                    _p(self.has_nbr), _p(self.nbr_ptr), _p(self.nbr_idx), self.mode_max,
+                    C.c_uint64(self.seed), C.c_uint32(self.cycle + 1), _p(self.val), _p(self.cost),
+                    _p(self.has_cost), _p(self.gain), _p(self.new_val))
+            decide_fn(C.byref(self.fg), _p(self.has_nbr), _p(self.nbr_ptr), _p(self.nbr_idx),
+                      _p(self.var_rank), _p(self.gain), _p(self.new_val), _p(self.val),
+                      _p(self.cost))
+            self.cycle += 1
+        return self
+
+
 def var_con_to_edges(inst):
     """DSA fixtures list constraint ids per variable (var_con); turn them into edge ids."""
     factor_ptr, edge_var = inst["factor_ptr"], inst["edge_var"]

@@ -1,7 +1,7 @@
 """Pins the CPU oracle (oracle/dcop_oracle.c) to the reference's own lock-step trajectories.
 
 tests/golden/*.npz were produced by oracle/make_golden.py from the unmodified reference
-(pydcop/algorithms/maxsum.py, dsa.py) — see that script.  The f64 oracle keeps the reference's
+(pydcop/algorithms/maxsum.py, dsa.py; mgm.py by oracle/make_golden_mgm.py) — see those scripts.  The f64 oracle keeps the reference's
 floating-point operand order, so messages, send flags and values must agree BIT FOR BIT at every
 cycle; only the reported selection cost (whose summation order in the reference is message
 *arrival* order, maxsum.py:608-610) is compared to 1e-12.
@@ -86,6 +86,34 @@ def test_dsa_oracle_exact_vs_reference(name, dtype):
             o.step()
         assert np.array_equal(o.val, inst["value"][k]), (name, k)
     assert o.cycle == int(inst["cycle_count"][-1].max())
+
+
+@pytest.mark.parametrize("name", golden_names("mgm_"))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_mgm_oracle_exact_vs_reference(name, dtype):
+    """Values, current costs, gains and intended moves of every cycle (fixtures written by
+    oracle/make_golden_mgm.py from the unmodified pydcop/algorithms/mgm.py).  All fixture costs
+    are integers or multiples of 1/8, so float32 is exact as well."""
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    o = orc.MgmOracle(inst, dtype, mode=meta["mode"], seed=meta["seed"], **meta["params"]).init()
+    for k in range(meta["n_cycles"] + 1):
+        ran = False
+        if k:
+            before = o.cycle
+            o.step()
+            ran = o.cycle > before
+        assert np.array_equal(o.val, inst["value"][k]), (name, k)
+        known = ~np.isnan(inst["cost"][k])
+        assert np.array_equal(known, o.has_cost.astype(bool)), (name, k)
+        assert np.array_equal(o.cost[known], inst["cost"][k][known].astype(dtype)), (name, k)
+        if ran:
+            m = ~np.isnan(inst["gain"][k])
+            assert np.array_equal(m, o.has_nbr.astype(bool))
+            assert np.array_equal(o.gain[m], inst["gain"][k][m].astype(dtype)), (name, k)
+            assert np.array_equal(o.new_val[m], inst["new_value"][k][m]), (name, k)
+    # cycle_count of the reference = rounds done + 1 for connected variables (mgm.py:404)
+    assert o.cycle + 1 == int(inst["cycle_count"][-1].max())
+    assert not inst["finished"][o.has_nbr.astype(bool)].any() or o.finished
 
 
 def test_philox_matches_python_definition():
