@@ -251,6 +251,55 @@ int fg_dsa_cycle_commit(fg_dsa_t h);
 int fg_dsa_current(fg_dsa_t h, int32_t *buf_index, int64_t *cycle);
 int64_t fg_dsa_launch_count(fg_dsa_t h);
 
+/* ------------------------------------------------------------------------------------------
+ * MGM  (next-tier row §8f.4; replaces MgmComputation.on_start mgm.py:283-310, the value phase
+ * _handle_value_message :343-397 with _compute_best_value :434-455 and find_arg_optimal
+ * relations.py:1554-1591, and the gain phase _handle_gain_message :497-537 with the lexicographic
+ * tie break :574-591 — for ALL variables at once).  Same constraint-hypergraph arrays as DSA.
+ * One cycle = two launches: every variable's best local gain, then every variable's decision.
+ * Draws: Philox4x32-10 keyed (seed; canonical variable id, cycle) — cycle 0xffffffff for the
+ * initial value, else the 1-based round (the reference's cycle_count when it draws).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t abi_version, precision;
+  int32_t n_vars, n_factors, n_edges, n_classes;
+  const fg_class_t *classes;      /* HOST [n_classes] */
+  const void *dev_tables;         /* T[...] */
+  const void *dev_unary;          /* T[...] variable costs (cost_for_val) */
+  const int64_t *dev_unary_off;   /* [n_vars+1] */
+  const int32_t *dev_dom_size;    /* [n_vars] */
+  const int32_t *dev_var_id;      /* [n_vars] canonical id = Philox counter */
+  const int32_t *dev_var_rank;    /* [n_vars] position of the variable's NAME in sorted order */
+  const int32_t *dev_edge_var;    /* [n_edges] */
+  const int32_t *dev_edge_class;  /* [n_edges] */
+  const int32_t *dev_var_ptr;     /* [n_vars+1] */
+  const int32_t *dev_slot_edge;   /* [n_edges] incident edges of v in node.constraints order */
+  const int32_t *dev_nbr_ptr;     /* [n_vars+1] distinct neighbours (mgm.py:245-252) */
+  const int32_t *dev_nbr_idx;     /* [nbr_ptr[n_vars]] */
+  const int32_t *dev_init_value;  /* [n_vars] value index or -1 (random), may be NULL */
+  int32_t *dev_value;             /* [n_vars] in/out; variables without neighbours are preset by the
+                                     host (optimal_cost_value, relations.py:1641-1669) */
+  void *dev_cost;                 /* T[n_vars] current_cost (preset for isolated variables) */
+  uint8_t *dev_has_cost;          /* [n_vars] current_cost is not None */
+  void *dev_gain;                 /* T[n_vars] */
+  int32_t *dev_new_value;         /* [n_vars] */
+  int32_t mode_max;
+  int32_t stop_cycle;             /* 0 = never; a run ends when round + 1 >= stop_cycle (mgm.py:404) */
+  uint64_t seed;
+} fg_mgm_desc_t;
+
+typedef struct fg_mgm *fg_mgm_t;
+
+int fg_mgm_create(const fg_mgm_desc_t *desc, fg_mgm_t *out);
+int fg_mgm_destroy(fg_mgm_t h);
+const char *fg_mgm_last_error(fg_mgm_t h);
+/* on_start for the variables that have neighbours: initial_value or an injected random choice. */
+int fg_mgm_init(fg_mgm_t h, void *stream);
+/* up to n_cycles value+gain rounds (stops as the reference does at stop_cycle). */
+int fg_mgm_step(fg_mgm_t h, int32_t n_cycles, void *stream);
+int fg_mgm_current(fg_mgm_t h, int64_t *cycle, int32_t *finished);
+int64_t fg_mgm_launch_count(fg_mgm_t h);
+
 /* Solution cost (next-tier row §8f.1; pydcop/dcop/dcop.py:319-367): sum over factors of
  * table[value of scope] + sum over variables of unary[value]; one double in dev_out[0], number of
  * factors at +/-infinity ("violations") in dev_out[1]. */

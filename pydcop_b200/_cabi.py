@@ -68,6 +68,18 @@ class FgDsaDesc(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class FgMgmDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("precision", C.c_int32),
+                ("n_vars", C.c_int32), ("n_factors", C.c_int32), ("n_edges", C.c_int32),
+                ("n_classes", C.c_int32), ("classes", C.POINTER(FgClass)),
+                ("dev_tables", P), ("dev_unary", P), ("dev_unary_off", P), ("dev_dom_size", P),
+                ("dev_var_id", P), ("dev_var_rank", P), ("dev_edge_var", P), ("dev_edge_class", P),
+                ("dev_var_ptr", P), ("dev_slot_edge", P), ("dev_nbr_ptr", P), ("dev_nbr_idx", P),
+                ("dev_init_value", P), ("dev_value", P), ("dev_cost", P), ("dev_has_cost", P),
+                ("dev_gain", P), ("dev_new_value", P),
+                ("mode_max", C.c_int32), ("stop_cycle", C.c_int32), ("seed", C.c_uint64)]
+
+
 # every symbol include/pydcop_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "fg_abi_version": (C.c_int, []),
@@ -100,6 +112,13 @@ SYMBOLS = {
     "fg_dsa_current": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fg_dsa_launch_count": (C.c_int64, [P]),
     "fg_selftest_approx_match": (C.c_int, [C.c_int32, C.c_int64, P, P, C.c_double, P, P, P]),
+    "fg_mgm_create": (C.c_int, [C.POINTER(FgMgmDesc), C.POINTER(P)]),
+    "fg_mgm_destroy": (C.c_int, [P]),
+    "fg_mgm_last_error": (C.c_char_p, [P]),
+    "fg_mgm_init": (C.c_int, [P, P]),
+    "fg_mgm_step": (C.c_int, [P, C.c_int32, P]),
+    "fg_mgm_current": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "fg_mgm_launch_count": (C.c_int64, [P]),
     "fg_solution_cost": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(FgClass), P, P, P, P, P,
                                    C.c_int32, P, P]),
 }

@@ -188,8 +188,13 @@ class GpuSession:
         p = dict(self.params)
         if factory is not None:
             return factory(self.kind, layout, inst, dict(p, mode=self.mode))
-        from ..engine import DsaEngine, MaxSumEngine
+        from ..engine import DsaEngine, MaxSumEngine, MgmEngine
         precision = p.get("precision", "f64")
+        if self.kind == "mgm":  # variables are packed in name order: rank == index
+            return MgmEngine(layout, precision=precision, mode=self.mode,
+                             stop_cycle=p.get("stop_cycle", 0), seed=p.get("seed", 0),
+                             break_mode=p.get("break_mode", "lexic"),
+                             isolated_value=inst.get("isolated_value"))
         if self.kind == "maxsum":
             return MaxSumEngine(layout, precision=precision, mode=self.mode,
                                 damping=p.get("damping", 0.5),
@@ -228,7 +233,7 @@ class GpuSession:
                     break
                 engine.step(n)
                 cycle += n
-                done = bool(stop_cycle and cycle >= stop_cycle)
+                done = bool(stop_cycle and cycle >= stop_cycle) or bool(getattr(engine, "finished", False))
                 self._publish(engine, cycle, done)
                 if done:
                     break

@@ -1,0 +1,271 @@
+// MGM for all variables at once: C-ABI entry points fg_mgm_* and their kernels.
+// Separate translation unit: the MaxSum / DSA code in engine.cu is not recompiled differently.
+//
+// One thread per variable, any arity / domain sizes (the generic shape of k_dsa_step_generic).
+// Floating-point operand order follows pydcop/algorithms/mgm.py so that the f64 build equals the
+// reference's Python floats and the f32 build equals the f32 oracle (oracle/dcop_oracle_impl.h):
+//   relation value of x  = ((f1(x) + f2(x)) + f3(x)) ...   in node.constraints order (mgm.py:443)
+//   evaluation           = best + own cost(CURRENT value) + neighbours' costs       (:446-452)
+//   gain                 = current_cost - evaluation                                (:381)
+#include <cstdio>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+struct fg_mgm {
+  fg_mgm_desc_t d;
+  std::vector<fg_class_t> classes;
+  fg_class_t *dev_classes = nullptr;
+  int64_t cycle = 0;
+  int64_t launches = 0;
+  char err[512] = {0};
+};
+
+static char g_mgm_static_err[64] = "invalid handle";
+
+struct MgmSide {
+  const fg_class_t *classes;
+  const int32_t *dom_size, *var_id, *var_rank, *edge_var, *edge_class, *var_ptr, *slot_edge;
+  const int32_t *nbr_ptr, *nbr_idx;
+  const int64_t *unary_off;
+};
+
+static inline unsigned mgm_blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// on_start (mgm.py:296-310): connected variables take initial_value or random.choice(domain)
+__global__ void k_mgm_init(MgmSide g, int n_vars, const int32_t *__restrict__ init_value, uint64_t seed,
+                           int32_t *__restrict__ value, uint8_t *__restrict__ has_cost) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vars || g.nbr_ptr[v + 1] == g.nbr_ptr[v]) return;
+  has_cost[v] = 0;
+  if (init_value && init_value[v] >= 0) { value[v] = init_value[v]; return; }
+  uint32_t b[4];
+  philox4x32_10((uint32_t)g.var_id[v], FG_PHILOX_INIT_CYCLE, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+  value[v] = philox_choice(b, g.dom_size[v]);
+}
+
+// value phase (mgm.py:343-397): best local gain and intended move of every connected variable
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_mgm_gain(MgmSide g, int n_vars, const T *__restrict__ tables, const T *__restrict__ unary,
+           const int32_t *__restrict__ val, T *__restrict__ cost, uint8_t *__restrict__ has_cost,
+           T *__restrict__ gain, int32_t *__restrict__ new_val, int mode_max, uint64_t seed, uint32_t cycle) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vars) return;
+  const int n0 = g.nbr_ptr[v], n1 = g.nbr_ptr[v + 1];
+  if (n0 == n1) return;
+  const int cur = val[v];
+  const int d = g.dom_size[v];
+  T rel[FG_MAX_DOM];
+  const int s0 = g.var_ptr[v], s1 = g.var_ptr[v + 1];
+  for (int s = s0; s < s1; ++s) {
+    const int e = g.slot_edge[s];
+    const fg_class_t &c = g.classes[g.edge_class[e]];
+    const int le = e - c.first_edge;
+    const int f = le / c.arity, j = le - f * c.arity;
+    const int e0 = c.first_edge + f * c.arity;
+    int64_t base = 0, stride = 1, stride_j = 0;
+    for (int i = c.arity - 1; i >= 0; --i) {
+      if (i == j) stride_j = stride;
+      else base += (int64_t)val[g.edge_var[e0 + i]] * stride;
+      stride *= c.dom[i];
+    }
+    const T *t = tables + c.table_base + (int64_t)f * c.table_size + base;
+    if (s == s0) {
+      for (int x = 0; x < d; ++x) rel[x] = t[x * stride_j];
+    } else {
+      for (int x = 0; x < d; ++x) rel[x] += t[x * stride_j];
+    }
+  }
+  const T own = unary[g.unary_off[v] + cur];
+  T cst;
+  if (!has_cost[v]) {  // first round: current_cost (mgm.py:349-368)
+    cst = rel[cur];
+    cst += own;
+    for (int i = n0; i < n1; ++i) {
+      const int u = g.nbr_idx[i];
+      cst += unary[g.unary_off[u] + val[u]];
+    }
+    cost[v] = cst;
+    has_cost[v] = 1;
+  } else {
+    cst = cost[v];
+  }
+  // find_arg_optimal (relations.py:1554-1591): starts from the int32 extreme, strict improvement,
+  // exact equality collects ties in domain order
+  T best = mode_max ? (T)-2147483648.0 : (T)2147483647.0;
+  int nbest = 0;
+  for (int x = 0; x < d; ++x) {
+    const T c = rel[x];
+    if (mode_max ? (best < c) : (best > c)) { best = c; nbest = 1; }
+    else if (c == best) ++nbest;
+  }
+  T evaluation = best + own;  // own cost at the CURRENT value (mgm.py:449)
+  for (int i = n0; i < n1; ++i) {
+    const int u = g.nbr_idx[i];
+    evaluation += unary[g.unary_off[u] + val[u]];
+  }
+  const T gn = cst - evaluation;
+  gain[v] = gn;
+  int nv = cur;
+  if (mode_max ? (gn < (T)0) : (gn > (T)0)) {  // mgm.py:382-385
+    uint32_t b[4];
+    philox4x32_10((uint32_t)g.var_id[v], cycle, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+    int pick = philox_choice(b, nbest);
+    for (int x = 0; x < d; ++x) {
+      if (rel[x] == best) {
+        if (pick == 0) { nv = x; break; }
+        --pick;
+      }
+    }
+  }
+  new_val[v] = nv;
+}
+
+// gain phase (mgm.py:497-537,574-591): the variable moves when its gain is strictly the largest of
+// its neighbourhood, or ties for it and has the smallest name among the tied
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_mgm_decide(MgmSide g, int n_vars, const T *__restrict__ gain, const int32_t *__restrict__ new_val,
+             int32_t *__restrict__ val, T *__restrict__ cost) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vars) return;
+  const int n0 = g.nbr_ptr[v], n1 = g.nbr_ptr[v + 1];
+  if (n0 == n1) return;
+  const T mine = gain[v];
+  const int my_rank = g.var_rank[v];
+  T mx = gain[g.nbr_idx[n0]];
+  for (int i = n0 + 1; i < n1; ++i) {
+    const T gu = gain[g.nbr_idx[i]];
+    if (gu > mx) mx = gu;
+  }
+  bool move = false;
+  if (mine > mx) {
+    move = true;
+  } else if (mine == mx) {
+    move = true;
+    for (int i = n0; i < n1; ++i) {
+      const int u = g.nbr_idx[i];
+      if (gain[u] == mx && g.var_rank[u] < my_rank) move = false;
+    }
+  }
+  if (move) {  // value_selection(new_value, current_cost - gain), mgm.py:518; nobody reads val here
+    val[v] = new_val[v];
+    cost[v] = cost[v] - mine;
+  }
+}
+
+static MgmSide mgm_side(const fg_mgm *h) {
+  const fg_mgm_desc_t &d = h->d;
+  return MgmSide{h->dev_classes, d.dev_dom_size, d.dev_var_id, d.dev_var_rank, d.dev_edge_var, d.dev_edge_class,
+                 d.dev_var_ptr, d.dev_slot_edge, d.dev_nbr_ptr, d.dev_nbr_idx, d.dev_unary_off};
+}
+
+extern "C" int fg_mgm_create(const fg_mgm_desc_t *desc, fg_mgm_t *out) {
+  if (!desc || !out) return FG_ERR_ARG;
+  *out = nullptr;
+  if (desc->abi_version != FG_ABI_VERSION) return FG_ERR_ARG;
+  if (desc->precision != FG_F32 && desc->precision != FG_F64) return FG_ERR_ARG;
+  fg_mgm *h = new (std::nothrow) fg_mgm();
+  if (!h) return FG_ERR_ARG;
+  h->d = *desc;
+  h->classes.assign(desc->classes, desc->classes + desc->n_classes);
+  h->d.classes = h->classes.data();
+  *out = h;
+  for (auto &c : h->classes) {
+    if (c.arity < 1 || c.arity > FG_MAX_ARITY) {
+      snprintf(h->err, sizeof(h->err), "class arity %d out of range", c.arity);
+      return FG_ERR_ARG;
+    }
+    int64_t ts = 1;
+    for (int i = 0; i < c.arity; ++i) {
+      if (c.dom[i] < 1 || c.dom[i] > FG_MAX_DOM) {
+        snprintf(h->err, sizeof(h->err), "domain size %d out of range", c.dom[i]);
+        return FG_ERR_ARG;
+      }
+      ts *= c.dom[i];
+    }
+    if (ts != c.table_size) {
+      snprintf(h->err, sizeof(h->err), "class size mismatch");
+      return FG_ERR_ARG;
+    }
+  }
+  if (desc->n_vars > 0 && (!desc->dev_nbr_ptr || !desc->dev_value || !desc->dev_cost || !desc->dev_has_cost ||
+                           !desc->dev_gain || !desc->dev_new_value || !desc->dev_var_rank || !desc->dev_var_id)) {
+    snprintf(h->err, sizeof(h->err), "missing device array in the descriptor");
+    return FG_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    snprintf(h->err, sizeof(h->err), "no CUDA device visible: pydcop_b200 has no CPU fallback");
+    return FG_ERR_CUDA;
+  }
+  size_t bytes = sizeof(fg_class_t) * (h->classes.empty() ? 1 : h->classes.size());
+  CUDA_TRY(h, cudaMalloc(&h->dev_classes, bytes));
+  if (!h->classes.empty())
+    CUDA_TRY(h, cudaMemcpy(h->dev_classes, h->classes.data(), sizeof(fg_class_t) * h->classes.size(), cudaMemcpyHostToDevice));
+  return FG_OK;
+}
+
+extern "C" int fg_mgm_destroy(fg_mgm_t h) {
+  if (h && h->dev_classes) cudaFree(h->dev_classes);
+  delete h;
+  return FG_OK;
+}
+
+extern "C" const char *fg_mgm_last_error(fg_mgm_t h) { return h ? h->err : g_mgm_static_err; }
+
+extern "C" int fg_mgm_init(fg_mgm_t h, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  const fg_mgm_desc_t &d = h->d;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d.n_vars) {
+    k_mgm_init<<<mgm_blocks(d.n_vars, 128), 128, 0, st>>>(mgm_side(h), d.n_vars, d.dev_init_value, d.seed, d.dev_value,
+                                                          d.dev_has_cost);
+    ++h->launches;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->cycle = 0;
+  return FG_OK;
+}
+
+static bool mgm_finished(const fg_mgm *h) { return h->d.stop_cycle && h->cycle + 1 >= h->d.stop_cycle; }
+
+template <typename T>
+static int mgm_cycle_t(fg_mgm *h, cudaStream_t st) {
+  const fg_mgm_desc_t &d = h->d;
+  if (d.n_vars) {
+    k_mgm_gain<T><<<mgm_blocks(d.n_vars, 128), 128, 0, st>>>(
+        mgm_side(h), d.n_vars, (const T *)d.dev_tables, (const T *)d.dev_unary, d.dev_value, (T *)d.dev_cost,
+        d.dev_has_cost, (T *)d.dev_gain, d.dev_new_value, d.mode_max, d.seed, (uint32_t)(h->cycle + 1));
+    k_mgm_decide<T><<<mgm_blocks(d.n_vars, 256), 256, 0, st>>>(mgm_side(h), d.n_vars, (const T *)d.dev_gain,
+                                                                d.dev_new_value, d.dev_value, (T *)d.dev_cost);
+    h->launches += 2;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  ++h->cycle;
+  return FG_OK;
+}
+
+extern "C" int fg_mgm_step(fg_mgm_t h, int32_t n_cycles, void *stream) {
+  if (!h) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_cycles; ++i) {
+    if (mgm_finished(h)) break;
+    int rc = h->d.precision == FG_F64 ? mgm_cycle_t<double>(h, st) : mgm_cycle_t<float>(h, st);
+    if (rc != FG_OK) return rc;
+  }
+  return FG_OK;
+}
+
+extern "C" int fg_mgm_current(fg_mgm_t h, int64_t *cycle, int32_t *finished) {
+  if (!h) return FG_ERR_ARG;
+  if (cycle) *cycle = h->cycle;
+  if (finished) *finished = mgm_finished(h) ? 1 : 0;
+  return FG_OK;
+}
+
+extern "C" int64_t fg_mgm_launch_count(fg_mgm_t h) { return h ? h->launches : -1; }

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import EngineError, FgClass, FgDsaDesc, FgMaxSumDesc, FgVarClass
+from ._cabi import EngineError, FgClass, FgDsaDesc, FgMaxSumDesc, FgMgmDesc, FgVarClass
 from .layout import FactorGraphLayout
 
 PRECISIONS = {"f32": (_cabi.FG_F32, torch.float32, np.float32),
@@ -402,3 +402,176 @@ class DsaEngine(_EngineBase):
         """Current value index per variable, canonical variable order."""
         L = self.layout
         return L.vars_to_canonical(self.value[self.cur][:L.n_vars].cpu().numpy())
+
+
+def distinct_neighbours(layout: FactorGraphLayout):
+    """CSR (nbr_ptr, nbr_idx) of every variable's DISTINCT neighbours (the other variables of its
+    constraints, mgm.py:245-252) in internal variable ids, each list in order of first appearance
+    over the variable's constraints (node.constraints order, then scope order) — the order the
+    oracle uses, so neighbour costs are added in the same sequence."""
+    L = layout
+    V, E = L.n_vars, L.n_edges
+    if not E:
+        return np.zeros(V + 1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+    arity = np.array([c.arity for c in L.classes], dtype=np.int64)
+    first_edge = np.array([c.first_edge for c in L.classes], dtype=np.int64)
+    e = L.slot_edge.astype(np.int64)
+    cl = L.edge_class[e].astype(np.int64)
+    a = arity[cl]
+    e0 = first_edge[cl] + ((e - first_edge[cl]) // a) * a
+    A = int(arity.max())
+    vs, seqs, us = [], [], []
+    slot = np.arange(E, dtype=np.int64)
+    for j in range(A):
+        m = a > j
+        u = L.edge_var[(e0 + j)[m]].astype(np.int64)
+        v = L.slot_var[m].astype(np.int64)
+        keep = u != v
+        vs.append(v[keep])
+        us.append(u[keep])
+        seqs.append((slot[m] * A + j)[keep])
+    v, u, seq = np.concatenate(vs), np.concatenate(us), np.concatenate(seqs)
+    o = np.lexsort((seq, u, v))            # by (v, u), earliest occurrence first
+    v, u, seq = v[o], u[o], seq[o]
+    first = np.ones(len(v), dtype=bool)
+    first[1:] = (v[1:] != v[:-1]) | (u[1:] != u[:-1])
+    v, u, seq = v[first], u[first], seq[first]
+    o = np.lexsort((seq, v))               # back to first-appearance order inside each variable
+    v, u = v[o], u[o]
+    ptr = np.zeros(V + 1, dtype=np.int32)
+    np.cumsum(np.bincount(v, minlength=V), out=ptr[1:])
+    return ptr, (u.astype(np.int32) if len(u) else np.zeros(1, dtype=np.int32))
+
+
+class MgmEngine(_EngineBase):
+    """All-variables-at-once MGM (pydcop/algorithms/mgm.py; parameters :78-81).
+
+    var_rank       canonical order: position of each variable's NAME in sorted order, the
+                   lexicographic tie break of mgm.py:574-583 (default: the canonical index)
+    isolated_value canonical order: value index of the variables without neighbours
+                   (optimal_cost_value over the real domain values, relations.py:1641-1669);
+                   default: argopt of the own cost with ties broken on the value index
+    `break_mode` is accepted for the reference's signature; its 'random' branch is dead code in
+    the reference (mgm.py:541 compares with the `random` module) and both settings act as 'lexic'.
+    """
+
+    def __init__(self, layout: FactorGraphLayout, device=None, precision="f32", mode="min",
+                 stop_cycle=0, seed=0, break_mode="lexic", var_rank=None, isolated_value=None):
+        self.lib = _cabi.load()
+        self.device = _require_cuda(device)
+        self.layout = L = layout
+        prec, tdt, self.np_dtype = PRECISIONS[precision]
+        if break_mode not in ("lexic", "random"):
+            raise ValueError(f"invalid break_mode {break_mode!r}")
+        if mode not in ("min", "max"):
+            raise ValueError(f"invalid mode {mode!r}")
+        nbr_ptr, nbr_idx = distinct_neighbours(L)
+        has_nbr = np.diff(nbr_ptr) > 0
+        rank = (np.arange(L.n_vars, dtype=np.int32) if var_rank is None
+                else np.asarray(var_rank, dtype=np.int32))[L.var_order]
+        value0 = np.zeros(L.n_vars, dtype=np.int32)
+        cost0 = np.zeros(L.n_vars, dtype=np.float64)
+        iso = np.nonzero(~has_nbr)[0]
+        if isolated_value is not None:
+            value0[iso] = np.asarray(isolated_value, dtype=np.int32)[L.var_order][iso]
+        for v in iso:
+            c = L.unary[L.unary_off[v]:L.unary_off[v] + L.dom_size[v]]
+            if isolated_value is None:
+                value0[v] = int(np.argmin(c)) if mode == "min" else int(len(c) - 1 - np.argmax(c[::-1]))
+            cost0[v] = c[value0[v]]
+        self.has_nbr_host = has_nbr
+        with torch.cuda.device(self.device):
+            self.tables = self._dev(L.tables, tdt)
+            self.unary = self._dev(L.unary, tdt)
+            self.unary_off = self._dev(L.unary_off, torch.int64)
+            self.dom_size = self._dev(L.dom_size, torch.int32)
+            self.var_id = self._dev(L.var_order, torch.int32)
+            self.var_rank = self._dev(rank, torch.int32)
+            self.edge_var = self._dev(L.edge_var, torch.int32)
+            self.edge_class = self._dev(L.edge_class, torch.int32)
+            self.var_ptr = self._dev(L.var_ptr, torch.int32)
+            self.slot_edge = self._dev(L.slot_edge, torch.int32)
+            self.nbr_ptr = self._dev(nbr_ptr, torch.int32)
+            self.nbr_idx = self._dev(nbr_idx, torch.int32)
+            self.init_value = self._dev(L.init_value, torch.int32)
+            n = max(L.n_vars, 1)
+            self.value = self._dev(np.resize(value0, n) if L.n_vars else np.zeros(1, np.int32), torch.int32)
+            self.cost = self._dev(np.resize(cost0, n) if L.n_vars else np.zeros(1), tdt)
+            self.has_cost = self._dev((~np.resize(has_nbr, n)).astype(np.uint8) if L.n_vars
+                                      else np.zeros(1, np.uint8), torch.uint8)
+            self.gain = torch.zeros(n, dtype=tdt, device=self.device)
+            self.new_value = torch.zeros(n, dtype=torch.int32, device=self.device)
+        self._classes = _class_array(L)
+        d = FgMgmDesc()
+        d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
+        d.n_vars, d.n_factors, d.n_edges, d.n_classes = L.n_vars, L.n_factors, L.n_edges, len(L.classes)
+        d.classes = C.cast(self._classes, C.POINTER(FgClass))
+        d.dev_tables, d.dev_unary, d.dev_unary_off = _ptr(self.tables), _ptr(self.unary), _ptr(self.unary_off)
+        d.dev_dom_size, d.dev_var_id, d.dev_var_rank = _ptr(self.dom_size), _ptr(self.var_id), _ptr(self.var_rank)
+        d.dev_edge_var, d.dev_edge_class = _ptr(self.edge_var), _ptr(self.edge_class)
+        d.dev_var_ptr, d.dev_slot_edge = _ptr(self.var_ptr), _ptr(self.slot_edge)
+        d.dev_nbr_ptr, d.dev_nbr_idx = _ptr(self.nbr_ptr), _ptr(self.nbr_idx)
+        d.dev_init_value = _ptr(self.init_value)
+        d.dev_value, d.dev_cost, d.dev_has_cost = _ptr(self.value), _ptr(self.cost), _ptr(self.has_cost)
+        d.dev_gain, d.dev_new_value = _ptr(self.gain), _ptr(self.new_value)
+        d.mode_max, d.stop_cycle, d.seed = int(mode == "max"), int(stop_cycle), int(seed) & (2 ** 64 - 1)
+        self._desc = d
+        self._h = C.c_void_p()
+        self._check(self.lib.fg_mgm_create(C.byref(d), C.byref(self._h)), "fg_mgm_create")
+
+    def _last_error(self):
+        return (self.lib.fg_mgm_last_error(self._h) or b"").decode()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.fg_mgm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_mgm_init(self._h, self._stream()), "fg_mgm_init")
+        return self
+
+    def step(self, n_cycles=1):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fg_mgm_step(self._h, int(n_cycles), self._stream()), "fg_mgm_step")
+        return self
+
+    def _current(self):
+        c, f = C.c_int64(), C.c_int32()
+        self.lib.fg_mgm_current(self._h, C.byref(c), C.byref(f))
+        return c.value, bool(f.value)
+
+    @property
+    def cycle(self):
+        return self._current()[0]
+
+    @property
+    def finished(self):
+        return self._current()[1]
+
+    @property
+    def launch_count(self):
+        return int(self.lib.fg_mgm_launch_count(self._h))
+
+    def values(self):
+        """(value index, current cost or NaN while the reference's is None) per variable,
+        canonical variable order."""
+        L = self.layout
+        n = L.n_vars
+        cost = self.cost[:n].double().cpu().numpy()
+        cost[self.has_cost[:n].cpu().numpy() == 0] = np.nan
+        return L.vars_to_canonical(self.value[:n].cpu().numpy()), L.vars_to_canonical(cost)
+
+    def gains(self):
+        """(gain, intended value) of the last round per variable, canonical order."""
+        L = self.layout
+        n = L.n_vars
+        return (L.vars_to_canonical(self.gain[:n].double().cpu().numpy()),
+                L.vars_to_canonical(self.new_value[:n].cpu().numpy()))

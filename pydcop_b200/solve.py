@@ -8,7 +8,8 @@ the same result keys `pydcop solve` prints (pydcop/infrastructure/orchestrator.p
 pydcop/commands/solve.py:611-624): status, assignment, cost, violation, time, cycle, msg_count,
 msg_size.
 
-Parameters and defaults are the reference algorithms' own (maxsum.py:212-220, dsa.py:130-135).
+Parameters and defaults are the reference algorithms' own (maxsum.py:212-220, dsa.py:130-135,
+mgm.py:78-81).
 MaxSum has no termination test of its own (maxsum.py: it runs until `stop_cycle` or the
 orchestrator's timeout), so one of `stop_cycle` / `timeout` is required here as well; status is
 FINISHED when `stop_cycle` was reached and TIMEOUT otherwise, as in the reference
@@ -30,16 +31,20 @@ from .layout import build_layout
 MAXSUM_DEFAULTS = {"damping": 0.5, "damping_nodes": "both", "stability": 0.1, "noise": 0.01,
                    "start_messages": "leafs", "stop_cycle": 0}
 DSA_DEFAULTS = {"probability": 0.7, "p_mode": "fixed", "variant": "B", "stop_cycle": 0}
+MGM_DEFAULTS = {"break_mode": "lexic", "stop_cycle": 0}
+DEFAULTS = {"maxsum": MAXSUM_DEFAULTS, "dsa": DSA_DEFAULTS, "mgm": MGM_DEFAULTS}
 _CHOICES = {"damping_nodes": ("vars", "factors", "both", "none"),
             "start_messages": ("leafs", "leafs_vars", "all"),
-            "p_mode": ("fixed", "arity"), "variant": ("A", "B", "C")}
-ALGOS = {"maxsum": "maxsum", "maxsum_gpu": "maxsum", "dsa": "dsa", "dsa_gpu": "dsa"}
+            "p_mode": ("fixed", "arity"), "variant": ("A", "B", "C"),
+            "break_mode": ("lexic", "random")}
+ALGOS = {"maxsum": "maxsum", "maxsum_gpu": "maxsum", "dsa": "dsa", "dsa_gpu": "dsa",
+         "mgm": "mgm", "mgm_gpu": "mgm"}
 
 
 def check_params(kind: str, params: Optional[Dict[str, Any]]) -> Dict[str, Any]:
     """Defaults + type / choice validation, the job of AlgoParameterDef
     (pydcop/algorithms/__init__.py:180-290): unknown names and invalid values raise ValueError."""
-    defaults = MAXSUM_DEFAULTS if kind == "maxsum" else DSA_DEFAULTS
+    defaults = DEFAULTS[kind]
     out = dict(defaults)
     for k, v in (params or {}).items():
         if k not in defaults:
@@ -113,8 +118,21 @@ def solution_cost(dcop: ingest.DcopArrays, value_index, infinity: float = 10000.
     return int(hard.sum()), float(costs[~hard].sum())
 
 
+def name_rank(dcop: ingest.DcopArrays) -> np.ndarray:
+    """Position of every variable's name in sorted order: MGM's tie break (mgm.py:574-583)."""
+    order = sorted(range(dcop.n_vars), key=lambda i: dcop.var_names[i])
+    rank = np.zeros(dcop.n_vars, dtype=np.int32)
+    rank[order] = np.arange(dcop.n_vars, dtype=np.int32)
+    return rank
+
+
 def _default_engine(kind, layout, dcop, params, mode, precision, device, seed):
-    from .engine import DsaEngine, MaxSumEngine
+    from .engine import DsaEngine, MaxSumEngine, MgmEngine
+    if kind == "mgm":
+        return MgmEngine(layout, device=device, precision=precision, mode=mode,
+                         stop_cycle=params["stop_cycle"], seed=seed or 0,
+                         break_mode=params["break_mode"], var_rank=name_rank(dcop),
+                         isolated_value=isolated_values(dcop, mode))
     if kind == "maxsum":
         return MaxSumEngine(layout, device=device, precision=precision, mode=mode,
                             damping=params["damping"], damping_nodes=params["damping_nodes"],
@@ -134,7 +152,7 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
     """Run `algo` on `problem` and return pyDcop's result dict.
 
     problem      see `load`
-    algo         maxsum | dsa (the *_gpu spellings of the plugin modules are accepted)
+    algo         maxsum | dsa | mgm (the *_gpu spellings of the plugin modules are accepted)
     algo_params  the reference's parameter names; `stop_cycle` bounds the run in cycles
     timeout      wall-clock bound in seconds (checked every `chunk` cycles)
     precision    f32 | f64 (f64 reproduces the reference's double arithmetic bit for bit)
@@ -157,7 +175,8 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
     layout = build_layout(**inst)
     t_packed = time.perf_counter()
     if engine_factory is not None:
-        engine = engine_factory(kind, layout, inst, dict(params, mode=mode, seed=seed or 0))
+        engine = engine_factory(kind, layout, dict(inst, var_rank=name_rank(dcop)),
+                                dict(params, mode=mode, seed=seed or 0))
     else:
         engine = _default_engine(kind, layout, dcop, params, mode, precision, device, seed)
     engine.init()

@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     prog = r'''
 #include <stdio.h>
 #include "pydcop_b200.h"
-int main(void){printf("%zu %zu %zu\n", sizeof(fg_class_t), sizeof(fg_maxsum_desc_t), sizeof(fg_dsa_desc_t));return 0;}
+int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(fg_class_t), sizeof(fg_maxsum_desc_t), sizeof(fg_dsa_desc_t), sizeof(fg_mgm_desc_t), sizeof(fg_varclass_t));return 0;}
 '''
     with tempfile.TemporaryDirectory() as td:
         src, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
@@ -44,7 +44,8 @@ int main(void){printf("%zu %zu %zu\n", sizeof(fg_class_t), sizeof(fg_maxsum_desc
                         os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert [int(x) for x in out] == [C.sizeof(_cabi.FgClass), C.sizeof(_cabi.FgMaxSumDesc),
-                                     C.sizeof(_cabi.FgDsaDesc)]
+                                     C.sizeof(_cabi.FgDsaDesc), C.sizeof(_cabi.FgMgmDesc),
+                                     C.sizeof(_cabi.FgVarClass)]
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -53,12 +54,14 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     import numpy as np
     from pydcop_b200 import build_layout
-    from pydcop_b200.engine import EngineError, MaxSumEngine, DsaEngine
+    from pydcop_b200.engine import EngineError, MaxSumEngine, DsaEngine, MgmEngine
     L = build_layout([2, 2], [0, 2], [0, 1], np.zeros(4))
     with pytest.raises(EngineError):
         MaxSumEngine(L)
     with pytest.raises(EngineError):
         DsaEngine(L)
+    with pytest.raises(EngineError):
+        MgmEngine(L)
 
 
 def test_create_validates_its_descriptor_before_touching_the_device():
@@ -71,6 +74,14 @@ def test_create_validates_its_descriptor_before_touching_the_device():
     h = C.c_void_p()
     assert lib.fg_maxsum_create(None, C.byref(h)) == _cabi.FG_ERR_ARG
     assert lib.fg_dsa_create(None, C.byref(h)) == _cabi.FG_ERR_ARG
+    assert lib.fg_mgm_create(None, C.byref(h)) == _cabi.FG_ERR_ARG
+    m = _cabi.FgMgmDesc()
+    m.abi_version, m.precision = _cabi.FG_ABI_VERSION, 9
+    assert lib.fg_mgm_create(C.byref(m), C.byref(h)) == _cabi.FG_ERR_ARG and not h.value
+    m.precision, m.n_vars = _cabi.FG_F64, 3  # device arrays missing
+    assert lib.fg_mgm_create(C.byref(m), C.byref(h)) == _cabi.FG_ERR_ARG
+    assert b"missing device array" in lib.fg_mgm_last_error(h)
+    lib.fg_mgm_destroy(h)
 
     d = _cabi.FgMaxSumDesc()
     d.abi_version, d.precision = _cabi.FG_ABI_VERSION + 1, _cabi.FG_F32

@@ -47,35 +47,7 @@ def pydcop_ready():
     logging.disable(logging.NOTSET)
 
 
-class _OracleEngine:
-    """Test double with the MaxSumEngine / DsaEngine driving API, backed by the CPU oracle."""
-
-    def __init__(self, kind, layout, inst, params):
-        self.kind = kind
-        if kind == "maxsum":
-            self.o = orc.MaxSumOracle(inst, np.float64, mode=params["mode"],
-                                      **{k: params[k] for k in ("damping", "damping_nodes", "stability",
-                                                                "start_messages") if k in params})
-        else:
-            inst = dict(inst)
-            self.o = orc.DsaOracle(inst, np.float64, mode=params["mode"],
-                                   **{k: params[k] for k in ("probability", "p_mode", "variant",
-                                                             "stop_cycle", "seed") if k in params})
-
-    def init(self):
-        self.o.init()
-        if self.kind == "dsa":
-            pass
-        return self
-
-    def step(self, n):
-        self.o.step(n)
-        return self
-
-    def values(self):
-        if self.kind == "maxsum":
-            return self.o.value.copy(), self.o.value_cost.copy()
-        return self.o.val.copy()
+from _oracle_engine import OracleEngine as _OracleEngine  # noqa: E402
 
 
 @pytest.fixture
@@ -103,6 +75,10 @@ def test_modules_are_discovered_and_loaded(pydcop_ready):
     assert gpud.GRAPH_TYPE == refd.GRAPH_TYPE == "constraints_hypergraph"
     for p in refd.algo_params:
         assert {q.name: q for q in gpud.algo_params}[p.name] == p
+    refm, gpum = load_algorithm_module("mgm"), load_algorithm_module("mgm_gpu")
+    assert "mgm_gpu" in names and gpum.GRAPH_TYPE == refm.GRAPH_TYPE == "constraints_hypergraph"
+    for p in refm.algo_params:
+        assert {q.name: q for q in gpum.algo_params}[p.name] == p
 
 
 def test_memory_and_load_models_match_reference(pydcop_ready):
@@ -118,10 +94,13 @@ def test_memory_and_load_models_match_reference(pydcop_ready):
             assert gpu.communication_load(node, nb) == ref.communication_load(node, nb)
     hg = constraints_hypergraph.build_computation_graph(dcop)
     refd, gpud = load_algorithm_module("dsa"), load_algorithm_module("dsa_gpu")
+    refm, gpum = load_algorithm_module("mgm"), load_algorithm_module("mgm_gpu")
     for node in hg.nodes:
         assert gpud.computation_memory(node) == refd.computation_memory(node)
+        assert gpum.computation_memory(node) == refm.computation_memory(node)
         for nb in node.neighbors:
             assert gpud.communication_load(node, nb) == refd.communication_load(node, nb)
+            assert gpum.communication_load(node, nb) == refm.communication_load(node, nb)
 
 
 @retry_once
@@ -189,6 +168,29 @@ def test_solve_api_dsa_gpu(oracle_seam):
     algo = AlgorithmDef.build_with_default_param("dsa_gpu", {"stop_cycle": 40, "seed": 3}, mode=dcop.objective)
     assignment = solve(dcop, algo, "oneagent", timeout=8)
     assert assignment in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
+
+
+@retry_once
+def test_solve_api_mgm_gpu_matches_reference_mgm_fixed_point(oracle_seam):
+    """MGM through the unmodified orchestrator with --algo mgm_gpu: a proper colouring of the
+    3-variable chain (tests/api/test_api_solve.py style), a 1-opt assignment on the 10-variable
+    instance: no single variable can improve alone — MGM's fixed point."""
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    from pydcop.algorithms import AlgorithmDef
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    algo = AlgorithmDef.build_with_default_param("mgm_gpu", {"stop_cycle": 20, "seed": 3}, mode=dcop.objective)
+    assignment = solve(dcop, algo, "oneagent", timeout=8)
+    assert assignment in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
+    oracle_seam.reset()
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring_10_4_15_0.1.yml")])
+    algo = AlgorithmDef.build_with_default_param("mgm_gpu", {"stop_cycle": 30, "seed": 5}, mode=dcop.objective)
+    assignment = solve(dcop, algo, "oneagent", timeout=8)
+    _, cost = dcop.solution_cost(assignment, 1e9)
+    for v in dcop.variables.values():
+        for x in v.domain:
+            _, c = dcop.solution_cost(dict(assignment, **{v.name: x}), 1e9)
+            assert c >= cost - 1e-9, (v.name, x)
 
 
 def test_no_gpu_means_loud_failure_not_fallback(pydcop_ready):

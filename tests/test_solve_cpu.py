@@ -58,6 +58,18 @@ def test_dsa_is_reproducible_from_the_seed_and_respects_stop_cycle():
     assert a["assignment"]["lonely"] == 0
 
 
+def test_mgm_reaches_a_one_opt_assignment():
+    d = ingest.load_yaml(SPLIT)
+    res = S.solve(d, "mgm", {"stop_cycle": 15}, seed=2, engine_factory=OracleEngine)
+    assert res["status"] == "FINISHED" and res["cycle"] == 15 and res["algo"] == "mgm"
+    idx = [d.values_of(i).index(res["assignment"][n]) for i, n in enumerate(d.var_names)]
+    o = orc.MgmOracle(dict(d.instance(), var_rank=S.name_rank(d)), np.float64, mode="max",
+                      stop_cycle=15, seed=2).init().step(15)
+    assert o.val.tolist() == idx and o.cycle == 14
+    assert S.name_rank(ingest.from_arrays(random_factor_graph(12, 2, 5, 2, seed=1))).tolist() == \
+        [0, 1, 4, 5, 6, 7, 8, 9, 10, 11, 2, 3]   # v0 v1 v10 v11 v2 ... : names sort as strings
+
+
 def test_timeout_ends_an_unbounded_run():
     calls = []
     res = S.solve(SPLIT, "maxsum", timeout=0.3, chunk=5, engine_factory=OracleEngine,
@@ -90,7 +102,7 @@ def test_reference_defaults_are_mirrored():
         pytest.skip("reference not available")
     ref_shim.install()
     from pydcop.algorithms import load_algorithm_module
-    for name, mine in (("maxsum", S.MAXSUM_DEFAULTS), ("dsa", S.DSA_DEFAULTS)):
+    for name, mine in (("maxsum", S.MAXSUM_DEFAULTS), ("dsa", S.DSA_DEFAULTS), ("mgm", S.MGM_DEFAULTS)):
         ref = {p.name: p for p in load_algorithm_module(name).algo_params}
         # stop_cycle on MaxSum is this package's extension (also on the maxsum_gpu plugin module)
         assert set(ref) == set(mine) - ({"stop_cycle"} if name == "maxsum" else set())
@@ -135,7 +147,7 @@ def test_engine_construction_arguments_exist():
     tree = ast.parse(inspect.getsource(S._default_engine))
     calls = {n.func.id: n for n in ast.walk(tree)
              if isinstance(n, ast.Call) and isinstance(n.func, ast.Name)}
-    for cls in (E.MaxSumEngine, E.DsaEngine):
+    for cls in (E.MaxSumEngine, E.DsaEngine, E.MgmEngine):
         names = {k.arg for k in calls[cls.__name__].keywords}
         sig = set(inspect.signature(cls.__init__).parameters)
         assert names and names <= sig, (cls.__name__, names - sig)
