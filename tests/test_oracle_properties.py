@@ -90,3 +90,45 @@ def test_fixtures_regenerate_bit_for_bit(tmp_path):
         old = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         for k in keys:
             assert np.array_equal(new[k], old[k]), (name, k)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+def test_mgm_fixtures_regenerate_bit_for_bit(tmp_path):
+    """oracle/make_golden_mgm.py re-run against the live reference reproduces the committed MGM
+    trajectories, including the one with variable costs (whose sums the reference accumulates in a
+    set's iteration order — exact for the dyadic costs of the fixture, so run-to-run stable)."""
+    code = (
+        "import sys, os; sys.path.insert(0, %r); sys.argv = ['make_golden_mgm.py', 'mgm_ties', 'mgm_var_costs', 'mgm_max']\n"
+        "import make_golden_mgm as m; m.G.GOLDEN = %r; m.main()\n") % (os.path.join(ROOT, "oracle"), str(tmp_path))
+    subprocess.run([sys.executable, "-W", "ignore", "-c", code], check=True, capture_output=True, timeout=300)
+    for name in ("mgm_ties", "mgm_var_costs", "mgm_max"):
+        new = np.load(os.path.join(str(tmp_path), name + ".npz"))
+        old = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        for k in ("value", "cost", "gain", "new_value", "cycle_count", "var_rank", "tables", "unary"):
+            assert np.array_equal(new[k], old[k], equal_nan=True), (name, k)
+
+
+@settings(max_examples=20, deadline=None)
+@given(st.integers(4, 30), st.integers(2, 6), st.integers(2, 40), st.sampled_from([2, 3]),
+       st.integers(0, 10_000))
+def test_mgm_properties(n_vars, d, n_factors, arity, seed):
+    """Per round no two neighbours move together, and with integer costs and fresh (non-stale)
+    information the global cost never increases: MGM's monotonicity, which the restatement keeps
+    in min mode as long as costs are exact."""
+    arity = min(arity, n_vars)
+    inst = random_factor_graph(n_vars, d, n_factors, arity, seed=seed, int_tables=True, noise=0.0)
+    vp, ve = default_var_csr(n_vars, inst["edge_var"])
+    inst = dict(inst, var_ptr=vp, var_edge=ve)
+    o = orc.MgmOracle(inst, np.float64, mode="min", seed=seed).init()
+    a = orc.MgmOracle(inst, np.float64, mode="min", seed=seed).init()
+    assert np.array_equal(o.val, a.val)
+    for _ in range(8):
+        before = o.val.copy()
+        o.step()
+        moved = np.nonzero(o.val != before)[0]
+        ms = set(moved.tolist())
+        for v in moved:
+            nb = set(o.nbr_idx[o.nbr_ptr[v]:o.nbr_ptr[v + 1]].tolist()) if o.has_nbr[v] else set()
+            assert not (nb & ms), "two neighbours moved in the same round"
+    a.step(8)
+    assert np.array_equal(o.val, a.val)  # deterministic given the seed
