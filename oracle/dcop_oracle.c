@@ -43,14 +43,15 @@ void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t 
 
 /* DSA on_start (dsa.py:277-295): random initial value for connected variables (injected draw,
  * cycle = 0xffffffff); isolated variables take argopt of (own cost, value) — tuple ordering of
- * relations.py:1641-1669 with value == domain index. */
+ * relations.py:1641-1669 with value == domain index.  var_id (may be NULL = identity) is the
+ * Philox counter of each variable: its id in the whole problem when `g` is one shard of it. */
 void dsa_oracle_init(const fg_t *g, const double *unary, const uint8_t *has_nbr, int mode_max,
-                     uint64_t seed, int32_t *val) {
+                     uint64_t seed, const int32_t *var_id, int32_t *val) {
   for (int v = 0; v < g->V; ++v) {
     int d = g->dom_size[v];
     if (has_nbr[v]) {
       uint32_t b[4];
-      philox4x32_10((uint32_t)v, 0xFFFFFFFFu, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+      philox4x32_10((uint32_t)(var_id ? var_id[v] : v), 0xFFFFFFFFu, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
       val[v] = (int32_t)(((uint64_t)b[2] * (uint64_t)d) >> 32);
     } else {
       int best = 0;

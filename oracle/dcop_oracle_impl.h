@@ -265,7 +265,8 @@ static REAL FN(con_value)(const fg_t *g, const REAL *tables, const int32_t *val,
 void FN(dsa_oracle_step)(const fg_t *g, const REAL *tables, const int32_t *edge_fac,
                          const uint8_t *has_nbr, const REAL *con_opt, const double *prob,
                          int mode_max, int variant, uint64_t seed, uint32_t cycle,
-                         const int32_t *val, int32_t *val_next, REAL *val_cost) {
+                         const int32_t *var_id, const int32_t *val, int32_t *val_next,
+                         REAL *val_cost) {
 #pragma omp parallel
   {
     REAL cost[MAX_DOM];
@@ -322,7 +323,8 @@ void FN(dsa_oracle_step)(const fg_t *g, const REAL *tables, const int32_t *edge_
       }
       if (attempt) { /* probabilistic_change, dsa.py:407-417 */
         uint32_t b[4];
-        philox4x32_10((uint32_t)v, cycle, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+        philox4x32_10((uint32_t)(var_id ? var_id[v] : v), cycle, 0u, 0u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), b);
         double u = ((double)(b[0] >> 5) * 67108864.0 + (double)(b[1] >> 6)) / 9007199254740992.0;
         if (prob[v] > u) {
           val_next[v] = best[(int)(((uint64_t)b[2] * (uint64_t)nbest) >> 32)];

@@ -131,7 +131,9 @@ class DsaOracle(_Graph):
     """Lock-step DSA with injected Philox draws (oracle/philox.py)."""
 
     def __init__(self, inst, dtype=np.float64, mode="min", probability=0.7, p_mode="fixed",
-                 variant="B", stop_cycle=0, seed=0, **_ignored):
+                 variant="B", stop_cycle=0, seed=0, var_id=None, frozen=None, **_ignored):
+        """var_id: Philox counter per variable (default: its index); frozen: variables that are
+        never evaluated (ghosts of a partition, pydcop_b200/multigpu_dsa.py)."""
         if "var_edge" not in inst:  # DSA fixtures carry var_con (constraint ids), derive edges
             inst = dict(inst)
             inst["var_edge"] = var_con_to_edges(inst)
@@ -149,6 +151,9 @@ class DsaOracle(_Graph):
             for s in range(self.var_ptr[v], self.var_ptr[v + 1]):
                 n_count[v] += arity[self.edge_fac[self.var_edge[s]]] - 1
         self.has_nbr = (n_count > 0).astype(np.uint8)
+        if frozen is not None:
+            self.has_nbr[np.asarray(frozen, dtype=bool)] = 0
+        self.var_id = None if var_id is None else np.ascontiguousarray(var_id, dtype=np.int32)
         if p_mode == "arity":  # dsa.py:257-260
             self.prob = np.array([1 / n * 1.2 if n else 0.0 for n in n_count], dtype=np.float64)
         else:
@@ -163,21 +168,40 @@ class DsaOracle(_Graph):
         getattr(lib(), "dsa_oracle_constraint_optima" + self.sfx)(
             C.byref(self.fg), _p(self.tables), self.mode_max, _p(self.con_opt))
         lib().dsa_oracle_init(C.byref(self.fg), _p(self.unary), _p(self.has_nbr), self.mode_max,
-                              C.c_uint64(self.seed), _p(self.val))
+                              C.c_uint64(self.seed), self._vid(), _p(self.val))
         self.cycle = 0
         return self
 
+    def _vid(self):
+        return _p(self.var_id) if self.var_id is not None else C.c_void_p(0)
+
+    @property
+    def stopped(self):
+        return bool(self.stop_cycle and self.cycle >= self.stop_cycle)
+
+    def compute(self):
+        """One evaluate_cycle of every variable: reads `val`, fills `val_next`."""
+        if self.stopped:
+            return self
+        getattr(lib(), "dsa_oracle_step" + self.sfx)(
+            C.byref(self.fg), _p(self.tables), _p(self.edge_fac), _p(self.has_nbr),
+            _p(self.con_opt), _p(self.prob), self.mode_max, self.variant,
+            C.c_uint64(self.seed), C.c_uint32(self.cycle), self._vid(), _p(self.val),
+            _p(self.val_next), _p(self.val_cost))
+        return self
+
+    def commit(self):
+        if self.stopped:
+            return self
+        self.val, self.val_next = self.val_next, self.val
+        self.cycle += 1
+        return self
+
     def step(self, n=1):
-        fn = getattr(lib(), "dsa_oracle_step" + self.sfx)
         for _ in range(n):
-            if self.stop_cycle and self.cycle >= self.stop_cycle:
+            if self.stopped:
                 break
-            fn(C.byref(self.fg), _p(self.tables), _p(self.edge_fac), _p(self.has_nbr),
-               _p(self.con_opt), _p(self.prob), self.mode_max, self.variant,
-               C.c_uint64(self.seed), C.c_uint32(self.cycle), _p(self.val), _p(self.val_next),
-               _p(self.val_cost))
-            self.val, self.val_next = self.val_next, self.val
-            self.cycle += 1
+            self.compute().commit()
         return self
 
 

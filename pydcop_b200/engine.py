@@ -258,7 +258,10 @@ class DsaEngine(_EngineBase):
 
     def __init__(self, layout: FactorGraphLayout, device=None, precision="f32", mode="min",
                  probability=0.7, p_mode="fixed", variant="B", stop_cycle=0, seed=0,
-                 isolated_value=None):
+                 isolated_value=None, var_global_id=None, frozen=None):
+        """var_global_id / frozen (canonical order) serve the multi-GPU partition
+        (pydcop_b200/multigpu_dsa.py): the Philox counter of each variable when the layout is a
+        shard of a larger problem, and the ghost variables whose value is only copied through."""
         self.lib = _cabi.load()
         self.device = _require_cuda(device)
         self.layout = L = layout
@@ -272,6 +275,10 @@ class DsaEngine(_EngineBase):
         if L.n_edges:
             np.add.at(n_count, L.slot_var, arity[L.edge_class[L.slot_edge]] - 1)
         has_nbr = (n_count > 0).astype(np.uint8)
+        if frozen is not None:
+            has_nbr[np.asarray(frozen, dtype=bool)[L.var_order]] = 0
+        var_id = (L.var_order if var_global_id is None
+                  else np.asarray(var_global_id, dtype=np.int32)[L.var_order])
         if p_mode == "arity":  # dsa.py:257-260: 1 / n_count * 1.2
             with np.errstate(divide="ignore"):
                 prob = np.where(n_count > 0, 1.0 / np.maximum(n_count, 1) * 1.2, 0.0)
@@ -282,7 +289,7 @@ class DsaEngine(_EngineBase):
             isolated_value = np.asarray(isolated_value, dtype=np.int32)[L.var_order]
         else:
             isolated_value = np.zeros(L.n_vars, dtype=np.int32)
-            for v in np.nonzero(has_nbr == 0)[0]:
+            for v in np.nonzero(n_count == 0)[0]:  # (frozen ghosts are filled by the exchange)
                 c = L.unary[L.unary_off[v]:L.unary_off[v] + L.dom_size[v]]
                 if mode == "min":
                     isolated_value[v] = int(np.argmin(c))
@@ -292,7 +299,7 @@ class DsaEngine(_EngineBase):
         with torch.cuda.device(self.device):
             self.tables = self._dev(L.tables, tdt)
             self.dom_size = self._dev(L.dom_size, torch.int32)
-            self.var_id = self._dev(L.var_order, torch.int32)
+            self.var_id = self._dev(var_id, torch.int32)
             self.edge_var = self._dev(L.edge_var, torch.int32)
             self.edge_class = self._dev(L.edge_class, torch.int32)
             self.var_ptr = self._dev(L.var_ptr, torch.int32)

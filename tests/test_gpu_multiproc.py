@@ -65,3 +65,51 @@ def test_two_process_sharded_matches_single_gpu(mode):
             p.kill()
     assert all(r[1] == "ok" for r in results), results
     assert all(r[2] == mode for r in results), results
+
+
+def _dsa_worker(rank, world, port, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        from pydcop_b200.engine import DsaEngine
+        from pydcop_b200.generators import random_factor_graph
+        from pydcop_b200.layout import build_layout
+        from pydcop_b200.multigpu_dsa import ShardedDsa
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        inst = random_factor_graph(4000, 20, 12000, 2, seed=22, noise=0.0)
+        inst["tables"] = np.floor(inst["tables"] / 3.0).astype(np.float32)
+        sh = ShardedDsa(inst, rank, world, dev, precision="f32", variant="B", seed=9).init().step(10)
+        got = sh.values()
+        ok = True
+        if rank == 0:
+            ref = DsaEngine(build_layout(**inst), device=dev, precision="f32", variant="B", seed=9).init().step(10)
+            ok = bool(np.array_equal(got, ref.values()))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok" if ok else "MISMATCH"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
+
+
+def test_two_process_sharded_dsa_matches_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dsa_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=90) for _ in procs]
+    for p in procs:
+        p.join(timeout=20)
+        if p.is_alive():
+            p.kill()
+    assert all(r[1] == "ok" for r in results), results
