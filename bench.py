@@ -132,8 +132,16 @@ def side_workload(args, dev):
     inst = {"c3": G.config_c3, "c5": G.config_c5, "target": G.config_target, "c4": G.config_c4}[w]()
     L = build_layout(**inst)
     vb = 4 if args.precision == "f32" else 8
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and w != "c4":
+        raise SystemExit("--workload %s is a single-GPU side line; multi-GPU runs: c2 (MaxSum) and c4 (DSA)" % w)
     if w == "c4":
-        eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
+        if world > 1:   # strong scaling: the same 1M-variable problem over `world` GPUs
+            from pydcop_b200.multigpu_dsa import ShardedDsa
+            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1)
+        else:
+            eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
         units, metric = L.n_vars, "dsa_variable_updates_per_s"
         d, k = 20, 6
         alg = L.n_vars * (k * (vb * d + 4 + 8 + vb) + 8)   # ~584 B per variable update
@@ -159,14 +167,24 @@ def side_workload(args, dev):
         evs.append((a, b))
     torch.cuda.synchronize(dev)
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        if rank != 0:
+            return
     peaks, kind = load_peaks()
     ach = alg / (ms * 1e-3) / 1e9
-    print(json.dumps({"metric": metric, "value": units / (ms * 1e-3), "unit": "updates/s", "n_gpus": 1,
-                      "steps": args.steps, "ms_per_step": ms, "dtype": args.precision,
-                      "config": {"workload": w, "n_vars": L.n_vars, "n_factors": L.n_factors,
-                                 "n_edges": L.n_edges},
-                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_step": int(alg)}}))
+    line = {"metric": metric, "value": units / (ms * 1e-3), "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "ms_per_step": ms, "dtype": args.precision,
+            "scaling": "strong" if world > 1 else None,
+            "config": {"workload": w, "n_vars": L.n_vars, "n_factors": L.n_factors, "n_edges": L.n_edges},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
+                         "frac": ach / (peaks["hbm_gbs"] * world), "algorithmic_bytes_per_step": int(alg)}}
+    if world > 1:
+        line["config"]["boundary_values"] = int(eng.shard.n_boundary)
+    print(json.dumps(line))
 
 
 def main():
