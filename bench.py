@@ -127,9 +127,10 @@ def side_workload(args, dev):
     import torch
     from pydcop_b200 import build_layout
     from pydcop_b200 import generators as G
-    from pydcop_b200.engine import DsaEngine, MaxSumEngine
+    from pydcop_b200.engine import DsaEngine, MaxSumEngine, MgmEngine
     w = args.workload
-    inst = {"c3": G.config_c3, "c5": G.config_c5, "target": G.config_target, "c4": G.config_c4}[w]()
+    inst = {"c3": G.config_c3, "c5": G.config_c5, "target": G.config_target, "c4": G.config_c4,
+            "mgm": G.config_c4}[w]()
     L = build_layout(**inst)
     vb = 4 if args.precision == "f32" else 8
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -145,6 +146,11 @@ def side_workload(args, dev):
         units, metric = L.n_vars, "dsa_variable_updates_per_s"
         d, k = 20, 6
         alg = L.n_vars * (k * (vb * d + 4 + 8 + vb) + 8)   # ~584 B per variable update
+    elif w == "mgm":    # MGM on the C4 instance (DESIGN.md §10 for the byte count)
+        eng = MgmEngine(L, device=dev, precision=args.precision, seed=1)
+        units, metric = L.n_vars, "mgm_variable_updates_per_s"
+        d, k = 20, 6
+        alg = L.n_vars * ((k * d + 2 * k + 2) * vb + 8 * k + 8)
     else:
         eng = MaxSumEngine(L, device=dev, precision=args.precision)
         units, metric = 2 * L.n_edges, METRIC
@@ -196,9 +202,9 @@ def main():
     ap.add_argument("--vars-per-gpu", type=int, default=100_000)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "target", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "target", "c4", "mgm"],
                     help="c2 (default, the driver's line) | c3 Ising 1024^2 | c5 arity-3 | target 1M vars "
-                         "| c4 DSA 1M vars d=20 (variable updates/s)")
+                         "| c4 DSA 1M vars d=20 (variable updates/s) | mgm: MGM on the c4 instance")
     ap.add_argument("--profile", action="store_true",
                     help="lean run for ncu: init + warmup + steps back to back, no flush/e2e/JSON")
     args = ap.parse_args()

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Everything that was written after round 1's GPU budget ran out, in one gpurun call (one GPU):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_validate_pending.sh'
+# Outputs land in gpurun_out/pending_* ; copy what should be judged into profiles/.
+set -u
+mkdir -p gpurun_out
+run() { echo "== $*" | tee -a gpurun_out/pending_summary.txt; "$@" 2>&1 | tail -n 25 | tee -a gpurun_out/pending_summary.txt; }
+: > gpurun_out/pending_summary.txt
+# 1. parity: MGM kernels, direct solve entry, session with the vectorised tabulation, sharded DSA emulation
+run timeout 300 python -m pytest tests/test_gpu_zz_mgm.py -q
+run timeout 200 python -m pytest tests/test_gpu_solve.py tests/test_gpu_session.py -q
+run timeout 300 python -m pytest tests/test_gpu_zz_sharded_dsa.py -q
+# 2. first MGM number (C4 instance, 1M variables) and the DSA line for comparison
+run timeout 300 python bench.py --workload mgm --steps 200 --warmup 5
+run timeout 300 python bench.py --workload c4 --steps 200 --warmup 5
+# 3. launch list of the MGM step for profiles/
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
+    --log-file gpurun_out/pending_mgm_launches.csv python bench.py --workload mgm --steps 10 --warmup 3 --profile \
+    > gpurun_out/pending_mgm_ncu.log 2>&1
+echo "== done" | tee -a gpurun_out/pending_summary.txt
