@@ -450,6 +450,29 @@ def distinct_neighbours(layout: FactorGraphLayout):
     return ptr, (u.astype(np.int32) if len(u) else np.zeros(1, dtype=np.int32))
 
 
+def mgm_host_arrays(layout: FactorGraphLayout, mode="min", var_rank=None, isolated_value=None):
+    """Everything MgmEngine derives on the host, in the layout's INTERNAL variable order: the
+    neighbour CSR, name ranks, and the preset value / cost of the variables without neighbours
+    (mgm.py:285-294: optimal_cost_value, then finished)."""
+    L = layout
+    nbr_ptr, nbr_idx = distinct_neighbours(L)
+    has_nbr = np.diff(nbr_ptr) > 0
+    rank = (np.arange(L.n_vars, dtype=np.int32) if var_rank is None
+            else np.asarray(var_rank, dtype=np.int32))[L.var_order]
+    value0 = np.zeros(L.n_vars, dtype=np.int32)
+    cost0 = np.zeros(L.n_vars, dtype=np.float64)
+    iso = np.nonzero(~has_nbr)[0]
+    if isolated_value is not None:
+        value0[iso] = np.asarray(isolated_value, dtype=np.int32)[L.var_order][iso]
+    for v in iso:
+        c = L.unary[L.unary_off[v]:L.unary_off[v] + L.dom_size[v]]
+        if isolated_value is None:
+            value0[v] = int(np.argmin(c)) if mode == "min" else int(len(c) - 1 - np.argmax(c[::-1]))
+        cost0[v] = c[value0[v]]
+    return dict(nbr_ptr=nbr_ptr, nbr_idx=nbr_idx, has_nbr=has_nbr, var_rank=rank.astype(np.int32),
+                value0=value0, cost0=cost0)
+
+
 class MgmEngine(_EngineBase):
     """All-variables-at-once MGM (pydcop/algorithms/mgm.py; parameters :78-81).
 
@@ -472,20 +495,9 @@ class MgmEngine(_EngineBase):
             raise ValueError(f"invalid break_mode {break_mode!r}")
         if mode not in ("min", "max"):
             raise ValueError(f"invalid mode {mode!r}")
-        nbr_ptr, nbr_idx = distinct_neighbours(L)
-        has_nbr = np.diff(nbr_ptr) > 0
-        rank = (np.arange(L.n_vars, dtype=np.int32) if var_rank is None
-                else np.asarray(var_rank, dtype=np.int32))[L.var_order]
-        value0 = np.zeros(L.n_vars, dtype=np.int32)
-        cost0 = np.zeros(L.n_vars, dtype=np.float64)
-        iso = np.nonzero(~has_nbr)[0]
-        if isolated_value is not None:
-            value0[iso] = np.asarray(isolated_value, dtype=np.int32)[L.var_order][iso]
-        for v in iso:
-            c = L.unary[L.unary_off[v]:L.unary_off[v] + L.dom_size[v]]
-            if isolated_value is None:
-                value0[v] = int(np.argmin(c)) if mode == "min" else int(len(c) - 1 - np.argmax(c[::-1]))
-            cost0[v] = c[value0[v]]
+        h = mgm_host_arrays(L, mode, var_rank, isolated_value)
+        nbr_ptr, nbr_idx, has_nbr, rank = h["nbr_ptr"], h["nbr_idx"], h["has_nbr"], h["var_rank"]
+        value0, cost0 = h["value0"], h["cost0"]
         self.has_nbr_host = has_nbr
         with torch.cuda.device(self.device):
             self.tables = self._dev(L.tables, tdt)
