@@ -17,4 +17,11 @@ run timeout 300 python bench.py --workload c4 --steps 200 --warmup 5
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/pending_mgm_launches.csv python bench.py --workload mgm --steps 10 --warmup 3 --profile \
     > gpurun_out/pending_mgm_ncu.log 2>&1
+# 4. one full capture each of the DSA step (19 % of the roofline in round 1, never profiled) and the MGM gain kernel
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_dsa_step -s 4 -c 1 \
+    -o gpurun_out/pending_dsa_c4 python bench.py --workload c4 --steps 3 --warmup 3 --profile \
+    > gpurun_out/pending_dsa_ncu.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_mgm_gain -s 4 -c 1 \
+    -o gpurun_out/pending_mgm_gain python bench.py --workload mgm --steps 3 --warmup 3 --profile \
+    > gpurun_out/pending_mgm_gain_ncu.log 2>&1
 echo "== done" | tee -a gpurun_out/pending_summary.txt
