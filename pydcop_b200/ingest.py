@@ -698,16 +698,16 @@ def save_instance(path: Union[str, os.PathLike], dcop: DcopArrays, table_dtype=n
             off += a.nbytes
         return off
 
-    # header length depends on the offsets it contains: iterate to a fixed point
-    hlen = 0
-    for _ in range(8):
-        layout(16 + hlen)
-        blob = json.dumps(header).encode("utf-8")
-        if len(blob) <= hlen:
-            break
-        hlen = len(blob) + 64
-    blob = blob.ljust(hlen, b" ")
+    # the header holds the offsets, and the offsets depend on the header's length: reserve room
+    # for the longest possible offsets (20 digits each) on top of the header written with zeros
+    layout(0)
+    for d in header["arrays"].values():
+        d["offset"] = 0
+    hlen = len(json.dumps(header).encode("utf-8")) + 20 * len(arrs) + 64
     end = layout(16 + hlen)
+    blob = json.dumps(header).encode("utf-8")
+    assert len(blob) <= hlen
+    blob = blob.ljust(hlen, b" ")
     with open(path, "wb") as f:
         f.write(MAGIC)
         f.write(struct.pack("<Q", hlen))
