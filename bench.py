@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 METRIC = "maxsum_edge_message_updates_per_s"
 UNIT = "updates/s"
 E2E_CYCLES = 30  # cycles per end-to-end solve (upload -> cycles -> read assignment)
+PARITY_CYCLES = 12  # N > 1: sharded run vs one engine with the whole problem, outside the timed regions
 
 
 def load_peaks():
@@ -364,7 +365,21 @@ def main():
                     f"assignment back to host; {e2e_ms:.3f} ms per solve"
                     + (" (max over ranks; bytes summed over ranks)" if world > 1 else "")}
 
+    parity = None
     if world > 1:
+        # outside every timed region: the sharded run (halo path as timed) against ONE engine holding the
+        # whole problem on rank 0's GPU, a few cycles from a fresh start — far from convergence, so a wrong
+        # or late boundary row changes the assignment
+        runner.init()
+        runner.step(PARITY_CYCLES)
+        got = runner.values()
+        if rank == 0:
+            ref = MaxSumEngine(build_layout(**inst), device=dev, precision=args.precision,
+                               record_sent=False).init().step(PARITY_CYCLES)
+            want = ref.values()[0]
+            parity = {"cycles": PARITY_CYCLES, "assignment_equals_single_gpu": bool(np.array_equal(got, want)),
+                      "n_differ": int((np.asarray(got) != np.asarray(want)).sum())}
+            del ref
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
@@ -391,6 +406,8 @@ def main():
                                "profiles/)"},
         "e2e": e2e,
     }
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(inst, L)
     print(json.dumps(line))

@@ -101,8 +101,11 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan
     own_f_edges = _ranges(factor_ptr[own_f], arity[own_f])
     ghost_vars = np.unique(edge_var[own_f_edges][e_vowner[own_f_edges] != rank]) if len(own_f_edges) \
         else np.zeros(0, np.int64)
-    # remote-factor edges of own variables (-> stub factors), ascending global edge id
+    # remote-factor edges of own variables (-> stub factors), grouped by the rank that produces
+    # their row, ascending global edge id inside a group: the rows one peer sends land in ONE
+    # contiguous block of this rank's r buffer, so its remote stores coalesce
     stub_edges = np.nonzero((e_vowner == rank) & (e_fowner != rank))[0]
+    stub_edges = stub_edges[np.argsort(e_fowner[stub_edges], kind="stable")]
 
     # local variable ids: own (ascending global id) then ghosts
     n_own, n_ghost = len(own_v), len(ghost_vars)
@@ -311,6 +314,15 @@ class HaloExchange:
                 flags[idx(recv_e)] = inn
 
 
+def destination_order(dst_off, rows_per_peer) -> np.ndarray:
+    """Permutation of the send rows (which are grouped by peer) that sorts every peer's group by
+    destination offset and leaves the grouping intact."""
+    dst_off = np.asarray(dst_off, dtype=np.int64)
+    peer = np.repeat(np.arange(len(rows_per_peer)), np.asarray(rows_per_peer, dtype=np.int64))
+    assert len(peer) == len(dst_off)
+    return np.lexsort((dst_off, peer)).astype(np.int64)
+
+
 class PeerPush:
     """Halo over NVLink peer memory: every rank maps the peers' message buffers (torch CUDA IPC) and
     its push kernel stores each boundary row straight into the consumer's `next` buffer; a barrier
@@ -370,9 +382,15 @@ class PeerPush:
         peer_of_q = np.repeat(np.arange(W), p.send_q_rows)
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)  # noqa: E731
         # absolute destination addresses for `next` buffer index b (0 / 1)
-        self.dst_r = [to(base[peer_of_r, 2 + b] + dst_r_off * elem) for b in range(2)]
-        self.dst_q = [to(base[peer_of_q, 0 + b] + dst_q_off * elem) for b in range(2)]
-        self.src_r_off, self.src_q_off = h.sr[0], h.sq[0]
+        # rows are independent: issue them in DESTINATION order inside each peer group, so that
+        # consecutive threads of the push kernel store to consecutive remote addresses (the local
+        # reads become gathers instead, which HBM absorbs)
+        perm_r = destination_order(dst_r_off, p.send_r_rows)
+        perm_q = destination_order(dst_q_off, p.send_q_rows)
+        self.dst_r = [to((base[peer_of_r, 2 + b] + dst_r_off * elem)[perm_r]) for b in range(2)]
+        self.dst_q = [to((base[peer_of_q, 0 + b] + dst_q_off * elem)[perm_q]) for b in range(2)]
+        self.src_r_off = to(np.asarray(p.send_r_off, dtype=np.int64)[perm_r])
+        self.src_q_off = to(np.asarray(p.send_q_off, dtype=np.int64)[perm_q])
         self.n_r, self.n_q = len(p.send_r_len), len(p.send_q_len)
         self.dom = int(p.layout.uniform_dom)
         self.token = torch.zeros(1, device=dev)

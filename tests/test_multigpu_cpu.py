@@ -159,3 +159,46 @@ def test_more_ranks_than_variables():
     for a in range(8):
         for b in range(8):
             assert plans[a].send_r_split[b] == plans[b].recv_r_split[a]
+
+
+def test_rows_of_one_peer_land_in_one_block_and_push_order_follows_destinations():
+    """Stub factors are grouped by producing rank, so the r rows rank a sends to rank b occupy one
+    contiguous block of b's buffer; `destination_order` then makes a's push walk that block in
+    address order (what the peer-push kernel needs to coalesce its NVLink stores)."""
+    from pydcop_b200.multigpu import destination_order
+    inst = random_factor_graph(400, 10, 800, 2, seed=11)
+    world = 4
+    plans = [build_shard(inst, r, world) for r in range(world)]
+    d = 10
+    for b, pb in enumerate(plans):
+        pos = 0
+        for a in range(world):
+            n = pb.recv_r_rows[a]
+            off = np.asarray(pb.recv_r_off[pos:pos + n])
+            if n:
+                assert np.array_equal(off, off[0] + d * np.arange(n)), (a, b)   # dense, ascending
+            pos += n
+    # the sender's permutation: grouped by peer as before, ascending destination inside a group
+    rng = np.random.default_rng(0)
+    rows = [3, 0, 5, 2]
+    dst = rng.permutation(100)[:10] * 40
+    perm = destination_order(dst, rows)
+    assert sorted(perm.tolist()) == list(range(10))
+    pos = 0
+    for n in rows:
+        grp = perm[pos:pos + n]
+        assert set(grp.tolist()) == set(range(pos, pos + n))
+        assert (np.diff(dst[grp]) > 0).all()
+        pos += n
+    # q rows: what a sends to b, taken in destination order, is dense inside every ghost class
+    for a, pa in enumerate(plans):
+        pos = 0
+        for b in range(world):
+            n = pa.send_q_rows[b]
+            if n:
+                pbq = plans[b]
+                rpos = sum(pbq.recv_q_rows[:a])
+                off = np.sort(np.asarray(pbq.recv_q_off[rpos:rpos + n]))
+                gaps = int((np.diff(off) != d).sum())
+                assert gaps <= len([c for c in pbq.layout.var_classes if c.tag]), (a, b, gaps)
+            pos += n
