@@ -64,6 +64,7 @@ class ShardPlan:
     n_cut_edges: int
     own_factor_edges: Optional[np.ndarray] = None   # global edge ids of the local real edges
     stub_edges: Optional[np.ndarray] = None         # global edge ids behind the local stub factors
+    local_inst: Optional[Dict[str, np.ndarray]] = None   # the closed local graph as front-door arrays
 
 
 def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan:
@@ -184,7 +185,9 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan
         send_r_edge=fe, send_q_edge=ve, recv_r_edge=ve, recv_q_edge=fe,
         send_r_split=sr_split, send_q_split=sq_split, recv_r_split=rr_split, recv_q_split=rq_split,
         send_r_rows=sr_rows, send_q_rows=sq_rows, recv_r_rows=rr_rows, recv_q_rows=rq_rows,
-        n_cut_edges=int(cut.sum()), own_factor_edges=own_f_edges, stub_edges=stub_edges)
+        n_cut_edges=int(cut.sum()), own_factor_edges=own_f_edges, stub_edges=stub_edges,
+        local_inst=dict(dom_size=l_dom, factor_ptr=l_factor_ptr, edge_var=l_edge_var, tables=l_tables,
+                        unary=l_unary, var_ptr=l_var_ptr, var_edge=l_var_edge, init_value=l_init))
 
 
 def _ranges(starts, lengths):

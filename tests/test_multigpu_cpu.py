@@ -202,3 +202,70 @@ def test_rows_of_one_peer_land_in_one_block_and_push_order_follows_destinations(
                 gaps = int((np.diff(off) != d).sum())
                 assert gaps <= len([c for c in pbq.layout.var_classes if c.tag]), (a, b, gaps)
             pos += n
+
+
+@pytest.mark.parametrize("kind,world,params", [
+    ("random", 2, {}),
+    ("random", 4, dict(damping_nodes="vars", start_messages="leafs_vars")),
+    ("grid", 3, dict(mode="max", start_messages="all")),
+])
+def test_sharded_maxsum_emulated_with_the_oracle_is_bit_identical(kind, world, params):
+    """The partition itself (ghost variables, stub factors grouped by producing rank, `links` order
+    of every own variable) run cycle by cycle with one oracle per shard and an in-process exchange
+    of the boundary rows: messages on every real edge and the assignment must equal the
+    single-process oracle bit for bit.  (The GPU version of this test is tests/test_gpu_sharded.py.)"""
+    import oracle as orc
+    from pydcop_b200.layout import default_var_csr
+    inst = _instance(kind)
+    V, E = len(inst["dom_size"]), len(inst["edge_var"])
+    vp, ve = default_var_csr(V, inst["edge_var"])
+    ref = orc.MaxSumOracle(dict(inst, var_ptr=vp, var_edge=ve), np.float64, **params).init()
+    plans = [build_shard(inst, r, world) for r in range(world)]
+    shards = [orc.MaxSumOracle(p.local_inst, np.float64, **params).init() for p in plans]
+    inv = []
+    for p in plans:
+        L = p.layout
+        i = np.zeros(L.n_edges, dtype=np.int64)
+        i[L.edge_perm] = np.arange(L.n_edges)
+        inv.append(i)
+
+    def exchange():
+        for a, pa in enumerate(plans):
+            for arr, flg, s_edge, r_edge, s_rows, r_rows in (
+                    ("r", "r_flags", "send_r_edge", "recv_r_edge", "send_r_rows", "recv_r_rows"),
+                    ("q", "q_flags", "send_q_edge", "recv_q_edge", "send_q_rows", "recv_q_rows")):
+                so = np.concatenate([[0], np.cumsum(getattr(pa, s_rows))]).astype(int)
+                for b, pb in enumerate(plans):
+                    ro = np.concatenate([[0], np.cumsum(getattr(pb, r_rows))]).astype(int)
+                    src = inv[a][getattr(pa, s_edge)[so[b]:so[b + 1]]]
+                    dst = inv[b][getattr(pb, r_edge)[ro[a]:ro[a + 1]]]
+                    assert len(src) == len(dst)
+                    oa, ob = shards[a], shards[b]
+                    for es, ed in zip(src, dst):
+                        d = int(oa.msg_off[es + 1] - oa.msg_off[es])
+                        getattr(ob, arr)[ob.msg_off[ed]:ob.msg_off[ed] + d] = \
+                            getattr(oa, arr)[oa.msg_off[es]:oa.msg_off[es] + d]
+                        fb = getattr(ob, flg)
+                        fb[ed] = (int(fb[ed]) & (0xFF ^ orc.FLAG_RECV)) | (int(getattr(oa, flg)[es]) & orc.FLAG_RECV)
+
+    def check(k):
+        dom = inst["dom_size"][inst["edge_var"]]
+        goff = np.concatenate([[0], np.cumsum(dom)])
+        val = np.full(V, -1)
+        for p, o in zip(plans, shards):
+            val[p.own_vars] = o.value[:p.n_own_vars]
+            canon = np.concatenate([p.own_factor_edges, p.stub_edges])
+            for le, ge in enumerate(canon):
+                d = int(dom[ge])
+                assert np.array_equal(o.r[o.msg_off[le]:o.msg_off[le] + d], ref.r[goff[ge]:goff[ge] + d]), (k, "r", ge)
+                assert np.array_equal(o.q[o.msg_off[le]:o.msg_off[le] + d], ref.q[goff[ge]:goff[ge] + d]), (k, "q", ge)
+        assert np.array_equal(val, ref.value), k
+
+    exchange()
+    check(0)
+    for k in range(1, 9):
+        ref.step()
+        for o in shards:
+            o.step()
+        exchange()
+        check(k)
