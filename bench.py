@@ -141,7 +141,8 @@ def side_workload(args, dev):
     if w == "c4":
         if world > 1:   # strong scaling: the same 1M-variable problem over `world` GPUs
             from pydcop_b200.multigpu_dsa import ShardedDsa
-            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1)
+            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1,
+                             partition=os.environ.get("PYDCOP_B200_PARTITION", "auto"))
         else:
             eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
         units, metric = L.n_vars, "dsa_variable_updates_per_s"
@@ -271,10 +272,14 @@ def main():
     n_edges_global = int(len(inst["edge_var"]))
     if world > 1:
         from pydcop_b200.multigpu import ShardedMaxSum
+        part = os.environ.get("PYDCOP_B200_PARTITION", "auto")
         runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision,
-                               halo=os.environ.get("PYDCOP_B200_HALO", "auto"))
+                               halo=os.environ.get("PYDCOP_B200_HALO", "auto"), partition=part)
         L = None
         config["cut_edges"] = runner.plan.n_cut_edges
+        config["partition"] = (f"{part}: the fewer-cut of contiguous blocks and a multilevel k-way split "
+                               f"(pydcop_b200/partition.py), {runner.plan.n_cut_edges} of {n_edges_global} edges cut"
+                               if part == "auto" else f"{part}, {runner.plan.n_cut_edges} of {n_edges_global} edges cut")
     else:
         L = build_layout(**inst)
         runner = MaxSumEngine(L, device=dev, precision=args.precision, record_sent=True)

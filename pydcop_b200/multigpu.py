@@ -67,7 +67,23 @@ class ShardPlan:
     local_inst: Optional[Dict[str, np.ndarray]] = None   # the closed local graph as front-door arrays
 
 
-def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan:
+def resolve_owner(inst, world: int, partition="blocks") -> np.ndarray:
+    """Owner rank of every variable: an explicit int array, or the name of a method of
+    pydcop_b200.partition.partition_variables ('blocks' | 'multilevel' | 'auto').  Every rank
+    must pass the same value (the methods are deterministic)."""
+    n_vars = len(np.asarray(inst["dom_size"]))
+    if isinstance(partition, str):
+        if partition == "blocks":
+            return variable_owner(n_vars, world)
+        from .partition import partition_variables
+        return partition_variables(n_vars, inst["factor_ptr"], inst["edge_var"], world, method=partition)
+    owner = np.asarray(partition, dtype=np.int32)
+    if owner.shape != (n_vars,) or (len(owner) and (owner.min() < 0 or owner.max() >= world)):
+        raise ValueError("owner array must give a rank in [0, world) for every variable")
+    return owner
+
+
+def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int, partition="blocks") -> ShardPlan:
     dom_size = np.asarray(inst["dom_size"], dtype=np.int32)
     factor_ptr = np.asarray(inst["factor_ptr"], dtype=np.int64)
     edge_var = np.asarray(inst["edge_var"], dtype=np.int64)
@@ -90,7 +106,7 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan
         vp, ve = default_var_csr(V, edge_var)
         g_var_ptr, g_var_edge = vp.astype(np.int64), ve.astype(np.int64)
 
-    owner_v = variable_owner(V, world)
+    owner_v = resolve_owner(inst, world, partition)
     fac_owner = owner_v[edge_var[factor_ptr[:-1]]] if F else np.zeros(0, np.int32)
     e_fowner = fac_owner[efac]
     e_vowner = owner_v[edge_var]
@@ -102,6 +118,8 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> ShardPlan
     own_f_edges = _ranges(factor_ptr[own_f], arity[own_f])
     ghost_vars = np.unique(edge_var[own_f_edges][e_vowner[own_f_edges] != rank]) if len(own_f_edges) \
         else np.zeros(0, np.int64)
+    # grouped by owner (ascending id inside a group): one dense block of q rows per peer and class
+    ghost_vars = ghost_vars[np.argsort(owner_v[ghost_vars], kind="stable")]
     # remote-factor edges of own variables (-> stub factors), grouped by the rank that produces
     # their row, ascending global edge id inside a group: the rows one peer sends land in ONE
     # contiguous block of this rank's r buffer, so its remote stores coalesce
@@ -421,12 +439,13 @@ class PeerPush:
 class ShardedMaxSum:
     """One rank of the partitioned MaxSum: same driving API as MaxSumEngine (init / step / values)."""
 
-    def __init__(self, inst, rank, world, device, precision="f32", group=None, halo="nccl", **params):
+    def __init__(self, inst, rank, world, device, precision="f32", group=None, halo="nccl",
+                 partition="blocks", **params):
         import torch
         from . import _cabi
         from .engine import MaxSumEngine, PRECISIONS
         self.torch = torch
-        self.plan = build_shard(inst, rank, world)
+        self.plan = build_shard(inst, rank, world, partition)
         self.rank, self.world = rank, world
         self.engine = MaxSumEngine(self.plan.layout, device=device, precision=precision, **params)
         self.device = self.engine.device

@@ -25,7 +25,7 @@ from typing import Dict, List
 import numpy as np
 
 from .layout import FactorGraphLayout, build_layout, default_var_csr, var_con_to_edges
-from .multigpu import _ranges, variable_owner
+from .multigpu import _ranges, resolve_owner
 
 
 @dataclass
@@ -70,7 +70,7 @@ def boundary_pairs(edge_var, factor_ptr, owner_v):
     return key % (int(owner_v.shape[0]) + 1), key // (int(owner_v.shape[0]) + 1)
 
 
-def build_dsa_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> DsaShard:
+def build_dsa_shard(inst: Dict[str, np.ndarray], rank: int, world: int, partition="blocks") -> DsaShard:
     dom_size = np.asarray(inst["dom_size"], dtype=np.int32)
     factor_ptr = np.asarray(inst["factor_ptr"], dtype=np.int64)
     edge_var = np.asarray(inst["edge_var"], dtype=np.int64)
@@ -96,7 +96,7 @@ def build_dsa_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> DsaSh
         vp, ve = default_var_csr(V, edge_var)
         g_var_ptr, g_var_edge = vp.astype(np.int64), ve.astype(np.int64)
 
-    owner_v = variable_owner(V, world)
+    owner_v = resolve_owner(inst, world, partition)
     own_v = np.nonzero(owner_v == rank)[0]
     n_own = len(own_v)
     # constraints with at least one owned variable, in global order
@@ -106,6 +106,7 @@ def build_dsa_shard(inst: Dict[str, np.ndarray], rank: int, world: int) -> DsaSh
     loc_edges = _ranges(factor_ptr[loc_f], arity[loc_f])
     scope_vars = edge_var[loc_edges] if len(loc_edges) else np.zeros(0, np.int64)
     ghosts = np.unique(scope_vars[owner_v[scope_vars] != rank]) if len(scope_vars) else np.zeros(0, np.int64)
+    ghosts = ghosts[np.argsort(owner_v[ghosts], kind="stable")]     # one block of values per peer
     n_ghost = len(ghosts)
     local_global = np.concatenate([own_v, ghosts]).astype(np.int64)
     g2l_var = np.full(V, -1, dtype=np.int64)
@@ -214,10 +215,10 @@ class ShardedDsa:
     DsaEngine + the CUDA halo kernels."""
 
     def __init__(self, inst, rank, world, device, precision="f32", group=None, engine_factory=None,
-                 pack=None, unpack=None, **params):
+                 pack=None, unpack=None, partition="blocks", **params):
         import torch
         self.torch = torch
-        self.shard = sh = build_dsa_shard(inst, rank, world)
+        self.shard = sh = build_dsa_shard(inst, rank, world, partition)
         self.rank, self.world = rank, world
         self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
         iso = params.pop("isolated_value", None)

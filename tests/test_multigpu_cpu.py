@@ -204,12 +204,15 @@ def test_rows_of_one_peer_land_in_one_block_and_push_order_follows_destinations(
             pos += n
 
 
-@pytest.mark.parametrize("kind,world,params", [
-    ("random", 2, {}),
-    ("random", 4, dict(damping_nodes="vars", start_messages="leafs_vars")),
-    ("grid", 3, dict(mode="max", start_messages="all")),
+@pytest.mark.parametrize("kind,world,params,partition", [
+    ("random", 2, {}, "blocks"),
+    ("random", 4, dict(damping_nodes="vars", start_messages="leafs_vars"), "blocks"),
+    ("grid", 3, dict(mode="max", start_messages="all"), "blocks"),
+    ("random", 3, {}, "scattered"),          # an arbitrary owner array
+    ("random", 4, {}, "multilevel"),
+    ("grid", 2, dict(start_messages="all"), "multilevel"),
 ])
-def test_sharded_maxsum_emulated_with_the_oracle_is_bit_identical(kind, world, params):
+def test_sharded_maxsum_emulated_with_the_oracle_is_bit_identical(kind, world, params, partition):
     """The partition itself (ghost variables, stub factors grouped by producing rank, `links` order
     of every own variable) run cycle by cycle with one oracle per shard and an in-process exchange
     of the boundary rows: messages on every real edge and the assignment must equal the
@@ -220,7 +223,10 @@ def test_sharded_maxsum_emulated_with_the_oracle_is_bit_identical(kind, world, p
     V, E = len(inst["dom_size"]), len(inst["edge_var"])
     vp, ve = default_var_csr(V, inst["edge_var"])
     ref = orc.MaxSumOracle(dict(inst, var_ptr=vp, var_edge=ve), np.float64, **params).init()
-    plans = [build_shard(inst, r, world) for r in range(world)]
+    if partition == "scattered":
+        partition = np.random.default_rng(4).integers(0, world, V).astype(np.int32)
+    plans = [build_shard(inst, r, world, partition) for r in range(world)]
+    assert sorted(np.concatenate([p.own_vars for p in plans]).tolist()) == list(range(V))
     shards = [orc.MaxSumOracle(p.local_inst, np.float64, **params).init() for p in plans]
     inv = []
     for p in plans:

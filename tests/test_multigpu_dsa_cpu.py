@@ -139,13 +139,14 @@ def test_dsa_shards_are_closed_and_halo_lists_pair_up(kind, world):
             pos += s.send_split[b]
 
 
-def _worker(rank, world, port, kind, params, n_cycles, q):
+def _worker(rank, world, port, kind, params, n_cycles, q, partition="blocks"):
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
         inst = _instance(kind)
         sd = ShardedDsa(inst, rank, world, torch.device("cpu"), precision="f64",
-                        engine_factory=FakeDsaEngine, pack=_pack, unpack=_unpack, **params).init()
+                        engine_factory=FakeDsaEngine, pack=_pack, unpack=_unpack, partition=partition,
+                        **params).init()
         traj = [sd.values()]
         for _ in range(n_cycles):
             sd.step()
@@ -158,13 +159,14 @@ def _worker(rank, world, port, kind, params, n_cycles, q):
         q.put((rank, "FAIL " + repr(e) + traceback.format_exc(), None, None))
 
 
-@pytest.mark.parametrize("kind,world,params", [
-    ("binary", 2, dict(variant="B", seed=11)),
-    ("mixed", 2, dict(variant="A", seed=12, mode="max")),
-    ("mixed", 3, dict(variant="C", probability=0.5, seed=13, p_mode="arity")),
-    ("binary", 3, dict(variant="B", seed=14, stop_cycle=5)),
+@pytest.mark.parametrize("kind,world,params,partition", [
+    ("binary", 2, dict(variant="B", seed=11), "blocks"),
+    ("mixed", 2, dict(variant="A", seed=12, mode="max"), "blocks"),
+    ("mixed", 3, dict(variant="C", probability=0.5, seed=13, p_mode="arity"), "blocks"),
+    ("binary", 3, dict(variant="B", seed=14, stop_cycle=5), "blocks"),
+    ("binary", 3, dict(variant="B", seed=15), "multilevel"),
 ])
-def test_sharded_dsa_equals_single_process_over_gloo(kind, world, params):
+def test_sharded_dsa_equals_single_process_over_gloo(kind, world, params, partition):
     n_cycles = 9
     inst = _instance(kind)
     if params.get("p_mode") == "arity":   # (divides by zero for isolated variables, dsa.py:258-260)
@@ -178,7 +180,8 @@ def test_sharded_dsa_equals_single_process_over_gloo(kind, world, params):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, params, n_cycles, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, params, n_cycles, q, partition))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
