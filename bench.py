@@ -136,13 +136,13 @@ def side_workload(args, dev):
     vb = 4 if args.precision == "f32" else 8
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if world > 1 and w != "c4":
-        raise SystemExit("--workload %s is a single-GPU side line; multi-GPU runs: c2 (MaxSum) and c4 (DSA)" % w)
+    if world > 1 and w == "mgm":
+        raise SystemExit("--workload mgm is a single-GPU side line (MGM is not sharded)")
+    part = os.environ.get("PYDCOP_B200_PARTITION", "auto")
     if w == "c4":
         if world > 1:   # strong scaling: the same 1M-variable problem over `world` GPUs
             from pydcop_b200.multigpu_dsa import ShardedDsa
-            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1,
-                             partition=os.environ.get("PYDCOP_B200_PARTITION", "auto"))
+            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1, partition=part)
         else:
             eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
         units, metric = L.n_vars, "dsa_variable_updates_per_s"
@@ -154,7 +154,12 @@ def side_workload(args, dev):
         d, k = 20, 6
         alg = L.n_vars * ((k * d + 2 * k + 2) * vb + 8 * k + 8)
     else:
-        eng = MaxSumEngine(L, device=dev, precision=args.precision)
+        if world > 1:   # strong scaling of the named instance (BASELINE configs[2]: the grid over 1 -> 8 GPUs)
+            from pydcop_b200.multigpu import ShardedMaxSum
+            eng = ShardedMaxSum(inst, rank, world, dev, precision=args.precision,
+                                halo=os.environ.get("PYDCOP_B200_HALO", "auto"), partition=part)
+        else:
+            eng = MaxSumEngine(L, device=dev, precision=args.precision)
         units, metric = 2 * L.n_edges, METRIC
         alg = G.algorithmic_bytes_per_cycle_inst(inst, vb)
     eng.init()
@@ -191,7 +196,12 @@ def side_workload(args, dev):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
                          "frac": ach / (peaks["hbm_gbs"] * world), "algorithmic_bytes_per_step": int(alg)}}
     if world > 1:
-        line["config"]["boundary_values"] = int(eng.shard.n_boundary)
+        line["config"]["partition"] = part
+        if w == "c4":
+            line["config"]["boundary_values"] = int(eng.shard.n_boundary)
+        else:
+            line["config"]["cut_edges"] = int(eng.plan.n_cut_edges)
+            line["config"]["halo"] = "peer push" if eng.peer is not None else "nccl all_to_all"
     print(json.dumps(line))
 
 
