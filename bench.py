@@ -142,7 +142,8 @@ def side_workload(args, dev):
     if w == "c4":
         if world > 1:   # strong scaling: the same 1M-variable problem over `world` GPUs
             from pydcop_b200.multigpu_dsa import ShardedDsa
-            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1, partition=part)
+            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1, partition=part,
+                             halo=os.environ.get("PYDCOP_B200_HALO", "auto"))
         else:
             eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
         units, metric = L.n_vars, "dsa_variable_updates_per_s"
@@ -180,11 +181,25 @@ def side_workload(args, dev):
         evs.append((a, b))
     torch.cuda.synchronize(dev)
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    parity = None
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        # sharded run (exchange path as timed) against ONE engine with the whole problem, fresh start
+        eng.init()
+        eng.step(PARITY_CYCLES)
+        got = eng.values()
+        if rank == 0:
+            if w == "c4":
+                want = DsaEngine(L, device=dev, precision=args.precision, seed=1).init().step(PARITY_CYCLES).values()
+            else:
+                want = MaxSumEngine(L, device=dev, precision=args.precision,
+                                    record_sent=False).init().step(PARITY_CYCLES).values()[0]
+            parity = {"cycles": PARITY_CYCLES, "assignment_equals_single_gpu": bool(np.array_equal(got, want)),
+                      "n_differ": int((np.asarray(got) != np.asarray(want)).sum())}
+        dist.barrier()
         if rank != 0:
             return
     peaks, kind = load_peaks()
@@ -196,9 +211,11 @@ def side_workload(args, dev):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
                          "frac": ach / (peaks["hbm_gbs"] * world), "algorithmic_bytes_per_step": int(alg)}}
     if world > 1:
+        line["parity"] = parity
         line["config"]["partition"] = part
         if w == "c4":
             line["config"]["boundary_values"] = int(eng.shard.n_boundary)
+            line["config"]["halo"] = "peer push" if eng.peer is not None else "nccl all_to_all"
         else:
             line["config"]["cut_edges"] = int(eng.plan.n_cut_edges)
             line["config"]["halo"] = "peer push" if eng.peer is not None else "nccl all_to_all"

@@ -207,6 +207,81 @@ class ValueHalo:
         self.unpack_values(values)
 
 
+class ValuePeerPush:
+    """Boundary values over NVLink peer memory, the DSA twin of multigpu.PeerPush: every rank maps
+    the peers' two value buffers (CUDA IPC) and ONE push kernel (fg_halo_push, rows of one 4-byte
+    element) stores each boundary value straight into the ghost entry of the consumer's `next`
+    buffer; an all-reduce closes the cycle.  Replaces pack -> all_to_all -> unpack."""
+
+    def __init__(self, sharded, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _cabi
+        from .multigpu import destination_order
+        self.torch, self.dist, self.group = torch, dist, group
+        e, sh, h = sharded.engine, sharded.shard, sharded.halo
+        self.engine = e
+        dev = e.device
+        W, me = sh.world, sh.rank
+        lib = e.lib
+        mine = []
+        for t in (e.value[0], e.value[1]):
+            hb = (C.c_ubyte * 64)()
+            off = C.c_int64()
+            rc = lib.fg_ipc_export(C.c_void_p(t.data_ptr()), C.cast(hb, C.c_void_p), C.byref(off))
+            if rc != 0:
+                raise RuntimeError(f"fg_ipc_export failed rc={rc}")
+            mine.append((bytes(hb), int(off.value)))
+        everyone = [None] * W
+        dist.all_gather_object(everyone, mine, group=group)
+        self._mapped = {}
+        base = np.zeros((W, 2), dtype=np.int64)
+        with torch.cuda.device(dev):
+            for rnk in range(W):
+                if rnk == me:
+                    base[rnk] = [e.value[0].data_ptr(), e.value[1].data_ptr()]
+                    continue
+                for i, (hbytes, off) in enumerate(everyone[rnk]):
+                    key = (rnk, hbytes)
+                    if key not in self._mapped:
+                        out = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(hbytes)
+                        rc = lib.fg_ipc_import(C.cast(buf, C.c_void_p), C.byref(out))
+                        if rc != 0:
+                            raise RuntimeError(f"fg_ipc_import failed rc={rc} (rank {rnk})")
+                        self._mapped[key] = int(out.value)
+                    base[rnk, i] = self._mapped[key] + off
+        # where my values land: the consumers' ghost indices (internal order), in my send order
+        perm = np.asarray(sh.layout.var_perm, dtype=np.int64)
+        out = torch.zeros(len(sh.send_var), dtype=torch.int64, device=dev)
+        inp = torch.from_numpy(np.ascontiguousarray(perm[sh.recv_var])).to(dev)
+        dist.all_to_all_single(out, inp, list(sh.send_split), list(sh.recv_split), group=group)
+        dst_idx = out.cpu().numpy()
+        peer_of = np.repeat(np.arange(W), np.asarray(sh.send_split, dtype=np.int64))
+        order = destination_order(dst_idx, sh.send_split)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)  # noqa: E731
+        self.dst = [to((base[peer_of, b] + dst_idx * 4)[order]) for b in range(2)]
+        self.src = to(perm[sh.send_var][order])
+        self.n = len(sh.send_var)
+        self.token = torch.zeros(1, device=dev)
+        self.launches = 0
+        self.prec = _cabi.FG_F32     # 4-byte elements, moved bit for bit
+        dist.barrier(group=group)
+
+    def push(self, buf_index):
+        e, torch = self.engine, self.torch
+        if self.n:
+            v = C.c_void_p(e.value[buf_index].data_ptr())
+            d = C.c_void_p(self.dst[buf_index].data_ptr())
+            s = C.c_void_p(self.src.data_ptr())
+            rc = e.lib.fg_halo_push(self.prec, v, v, s, s, d, d, self.n, 0, 1,
+                                    C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"fg_halo_push failed rc={rc}")
+            self.launches += 1
+        self.dist.all_reduce(self.token, group=self.group)
+
+
 class ShardedDsa:
     """One rank of the partitioned DSA: same driving API as DsaEngine (init / step / values).
 
@@ -215,7 +290,7 @@ class ShardedDsa:
     DsaEngine + the CUDA halo kernels."""
 
     def __init__(self, inst, rank, world, device, precision="f32", group=None, engine_factory=None,
-                 pack=None, unpack=None, partition="blocks", **params):
+                 pack=None, unpack=None, partition="blocks", halo="nccl", **params):
         import torch
         self.torch = torch
         self.shard = sh = build_dsa_shard(inst, rank, world, partition)
@@ -250,6 +325,8 @@ class ShardedDsa:
 
             pack, unpack = mover(lib.fg_halo_pack, "fg_halo_pack"), mover(lib.fg_halo_unpack, "fg_halo_unpack")
         self.halo = ValueHalo(sh, sh.layout, self.device, pack, unpack, group)
+        self.halo_mode = halo if engine_factory is None else "nccl"
+        self.peer = None
 
     @property
     def layout(self):
@@ -259,6 +336,13 @@ class ShardedDsa:
         e = self.engine
         e.init()
         self.halo.exchange(e.value[e.cur])       # ghosts learn their owners' initial values
+        if self.halo_mode in ("p2p", "auto") and self.peer is None and self.world > 1:
+            try:
+                self.peer = ValuePeerPush(self, self.halo.group)
+            except Exception as ex:  # noqa: BLE001 — no peer mapping: keep the NCCL exchange
+                if self.halo_mode == "p2p":
+                    raise
+                self.peer_error = repr(ex)
         return self
 
     def step(self, n_cycles=1):
@@ -266,7 +350,10 @@ class ShardedDsa:
         for _ in range(int(n_cycles)):
             before = e.cycle
             e.cycle_compute()
-            self.halo.exchange(e.value[e.cur ^ 1])
+            if self.peer is not None:
+                self.peer.push(e.cur ^ 1)
+            else:
+                self.halo.exchange(e.value[e.cur ^ 1])
             e.cycle_commit()
             if e.cycle == before:                 # stop_cycle reached: nothing moves any more
                 break
@@ -278,7 +365,7 @@ class ShardedDsa:
 
     @property
     def launch_count(self):
-        return self.engine.launch_count + self.halo.launches
+        return self.engine.launch_count + self.halo.launches + (self.peer.launches if self.peer else 0)
 
     def local_values(self):
         """(global variable ids, value indices) of the variables this rank owns."""

@@ -67,7 +67,7 @@ def test_two_process_sharded_matches_single_gpu(mode):
     assert all(r[2] == mode for r in results), results
 
 
-def _dsa_worker(rank, world, port, q):
+def _dsa_worker(rank, world, port, mode, q):
     try:
         import torch
         import torch.distributed as dist
@@ -81,21 +81,24 @@ def _dsa_worker(rank, world, port, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         inst = random_factor_graph(4000, 20, 12000, 2, seed=22, noise=0.0)
         inst["tables"] = np.floor(inst["tables"] / 3.0).astype(np.float32)
-        sh = ShardedDsa(inst, rank, world, dev, precision="f32", variant="B", seed=9).init().step(10)
+        sh = ShardedDsa(inst, rank, world, dev, precision="f32", variant="B", seed=9, halo=mode,
+                        partition="multilevel").init().step(10)
         got = sh.values()
+        used = "p2p" if sh.peer is not None else "nccl"
         ok = True
         if rank == 0:
             ref = DsaEngine(build_layout(**inst), device=dev, precision="f32", variant="B", seed=9).init().step(10)
             ok = bool(np.array_equal(got, ref.values()))
         dist.barrier()
         dist.destroy_process_group()
-        q.put((rank, "ok" if ok else "MISMATCH"))
+        q.put((rank, "ok" if ok else "MISMATCH", used))
     except Exception as e:  # noqa: BLE001
         import traceback
-        q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
+        q.put((rank, "FAIL " + repr(e) + traceback.format_exc(), "?"))
 
 
-def test_two_process_sharded_dsa_matches_single_gpu():
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_two_process_sharded_dsa_matches_single_gpu(mode):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -104,7 +107,7 @@ def test_two_process_sharded_dsa_matches_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_dsa_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_dsa_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=90) for _ in procs]
@@ -113,3 +116,4 @@ def test_two_process_sharded_dsa_matches_single_gpu():
         if p.is_alive():
             p.kill()
     assert all(r[1] == "ok" for r in results), results
+    assert all(r[2] == mode for r in results), results
