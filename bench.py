@@ -242,7 +242,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     from pydcop_b200 import build_layout
-    from pydcop_b200.generators import algorithmic_bytes_per_cycle, config_c2
+    from pydcop_b200.generators import config_c2
 
     n_vars = args.vars_per_gpu * max(1, world)
     config = {"workload": f"random binary DCOP {n_vars} vars d=10 deg=4 (BASELINE configs[1] "

@@ -15,8 +15,6 @@ heur_comhost.py, with the algorithms' `communication_load`, maxsum.py:166-209). 
 idea for ranks of one box; it does not touch the algorithm: any owner array gives bit-identical
 results (tests/test_multigpu_cpu.py runs the partition emulation with arbitrary owners).
 """
-from typing import Optional
-
 import numpy as np
 
 
@@ -83,7 +81,6 @@ def _match(A, w, max_w, rng, rounds=3):
         v = np.nonzero(prop >= 0)[0]
         mutual = v[prop[prop[v]] == v]
         mate[mutual] = prop[mutual]
-    cid = np.full(n, -1, dtype=np.int64)
     rep = np.where((mate >= 0) & (mate < np.arange(n)), mate, np.arange(n))   # smaller id represents
     uniq, cid = np.unique(rep, return_inverse=True)
     P = sp.csr_matrix((np.ones(n), (np.arange(n), cid)), shape=(n, len(uniq)))
@@ -177,7 +174,6 @@ def _rebalance(A, w, label, k, cap, rng):
         mine = np.nonzero(label == p)[0]
         S = np.asarray((A[mine] @ H).todense())
         stay = S[:, p].copy()
-        S[:, p] = -1.0
         S[:, load >= cap] = -1.0
         S[:, p] = -1.0
         best = S.argmax(axis=1)

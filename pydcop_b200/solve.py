@@ -21,7 +21,7 @@ the host logic can be tested without one.
 import json
 import os
 import time
-from typing import Any, Callable, Dict, Optional, Union
+from typing import Any, Callable, Dict, Optional
 
 import numpy as np
 
