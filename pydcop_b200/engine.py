@@ -6,6 +6,7 @@ kernels); torch only owns the buffers.  There is no CPU path: constructing an en
 CUDA device raises EngineError.
 """
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -253,6 +254,34 @@ class MaxSumEngine(_EngineBase):
                 L.vars_to_canonical(self.value_cost[:n].double().cpu().numpy()))
 
 
+def dsa_fast_arrays(layout: FactorGraphLayout, tables: torch.Tensor, mode="min"):
+    """Arrays of the DSA fast path, or None when the instance does not qualify (every constraint
+    binary over ONE domain size).  Per slot (variable v, incident constraint c, neighbour u) the
+    table of c is read ORIENTED so that row y = value of u is contiguous over v's values: slots at
+    scope position 1 read the table as stored, slots at position 0 read a transposed copy.
+    Returns (tables_or, slot_tab, slot_nbr, slot_opt, D) as tensors on `tables.device`."""
+    L = layout
+    if not (len(L.classes) == 1 and L.classes[0].arity == 2 and L.classes[0].dom[0] == L.classes[0].dom[1]
+            and L.n_edges and not L.classes[0].tag):
+        return None
+    dev = tables.device
+    c0 = L.classes[0]
+    D = c0.dom[0]
+    S = D * D
+    nF = c0.n_factors
+    t = tables[c0.table_base:c0.table_base + nF * S].view(nF, D, D)
+    tables_or = torch.cat([t.reshape(-1), t.transpose(1, 2).contiguous().reshape(-1)])
+    opt = (t.reshape(nF, S).max(dim=1).values if mode == "max" else t.reshape(nF, S).min(dim=1).values)
+    e = L.slot_edge.astype(np.int64) - c0.first_edge
+    f, j = e // 2, e % 2
+    # position 1 (me second): T[y][x] is already row-contiguous; position 0: transposed copy
+    slot_tab = np.where(j == 1, f * S, nF * S + f * S).astype(np.int64)
+    slot_nbr = L.edge_var[c0.first_edge + f * 2 + (1 - j)].astype(np.int32)
+    return (tables_or, torch.from_numpy(np.ascontiguousarray(slot_tab)).to(dev),
+            torch.from_numpy(np.ascontiguousarray(slot_nbr)).to(dev),
+            opt[torch.from_numpy(f).to(dev)].contiguous(), D)
+
+
 class DsaEngine(_EngineBase):
     """All-variables-at-once DSA-A/B/C (pydcop/algorithms/dsa.py:130-135 parameters)."""
 
@@ -315,27 +344,10 @@ class DsaEngine(_EngineBase):
         # row per incidence (transposed copy for scope position 0)
         self.tables_or = self.slot_nbr = self.slot_tab = self.slot_opt = None
         fast_dom = 0
-        if (len(L.classes) == 1 and L.classes[0].arity == 2 and L.classes[0].dom[0] == L.classes[0].dom[1]
-                and L.n_edges and not L.classes[0].tag):
-            c0 = L.classes[0]
-            D = c0.dom[0]
-            S = D * D
-            nF = c0.n_factors
-            with torch.cuda.device(self.device):
-                t = self.tables[c0.table_base:c0.table_base + nF * S].view(nF, D, D)
-                self.tables_or = torch.cat([t.reshape(-1), t.transpose(1, 2).contiguous().reshape(-1)])
-                opt = (t.reshape(nF, S).max(dim=1).values if mode == "max"
-                       else t.reshape(nF, S).min(dim=1).values)
-            e = L.slot_edge.astype(np.int64) - c0.first_edge
-            f, j = e // 2, e % 2
-            # position 1 (me second): T[y][x] is already row-contiguous; position 0: transposed copy
-            slot_tab = np.where(j == 1, f * S, nF * S + f * S).astype(np.int64)
-            slot_nbr = L.edge_var[c0.first_edge + f * 2 + (1 - j)].astype(np.int32)
-            with torch.cuda.device(self.device):
-                self.slot_tab = self._dev(slot_tab, torch.int64)
-                self.slot_nbr = self._dev(slot_nbr, torch.int32)
-                self.slot_opt = opt[torch.from_numpy(f).to(self.device)].contiguous()
-            fast_dom = D
+        with torch.cuda.device(self.device):
+            fast = dsa_fast_arrays(L, self.tables, mode)
+        if fast is not None:
+            self.tables_or, self.slot_tab, self.slot_nbr, self.slot_opt, fast_dom = fast
         self._classes = _class_array(L)
         d = FgDsaDesc()
         d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
@@ -356,6 +368,10 @@ class DsaEngine(_EngineBase):
         self._desc = d
         self._h = C.c_void_p()
         self._check(self.lib.fg_dsa_create(C.byref(d), C.byref(self._h)), "fg_dsa_create")
+        # PYDCOP_B200_DSA_V2=2|4 selects the chunked kernel where it applies (else the default path)
+        chunk = int(os.environ.get("PYDCOP_B200_DSA_V2", "0") or 0)
+        self._v2_chunk = chunk if (chunk in (2, 4) and fast_dom in (4, 8, 10, 16, 20)) else 0
+        self._v2_launches = 0
 
     def _last_error(self):
         return (self.lib.fg_dsa_last_error(self._h) or b"").decode()
@@ -377,12 +393,23 @@ class DsaEngine(_EngineBase):
         return self
 
     def step(self, n_cycles=1):
+        if self._v2_chunk:
+            for _ in range(int(n_cycles)):
+                self.cycle_compute()
+                self.cycle_commit()
+            return self
         with torch.cuda.device(self.device):
             self._check(self.lib.fg_dsa_step(self._h, int(n_cycles), self._stream()), "fg_dsa_step")
         return self
 
     def cycle_compute(self):
         with torch.cuda.device(self.device):
+            if self._v2_chunk:   # opt-in experiment: chunked fast kernel (csrc/dsa_v2.cu), same results
+                cur, cyc = self._current()
+                self._check(self.lib.fg_dsa_step_v2(C.byref(self._desc), cur, cyc, self._v2_chunk,
+                                                    self._stream()), "fg_dsa_step_v2")
+                self._v2_launches += 1
+                return
             self._check(self.lib.fg_dsa_cycle_compute(self._h, self._stream()), "fg_dsa_cycle_compute")
 
     def cycle_commit(self):
@@ -403,7 +430,7 @@ class DsaEngine(_EngineBase):
 
     @property
     def launch_count(self):
-        return int(self.lib.fg_dsa_launch_count(self._h))
+        return int(self.lib.fg_dsa_launch_count(self._h)) + self._v2_launches
 
     def values(self):
         """Current value index per variable, canonical variable order."""
