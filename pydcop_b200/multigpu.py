@@ -344,6 +344,27 @@ def destination_order(dst_off, rows_per_peer) -> np.ndarray:
     return np.lexsort((dst_off, peer)).astype(np.int64)
 
 
+def push_tables(plan: ShardPlan, base: np.ndarray, dst_r_off, dst_q_off, elem: int):
+    """Source offsets and absolute destination addresses of the peer push.
+    base[rank] = addresses of that rank's (q[0], q[1], r[0], r[1]) as mapped into this process;
+    dst_*_off = the consumers' element offsets of my send rows (my send order).
+    Rows are independent: they are issued in DESTINATION order inside each peer group, so that
+    consecutive threads of the push kernel store to consecutive remote addresses (the local reads
+    become gathers instead, which HBM absorbs)."""
+    W = plan.world
+    peer_of_r = np.repeat(np.arange(W), np.asarray(plan.send_r_rows, dtype=np.int64))
+    peer_of_q = np.repeat(np.arange(W), np.asarray(plan.send_q_rows, dtype=np.int64))
+    dst_r_off = np.asarray(dst_r_off, dtype=np.int64)
+    dst_q_off = np.asarray(dst_q_off, dtype=np.int64)
+    perm_r = destination_order(dst_r_off, plan.send_r_rows)
+    perm_q = destination_order(dst_q_off, plan.send_q_rows)
+    return dict(
+        dst_r=[(base[peer_of_r, 2 + b] + dst_r_off * elem)[perm_r] for b in range(2)],
+        dst_q=[(base[peer_of_q, 0 + b] + dst_q_off * elem)[perm_q] for b in range(2)],
+        src_r_off=np.asarray(plan.send_r_off, dtype=np.int64)[perm_r],
+        src_q_off=np.asarray(plan.send_q_off, dtype=np.int64)[perm_q])
+
+
 class PeerPush:
     """Halo over NVLink peer memory: every rank maps the peers' message buffers (torch CUDA IPC) and
     its push kernel stores each boundary row straight into the consumer's `next` buffer; a barrier
@@ -399,19 +420,10 @@ class PeerPush:
         dst_r_off = peer_offsets(p.recv_r_off, p.recv_r_rows, p.send_r_rows)   # offsets in the peer's r
         dst_q_off = peer_offsets(p.recv_q_off, p.recv_q_rows, p.send_q_rows)
         elem = e.q[0].element_size()
-        peer_of_r = np.repeat(np.arange(W), p.send_r_rows)
-        peer_of_q = np.repeat(np.arange(W), p.send_q_rows)
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)  # noqa: E731
-        # absolute destination addresses for `next` buffer index b (0 / 1)
-        # rows are independent: issue them in DESTINATION order inside each peer group, so that
-        # consecutive threads of the push kernel store to consecutive remote addresses (the local
-        # reads become gathers instead, which HBM absorbs)
-        perm_r = destination_order(dst_r_off, p.send_r_rows)
-        perm_q = destination_order(dst_q_off, p.send_q_rows)
-        self.dst_r = [to((base[peer_of_r, 2 + b] + dst_r_off * elem)[perm_r]) for b in range(2)]
-        self.dst_q = [to((base[peer_of_q, 0 + b] + dst_q_off * elem)[perm_q]) for b in range(2)]
-        self.src_r_off = to(np.asarray(p.send_r_off, dtype=np.int64)[perm_r])
-        self.src_q_off = to(np.asarray(p.send_q_off, dtype=np.int64)[perm_q])
+        t = push_tables(p, base, dst_r_off, dst_q_off, elem)
+        self.dst_r, self.dst_q = [to(a) for a in t["dst_r"]], [to(a) for a in t["dst_q"]]
+        self.src_r_off, self.src_q_off = to(t["src_r_off"]), to(t["src_q_off"])
         self.n_r, self.n_q = len(p.send_r_len), len(p.send_q_len)
         self.dom = int(p.layout.uniform_dom)
         self.token = torch.zeros(1, device=dev)

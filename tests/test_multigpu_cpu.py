@@ -275,3 +275,57 @@ def test_sharded_maxsum_emulated_with_the_oracle_is_bit_identical(kind, world, p
             o.step()
         exchange()
         check(k)
+
+
+@pytest.mark.parametrize("world,partition", [(2, "blocks"), (4, "multilevel")])
+def test_peer_push_tables_move_every_boundary_row_to_its_ghost_row(world, partition):
+    """The address tables of the NVLink peer push (multigpu.push_tables) in a simulated address
+    space: every rank's q/r buffers are numpy arrays at fake base addresses; executing the push as
+    plain copies must fill exactly the rows the all_to_all exchange fills, with the same data."""
+    from pydcop_b200.multigpu import push_tables
+    inst = random_factor_graph(300, 10, 600, 2, seed=13)
+    plans = [build_shard(inst, r, world, partition) for r in range(world)]
+    elem, stride = 4, 1 << 40
+    base = np.array([[r * 4 * stride + b * stride for b in range(4)] for r in range(world)], dtype=np.int64)
+    rng = np.random.default_rng(0)
+    bufs = [[rng.integers(1, 1 << 30, size=max(p.layout.n_msg_q, 1)).astype(np.int64),
+             None, rng.integers(1, 1 << 30, size=max(p.layout.n_msg, 1)).astype(np.int64), None] for p in plans]
+    for b in bufs:
+        b[1], b[3] = b[0].copy(), b[2].copy()
+    want = [[x.copy() for x in b] for b in bufs]
+    d = 10
+    # reference: what pack -> all_to_all -> unpack does on buffer index 1 (q[1], r[1])
+    for a, pa in enumerate(plans):
+        so_r = np.concatenate([[0], np.cumsum(pa.send_r_rows)]).astype(int)
+        so_q = np.concatenate([[0], np.cumsum(pa.send_q_rows)]).astype(int)
+        for bb, pb in enumerate(plans):
+            ro_r = np.concatenate([[0], np.cumsum(pb.recv_r_rows)]).astype(int)
+            ro_q = np.concatenate([[0], np.cumsum(pb.recv_q_rows)]).astype(int)
+            for s_off, r_off, arr in ((pa.send_r_off[so_r[bb]:so_r[bb + 1]], pb.recv_r_off[ro_r[a]:ro_r[a + 1]], 3),
+                                      (pa.send_q_off[so_q[bb]:so_q[bb + 1]], pb.recv_q_off[ro_q[a]:ro_q[a + 1]], 1)):
+                for s, t in zip(s_off, r_off):
+                    want[bb][arr][t:t + d] = bufs[a][arr][s:s + d]
+    # the push: dst offsets as the all_to_all of recv offsets delivers them, then plain copies
+    got = [[x.copy() for x in b] for b in bufs]
+    for a, pa in enumerate(plans):
+        dst_r, dst_q = [], []
+        for bb, pb in enumerate(plans):
+            ro_r = np.concatenate([[0], np.cumsum(pb.recv_r_rows)]).astype(int)
+            ro_q = np.concatenate([[0], np.cumsum(pb.recv_q_rows)]).astype(int)
+            dst_r.append(np.asarray(pb.recv_r_off[ro_r[a]:ro_r[a + 1]], dtype=np.int64))
+            dst_q.append(np.asarray(pb.recv_q_off[ro_q[a]:ro_q[a + 1]], dtype=np.int64))
+        t = push_tables(pa, base, np.concatenate(dst_r), np.concatenate(dst_q), elem)
+        for src, dst, arr in ((t["src_r_off"], t["dst_r"][1], 3), (t["src_q_off"], t["dst_q"][1], 1)):
+            assert len(src) == len(dst)
+            for s, addr in zip(src, dst):
+                rank, rem = divmod(int(addr), 4 * stride)
+                which, byte = divmod(rem, stride)
+                assert which == arr and rank != a and byte % elem == 0
+                o = byte // elem
+                got[rank][arr][o:o + d] = bufs[a][arr][s:s + d]
+            if len(dst) > 1:   # ascending addresses inside every peer group
+                peer = np.asarray(dst) // (4 * stride)
+                assert (np.diff(np.asarray(dst))[np.diff(peer) == 0] > 0).all()
+    for r in range(world):
+        for arr in (1, 3):
+            assert np.array_equal(got[r][arr], want[r][arr]), (r, arr)
