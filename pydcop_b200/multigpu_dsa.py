@@ -207,6 +207,20 @@ class ValueHalo:
         self.unpack_values(values)
 
 
+def value_push_tables(shard: DsaShard, base: np.ndarray, dst_idx):
+    """Source indices (internal variable order) and absolute destination addresses of the value
+    push.  base[rank] = addresses of that rank's two value buffers as mapped into this process;
+    dst_idx = the consumers' internal ghost indices of my send list (my send order).  Issued in
+    destination order inside each peer group, like multigpu.push_tables."""
+    from .multigpu import destination_order
+    perm = np.asarray(shard.layout.var_perm, dtype=np.int64)
+    dst_idx = np.asarray(dst_idx, dtype=np.int64)
+    peer_of = np.repeat(np.arange(shard.world), np.asarray(shard.send_split, dtype=np.int64))
+    order = destination_order(dst_idx, shard.send_split)
+    return dict(dst=[(base[peer_of, b] + dst_idx * 4)[order] for b in range(2)],
+                src=perm[shard.send_var][order])
+
+
 class ValuePeerPush:
     """Boundary values over NVLink peer memory, the DSA twin of multigpu.PeerPush: every rank maps
     the peers' two value buffers (CUDA IPC) and ONE push kernel (fg_halo_push, rows of one 4-byte
@@ -217,7 +231,6 @@ class ValuePeerPush:
         import torch
         import torch.distributed as dist
         from . import _cabi
-        from .multigpu import destination_order
         self.torch, self.dist, self.group = torch, dist, group
         e, sh, h = sharded.engine, sharded.shard, sharded.halo
         self.engine = e
@@ -256,12 +269,9 @@ class ValuePeerPush:
         out = torch.zeros(len(sh.send_var), dtype=torch.int64, device=dev)
         inp = torch.from_numpy(np.ascontiguousarray(perm[sh.recv_var])).to(dev)
         dist.all_to_all_single(out, inp, list(sh.send_split), list(sh.recv_split), group=group)
-        dst_idx = out.cpu().numpy()
-        peer_of = np.repeat(np.arange(W), np.asarray(sh.send_split, dtype=np.int64))
-        order = destination_order(dst_idx, sh.send_split)
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)  # noqa: E731
-        self.dst = [to((base[peer_of, b] + dst_idx * 4)[order]) for b in range(2)]
-        self.src = to(perm[sh.send_var][order])
+        t = value_push_tables(sh, base, out.cpu().numpy())
+        self.dst, self.src = [to(a) for a in t["dst"]], to(t["src"])
         self.n = len(sh.send_var)
         self.token = torch.zeros(1, device=dev)
         self.launches = 0

@@ -192,3 +192,37 @@ def test_sharded_dsa_equals_single_process_over_gloo(kind, world, params, partit
         assert np.array_equal(traj, want), rank
         assert cycle == o.cycle
     assert len({tuple(map(tuple, w)) for w in [want]}) == 1 and (np.diff(want, axis=0) != 0).any()
+
+
+@pytest.mark.parametrize("world,partition", [(3, "blocks"), (4, "multilevel")])
+def test_value_push_tables_fill_every_ghost(world, partition):
+    """The address tables of the DSA peer push in a simulated address space: after executing the
+    push as plain copies every ghost holds its owner's value."""
+    from pydcop_b200.multigpu_dsa import value_push_tables
+    inst = _instance("binary")
+    V = len(inst["dom_size"])
+    shards = [build_dsa_shard(inst, r, world, partition) for r in range(world)]
+    stride = 1 << 40
+    base = np.array([[r * 2 * stride + b * stride for b in range(2)] for r in range(world)], dtype=np.int64)
+    truth = np.arange(V) * 7 + 3                       # "value" of every global variable
+    bufs = []
+    for s in shards:                                   # internal order; ghosts start out wrong
+        perm = np.asarray(s.layout.var_perm, dtype=np.int64)
+        b = np.full(s.layout.n_vars, -1, dtype=np.int64)
+        b[perm[:s.n_own_vars]] = truth[s.own_vars]
+        bufs.append(b)
+    for a, sa in enumerate(shards):
+        dst_idx = []
+        for b, sb in enumerate(shards):
+            off = sum(sb.recv_split[:a])
+            perm_b = np.asarray(sb.layout.var_perm, dtype=np.int64)
+            dst_idx.append(perm_b[sb.recv_var[off:off + sb.recv_split[a]]])
+        t = value_push_tables(sa, base, np.concatenate(dst_idx) if dst_idx else np.zeros(0, np.int64))
+        for src, addr in zip(t["src"], t["dst"][1]):
+            rank, rem = divmod(int(addr), 2 * stride)
+            which, byte = divmod(rem, stride)
+            assert which == 1 and rank != a and byte % 4 == 0
+            bufs[rank][byte // 4] = bufs[a][src]
+    for s, b in zip(shards, bufs):
+        perm = np.asarray(s.layout.var_perm, dtype=np.int64)
+        assert np.array_equal(b[perm], truth[s.local_global_id])
