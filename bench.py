@@ -123,6 +123,32 @@ def cpu_baseline(inst, L, seconds=12.0, dtype=np.float32):
                       f"{'f32' if dtype == np.float32 else 'f64'}, OpenMP {cores} threads, {dt:.1f}s"}
 
 
+def shared_partition(inst, world, rank, dev, part):
+    """Owner array for a multi-GPU run: computed ONCE on rank 0 and broadcast, so every rank builds its
+    shard from the same array whatever the host libraries do; contiguous blocks if it fails.
+    Returns (method name, owner array or 'blocks', error text or None)."""
+    import torch
+    import torch.distributed as dist
+    if part == "blocks" or world <= 1:
+        return "blocks", "blocks", None
+    n_vars = len(inst["dom_size"])
+    owner_t = torch.zeros(n_vars, dtype=torch.int32, device=dev)
+    ok = torch.zeros(1, dtype=torch.int32, device=dev)
+    err = None
+    if rank == 0:
+        try:
+            from pydcop_b200.multigpu import resolve_owner
+            owner_t.copy_(torch.from_numpy(np.ascontiguousarray(resolve_owner(inst, world, part), dtype=np.int32)))
+            ok[0] = 1
+        except Exception as ex:  # noqa: BLE001 — keep the run
+            err = repr(ex)
+    dist.broadcast(ok, 0)
+    if int(ok.item()) != 1:
+        return "blocks", "blocks", err or "partition failed on rank 0"
+    dist.broadcast(owner_t, 0)
+    return part, owner_t.cpu().numpy(), None
+
+
 def side_workload(args, dev):
     """Other BASELINE configs on one GPU (not the driver's line): same timing rules."""
     import torch
@@ -138,11 +164,11 @@ def side_workload(args, dev):
     rank = int(os.environ.get("RANK", "0"))
     if world > 1 and w == "mgm":
         raise SystemExit("--workload mgm is a single-GPU side line (MGM is not sharded)")
-    part = os.environ.get("PYDCOP_B200_PARTITION", "auto")
+    part, part_owner, _perr = shared_partition(inst, world, rank, dev, os.environ.get("PYDCOP_B200_PARTITION", "auto"))
     if w == "c4":
         if world > 1:   # strong scaling: the same 1M-variable problem over `world` GPUs
             from pydcop_b200.multigpu_dsa import ShardedDsa
-            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1, partition=part,
+            eng = ShardedDsa(inst, rank, world, dev, precision=args.precision, seed=1, partition=part_owner,
                              halo=os.environ.get("PYDCOP_B200_HALO", "auto"))
         else:
             eng = DsaEngine(L, device=dev, precision=args.precision, seed=1)
@@ -158,7 +184,7 @@ def side_workload(args, dev):
         if world > 1:   # strong scaling of the named instance (BASELINE configs[2]: the grid over 1 -> 8 GPUs)
             from pydcop_b200.multigpu import ShardedMaxSum
             eng = ShardedMaxSum(inst, rank, world, dev, precision=args.precision,
-                                halo=os.environ.get("PYDCOP_B200_HALO", "auto"), partition=part)
+                                halo=os.environ.get("PYDCOP_B200_HALO", "auto"), partition=part_owner)
         else:
             eng = MaxSumEngine(L, device=dev, precision=args.precision)
         units, metric = 2 * L.n_edges, METRIC
@@ -299,16 +325,10 @@ def main():
     n_edges_global = int(len(inst["edge_var"]))
     if world > 1:
         from pydcop_b200.multigpu import ShardedMaxSum
-        part = os.environ.get("PYDCOP_B200_PARTITION", "auto")
-        if part != "blocks":   # deterministic, so every rank takes the same branch
-            from pydcop_b200.multigpu import resolve_owner
-            try:
-                part_owner = resolve_owner(inst, world, part)
-            except Exception as ex:  # noqa: BLE001 — keep the run: contiguous blocks always work
-                config["partition_error"] = repr(ex)
-                part, part_owner = "blocks", "blocks"
-        else:
-            part_owner = "blocks"
+        part, part_owner, perr = shared_partition(inst, world, rank, dev,
+                                                  os.environ.get("PYDCOP_B200_PARTITION", "auto"))
+        if perr:
+            config["partition_error"] = perr
         runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision,
                                halo=os.environ.get("PYDCOP_B200_HALO", "auto"), partition=part_owner)
         L = None
