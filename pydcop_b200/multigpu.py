@@ -452,16 +452,29 @@ class ShardedMaxSum:
     """One rank of the partitioned MaxSum: same driving API as MaxSumEngine (init / step / values)."""
 
     def __init__(self, inst, rank, world, device, precision="f32", group=None, halo="nccl",
-                 partition="blocks", **params):
+                 partition="blocks", engine_factory=None, pack=None, unpack=None, **params):
+        """`engine_factory(layout, precision=…, **params)`, `pack` and `unpack` exist so that the
+        partition, the exchange and this class's own cycle logic can run on a box without a GPU
+        (tests: the kernel source through the host shim, gloo); the product path leaves them at
+        None and gets MaxSumEngine + the CUDA halo kernels."""
         import torch
         from . import _cabi
         from .engine import MaxSumEngine, PRECISIONS
         self.torch = torch
         self.plan = build_shard(inst, rank, world, partition)
         self.rank, self.world = rank, world
+        prec, tdt, _ = PRECISIONS[precision]
+        self.global_n_edges = int(len(np.asarray(inst["edge_var"])))
+        self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
+        self.peer = None
+        if engine_factory is not None:
+            self.engine = engine_factory(self.plan.layout, precision=precision, **params)
+            self.device = torch.device(device) if device is not None else torch.device("cpu")
+            self.halo = HaloExchange(self.plan, tdt, self.device, pack, unpack, group)
+            self.halo_mode = "nccl"
+            return
         self.engine = MaxSumEngine(self.plan.layout, device=device, precision=precision, **params)
         self.device = self.engine.device
-        prec, tdt, _ = PRECISIONS[precision]
         lib = self.engine.lib
 
         def stream():
@@ -495,9 +508,6 @@ class ShardedMaxSum:
         if self.plan.layout.uniform_dom:
             self.halo.fused = fused
         self.halo_mode = halo
-        self.peer = None
-        self.global_n_edges = int(len(np.asarray(inst["edge_var"])))
-        self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
 
     @property
     def layout(self):
