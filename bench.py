@@ -124,29 +124,13 @@ def cpu_baseline(inst, L, seconds=12.0, dtype=np.float32):
 
 
 def shared_partition(inst, world, rank, dev, part):
-    """Owner array for a multi-GPU run: computed ONCE on rank 0 and broadcast, so every rank builds its
-    shard from the same array whatever the host libraries do; contiguous blocks if it fails.
-    Returns (method name, owner array or 'blocks', error text or None)."""
-    import torch
-    import torch.distributed as dist
-    if part == "blocks" or world <= 1:
-        return "blocks", "blocks", None
-    n_vars = len(inst["dom_size"])
-    owner_t = torch.zeros(n_vars, dtype=torch.int32, device=dev)
-    ok = torch.zeros(1, dtype=torch.int32, device=dev)
-    err = None
-    if rank == 0:
-        try:
-            from pydcop_b200.multigpu import resolve_owner
-            owner_t.copy_(torch.from_numpy(np.ascontiguousarray(resolve_owner(inst, world, part), dtype=np.int32)))
-            ok[0] = 1
-        except Exception as ex:  # noqa: BLE001 — keep the run
-            err = repr(ex)
-    dist.broadcast(ok, 0)
-    if int(ok.item()) != 1:
-        return "blocks", "blocks", err or "partition failed on rank 0"
-    dist.broadcast(owner_t, 0)
-    return part, owner_t.cpu().numpy(), None
+    """(method name, owner array or 'blocks', error text or None): the partition is computed once on
+    rank 0 and broadcast (pydcop_b200.multigpu.broadcast_owner); contiguous blocks if it fails."""
+    from pydcop_b200.multigpu import broadcast_owner
+    owner, err = broadcast_owner(inst, world, rank, dev, part)
+    if isinstance(owner, str):
+        return "blocks", "blocks", err
+    return part, owner, None
 
 
 def side_workload(args, dev):

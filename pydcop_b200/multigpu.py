@@ -83,6 +83,32 @@ def resolve_owner(inst, world: int, partition="blocks") -> np.ndarray:
     return owner
 
 
+def broadcast_owner(inst, world: int, rank: int, device, method="auto", group=None):
+    """Owner array for a multi-process run, computed ONCE on rank 0 and broadcast so that every
+    rank builds its shard from the same array whatever the host libraries do.  Falls back to
+    contiguous blocks when the partitioner fails.  Returns (owner array or 'blocks', error text
+    or None); a collective — every rank must call it."""
+    import torch
+    import torch.distributed as dist
+    if method == "blocks" or world <= 1:
+        return "blocks", None
+    n_vars = len(np.asarray(inst["dom_size"]))
+    owner_t = torch.zeros(n_vars, dtype=torch.int32, device=device)
+    ok = torch.zeros(1, dtype=torch.int32, device=device)
+    err = None
+    if rank == 0:
+        try:
+            owner_t.copy_(torch.from_numpy(np.ascontiguousarray(resolve_owner(inst, world, method), dtype=np.int32)))
+            ok[0] = 1
+        except Exception as ex:  # noqa: BLE001 — keep the run: contiguous blocks always work
+            err = repr(ex)
+    dist.broadcast(ok, 0, group=group)
+    if int(ok.item()) != 1:
+        return "blocks", err or "partition failed on rank 0"
+    dist.broadcast(owner_t, 0, group=group)
+    return owner_t.cpu().numpy(), None
+
+
 def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int, partition="blocks") -> ShardPlan:
     dom_size = np.asarray(inst["dom_size"], dtype=np.int32)
     factor_ptr = np.asarray(inst["factor_ptr"], dtype=np.int64)

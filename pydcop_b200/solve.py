@@ -144,12 +144,50 @@ def _default_engine(kind, layout, dcop, params, mode, precision, device, seed):
                      isolated_value=isolated_values(dcop, mode))
 
 
+def _sharded_engine(kind, inst, dcop, params, mode, precision, device, seed, partition, halo, sharded_kwargs):
+    """One rank's engine of a multi-process run (torch.distributed is initialised): the variables
+    are split over the ranks (rank 0 computes the partition and broadcasts it), boundary rows /
+    values are exchanged every cycle (pydcop_b200.multigpu, multigpu_dsa)."""
+    import torch
+    import torch.distributed as dist
+    from .multigpu import ShardedMaxSum, broadcast_owner
+    from .multigpu_dsa import ShardedDsa
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if kind == "mgm":
+        raise ValueError("mgm is not sharded: run it on one GPU")
+    kw = dict(sharded_kwargs or {})
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if torch.cuda.is_available() and "engine_factory" not in kw
+                                             else torch.device("cpu"))
+    owner, err = broadcast_owner(inst, world, rank, dev, partition)
+    if kind == "maxsum":
+        eng = ShardedMaxSum(inst, rank, world, dev, precision=precision, halo=halo, partition=owner, mode=mode,
+                            damping=params["damping"], damping_nodes=params["damping_nodes"],
+                            stability=params["stability"], start_messages=params["start_messages"],
+                            **dict({"record_sent": False} if "engine_factory" not in kw else {}, **kw))
+    else:
+        eng = ShardedDsa(inst, rank, world, dev, precision=precision, halo=halo, partition=owner, mode=mode,
+                         probability=params["probability"], p_mode=params["p_mode"], variant=params["variant"],
+                         stop_cycle=params["stop_cycle"], seed=seed or 0,
+                         isolated_value=isolated_values(dcop, mode), **kw)
+    eng.partition_error = err
+    return eng
+
+
 def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] = None,
           timeout: Optional[float] = None, precision: str = "f32", device=None,
           seed: Optional[int] = None, infinity: float = 10000.0, chunk: int = 50,
           on_cycle: Optional[Callable[[int, np.ndarray], None]] = None,
-          engine_factory: Optional[Callable] = None) -> Dict[str, Any]:
+          engine_factory: Optional[Callable] = None, distributed: Optional[bool] = None,
+          partition="auto", halo: str = "auto", sharded_kwargs: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
     """Run `algo` on `problem` and return pyDcop's result dict.
+
+    Under `torchrun` (torch.distributed initialised, world size > 1; `distributed` None = detect)
+    every rank calls solve() with the same arguments: the variables are partitioned over the
+    ranks (`partition`: auto | blocks | multilevel | an owner array), each rank runs its shard on
+    its GPU and boundary messages / values are exchanged every cycle (`halo`: auto | p2p | nccl);
+    every rank returns the same result.  `seed` defaults to 0 there (all ranks must draw the same
+    noise).
 
     problem      see `load`
     algo         maxsum | dsa | mgm (the *_gpu spellings of the plugin modules are accepted)
@@ -166,19 +204,34 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
     stop_cycle = int(params["stop_cycle"])
     if not stop_cycle and timeout is None:
         raise ValueError(f"{kind} does not stop by itself: give algo_params['stop_cycle'] or a timeout")
+    if distributed is None:
+        try:
+            import torch.distributed as dist
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except ImportError:
+            distributed = False
+    if distributed and seed is None:
+        seed = 0
     t0 = time.perf_counter()
     dcop = load(problem, seed)
     mode = dcop.objective
     inst = dcop.instance()
     if kind == "maxsum":
         inst["unary"] = ingest.add_noise(inst["unary"], params["noise"], seed)
-    layout = build_layout(**inst)
-    t_packed = time.perf_counter()
-    if engine_factory is not None:
-        engine = engine_factory(kind, layout, dict(inst, var_rank=name_rank(dcop)),
-                                dict(params, mode=mode, seed=seed or 0))
+    n_gpus = 1
+    if distributed:
+        import torch.distributed as dist
+        engine = _sharded_engine(kind, inst, dcop, params, mode, precision, device, seed, partition, halo,
+                                 sharded_kwargs)
+        n_gpus = dist.get_world_size()
     else:
-        engine = _default_engine(kind, layout, dcop, params, mode, precision, device, seed)
+        layout = build_layout(**inst)
+        if engine_factory is not None:
+            engine = engine_factory(kind, layout, dict(inst, var_rank=name_rank(dcop)),
+                                    dict(params, mode=mode, seed=seed or 0))
+        else:
+            engine = _default_engine(kind, layout, dcop, params, mode, precision, device, seed)
+    t_packed = time.perf_counter()
     engine.init()
     cycle, status = 0, "FINISHED"
     deadline = None if timeout is None else t0 + float(timeout)
@@ -186,7 +239,13 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
         n = chunk if not stop_cycle else min(chunk, stop_cycle - cycle)
         if n <= 0:
             break
-        if deadline is not None and time.perf_counter() >= deadline:
+        expired = deadline is not None and time.perf_counter() >= deadline
+        if distributed and deadline is not None:   # every rank must leave the loop in the same round
+            import torch
+            flag = torch.tensor([int(expired)], dtype=torch.int32, device=engine.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            expired = bool(flag.item())
+        if expired:
             status = "TIMEOUT"
             break
         engine.step(n)
@@ -198,7 +257,7 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
     return {"status": status, "assignment": dcop.assignment(idx), "cost": cost,
             "violation": violation, "time": time.perf_counter() - t0, "cycle": cycle,
             "msg_count": 0, "msg_size": 0,  # nothing crosses an agent boundary
-            "algo": kind, "precision": precision,
+            "algo": kind, "precision": precision, "n_gpus": n_gpus,
             "ingest_time": t_packed - t0}
 
 
@@ -223,7 +282,16 @@ def main(argv=None):
     ap.add_argument("--no-assignment", action="store_true",
                     help="omit the assignment from the output (10^6 variables)")
     ap.add_argument("--save", metavar="FILE", help="also write the instance as a binary container")
+    ap.add_argument("--partition", default="auto", choices=["auto", "blocks", "multilevel"],
+                    help="under torchrun: how the variables are split over the GPUs")
     args = ap.parse_args(argv)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:   # launched by torchrun: one process per GPU over NCCL
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     params = {}
     for p in args.algo_params:
         if ":" not in p:
@@ -232,13 +300,16 @@ def main(argv=None):
         params[k] = v
     files = args.dcop_files if len(args.dcop_files) > 1 else args.dcop_files[0]
     dcop = load(files, args.seed)
-    if args.save:
+    if args.save and rank == 0:
         ingest.save_instance(args.save, dcop)
     res = solve(dcop, args.algo, params, args.timeout, args.precision, seed=args.seed,
-                infinity=args.infinity)
+                infinity=args.infinity, partition=args.partition)
     if args.no_assignment:
         res.pop("assignment")
-    print(json.dumps(res, indent=2, sort_keys=True, default=str))
+    if rank == 0:
+        print(json.dumps(res, indent=2, sort_keys=True, default=str))
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 
