@@ -153,10 +153,13 @@ def _grow(A, w, k, cap, rng):
             take = mv[np.cumsum(w[mv]) <= (cap - load[p]) * 0.5 + w[mv].min()]   # grow in steps
             label[take] = p
             load[p] += w[take].sum()
-    for v in np.nonzero(label < 0)[0]:      # disconnected leftovers: lightest part
-        p = int(np.argmin(load))
-        label[v] = p
-        load[p] += w[v]
+    left = np.nonzero(label < 0)[0]         # disconnected leftovers: fill the parts up to the mean load
+    if len(left):
+        room = np.maximum((w.sum() / k) - load, 0.0)
+        if room.sum() <= 0:
+            room = np.ones(k)
+        fill = np.cumsum(room) * (w[left].sum() / room.sum())
+        label[left] = np.minimum(np.searchsorted(fill, np.cumsum(w[left]), side="left"), k - 1)
     return label
 
 
