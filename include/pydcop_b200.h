@@ -293,6 +293,13 @@ typedef struct {
   int32_t mode_max;
   int32_t stop_cycle;             /* 0 = never; a run ends when round + 1 >= stop_cycle (mgm.py:404) */
   uint64_t seed;
+  /* optional fast shape (opt-in experiment): every constraint binary over one domain size `fast_dom`
+   * in {4, 8, 10, 16, 20}; the oriented tables of the DSA fast path (fg_dsa_desc_t) and the number of
+   * incidences handled per trip (2 | 4).  All NULL / 0 = the generic value-phase kernel. */
+  const void *dev_tables_or;      /* T[...] */
+  const int32_t *dev_slot_nbr;    /* [n_edges] */
+  const int64_t *dev_slot_tab;    /* [n_edges] */
+  int32_t fast_dom, fast_chunk;
 } fg_mgm_desc_t;
 
 typedef struct fg_mgm *fg_mgm_t;

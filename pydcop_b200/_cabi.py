@@ -77,7 +77,9 @@ class FgMgmDesc(C.Structure):
                 ("dev_var_ptr", P), ("dev_slot_edge", P), ("dev_nbr_ptr", P), ("dev_nbr_idx", P),
                 ("dev_init_value", P), ("dev_value", P), ("dev_cost", P), ("dev_has_cost", P),
                 ("dev_gain", P), ("dev_new_value", P),
-                ("mode_max", C.c_int32), ("stop_cycle", C.c_int32), ("seed", C.c_uint64)]
+                ("mode_max", C.c_int32), ("stop_cycle", C.c_int32), ("seed", C.c_uint64),
+                ("dev_tables_or", P), ("dev_slot_nbr", P), ("dev_slot_tab", P),
+                ("fast_dom", C.c_int32), ("fast_chunk", C.c_int32)]
 
 
 # every symbol include/pydcop_b200.h declares: (restype, argtypes)

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "mgm_kernels.cuh"
+#include "mgm_fast_kernels.cuh"
 
 struct fg_mgm {
   fg_mgm_desc_t d;
@@ -104,13 +105,40 @@ extern "C" int fg_mgm_init(fg_mgm_t h, void *stream) {
 
 static bool mgm_finished(const fg_mgm *h) { return h->d.stop_cycle && h->cycle + 1 >= h->d.stop_cycle; }
 
+template <typename T, int D, int U>
+static void mgm_gain_fast_launch(fg_mgm *h, cudaStream_t st) {
+  const fg_mgm_desc_t &d = h->d;
+  k_mgm_gain_bin<T, D, U><<<mgm_blocks(d.n_vars, 128), 128, 0, st>>>(
+      mgm_side(h), d.n_vars, d.dev_slot_nbr, d.dev_slot_tab, (const T *)d.dev_tables_or, (const T *)d.dev_unary,
+      d.dev_value, (T *)d.dev_cost, d.dev_has_cost, (T *)d.dev_gain, d.dev_new_value, d.mode_max, d.seed,
+      (uint32_t)(h->cycle + 1));
+}
+
+// the fast value-phase kernel when the descriptor carries the oriented tables (opt-in), else false
+template <typename T>
+static bool mgm_gain_fast(fg_mgm *h, cudaStream_t st) {
+  const fg_mgm_desc_t &d = h->d;
+  if (!d.dev_tables_or || !d.dev_slot_nbr || !d.dev_slot_tab || (d.fast_chunk != 2 && d.fast_chunk != 4)) return false;
+#define FG_MGM_CASE(n)                                                              \
+  case n:                                                                           \
+    if (d.fast_chunk == 2) mgm_gain_fast_launch<T, n, 2>(h, st);                    \
+    else mgm_gain_fast_launch<T, n, 4>(h, st);                                      \
+    return true;
+  switch (d.fast_dom) {
+    FG_MGM_CASE(4) FG_MGM_CASE(8) FG_MGM_CASE(10) FG_MGM_CASE(16) FG_MGM_CASE(20)
+  }
+#undef FG_MGM_CASE
+  return false;
+}
+
 template <typename T>
 static int mgm_cycle_t(fg_mgm *h, cudaStream_t st) {
   const fg_mgm_desc_t &d = h->d;
   if (d.n_vars) {
-    k_mgm_gain<T><<<mgm_blocks(d.n_vars, 128), 128, 0, st>>>(
-        mgm_side(h), d.n_vars, (const T *)d.dev_tables, (const T *)d.dev_unary, d.dev_value, (T *)d.dev_cost,
-        d.dev_has_cost, (T *)d.dev_gain, d.dev_new_value, d.mode_max, d.seed, (uint32_t)(h->cycle + 1));
+    if (!mgm_gain_fast<T>(h, st))
+      k_mgm_gain<T><<<mgm_blocks(d.n_vars, 128), 128, 0, st>>>(
+          mgm_side(h), d.n_vars, (const T *)d.dev_tables, (const T *)d.dev_unary, d.dev_value, (T *)d.dev_cost,
+          d.dev_has_cost, (T *)d.dev_gain, d.dev_new_value, d.mode_max, d.seed, (uint32_t)(h->cycle + 1));
     k_mgm_decide<T><<<mgm_blocks(d.n_vars, 256), 256, 0, st>>>(mgm_side(h), d.n_vars, (const T *)d.dev_gain,
                                                                 d.dev_new_value, d.dev_value, (T *)d.dev_cost);
     h->launches += 2;

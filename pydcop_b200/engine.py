@@ -561,6 +561,19 @@ class MgmEngine(_EngineBase):
         d.dev_value, d.dev_cost, d.dev_has_cost = _ptr(self.value), _ptr(self.cost), _ptr(self.has_cost)
         d.dev_gain, d.dev_new_value = _ptr(self.gain), _ptr(self.new_value)
         d.mode_max, d.stop_cycle, d.seed = int(mode == "max"), int(stop_cycle), int(seed) & (2 ** 64 - 1)
+        # PYDCOP_B200_MGM_FAST=2|4: the fast value-phase kernel on the DSA fast-path arrays (opt-in
+        # experiment; binary constraints over one domain size in {4, 8, 10, 16, 20})
+        self.fast_chunk = 0
+        chunk = int(os.environ.get("PYDCOP_B200_MGM_FAST", "0") or 0)
+        if chunk in (2, 4):
+            with torch.cuda.device(self.device):
+                fast = dsa_fast_arrays(L, self.tables, mode)
+            if fast is not None and fast[4] in (4, 8, 10, 16, 20):
+                self.tables_or, self.slot_tab, self.slot_nbr, _, fast_dom = fast
+                d.dev_tables_or, d.dev_slot_nbr, d.dev_slot_tab = (_ptr(self.tables_or), _ptr(self.slot_nbr),
+                                                                   _ptr(self.slot_tab))
+                d.fast_dom, d.fast_chunk = fast_dom, chunk
+                self.fast_chunk = chunk
         self._desc = d
         self._h = C.c_void_p()
         self._check(self.lib.fg_mgm_create(C.byref(d), C.byref(self._h)), "fg_mgm_create")

@@ -13,7 +13,10 @@ static thread_local Dim3 blockIdx, blockDim, threadIdx;
 #define __restrict__
 #define __launch_bounds__(n)
 
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
 #include "../../pydcop_b200/csrc/mgm_kernels.cuh"
+#include "../../pydcop_b200/csrc/mgm_fast_kernels.cuh"
 
 template <typename F>
 static void launch(int n, int block, F body) {
@@ -72,4 +75,40 @@ void mgm_host_cycle(const mgm_host_arrays *a, uint32_t cycle) {
   if (a->precision == FG_F64) cycle_t<double>(a, cycle);
   else cycle_t<float>(a, cycle);
 }
+}
+
+// ---- fast value phase (mgm_fast_kernels.cuh) ------------------------------------------------
+struct mgm_host_fast {
+  const int32_t *slot_nbr;
+  const int64_t *slot_tab;
+  const void *tables_or;
+  int32_t dom, chunk;
+};
+
+template <typename T, int D, int U>
+static void fast_cycle(const mgm_host_arrays *a, const mgm_host_fast *f, uint32_t cycle) {
+  launch(a->n_vars, 128, [&] {
+    k_mgm_gain_bin<T, D, U>(side(a), a->n_vars, f->slot_nbr, f->slot_tab, (const T *)f->tables_or, (const T *)a->unary,
+                            a->value, (T *)a->cost, a->has_cost, (T *)a->gain, a->new_value, a->mode_max, a->seed, cycle);
+  });
+  launch(a->n_vars, 256, [&] {
+    k_mgm_decide<T>(side(a), a->n_vars, (const T *)a->gain, a->new_value, a->value, (T *)a->cost);
+  });
+}
+
+template <typename T, int U>
+static int fast_by_dom(const mgm_host_arrays *a, const mgm_host_fast *f, uint32_t cycle) {
+  switch (f->dom) {
+    case 4: fast_cycle<T, 4, U>(a, f, cycle); return 0;
+    case 8: fast_cycle<T, 8, U>(a, f, cycle); return 0;
+    case 10: fast_cycle<T, 10, U>(a, f, cycle); return 0;
+    case 16: fast_cycle<T, 16, U>(a, f, cycle); return 0;
+    case 20: fast_cycle<T, 20, U>(a, f, cycle); return 0;
+  }
+  return 3;
+}
+
+extern "C" int mgm_host_cycle_fast(const mgm_host_arrays *a, const mgm_host_fast *f, uint32_t cycle) {
+  if (a->precision == FG_F64) return f->chunk == 2 ? fast_by_dom<double, 2>(a, f, cycle) : fast_by_dom<double, 4>(a, f, cycle);
+  return f->chunk == 2 ? fast_by_dom<float, 2>(a, f, cycle) : fast_by_dom<float, 4>(a, f, cycle);
 }

@@ -35,6 +35,8 @@ class _Arrays(C.Structure):
 def shim():
     deps = [SHIM_SRC, os.path.join(ROOT, "pydcop_b200", "csrc", "mgm_kernels.cuh"),
             os.path.join(ROOT, "pydcop_b200", "csrc", "philox.cuh"),
+            os.path.join(ROOT, "pydcop_b200", "csrc", "mgm_fast_kernels.cuh"),
+            os.path.join(ROOT, "pydcop_b200", "csrc", "dsa_v2_kernels.cuh"),
             os.path.join(ROOT, "include", "pydcop_b200.h")]
     if not os.path.exists(SHIM_SO) or any(os.path.getmtime(d) > os.path.getmtime(SHIM_SO) for d in deps):
         os.makedirs(os.path.dirname(SHIM_SO), exist_ok=True)
@@ -155,3 +157,63 @@ def test_kernel_source_matches_oracle_with_float_costs(shim, precision, d, arity
         assert np.array_equal(gain.astype(dt), o.gain) and np.array_equal(new_value, o.new_val), k
         moved += int((prev != o.val).sum())
     assert moved > 0
+
+
+class _Fast(C.Structure):
+    _fields_ = [("slot_nbr", P), ("slot_tab", P), ("tables_or", P), ("dom", C.c_int32), ("chunk", C.c_int32)]
+
+
+class HostMgmFast(HostMgm):
+    """HostMgm stepping the FAST value-phase kernel on the DSA fast-path arrays."""
+
+    def __init__(self, lib, layout, precision, chunk, mode="min", **kw):
+        import torch
+        from pydcop_b200.engine import dsa_fast_arrays
+        super().__init__(lib, layout, precision=precision, mode=mode, **kw)
+        dt = np.float64 if precision == "f64" else np.float32
+        fast = dsa_fast_arrays(layout, torch.from_numpy(np.ascontiguousarray(layout.tables, dtype=dt)), mode)
+        assert fast is not None
+        tables_or, slot_tab, slot_nbr, _, D = fast
+        self.fkeep = dict(slot_nbr=np.ascontiguousarray(slot_nbr.numpy(), np.int32),
+                          slot_tab=np.ascontiguousarray(slot_tab.numpy(), np.int64),
+                          tables_or=np.ascontiguousarray(tables_or.numpy(), dt))
+        self.f = _Fast(P(self.fkeep["slot_nbr"].ctypes.data), P(self.fkeep["slot_tab"].ctypes.data),
+                       P(self.fkeep["tables_or"].ctypes.data), D, chunk)
+
+    def step(self, n=1):
+        for _ in range(n):
+            if self.finished:
+                break
+            assert self.lib.mgm_host_cycle_fast(C.byref(self.a), C.byref(self.f), C.c_uint32(self.cycle + 1)) == 0
+            self.cycle += 1
+        return self
+
+
+@pytest.mark.parametrize("d,mode,precision,chunk", [(4, "min", "f64", 4), (8, "max", "f32", 2), (10, "min", "f32", 4),
+                                                    (16, "min", "f64", 2), (20, "min", "f32", 4), (20, "max", "f64", 4)])
+def test_fast_value_phase_source_matches_generic_and_oracle(shim, d, mode, precision, chunk):
+    n = 2500
+    inst = random_factor_graph(n, d, int(n * 2.7), 2, seed=d + 1, noise=0.5, int_tables=False)
+    rng = np.random.default_rng(d)
+    inst["var_rank"] = rng.permutation(n).astype(np.int32)
+    inst["init_value"] = np.where(rng.random(n) < 0.3, rng.integers(0, d, n), -1).astype(np.int32)
+    inst["var_ptr"], inst["var_edge"] = default_var_csr(n, inst["edge_var"])
+    dt = np.float64 if precision == "f64" else np.float32
+    L = layout_from_instance(inst)
+    o = orc.MgmOracle(inst, dt, mode=mode, seed=23).init()
+    fast = HostMgmFast(shim, L, precision, chunk, mode=mode, seed=23, var_rank=inst["var_rank"]).init()
+    slow = HostMgm(shim, L, precision=precision, mode=mode, seed=23, var_rank=inst["var_rank"]).init()
+    moved = 0
+    for k in range(1, 10):
+        prev = o.val.copy()
+        o.step()
+        fast.step()
+        slow.step()
+        for e in (fast, slow):
+            val, cost = e.values()
+            assert np.array_equal(val, o.val), k
+            assert np.array_equal(cost.astype(dt), o.cost), k
+            gain, new_value = e.gains()
+            assert np.array_equal(gain.astype(dt), o.gain) and np.array_equal(new_value, o.new_val), k
+        moved += int((prev != o.val).sum())
+    assert moved > 0 and np.diff(inst["var_ptr"]).max() > 2 * chunk

@@ -13,7 +13,8 @@ run timeout 300 python -m pytest tests/test_gpu_zz_dsa_v2.py -q
 for u in 0 2 4; do run env PYDCOP_B200_DSA_V2=$u timeout 300 python bench.py --workload c4 --steps 200 --warmup 5; done
 run timeout 300 python -m pytest tests/test_gpu_zz_sharded_dsa.py tests/test_gpu_zz_partition.py tests/test_gpu_sharded.py -q
 # 2. first MGM number (C4 instance, 1M variables) and the DSA line for comparison
-run timeout 300 python bench.py --workload mgm --steps 200 --warmup 5
+run timeout 300 python -m pytest tests/test_gpu_zz_mgm_fast.py -q
+for u in 0 2 4; do run env PYDCOP_B200_MGM_FAST=$u timeout 300 python bench.py --workload mgm --steps 200 --warmup 5; done
 run timeout 300 python bench.py --workload c4 --steps 200 --warmup 5
 # 3. launch list of the MGM step for profiles/
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
