@@ -202,3 +202,27 @@ def test_generic_kernel_source_fuzz(seed, n_vars, damping_nodes, start, mode):
             eng.step()
             o.step()
         _compare(eng, o, k, np.float64)
+
+
+@pytest.mark.parametrize("name", golden_names("msx_"))
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_generic_kernel_source_with_infinite_costs(name, precision):
+    """+/-inf table entries: inf and NaN messages.  f64 against the reference trajectory, f32 against
+    the f32 oracle; NaN positions, send decisions and values included."""
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    params = {k: v for k, v in meta["params"].items() if k != "noise"}
+    dt = np.float64 if precision == "f64" else np.float32
+    eng = HostMaxSum(layout_from_instance(inst), precision, mode=meta["mode"], **params).init()
+    o = orc.MaxSumOracle(inst, dt, mode=meta["mode"], **params).init()
+    for k in range(meta["n_cycles"] + 1):
+        if k:
+            eng.step()
+            o.step()
+        q, r = eng.messages()
+        assert np.array_equal(q.astype(dt), o.q, equal_nan=True) and np.array_equal(r.astype(dt), o.r, equal_nan=True), k
+        if precision == "f64":
+            assert np.array_equal(q, inst["q_state"][k], equal_nan=True), k
+            assert np.array_equal(r, inst["r_state"][k], equal_nan=True), k
+        assert np.array_equal(eng.values()[0], o.value), k
+        qs, rs = eng.sent()
+        assert np.array_equal(qs, o.q_sent) and np.array_equal(rs, o.r_sent), k

@@ -88,6 +88,25 @@ def test_dsa_oracle_exact_vs_reference(name, dtype):
     assert o.cycle == int(inst["cycle_count"][-1].max())
 
 
+@pytest.mark.parametrize("name", golden_names("msx_"))
+def test_maxsum_oracle_with_infinite_costs(name):
+    """Hard constraints (+/-inf table entries, oracle/make_golden_extra.py): the reference's messages
+    become inf and NaN (inf - inf in the normalisation and in approx_match); the oracle must produce
+    the same inf / NaN pattern, the same send decisions and the same values at every cycle."""
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    params = {k: v for k, v in meta["params"].items() if k != "noise"}
+    o = orc.MaxSumOracle(inst, np.float64, mode=meta["mode"], **params).init()
+    assert np.isinf(inst["tables"]).any()
+    for k in range(meta["n_cycles"] + 1):
+        if k:
+            o.step()
+        assert np.array_equal(o.q, inst["q_state"][k], equal_nan=True), (name, k)
+        assert np.array_equal(o.r, inst["r_state"][k], equal_nan=True), (name, k)
+        assert np.array_equal(o.q_sent, inst["q_sent"][k]) and np.array_equal(o.r_sent, inst["r_sent"][k]), (name, k)
+        assert np.array_equal(o.value, inst["value"][k]), (name, k)
+    assert np.isnan(inst["q_state"][-1]).any() and np.isinf(inst["r_state"][-1]).any()
+
+
 @pytest.mark.parametrize("name", golden_names("mgm_"))
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_mgm_oracle_exact_vs_reference(name, dtype):
