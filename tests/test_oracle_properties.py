@@ -132,3 +132,16 @@ def test_mgm_properties(n_vars, d, n_factors, arity, seed):
             assert not (nb & ms), "two neighbours moved in the same round"
     a.step(8)
     assert np.array_equal(o.val, a.val)  # deterministic given the seed
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+def test_infinite_cost_fixtures_regenerate_bit_for_bit(tmp_path):
+    code = (
+        "import sys, os; sys.path.insert(0, %r); sys.argv = ['make_golden_extra.py']\n"
+        "import make_golden_extra as m; m.G.GOLDEN = %r; m.main()\n") % (os.path.join(ROOT, "oracle"), str(tmp_path))
+    subprocess.run([sys.executable, "-W", "ignore", "-c", code], check=True, capture_output=True, timeout=300)
+    for name in ("msx_hard_inf_min", "msx_hard_inf_max"):
+        new = np.load(os.path.join(str(tmp_path), name + ".npz"))
+        old = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        for k in ("r_state", "q_state", "r_sent", "q_sent", "value", "tables"):
+            assert np.array_equal(new[k], old[k], equal_nan=True), (name, k)
