@@ -151,10 +151,11 @@ def _mixed_instance(rng, n_vars, doms, shapes):
             fp.append(len(ev))
             tabs.append(rng.uniform(-3, 3, size=int(np.prod(dom_size[scope]))).astype(np.float32))
     return dict(dom_size=dom_size, factor_ptr=np.array(fp, np.int64), edge_var=np.array(ev, np.int32),
-                tables=np.concatenate(tabs), unary=rng.uniform(0, 0.5, size=int(dom_size.sum())))
+                tables=np.concatenate(tabs) if tabs else np.zeros(0, np.float32),
+                unary=rng.uniform(0, 0.5, size=int(dom_size.sum())))
 
 
-@pytest.mark.parametrize("case", ["high_arity", "big_domains", "hub", "unary_only"])
+@pytest.mark.parametrize("case", ["high_arity", "big_domains", "hub", "unary_only", "max_arity", "max_domain", "no_factors"])
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_generic_kernel_source_on_shapes_beyond_the_gpu_tests(case, precision):
     rng = np.random.default_rng(hash(case) % 1000)
@@ -171,6 +172,12 @@ def test_generic_kernel_source_on_shapes_beyond_the_gpu_tests(case, precision):
             fp.append(len(ev))
             tabs.append(rng.uniform(-3, 3, size=int(inst["dom_size"][0] * inst["dom_size"][other])).astype(np.float32))
         inst.update(factor_ptr=np.array(fp, np.int64), edge_var=np.array(ev, np.int32), tables=np.concatenate(tabs))
+    elif case == "max_arity":         # FG_MAX_ARITY = 8 over binary variables (256-entry tables)
+        inst = _mixed_instance(rng, 12, [2], [(8, 3), (2, 6)])
+    elif case == "max_domain":        # FG_MAX_DOM = 256
+        inst = _mixed_instance(rng, 5, [256, 3], [(2, 4), (1, 2)])
+    elif case == "no_factors":        # variables only: every cycle is a no-op that must not crash
+        inst = _mixed_instance(rng, 6, [2, 4], [])
     else:                              # unary factors only + isolated variables
         inst = _mixed_instance(rng, 12, [3, 5], [(1, 7)])
     L = build_layout(**inst)
