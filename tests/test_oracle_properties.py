@@ -145,3 +145,17 @@ def test_infinite_cost_fixtures_regenerate_bit_for_bit(tmp_path):
         old = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         for k in ("r_state", "q_state", "r_sent", "q_sent", "value", "tables"):
             assert np.array_equal(new[k], old[k], equal_nan=True), (name, k)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_equals_live_reference_on_random_cases(seed):
+    """oracle/fuzz_vs_reference.py: random instances, parameters and cost scales (1e-6 .. 1e18) through the
+    unmodified reference in lock-step and through the oracle — MaxSum messages / send decisions / values,
+    DSA and MGM values and costs, every cycle."""
+    import json
+    r = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "oracle", "fuzz_vs_reference.py"),
+                        "30", str(seed)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["cases"] == 30 and out["failures"] == [], out["failures"]
