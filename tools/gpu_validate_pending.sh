@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Everything that was written after round 1's GPU budget ran out, in one gpurun call (one GPU):
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_validate_pending.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_validate_pending.sh'
 # Outputs land in gpurun_out/pending_* ; copy what should be judged into profiles/.
 set -u
 mkdir -p gpurun_out
@@ -15,7 +15,6 @@ run timeout 300 python -m pytest tests/test_gpu_zz_sharded_dsa.py tests/test_gpu
 # 2. first MGM number (C4 instance, 1M variables) and the DSA line for comparison
 run timeout 300 python -m pytest tests/test_gpu_zz_mgm_fast.py -q
 for u in 0 2 4; do run env PYDCOP_B200_MGM_FAST=$u timeout 300 python bench.py --workload mgm --steps 200 --warmup 5; done
-run timeout 300 python bench.py --workload c4 --steps 200 --warmup 5
 # 3. launch list of the MGM step for profiles/
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/pending_mgm_launches.csv python bench.py --workload mgm --steps 10 --warmup 3 --profile \
