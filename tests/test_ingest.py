@@ -345,3 +345,21 @@ def test_text_level_sharing_is_safe():
     assert table("ph") == (["_a0", "v1"], [2.0 * x + y for x in range(3) for y in range(3)])
     assert table("loc") == (["v1", "v2"], [2.0 * x + y for x in range(3) for y in range(3)])
     assert d.meta["tabulation"]["shared"] == 2
+
+
+def test_random_expressions_tabulate_like_the_reference():
+    """oracle/fuzz_ingest_vs_reference.py: 60 random YAML problems (480 intentional constraints) through
+    the reference loader, assignment by assignment, and through the ingestion — identical tables whichever
+    of the vectorised / scalar / shared routes a constraint took."""
+    import re
+    import subprocess
+    import sys
+    _reference()
+    r = subprocess.run([sys.executable, "-W", "ignore",
+                        os.path.join(os.path.dirname(HERE), "oracle", "fuzz_ingest_vs_reference.py"), "60"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"constraints compared (\\d+) bad (\\d+) (\\{.*\\})", r.stdout)
+    assert m, r.stdout[-500:]
+    assert int(m.group(1)) >= 400 and int(m.group(2)) == 0, r.stdout[-1500:]
+    assert "'vectorised': 0" not in m.group(3) and "'scalar': 0" not in m.group(3)
