@@ -359,7 +359,7 @@ def test_random_expressions_tabulate_like_the_reference():
                         os.path.join(os.path.dirname(HERE), "oracle", "fuzz_ingest_vs_reference.py"), "60"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    m = re.search(r"constraints compared (\\d+) bad (\\d+) (\\{.*\\})", r.stdout)
+    m = re.search(r"constraints compared (\d+) bad (\d+) (\{.*\})", r.stdout)
     assert m, r.stdout[-500:]
     assert int(m.group(1)) >= 400 and int(m.group(2)) == 0, r.stdout[-1500:]
     assert "'vectorised': 0" not in m.group(3) and "'scalar': 0" not in m.group(3)
