@@ -49,6 +49,28 @@ for seed in range(int(sys.argv[1]) if len(sys.argv)>1 else 40):
         sub = rnd.sample(names, rnd.randint(1, 3))
         expr = rand_expr(rnd, sub)
         lines.append(f"  c{c}: {{type: intention, function: \"{expr}\"}}")
+    var_dom = {n: None for n in names}
+    for ln in lines:
+        for n in names:
+            if ln.startswith(f"  {n}: {{domain: "):
+                var_dom[n] = ln.split("domain: ")[1].rstrip("}")
+    real = {"di": doms["di"], "df": doms["df"], "dr": [0, 1, 2, 3, 4]}
+    for c in range(3):      # extensional constraints: cost -> "a b | c d", some cells left to `default`
+        sub = rnd.sample(names, rnd.randint(1, 2))
+        cells = list(itertools.product(*[real[var_dom[n]] for n in sub]))
+        by_cost = {}
+        for cell in cells:
+            if rnd.random() < 0.8:
+                by_cost.setdefault(rnd.choice([0, 1, 2.5, -3, 10]), []).append(" ".join(str(x) for x in cell))
+        lines.append(f"  e{c}:")
+        lines.append("    type: extensional")
+        lines.append(f"    variables: {sub[0] if len(sub) == 1 and rnd.random() < 0.5 else '[' + ', '.join(sub) + ']'}")
+        lines.append(f"    default: {rnd.choice([0, 7, -1.5])}")
+        lines.append("    values:")
+        for cost, asg in by_cost.items():
+            lines.append(f"      {cost}: \"{' | '.join(asg)}\"")
+        if not by_cost:
+            lines[-1] = "    values: {}"
     text = "\n".join(lines) + "\n"
     try:
         ref = load_dcop(text)
@@ -78,5 +100,5 @@ for seed in range(int(sys.argv[1]) if len(sys.argv)>1 else 40):
         want = [float(c(**dict(zip(scope, combo)))) for combo in itertools.product(*doms_)]
         total += 1
         if not np.array_equal(t, np.array(want), equal_nan=True):
-            print("TABLE", seed, cn, c.expression, t[:5], want[:5]); bad += 1
+            print("TABLE", seed, cn, getattr(c, "expression", "extensional"), t[:5], want[:5]); bad += 1
 print("constraints compared", total, "bad", bad, stats)
