@@ -165,3 +165,23 @@ def test_cli_prints_json(tmp_path, capsys, monkeypatch):
     res = json.loads(capsys.readouterr().out)
     assert res["cycle"] == 5 and res["algo"] == "dsa" and len(res["assignment"]) == 6
     assert ingest.load_instance(out).n_vars == 6
+
+
+def test_reference_cli_known_answers():
+    """The end-to-end known answers of the reference's CLI tests (tests/dcop_cli/test_solve.py:41-48,
+    102-108): graph_coloring1.yaml -> {v1: R, v2: G, v3: R}, secp_simple1.yaml -> {l1: 0, l2: 3, l3: 4,
+    m1: 3}, through the direct entry (ingestion of the reference's own YAML files + MaxSum)."""
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference not available")
+    inst_dir = os.path.join(ref_shim.REFERENCE_ROOT, "tests", "instances")
+    r = S.solve(os.path.join(inst_dir, "graph_coloring1.yaml"), "maxsum", {"stop_cycle": 30}, seed=1,
+                engine_factory=OracleEngine)
+    assert r["assignment"] == {"v1": "R", "v2": "G", "v3": "R"} and r["violation"] == 0
+    r = S.solve(os.path.join(inst_dir, "secp_simple1.yaml"), "maxsum", {"stop_cycle": 30}, seed=1,
+                engine_factory=OracleEngine)
+    assert r["assignment"] == {"l1": 0, "l2": 3, "l3": 4, "m1": 3}
+    # the committed trajectory of the same instance ends in the same assignment
+    inst, meta = orc.load_golden(os.path.join(HERE, "golden", "ms_secp_simple1.npz"))
+    names = [str(n) for n in inst["var_names"]]
+    assert dict(zip(names, inst["value"][-1].tolist())) == {"l1": 0, "l2": 3, "l3": 4, "m1": 3}
