@@ -88,3 +88,34 @@ def test_layout_scales_vectorised():
     ev = np.stack([rng.integers(0, V, F), rng.integers(0, V, F)], 1).reshape(-1)
     L = build_layout(np.full(V, d), np.arange(F + 1) * 2, ev, rng.integers(0, 10, F * d * d))
     assert L.n_edges == 2 * F and len(L.classes) == 1 and L.n_msg >= 2 * F * d
+
+
+def test_table_packing_takes_slices_for_contiguous_runs_and_gathers_otherwise():
+    """layout._gather_tables: one run -> a view of the caller's array, a few runs -> slices, scattered ->
+    index gather; the packed tables are the same whichever route was taken."""
+    from pydcop_b200.layout import _gather_tables
+    t = np.arange(1000, dtype=np.float32)
+    one = _gather_tables(t, np.arange(5, dtype=np.int64) * 20 + 40, 20)
+    assert one.base is t and np.array_equal(one, t[40:140])
+    starts = np.concatenate([np.arange(130, dtype=np.int64) * 4, [800, 804, 808]])
+    few = _gather_tables(t, starts, 4)
+    assert np.array_equal(few, np.concatenate([t[0:520], t[800:812]]))
+    scat = _gather_tables(t, np.array([900, 10, 500, 20], dtype=np.int64), 10)
+    assert np.array_equal(scat, np.concatenate([t[900:910], t[10:20], t[500:510], t[20:30]]))
+    assert len(_gather_tables(t, np.zeros(0, np.int64), 7)) == 0
+    # end to end: two interleaved classes (scattered) and one class (view) give the tables the engine expects
+    rng = np.random.default_rng(3)
+    dom = np.array([2, 3] * 10, dtype=np.int32)
+    fp, ev, tabs = [0], [], []
+    for k in range(12):
+        a, b = (0, 2) if k % 2 == 0 else (1, 3)          # (2,2) and (3,3) tables alternate in the input
+        ev += [a + 4 * (k % 3), b + 4 * (k % 3)]
+        fp.append(len(ev))
+        tabs.append(rng.uniform(size=int(dom[ev[-2]] * dom[ev[-1]])).astype(np.float32) + k)
+    L = build_layout(dom, np.array(fp), np.array(ev, np.int32), np.concatenate(tabs))
+    off = np.concatenate([[0], np.cumsum([len(x) for x in tabs])])
+    for c in L.classes:
+        for i in range(c.n_factors):
+            canon = int(np.nonzero(L.factor_perm == c.first_factor + i)[0][0])
+            assert np.array_equal(L.tables[c.table_base + i * c.table_size:c.table_base + (i + 1) * c.table_size],
+                                  tabs[canon]), (c.dom, i)
