@@ -75,10 +75,10 @@ class DsaGpuComputation(VariableComputation):
         if snap is None or snap.cycle == self._seen_cycle:
             return
         self._seen_cycle = snap.cycle
+        value, cost = snap.values[self.name]
+        self.value_selection(value, cost)      # before new_cycle(): the cycle notification carries it
         while self.cycle_count < snap.cycle:
             self.new_cycle()
-        value, cost = snap.values[self.name]
-        self.value_selection(value, cost)
         if snap.finished:
             self.finished()
             self.stop()

@@ -136,9 +136,11 @@ class MaxSumGpuVariableComputation(_ProxyMixin, VariableComputation):
         if snap is None or snap.cycle == self._seen_cycle:
             return
         self._seen_cycle = snap.cycle
-        self._advance_cycle(snap.cycle)
+        # value first, then the cycle counter: the reference's cycle-change notification carries the
+        # value selected IN that cycle (computations.py:915-928), `--collect_on cycle_change` reads it
         value, cost = snap.values[self.name]
         self.value_selection(value, cost)
+        self._advance_cycle(snap.cycle)
         if snap.finished:
             self.finished()
             self.stop()

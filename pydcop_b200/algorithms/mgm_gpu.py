@@ -75,11 +75,12 @@ class MgmGpuComputation(VariableComputation):
         if snap is None or snap.cycle == self._seen_cycle:
             return
         self._seen_cycle = snap.cycle
+        value, cost = snap.values[self.name]
+        # current_cost stays None until the first round (mgm.py:349); value before new_cycle(): the
+        # cycle notification carries it
+        self.value_selection(value, None if cost is None or math.isnan(cost) else cost)
         while self.cycle_count < snap.cycle:
             self.new_cycle()
-        value, cost = snap.values[self.name]
-        # current_cost stays None until the first round (mgm.py:349)
-        self.value_selection(value, None if cost is None or math.isnan(cost) else cost)
         if snap.finished:
             self.finished()
             self.stop()

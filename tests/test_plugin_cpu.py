@@ -247,3 +247,38 @@ def test_cli_drop_in_without_gpu_reports_the_engine_error(pydcop_ready, tmp_path
                        timeout=120, cwd=str(tmp_path))
     assert "EngineError" in r.stderr and "no CPU fallback" in r.stderr, r.stderr[-2000:]
     assert '"assignment": {}' in r.stdout            # nothing was computed on the CPU instead
+
+
+@retry_once
+@pytest.mark.parametrize("algo,extra", [("maxsum_gpu", []), ("dsa_gpu", ["--algo_params", "seed:3"]),
+                                        ("mgm_gpu", ["--algo_params", "seed:3"])])
+def test_cli_solve_end_to_end_with_cycle_metrics(pydcop_ready, tmp_path, algo, extra):
+    """The unmodified `pydcop solve` CLI (argument parsing, distribution, orchestrator, agents, metrics
+    collection on every cycle, JSON result) with --algo <x>_gpu; the engine seam holds the oracle since
+    this container has no GPU.  tests/dcop_cli/test_solve.py:39-108 of the reference, for the GPU modules."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    metrics = tmp_path / "run.csv"
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import ref_shim; ref_shim.install()\n"
+        "from pydcop_b200 import launcher\n"
+        "from pydcop_b200.algorithms._session import GpuSession\n"
+        "from _oracle_engine import OracleEngine\n"
+        "GpuSession.engine_factory = OracleEngine\n"
+        "launcher.main(['-t', '20', 'solve', '--algo', %r, '--algo_params', 'stop_cycle:20', *%r,"
+        " '--collect_on', 'cycle_change', '--run_metrics', %r, '-d', 'oneagent', %r])\n"
+    ) % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), algo, extra, str(metrics),
+         os.path.join(INSTANCES, "graph_coloring1.yaml"))
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True,
+                       timeout=180, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout[r.stdout.index("{"):])
+    assert out["status"] == "FINISHED" and out["cycle"] == 20 and out["violation"] == 0
+    assert out["assignment"] in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
+    if algo == "maxsum_gpu":
+        assert out["assignment"] == {"v1": "R", "v2": "G", "v3": "R"}
+    rows = [ln for ln in metrics.read_text().splitlines() if ln.strip()]
+    assert len(rows) >= 5 and "cycle" in rows[0]          # header + one line per collected cycle
