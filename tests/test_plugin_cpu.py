@@ -282,3 +282,35 @@ def test_cli_solve_end_to_end_with_cycle_metrics(pydcop_ready, tmp_path, algo, e
         assert out["assignment"] == {"v1": "R", "v2": "G", "v3": "R"}
     rows = [ln for ln in metrics.read_text().splitlines() if ln.strip()]
     assert len(rows) >= 5 and "cycle" in rows[0]          # header + one line per collected cycle
+
+
+@retry_once
+@pytest.mark.parametrize("collect,dist", [(["--collect_on", "value_change"], "adhoc"),
+                                          (["--collect_on", "period", "--period", "0.1"], "oneagent")])
+def test_cli_solve_other_collection_modes_and_distributions(pydcop_ready, tmp_path, collect, dist):
+    """Same CLI path with the other metric collection modes of commands/solve.py:278-293 and the adhoc
+    distribution (which calls the module's computation_memory / communication_load)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    metrics = tmp_path / "run.csv"
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import ref_shim; ref_shim.install()\n"
+        "from pydcop_b200 import launcher\n"
+        "from pydcop_b200.algorithms._session import GpuSession\n"
+        "from _oracle_engine import OracleEngine\n"
+        "GpuSession.engine_factory = OracleEngine\n"
+        "launcher.main(['-t', '20', 'solve', '--algo', 'maxsum_gpu', '--algo_params', 'stop_cycle:30', *%r,"
+        " '--run_metrics', %r, '-d', %r, %r])\n"
+    ) % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), collect, str(metrics), dist,
+         os.path.join(INSTANCES, "graph_coloring1.yaml"))
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True,
+                       timeout=180, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout[r.stdout.index("{"):])
+    assert out["status"] == "FINISHED" and out["cycle"] == 30
+    assert out["assignment"] == {"v1": "R", "v2": "G", "v3": "R"} and out["violation"] == 0
+    assert out["cost"] == pytest.approx(-0.1, abs=1e-9)
+    assert metrics.exists() and len(metrics.read_text().splitlines()) >= 2
