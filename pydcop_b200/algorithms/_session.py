@@ -72,6 +72,7 @@ class GpuSession:
         self.closed = False
         self.var_order: List[str] = []
         self.cycles_per_poll = 10
+        self._first_start: Optional[float] = None
 
     # -- registry ---------------------------------------------------------------------------
     @classmethod
@@ -118,9 +119,14 @@ class GpuSession:
                 and self.needed_vars <= set(self.variables) and bool(self.members))
 
     # -- lifecycle --------------------------------------------------------------------------
+    #: seconds a started but incomplete session waits before it reports itself as stuck
+    incomplete_grace = 5.0
+
     def notify_started(self, name):
         with self.lock:
             self.started.add(name)
+            if self._first_start is None:
+                self._first_start = time.monotonic()
             if (self.thread is None and self.error is None and self.is_complete()
                     and self.members <= self.started):
                 self.thread = threading.Thread(target=self._run, name=f"gpu-session-{self.key}",
@@ -137,6 +143,21 @@ class GpuSession:
 
     def poll(self) -> Optional[Snapshot]:
         if self.error is not None:
+            raise self.error
+        if (self.thread is None and self._first_start is not None and not self.is_complete()
+                and time.monotonic() - self._first_start > self.incomplete_grace):
+            # every computation of the graph must live in THIS process (thread mode): with
+            # `pydcop solve -m process` each agent process only ever sees its own nodes
+            missing = sorted((self.needed_factors - set(self.constraints))
+                             | (self.needed_vars - set(self.variables)))
+            self.error = RuntimeError(
+                f"pydcop_b200: {self.kind}_gpu session '{self.key}' never saw the whole graph in this process "
+                f"(missing {missing[:5]}{'...' if len(missing) > 5 else ''}): the GPU modules need thread mode "
+                "(`pydcop solve -m thread`), one process cannot share a device session with another")
+            import logging
+            import sys
+            logging.getLogger("pydcop_b200").critical(str(self.error))
+            print(str(self.error), file=sys.stderr, flush=True)
             raise self.error
         return self.snapshot
 

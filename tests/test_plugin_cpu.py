@@ -314,3 +314,36 @@ def test_cli_solve_other_collection_modes_and_distributions(pydcop_ready, tmp_pa
     assert out["assignment"] == {"v1": "R", "v2": "G", "v3": "R"} and out["violation"] == 0
     assert out["cost"] == pytest.approx(-0.1, abs=1e-9)
     assert metrics.exists() and len(metrics.read_text().splitlines()) >= 2
+
+
+def test_incomplete_session_reports_itself_instead_of_waiting_forever(pydcop_ready):
+    """Process mode puts every agent in its own OS process: a session then only ever sees a part of the
+    graph.  After a grace period the proxies get a clear error instead of polling until the timeout."""
+    from pydcop_b200.algorithms._session import GpuSession
+    from pydcop.algorithms import AlgorithmDef, ComputationDef, load_algorithm_module
+    from pydcop.computations_graph import factor_graph
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    GpuSession.reset()
+    old = GpuSession.incomplete_grace
+    GpuSession.incomplete_grace = 0.2
+    try:
+        dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+        algo = AlgorithmDef.build_with_default_param("maxsum_gpu", {"session": "partial"}, mode="min")
+        module = load_algorithm_module("maxsum_gpu")
+        nodes = factor_graph.build_computation_graph(dcop).nodes
+        comps = []
+        for node in nodes[:2]:                      # only a part of the graph lives "in this process"
+            c = module.build_computation(ComputationDef(node, algo))
+            c.message_sender = lambda *a, **k: None
+            c.periodic_action_handler = type("H", (), {"set_periodic_action": lambda s, p, cb: cb,
+                                                       "remove_periodic_action": lambda s, h: None})()
+            comps.append(c)
+        for c in comps:
+            c.start()
+        assert comps[0]._session.poll() is None     # inside the grace period: just not ready
+        time.sleep(0.3)
+        with pytest.raises(RuntimeError, match="thread mode"):
+            comps[0]._poll()
+    finally:
+        GpuSession.incomplete_grace = old
+        GpuSession.reset()
