@@ -347,3 +347,31 @@ def test_incomplete_session_reports_itself_instead_of_waiting_forever(pydcop_rea
     finally:
         GpuSession.incomplete_grace = old
         GpuSession.reset()
+
+
+def test_every_reference_instance_runs_through_the_drop_in(oracle_seam):
+    """All YAML instances of the reference's test suite (string domains, cost functions, extensional and
+    intentional constraints, external python sources, external variables in SimpleHouse) through the
+    unmodified orchestrator with --algo maxsum_gpu: a complete assignment every time, and on the
+    instances with a unique optimum the reference's own answer."""
+    import contextlib
+    import glob
+    import io
+    from pydcop.algorithms import AlgorithmDef
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    files = sorted(glob.glob(os.path.join(INSTANCES, "*.y*ml")))
+    assert len(files) >= 15
+    known = {"graph_coloring1.yaml": -0.1, "graph_coloring_tuto.yaml": 12, "graph_coloring_tuto_max.yaml": 53,
+             "secp_simple1.yaml": 2.3, "graph_coloring_csp.yaml": 0}
+    for fn in files:
+        oracle_seam.reset()
+        dcop = load_dcop_from_file([fn])
+        algo = AlgorithmDef.build_with_default_param("maxsum_gpu", {"stop_cycle": 25, "seed": 1}, mode=dcop.objective)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = solve(dcop, algo, "adhoc", timeout=2)
+        assert set(res) == set(dcop.variables), os.path.basename(fn)
+        violation, cost = dcop.solution_cost(res, 10000)
+        name = os.path.basename(fn)
+        if name in known:
+            assert violation == 0 and cost == pytest.approx(known[name], abs=1e-9), (name, cost)
