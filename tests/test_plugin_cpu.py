@@ -375,3 +375,26 @@ def test_every_reference_instance_runs_through_the_drop_in(oracle_seam):
         name = os.path.basename(fn)
         if name in known:
             assert violation == 0 and cost == pytest.approx(known[name], abs=1e-9), (name, cost)
+
+
+@retry_once
+def test_without_stop_cycle_the_run_ends_at_the_timeout_and_the_worker_stops(oracle_seam):
+    """Like the reference's MaxSum (no termination test, maxsum.py:62): without stop_cycle the engine keeps
+    cycling until the orchestrator's timeout stops the computations; the assignment so far is returned and the
+    session's worker thread ends."""
+    import contextlib
+    import io
+    from pydcop.algorithms import AlgorithmDef
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    algo = AlgorithmDef.build_with_default_param("maxsum_gpu", {"session": "no_stop", "seed": 2}, mode=dcop.objective)
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = solve(dcop, algo, "adhoc", timeout=2)
+    assert res == {"v1": "R", "v2": "G", "v3": "R"}
+    session = oracle_seam.get("maxsum:no_stop", "maxsum")
+    assert session.snapshot is not None and session.snapshot.cycle > 30 and not session.snapshot.finished
+    deadline = time.time() + 10
+    while session.thread.is_alive() and time.time() < deadline:
+        time.sleep(0.05)
+    assert not session.thread.is_alive()
