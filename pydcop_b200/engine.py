@@ -65,7 +65,10 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class _EngineBase:
     def _dev(self, a, dtype):
-        t = torch.from_numpy(np.ascontiguousarray(a))
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:      # e.g. a read-only memory map of the binary container
+            a = a.copy()
+        t = torch.from_numpy(a)
         return t.to(device=self.device, dtype=dtype)
 
     def _stream(self):
