@@ -16,6 +16,8 @@ Output: factors grouped into classes of identical shape so that tables and messa
 affine in the factor index (include/pydcop_b200.h), plus the permutations needed to move between
 canonical and internal order.  Everything is vectorised numpy: 10^6-variable graphs pack in
 seconds (the reference's own graph build is O(|V|*|C|), pydcop/dcop/relations.py:1245-1247).
+`FactorGraphLayout.tables` may be a VIEW of the caller's `tables` (one class, factors already adjacent): treat the
+input as read-only while the layout is in use.
 """
 from dataclasses import dataclass, field
 from typing import List, Optional
