@@ -282,6 +282,10 @@ def main(argv=None):
     ap.add_argument("--no-assignment", action="store_true",
                     help="omit the assignment from the output (10^6 variables)")
     ap.add_argument("--save", metavar="FILE", help="also write the instance as a binary container")
+    ap.add_argument("--run_metrics", metavar="FILE",
+                    help="CSV of cycle,time,cost,violation,msg_count,msg_size,status every --metrics_every "
+                         "cycles (the columns of `pydcop solve --run_metrics`, commands/solve.py:356-375)")
+    ap.add_argument("--metrics_every", type=int, default=10, metavar="CYCLES")
     ap.add_argument("--partition", default="auto", choices=["auto", "blocks", "multilevel"],
                     help="under torchrun: how the variables are split over the GPUs")
     args = ap.parse_args(argv)
@@ -302,8 +306,23 @@ def main(argv=None):
     dcop = load(files, args.seed)
     if args.save and rank == 0:
         ingest.save_instance(args.save, dcop)
+    rows, t_start = [], time.perf_counter()
+
+    def collect(cycle, idx):
+        violation, cost = solution_cost(dcop, idx, args.infinity)
+        rows.append((cycle, time.perf_counter() - t_start, cost, violation, 0, 0, "RUNNING"))
+
     res = solve(dcop, args.algo, params, args.timeout, args.precision, seed=args.seed,
-                infinity=args.infinity, partition=args.partition)
+                infinity=args.infinity, partition=args.partition,
+                chunk=max(1, args.metrics_every) if args.run_metrics else 50,
+                on_cycle=collect if args.run_metrics else None)
+    if args.run_metrics and rank == 0:
+        import csv
+        with open(args.run_metrics, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["cycle", "time", "cost", "violation", "msg_count", "msg_size", "status"])
+            w.writerows(rows)
+            w.writerow([res["cycle"], res["time"], res["cost"], res["violation"], 0, 0, res["status"]])
     if args.no_assignment:
         res.pop("assignment")
     if rank == 0:

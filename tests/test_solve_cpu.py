@@ -165,6 +165,16 @@ def test_cli_prints_json(tmp_path, capsys, monkeypatch):
     res = json.loads(capsys.readouterr().out)
     assert res["cycle"] == 5 and res["algo"] == "dsa" and len(res["assignment"]) == 6
     assert ingest.load_instance(out).n_vars == 6
+    # per-cycle metrics in the reference's CSV columns
+    csvf = tmp_path / "run.csv"
+    rc = S.main(["-a", "maxsum", "-p", "stop_cycle:12", "-p", "noise:0", "--run_metrics", str(csvf),
+                 "--metrics_every", "4", *SPLIT])
+    assert rc == 0
+    final = json.loads(capsys.readouterr().out)
+    lines = csvf.read_text().strip().splitlines()
+    assert lines[0] == "cycle,time,cost,violation,msg_count,msg_size,status"
+    assert [int(ln.split(",")[0]) for ln in lines[1:]] == [4, 8, 12, 12]
+    assert lines[-1].endswith("FINISHED") and float(lines[-1].split(",")[2]) == final["cost"]
 
 
 def test_reference_cli_known_answers():
