@@ -27,6 +27,7 @@ struct fg_maxsum {
   std::vector<fg_class_t> classes;
   std::vector<fg_varclass_t> varclasses;
   MaxSumFastPlan fast;
+  bool fast_first = false;  // PYDCOP_B200_FAST_FIRST=1 (experiment): tiled kernels in cycle 1 as well
   int cur = 0;
   int64_t cycle = 0;
   int64_t launches = 0;
@@ -97,6 +98,7 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
+  h->fast_first = fg_env_int("PYDCOP_B200_FAST_FIRST", 0) != 0;
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -158,7 +160,11 @@ template <typename T>
 static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
   const fg_maxsum_desc_t &d = h->d;
   const int cur = h->cur, nxt = cur ^ 1;
-  const bool first = (h->cycle == 0);  // cycle 1 consults the validity arrays
+  // cycle 1 consults the validity arrays (generic kernels).  Experiment (off by default): the buffers
+  // are zero-filled at init and a never-sent message counts as zeros in every sum (maxsum.py:430-436,
+  // 656-661), so the tiled kernels, which read every row, compute the same values in cycle 1 too.
+  const bool first = (h->cycle == 0) && !h->fast_first;
+  const bool first_cycle = (h->cycle == 0);
   MaxSumParams p{d.mode_max, d.damp_vars, d.damp_factors, d.damping, 1.0 - d.damping, d.stability};
   const T *q_cur = (const T *)d.dev_q[cur], *r_cur = (const T *)d.dev_r[cur];
   T *q_next = (T *)d.dev_q[nxt], *r_next = (T *)d.dev_r[nxt];
@@ -215,7 +221,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
     CUDA_TRY(h, cudaStreamWaitEvent(st_f, h->ev_join, 0));
     st = st_f;
   }
-  if (first && d.n_edges) {  // every edge has posted in cycle 1: all messages are valid from now on
+  if (first_cycle && d.n_edges) {  // every edge has posted in cycle 1: all messages are valid from now on
     CUDA_TRY(h, cudaMemsetAsync(d.dev_q_valid, 1, (size_t)d.n_edges, st));
     CUDA_TRY(h, cudaMemsetAsync(d.dev_r_valid, 1, (size_t)d.n_edges, st));
   }

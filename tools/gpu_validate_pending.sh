@@ -9,6 +9,8 @@ run() { echo "== $*" | tee -a gpurun_out/pending_summary.txt; "$@" 2>&1 | tail -
 # 1. parity: MGM kernels, direct solve entry, session with the vectorised tabulation, sharded DSA emulation
 run timeout 300 python -m pytest tests/test_gpu_zz_mgm.py -q
 run timeout 200 python -m pytest tests/test_gpu_solve.py tests/test_gpu_session.py -q
+run timeout 300 python -m pytest tests/test_gpu_zz_fast_first.py -q
+for u in 0 1; do run env PYDCOP_B200_FAST_FIRST=$u timeout 300 python bench.py --steps 300 --warmup 5 --no-cpu-baseline; done
 run timeout 300 python -m pytest tests/test_gpu_zz_dsa_v2.py -q
 for u in 0 2 4; do run env PYDCOP_B200_DSA_V2=$u timeout 300 python bench.py --workload c4 --steps 200 --warmup 5; done
 run timeout 300 python -m pytest tests/test_gpu_zz_sharded_dsa.py tests/test_gpu_zz_partition.py tests/test_gpu_sharded.py -q
