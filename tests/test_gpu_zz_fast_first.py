@@ -40,4 +40,4 @@ def test_fast_first_cycle_equals_default_and_oracle(monkeypatch, kind, start, pr
             assert np.array_equal(e.values()[0], o.value), (k, e is fast)
             f = e.flags()
             assert np.array_equal(f["q_sent"], o.q_sent) and np.array_equal(f["r_sent"], o.r_sent), (k, e is fast)
-    assert fast.launch_count < base.launch_count      # cycle 1 took the tiled launches
+    assert fast.launch_count <= base.launch_count     # cycle 1 took the tiled launches (equal when there is one class per side)
