@@ -251,13 +251,6 @@ int fg_dsa_cycle_commit(fg_dsa_t h);
 int fg_dsa_current(fg_dsa_t h, int32_t *buf_index, int64_t *cycle);
 int64_t fg_dsa_launch_count(fg_dsa_t h);
 
-/* Opt-in experiment: one evaluate_cycle of every variable with the CHUNKED fast kernel
- * (chunk = 2 | 4 incidences per trip, binary constraints over one domain size in {4, 8, 10, 16, 20});
- * same results as fg_dsa_cycle_compute.  `desc` is the descriptor given to fg_dsa_create, `cur` / `cycle`
- * come from fg_dsa_current; commit with fg_dsa_cycle_commit.  FG_ERR_UNSUPPORTED when the instance has
- * no fast-path arrays or the domain size is not compiled. */
-int fg_dsa_step_v2(const fg_dsa_desc_t *desc, int32_t cur, int64_t cycle, int32_t chunk, void *stream);
-
 /* ------------------------------------------------------------------------------------------
  * MGM  (next-tier row §8f.4; replaces MgmComputation.on_start mgm.py:283-310, the value phase
  * _handle_value_message :343-397 with _compute_best_value :434-455 and find_arg_optimal

@@ -114,7 +114,6 @@ SYMBOLS = {
     "fg_dsa_current": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fg_dsa_launch_count": (C.c_int64, [P]),
     "fg_selftest_approx_match": (C.c_int, [C.c_int32, C.c_int64, P, P, C.c_double, P, P, P]),
-    "fg_dsa_step_v2": (C.c_int, [C.POINTER(FgDsaDesc), C.c_int32, C.c_int64, C.c_int32, P]),
     "fg_mgm_create": (C.c_int, [C.POINTER(FgMgmDesc), C.POINTER(P)]),
     "fg_mgm_destroy": (C.c_int, [P]),
     "fg_mgm_last_error": (C.c_char_p, [P]),

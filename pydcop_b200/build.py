@@ -47,8 +47,8 @@ def build(force=False, verbose=False):
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libpydcop_b200.so")
     os.makedirs(LIB_DIR, exist_ok=True)
-    # one translation unit per family: engine.cu (MaxSum, DSA, halo, cost), mgm.cu (MGM), dsa_v2.cu (experiment)
-    units = [os.path.join(CSRC, f) for f in ("engine.cu", "mgm.cu", "dsa_v2.cu")]
+    # one translation unit per family: engine.cu (MaxSum, DSA, halo, cost), mgm.cu (MGM)
+    units = [os.path.join(CSRC, f) for f in ("engine.cu", "mgm.cu")]
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *units, "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")

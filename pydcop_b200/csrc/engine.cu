@@ -27,7 +27,7 @@ struct fg_maxsum {
   std::vector<fg_class_t> classes;
   std::vector<fg_varclass_t> varclasses;
   MaxSumFastPlan fast;
-  bool fast_first = false;  // PYDCOP_B200_FAST_FIRST=1 (experiment): tiled kernels in cycle 1 as well
+  bool fast_first = true;   // tiled kernels in cycle 1 as well (PYDCOP_B200_FAST_FIRST=0: generic kernels)
   int cur = 0;
   int64_t cycle = 0;
   int64_t launches = 0;
@@ -98,7 +98,7 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
-  h->fast_first = fg_env_int("PYDCOP_B200_FAST_FIRST", 0) != 0;
+  { const char *e = getenv("PYDCOP_B200_FAST_FIRST"); h->fast_first = !(e && e[0] == '0'); }
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -160,9 +160,10 @@ template <typename T>
 static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
   const fg_maxsum_desc_t &d = h->d;
   const int cur = h->cur, nxt = cur ^ 1;
-  // cycle 1 consults the validity arrays (generic kernels).  Experiment (off by default): the buffers
-  // are zero-filled at init and a never-sent message counts as zeros in every sum (maxsum.py:430-436,
-  // 656-661), so the tiled kernels, which read every row, compute the same values in cycle 1 too.
+  // The generic kernels of cycle 1 consult the validity arrays.  The buffers are zero-filled at init and
+  // a never-sent message counts as zeros in every sum (maxsum.py:430-436, 656-661), so the tiled
+  // kernels, which read every row, compute the same values in cycle 1 too (default; validated on the
+  // B200 against the generic kernels and the oracle, tests/test_gpu_zz_fast_first.py).
   const bool first = (h->cycle == 0) && !h->fast_first;
   const bool first_cycle = (h->cycle == 0);
   MaxSumParams p{d.mode_max, d.damp_vars, d.damp_factors, d.damping, 1.0 - d.damping, d.stability};

@@ -2,13 +2,13 @@
 // Same arithmetic and results as k_mgm_gain (mgm_kernels.cuh); the table of each incidence is read
 // ORIENTED (the DSA fast-path arrays, engine.py::dsa_fast_arrays: row y = value of the neighbour is
 // contiguous over my values) so an incidence costs one contiguous row instead of D strided reads, and
-// the slot loop handles U incidences per trip as in dsa_v2_kernels.cuh.
+// the slot loop handles U incidences per trip.
 // Free of CUDA runtime includes (tests/hostshim/ runs it on the CPU).
 #pragma once
 #include <stdint.h>
 
 #include "../../include/pydcop_b200.h"
-#include "dsa_v2_kernels.cuh"  // dsa_v2_load_row
+#include "row_load.cuh"       // fg_load_row
 #include "mgm_kernels.cuh"     // MgmSide
 
 template <typename T, int D, int U>
@@ -43,7 +43,7 @@ k_mgm_gain_bin(MgmSide g, int n_vars, const int32_t *__restrict__ slot_nbr, cons
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       T r[D];
-      dsa_v2_load_row<T, D>(tables_or + tb[i] + (int64_t)y[i] * D, r);
+      fg_load_row<T, D>(tables_or + tb[i] + (int64_t)y[i] * D, r);
       const bool first = (s + i == s0);   // ((f1 + f2) + f3)...: the first constraint starts the sum (mgm.py:443)
 #pragma unroll
       for (int x = 0; x < D; ++x) {

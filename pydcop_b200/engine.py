@@ -371,10 +371,6 @@ class DsaEngine(_EngineBase):
         self._desc = d
         self._h = C.c_void_p()
         self._check(self.lib.fg_dsa_create(C.byref(d), C.byref(self._h)), "fg_dsa_create")
-        # PYDCOP_B200_DSA_V2=2|4 selects the chunked kernel where it applies (else the default path)
-        chunk = int(os.environ.get("PYDCOP_B200_DSA_V2", "0") or 0)
-        self._v2_chunk = chunk if (chunk in (2, 4) and fast_dom in (4, 8, 10, 16, 20)) else 0
-        self._v2_launches = 0
 
     def _last_error(self):
         return (self.lib.fg_dsa_last_error(self._h) or b"").decode()
@@ -396,23 +392,12 @@ class DsaEngine(_EngineBase):
         return self
 
     def step(self, n_cycles=1):
-        if self._v2_chunk:
-            for _ in range(int(n_cycles)):
-                self.cycle_compute()
-                self.cycle_commit()
-            return self
         with torch.cuda.device(self.device):
             self._check(self.lib.fg_dsa_step(self._h, int(n_cycles), self._stream()), "fg_dsa_step")
         return self
 
     def cycle_compute(self):
         with torch.cuda.device(self.device):
-            if self._v2_chunk:   # opt-in experiment: chunked fast kernel (csrc/dsa_v2.cu), same results
-                cur, cyc = self._current()
-                self._check(self.lib.fg_dsa_step_v2(C.byref(self._desc), cur, cyc, self._v2_chunk,
-                                                    self._stream()), "fg_dsa_step_v2")
-                self._v2_launches += 1
-                return
             self._check(self.lib.fg_dsa_cycle_compute(self._h, self._stream()), "fg_dsa_cycle_compute")
 
     def cycle_commit(self):
@@ -433,7 +418,7 @@ class DsaEngine(_EngineBase):
 
     @property
     def launch_count(self):
-        return int(self.lib.fg_dsa_launch_count(self._h)) + self._v2_launches
+        return int(self.lib.fg_dsa_launch_count(self._h))
 
     def values(self):
         """Current value index per variable, canonical variable order."""
@@ -564,10 +549,11 @@ class MgmEngine(_EngineBase):
         d.dev_value, d.dev_cost, d.dev_has_cost = _ptr(self.value), _ptr(self.cost), _ptr(self.has_cost)
         d.dev_gain, d.dev_new_value = _ptr(self.gain), _ptr(self.new_value)
         d.mode_max, d.stop_cycle, d.seed = int(mode == "max"), int(stop_cycle), int(seed) & (2 ** 64 - 1)
-        # PYDCOP_B200_MGM_FAST=2|4: the fast value-phase kernel on the DSA fast-path arrays (opt-in
-        # experiment; binary constraints over one domain size in {4, 8, 10, 16, 20})
+        # the fast value-phase kernel on the DSA fast-path arrays (binary constraints over one domain size
+        # in {4, 8, 10, 16, 20}); 2 incidences per trip measured fastest on the B200 (C4 instance: 605 us
+        # per cycle vs 1869 us generic, profiles/r02_call1_pending_summary.txt).  PYDCOP_B200_MGM_FAST=0|2|4
         self.fast_chunk = 0
-        chunk = int(os.environ.get("PYDCOP_B200_MGM_FAST", "0") or 0)
+        chunk = int(os.environ.get("PYDCOP_B200_MGM_FAST", "2") or 0)
         if chunk in (2, 4):
             with torch.cuda.device(self.device):
                 fast = dsa_fast_arrays(L, self.tables, mode)

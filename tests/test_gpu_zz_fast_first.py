@@ -1,5 +1,5 @@
-"""GPU: the opt-in PYDCOP_B200_FAST_FIRST=1 experiment (tiled kernels in cycle 1 instead of the generic
-ones) against the default engine and the oracle: same messages, send decisions and values at every
+"""GPU: tiled kernels in cycle 1 (the default) against the generic first-cycle kernels
+(PYDCOP_B200_FAST_FIRST=0) and the oracle: same messages, send decisions and values at every
 cycle, for every start protocol."""
 import numpy as np
 import pytest
@@ -24,7 +24,7 @@ def test_fast_first_cycle_equals_default_and_oracle(monkeypatch, kind, start, pr
         inst = random_factor_graph(3000, 8, 3000, 3, seed=7)
     L = build_layout(**inst)
     dt = np.float64 if precision == "f64" else np.float32
-    monkeypatch.delenv("PYDCOP_B200_FAST_FIRST", raising=False)
+    monkeypatch.setenv("PYDCOP_B200_FAST_FIRST", "0")
     base = MaxSumEngine(L, precision=precision, start_messages=start).init()
     monkeypatch.setenv("PYDCOP_B200_FAST_FIRST", "1")
     fast = MaxSumEngine(L, precision=precision, start_messages=start).init()

@@ -21,7 +21,7 @@ def test_fast_value_phase_equals_default_and_oracle(monkeypatch, d, mode, precis
     rank = rng.permutation(n).astype(np.int32)
     L = build_layout(**inst)
     dt = np.float64 if precision == "f64" else np.float32
-    monkeypatch.delenv("PYDCOP_B200_MGM_FAST", raising=False)
+    monkeypatch.setenv("PYDCOP_B200_MGM_FAST", "0")
     base = MgmEngine(L, precision=precision, mode=mode, seed=5, var_rank=rank).init()
     monkeypatch.setenv("PYDCOP_B200_MGM_FAST", str(chunk))
     fast = MgmEngine(L, precision=precision, mode=mode, seed=5, var_rank=rank).init()

@@ -36,7 +36,7 @@ def shim():
     deps = [SHIM_SRC, os.path.join(ROOT, "pydcop_b200", "csrc", "mgm_kernels.cuh"),
             os.path.join(ROOT, "pydcop_b200", "csrc", "philox.cuh"),
             os.path.join(ROOT, "pydcop_b200", "csrc", "mgm_fast_kernels.cuh"),
-            os.path.join(ROOT, "pydcop_b200", "csrc", "dsa_v2_kernels.cuh"),
+            os.path.join(ROOT, "pydcop_b200", "csrc", "row_load.cuh"),
             os.path.join(ROOT, "include", "pydcop_b200.h")]
     if not os.path.exists(SHIM_SO) or any(os.path.getmtime(d) > os.path.getmtime(SHIM_SO) for d in deps):
         os.makedirs(os.path.dirname(SHIM_SO), exist_ok=True)
