@@ -334,8 +334,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     runner.init()
     if world > 1:
-        config["halo"] = ("ONE push kernel storing boundary rows straight into the peers' buffers over "
-                          "NVLink (CUDA IPC) + barrier per cycle" if runner.peer is not None else
+        config["halo"] = ("push kernel storing boundary rows straight into the peers' buffers over NVLink (CUDA "
+                          "IPC), its last block releasing the cycle's epoch flag to the peers; device-side "
+                          "acquire wait; whole cycle enqueued by one C call (fg_maxsum_shard_step)"
+                          + ("; split push" if os.environ.get("PYDCOP_B200_PUSH_SPLIT", "0") not in ("", "0") else "")
+                          if runner.peer is not None else
                           "pack kernel + ONE NCCL all_to_all (q and r rows together) + unpack kernel per cycle")
     for _ in range(max(3, args.warmup)):
         runner.step(1)
@@ -366,8 +369,11 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
-    if world > 1 and os.environ.get("PYDCOP_B200_BREAKDOWN", "0") not in ("", "0") and runner.peer is None:
-        config["breakdown_ms_rank0"] = runner.timed_breakdown(50)
+    breakdown = None
+    if world > 1:   # device time of the phases of a cycle on rank 0 (separate short loop, phases serialised)
+        breakdown = {k: round(1e3 * v, 2) for k, v in runner.timed_breakdown(50).items()}
+        breakdown["unit"] = "us per cycle, rank 0"
+        runner.check()
 
     # end to end through the public API: pinned host arrays -> device, E2E_CYCLES cycles, values back
     # (N > 1: every rank uploads its own shard; time = max over ranks)
@@ -457,6 +463,8 @@ def main():
     }
     if parity is not None:
         line["parity"] = parity
+    if breakdown is not None:
+        line["breakdown"] = breakdown
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(inst, L)
     print(json.dumps(line))

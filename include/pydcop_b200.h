@@ -217,7 +217,9 @@ typedef struct {
   const int32_t *dev_edge_class; /* [n_edges] class of edge e */
   const int32_t *dev_var_ptr;    /* [n_vars+1] */
   const int32_t *dev_slot_edge;  /* [n_edges] incident edges of v in node.constraints order */
-  const uint8_t *dev_has_nbr;    /* [n_vars] variable has >= 1 neighbour (dsa.py:278) */
+  const uint8_t *dev_has_nbr;    /* [n_vars] 1: variable has >= 1 neighbour (dsa.py:278); 0: isolated, its
+                                    value is carried over; 2: ghost of a variable another rank owns (multi-GPU):
+                                    never written by the kernels, filled by the owner's push / halo unpack */
   const double *dev_prob;        /* [n_vars] change threshold (p_mode fixed|arity, dsa.py:252-263) */
   void *dev_con_opt;             /* T[n_factors] per-constraint optimum, filled by fg_dsa_init */
   /* optional fast path: every constraint binary over one domain size `fast_dom` (else NULL / 0).
@@ -250,6 +252,58 @@ int fg_dsa_cycle_compute(fg_dsa_t h, void *stream);
 int fg_dsa_cycle_commit(fg_dsa_t h);
 int fg_dsa_current(fg_dsa_t h, int32_t *buf_index, int64_t *cycle);
 int64_t fg_dsa_launch_count(fg_dsa_t h);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-side cycle barrier + fused peer push (multi-GPU; replaces the per-cycle NCCL all_reduce and
+ * the host-driven compute -> push -> barrier chain; reference counterpart: the cycle_id handshake of
+ * SynchronousComputationMixin, pydcop/infrastructure/computations.py:696-718, and Messaging.post_msg
+ * for cut edges, communication.py:588-698).
+ *
+ * Every rank owns an array of `world` 64-bit EPOCH FLAGS in its own device memory, mapped into the
+ * peers through CUDA IPC; slot p is written only by rank p.  After its boundary rows of a cycle are
+ * stored in the peers' buffers, a rank releases (fence.sys + st.release.sys) the new epoch into its
+ * slot on every peer; before it reads rows the peers wrote it acquires (ld.acquire.sys, spinning)
+ * the same epoch from every peer's slot in its own array.  No host round trip, no collective.
+ * A wait that does not complete within `timeout_ns` stores peer rank + 1 in *dev_error and returns,
+ * so a lost peer cannot hang the device.
+ * ------------------------------------------------------------------------------------------ */
+#define FG_MAX_PEERS 16
+typedef struct {
+  int32_t n_peers;                    /* ranks this rank exchanges with (<= FG_MAX_PEERS) */
+  int32_t my_rank;
+  const uint64_t *dev_flags;          /* MY flag array [world], zeroed by the caller at creation */
+  int32_t peer_rank[FG_MAX_PEERS];    /* slot of dev_flags written by peer i */
+  uint64_t *peer_slot[FG_MAX_PEERS];  /* address, as mapped into THIS process, of slot my_rank in
+                                         peer i's flag array */
+  int32_t *dev_error;                 /* one int32, zeroed by the caller */
+  uint64_t timeout_ns;                /* 0 = 20 s */
+} fg_peer_sync_t;
+
+int fg_peer_signal(const fg_peer_sync_t *ps, uint64_t epoch, void *stream);
+int fg_peer_wait(const fg_peer_sync_t *ps, uint64_t epoch, void *stream);
+
+/* Rows a rank pushes every cycle: row i of list r is `dom` elements at dev_r + src_r_off[i] and is
+ * stored at the absolute (peer) address dst_r[b][i] when the cycle writes buffer b; likewise q.
+ * For DSA the "rows" are single 4-byte values (dom = 1, list r only). */
+typedef struct {
+  int32_t elem_bytes, dom;
+  int64_t n_r, n_q;
+  const int64_t *dev_src_r_off, *dev_src_q_off;
+  const int64_t *dev_dst_r[2], *dev_dst_q[2];
+  uint32_t *dev_counter;              /* one zeroed uint32: last-block detection of the push kernel */
+  fg_peer_sync_t sync;
+} fg_halo_plan_t;
+
+/* Attach a push plan to an engine (copied).  From then on fg_*_shard_step runs whole cycles on the
+ * device without the host: compute -> push boundary rows into the peers' `next` buffers, the last
+ * block of the push kernel releasing epoch+1 -> wait for every peer's epoch+1 -> commit.  The epoch
+ * counter only grows (it survives fg_*_init), so every rank must run the same number of cycles. */
+int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan);
+int fg_maxsum_shard_step(fg_maxsum_t h, int32_t n_cycles, void *stream);
+/* One phase of a cycle, for timing breakdowns: 0 compute, 1 push + signal, 2 wait, 3 commit. */
+int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream);
+int fg_dsa_shard_attach(fg_dsa_t h, const fg_halo_plan_t *plan);
+int fg_dsa_shard_step(fg_dsa_t h, int32_t n_cycles, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * MGM  (next-tier row §8f.4; replaces MgmComputation.on_start mgm.py:283-310, the value phase

@@ -82,6 +82,21 @@ class FgMgmDesc(C.Structure):
                 ("fast_dom", C.c_int32), ("fast_chunk", C.c_int32)]
 
 
+FG_MAX_PEERS = 16
+
+
+class FgPeerSync(C.Structure):
+    _fields_ = [("n_peers", C.c_int32), ("my_rank", C.c_int32), ("dev_flags", P),
+                ("peer_rank", C.c_int32 * FG_MAX_PEERS), ("peer_slot", P * FG_MAX_PEERS),
+                ("dev_error", P), ("timeout_ns", C.c_uint64)]
+
+
+class FgHaloPlan(C.Structure):
+    _fields_ = [("elem_bytes", C.c_int32), ("dom", C.c_int32), ("n_r", C.c_int64), ("n_q", C.c_int64),
+                ("dev_src_r_off", P), ("dev_src_q_off", P), ("dev_dst_r", P * 2), ("dev_dst_q", P * 2),
+                ("dev_counter", P), ("sync", FgPeerSync)]
+
+
 # every symbol include/pydcop_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "fg_abi_version": (C.c_int, []),
@@ -104,6 +119,13 @@ SYMBOLS = {
     "fg_ipc_import": (C.c_int, [P, C.POINTER(P)]),
     "fg_ipc_close": (C.c_int, [P]),
     "fg_halo_push": (C.c_int, [C.c_int32, P, P, P, P, P, P, C.c_int64, C.c_int64, C.c_int32, P]),
+    "fg_peer_signal": (C.c_int, [C.POINTER(FgPeerSync), C.c_uint64, P]),
+    "fg_peer_wait": (C.c_int, [C.POINTER(FgPeerSync), C.c_uint64, P]),
+    "fg_maxsum_shard_attach": (C.c_int, [P, C.POINTER(FgHaloPlan)]),
+    "fg_maxsum_shard_step": (C.c_int, [P, C.c_int32, P]),
+    "fg_maxsum_shard_phase": (C.c_int, [P, C.c_int32, P]),
+    "fg_dsa_shard_attach": (C.c_int, [P, C.POINTER(FgHaloPlan)]),
+    "fg_dsa_shard_step": (C.c_int, [P, C.c_int32, P]),
     "fg_dsa_create": (C.c_int, [C.POINTER(FgDsaDesc), C.POINTER(P)]),
     "fg_dsa_destroy": (C.c_int, [P]),
     "fg_dsa_last_error": (C.c_char_p, [P]),

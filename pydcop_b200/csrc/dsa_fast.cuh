@@ -21,7 +21,11 @@ k_dsa_step_bin(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t *_
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vars) return;
   const int cur = val[v];
-  if (!has_nbr[v]) { val_next[v] = cur; return; }
+  const uint8_t hn = has_nbr[v];  // 0 isolated (value carried over), 1 active, 2 ghost of another rank's variable:
+  if (hn != 1) {                  // never written here — its owner's push / the halo unpack fills `next`
+    if (hn == 0) val_next[v] = cur;
+    return;
+  }
   T cost[D];
 #pragma unroll
   for (int x = 0; x < D; ++x) cost[x] = (T)0;

@@ -28,7 +28,7 @@ __global__ void k_dsa_con_opt(const fg_class_t c, const T *__restrict__ tables, 
 // on_start (dsa.py:277-295): injected random initial value for connected variables
 __global__ void k_dsa_init(DsaSide g, int n_vars, uint64_t seed, int32_t *__restrict__ value) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_vars || !g.has_nbr[v]) return;
+  if (v >= n_vars || g.has_nbr[v] != 1) return;
   uint32_t b[4];
   philox4x32_10((uint32_t)g.var_id[v], FG_PHILOX_INIT_CYCLE, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
   value[v] = philox_choice(b, g.dom_size[v]);
@@ -44,7 +44,11 @@ k_dsa_step_generic(DsaSide g, int n_vars, const T *__restrict__ tables,
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vars) return;
   const int cur = val[v];
-  if (!g.has_nbr[v]) { val_next[v] = cur; return; }
+  const uint8_t hn = g.has_nbr[v];  // 0 isolated (value carried over), 1 active, 2 ghost of another rank's variable:
+  if (hn != 1) {                    // never written here — its owner's push / the halo unpack fills `next`
+    if (hn == 0) val_next[v] = cur;
+    return;
+  }
   const int d = g.dom_size[v];
   T cost[FG_MAX_DOM];
   for (int x = 0; x < d; ++x) cost[x] = (T)0;

@@ -11,6 +11,7 @@
 #include "maxsum_generic.cuh"
 #include "maxsum_fast.cuh"
 #include "dsa_fast.cuh"
+#include "peer_sync.cuh"
 
 namespace {
 
@@ -31,6 +32,11 @@ struct fg_maxsum {
   int cur = 0;
   int64_t cycle = 0;
   int64_t launches = 0;
+  // multi-GPU: push plan + device-side barrier (fg_maxsum_shard_*)
+  bool has_halo = false;
+  bool split_push = false;  // PYDCOP_B200_PUSH_SPLIT=1: r rows right behind the factor side, q rows on the side stream
+  fg_halo_plan_t halo;
+  uint64_t epoch = 0;
   char err[512] = {0};
 };
 
@@ -41,6 +47,9 @@ struct fg_dsa {
   int cur = 0;
   int64_t cycle = 0;
   int64_t launches = 0;
+  bool has_halo = false;
+  fg_halo_plan_t halo;
+  uint64_t epoch = 0;
   char err[512] = {0};
 };
 
@@ -156,8 +165,10 @@ extern "C" int fg_maxsum_init(fg_maxsum_t h, void *stream) {
   return h->d.precision == FG_F64 ? maxsum_init_t<double>(h, st) : maxsum_init_t<float>(h, st);
 }
 
+// push_split: multi-GPU only — the boundary r rows leave right behind the factor side (main stream), the q
+// rows right behind the variable side (side stream), each overlapping the other side's compute
 template <typename T>
-static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
+static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = false) {
   const fg_maxsum_desc_t &d = h->d;
   const int cur = h->cur, nxt = cur ^ 1;
   // The generic kernels of cycle 1 consult the validity arrays.  The buffers are zero-filled at init and
@@ -190,6 +201,10 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
                                                              d.dev_edge_qoff, d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
     ++h->launches;
   }
+  if (push_split && h->halo.n_r > 0) {
+    int rc = halo_push_launch(h->halo, r_next, q_next, nxt, h->halo.n_r, 0, 0, 0, st, h->launches);
+    if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (r rows) failed"); return rc; }
+  }
   // variable -> factor (+ value selection).  Both sides only READ the current buffers and WRITE
   // disjoint next buffers (Jacobi), so from cycle 2 on the variable side runs on a second stream,
   // concurrently with the factor side: one is HBM-streaming, the other gather/latency-bound.
@@ -216,6 +231,10 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st) {
         ++h->launches;
       }
     }
+  }
+  if (push_split && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
+    int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, st, h->launches);
+    if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows) failed"); return rc; }
   }
   if (fork) {
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
@@ -261,6 +280,71 @@ extern "C" int fg_maxsum_current(fg_maxsum_t h, int32_t *buf_index, int64_t *cyc
 }
 
 extern "C" int64_t fg_maxsum_launch_count(fg_maxsum_t h) { return h ? h->launches : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU cycle on the device: compute -> peer push (+ release) -> wait -> commit
+// ---------------------------------------------------------------------------------------------
+static int halo_plan_check(const fg_halo_plan_t *p) {
+  if (!p || p->dom < 1 || (p->elem_bytes != 4 && p->elem_bytes != 8) || p->n_r < 0 || p->n_q < 0) return FG_ERR_ARG;
+  if (p->n_r && (!p->dev_src_r_off || !p->dev_dst_r[0] || !p->dev_dst_r[1])) return FG_ERR_ARG;
+  if (p->n_q && (!p->dev_src_q_off || !p->dev_dst_q[0] || !p->dev_dst_q[1])) return FG_ERR_ARG;
+  if (!p->dev_counter) return FG_ERR_ARG;
+  return peer_sync_check(&p->sync);
+}
+
+extern "C" int fg_peer_signal(const fg_peer_sync_t *ps, uint64_t epoch, void *stream) {
+  if (peer_sync_check(ps) != FG_OK) return FG_ERR_ARG;
+  if (!ps->n_peers) return FG_OK;
+  k_peer_signal<<<1, 32, 0, (cudaStream_t)stream>>>(peer_slots_of(*ps), epoch);
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
+extern "C" int fg_peer_wait(const fg_peer_sync_t *ps, uint64_t epoch, void *stream) {
+  if (peer_sync_check(ps) != FG_OK) return FG_ERR_ARG;
+  int64_t n = 0;
+  return peer_wait_launch(*ps, epoch, (cudaStream_t)stream, n);
+}
+
+extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan) {
+  if (!h) return FG_ERR_ARG;
+  if (halo_plan_check(plan) != FG_OK) { snprintf(h->err, sizeof(h->err), "invalid halo plan"); return FG_ERR_ARG; }
+  if ((size_t)plan->elem_bytes != prec_size(h->d.precision)) { snprintf(h->err, sizeof(h->err), "halo plan element size"); return FG_ERR_ARG; }
+  h->halo = *plan;
+  h->has_halo = true;
+  h->epoch = 0;
+  h->split_push = fg_env_int("PYDCOP_B200_PUSH_SPLIT", 0) != 0;
+  return FG_OK;
+}
+
+extern "C" int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream) {
+  if (!h || !h->has_halo) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nxt = h->cur ^ 1;
+  switch (phase) {
+    case 0: {
+      const bool split = h->split_push && h->cycle > 0;
+      return h->d.precision == FG_F64 ? maxsum_compute_t<double>(h, st, split) : maxsum_compute_t<float>(h, st, split);
+    }
+    case 1: {
+      const bool split = h->split_push && h->cycle > 0;   // rows already on their way: release only
+      return halo_push_launch(h->halo, h->d.dev_r[nxt], h->d.dev_q[nxt], nxt, split ? 0 : h->halo.n_r,
+                              split ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches);
+    }
+    case 2: return peer_wait_launch(h->halo.sync, h->epoch + 1, st, h->launches);
+    case 3: ++h->epoch; return fg_maxsum_cycle_commit(h);
+  }
+  return FG_ERR_ARG;
+}
+
+extern "C" int fg_maxsum_shard_step(fg_maxsum_t h, int32_t n_cycles, void *stream) {
+  if (!h || !h->has_halo) return FG_ERR_ARG;
+  for (int i = 0; i < n_cycles; ++i)
+    for (int ph = 0; ph < 4; ++ph) {
+      int rc = fg_maxsum_shard_phase(h, ph, stream);
+      if (rc != FG_OK) return rc;
+    }
+  return FG_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // halo pack / unpack: one warp per boundary row
@@ -562,6 +646,38 @@ extern "C" int fg_dsa_current(fg_dsa_t h, int32_t *buf_index, int64_t *cycle) {
 }
 
 extern "C" int64_t fg_dsa_launch_count(fg_dsa_t h) { return h ? h->launches : -1; }
+
+extern "C" int fg_dsa_shard_attach(fg_dsa_t h, const fg_halo_plan_t *plan) {
+  if (!h) return FG_ERR_ARG;
+  if (halo_plan_check(plan) != FG_OK || plan->elem_bytes != 4 || plan->dom != 1 || plan->n_q != 0) {
+    snprintf(h->err, sizeof(h->err), "invalid halo plan (DSA pushes single 4-byte values, list r only)");
+    return FG_ERR_ARG;
+  }
+  h->halo = *plan;
+  h->has_halo = true;
+  h->epoch = 0;
+  return FG_OK;
+}
+
+// whole DSA cycles of one shard on the device: evaluate_cycle -> boundary values into the peers' ghost
+// entries of `next` (+ release) -> wait -> commit.  Ghost (frozen) variables are never written locally.
+extern "C" int fg_dsa_shard_step(fg_dsa_t h, int32_t n_cycles, void *stream) {
+  if (!h || !h->has_halo) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_cycles; ++i) {
+    if (h->d.stop_cycle && h->cycle >= h->d.stop_cycle) break;
+    int rc = fg_dsa_cycle_compute(h, stream);
+    if (rc != FG_OK) return rc;
+    const int nxt = h->cur ^ 1;
+    rc = halo_push_launch(h->halo, h->d.dev_value[nxt], h->d.dev_value[nxt], nxt, h->halo.n_r, 0, 1, h->epoch + 1, st,
+                          h->launches);
+    if (rc == FG_OK) rc = peer_wait_launch(h->halo.sync, h->epoch + 1, st, h->launches);
+    if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push / wait launch failed"); return rc; }
+    ++h->epoch;
+    fg_dsa_cycle_commit(h);
+  }
+  return FG_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // solution cost (dcop.py:319-367)

@@ -307,8 +307,8 @@ class DsaEngine(_EngineBase):
         if L.n_edges:
             np.add.at(n_count, L.slot_var, arity[L.edge_class[L.slot_edge]] - 1)
         has_nbr = (n_count > 0).astype(np.uint8)
-        if frozen is not None:
-            has_nbr[np.asarray(frozen, dtype=bool)[L.var_order]] = 0
+        if frozen is not None:   # 2 = ghost of another rank's variable: never written by the local kernels
+            has_nbr[np.asarray(frozen, dtype=bool)[L.var_order]] = 2
         var_id = (L.var_order if var_global_id is None
                   else np.asarray(var_global_id, dtype=np.int32)[L.var_order])
         if p_mode == "arity":  # dsa.py:257-260: 1 / n_count * 1.2

@@ -392,50 +392,28 @@ def push_tables(plan: ShardPlan, base: np.ndarray, dst_r_off, dst_q_off, elem: i
 
 
 class PeerPush:
-    """Halo over NVLink peer memory: every rank maps the peers' message buffers (torch CUDA IPC) and
-    its push kernel stores each boundary row straight into the consumer's `next` buffer; a barrier
-    closes the cycle.  One kernel + one barrier instead of pack -> all_to_all -> unpack."""
+    """Halo over NVLink peer memory: every rank maps the peers' message buffers (CUDA IPC) and its
+    push kernel stores each boundary row straight into the consumer's `next` buffer.  The cycle is
+    closed on the DEVICE: the last block of the push kernel releases the new epoch into the peers'
+    flag arrays and a one-warp kernel acquires the peers' epochs (pydcop_b200/peer.py,
+    csrc/peer_sync.cuh) — no NCCL call, no host round trip per cycle.  The whole cycle
+    (compute -> push + release -> wait -> commit) is enqueued by ONE C call, fg_maxsum_shard_step."""
 
     def __init__(self, sharded, group=None):
         import torch
         import torch.distributed as dist
+        from . import _cabi
+        from .peer import PeerMap, PeerSync
         self.torch, self.dist, self.group = torch, dist, group
-        e, p, h = sharded.engine, sharded.plan, sharded.halo
+        e, p = sharded.engine, sharded.plan
         self.engine, self.plan, self.sharded = e, p, sharded
         dev = e.device
         W, me = p.world, p.rank
         if not p.layout.uniform_dom:
             raise RuntimeError("peer push needs a uniform domain size")
-        # 1. share my four message buffers (CUDA IPC handle of the containing allocation + offset),
-        #    map everybody else's with MY device as the accessor
-        lib = e.lib
-        mine = []
-        for t in (e.q[0], e.q[1], e.r[0], e.r[1]):
-            hb = (C.c_ubyte * 64)()
-            off = C.c_int64()
-            rc = lib.fg_ipc_export(C.c_void_p(t.data_ptr()), C.cast(hb, C.c_void_p), C.byref(off))
-            if rc != 0:
-                raise RuntimeError(f"fg_ipc_export failed rc={rc}")
-            mine.append((bytes(hb), int(off.value)))
-        everyone = [None] * W
-        dist.all_gather_object(everyone, mine, group=group)
-        self._mapped = {}   # (rank, handle bytes) -> base address in this process
-        base = np.zeros((W, 4), dtype=np.int64)
-        with torch.cuda.device(dev):
-            for rnk in range(W):
-                if rnk == me:
-                    base[rnk] = [t.data_ptr() for t in (e.q[0], e.q[1], e.r[0], e.r[1])]
-                    continue
-                for i, (hbytes, off) in enumerate(everyone[rnk]):
-                    key = (rnk, hbytes)
-                    if key not in self._mapped:
-                        out = C.c_void_p()
-                        buf = (C.c_ubyte * 64).from_buffer_copy(hbytes)
-                        rc = lib.fg_ipc_import(C.cast(buf, C.c_void_p), C.byref(out))
-                        if rc != 0:
-                            raise RuntimeError(f"fg_ipc_import failed rc={rc} (rank {rnk})")
-                        self._mapped[key] = int(out.value)
-                    base[rnk, i] = self._mapped[key] + off
+        # 1. map everybody's four message buffers with MY device as the accessor
+        self.pmap = PeerMap(e.lib, dev, me, W, group)
+        base = self.pmap.map([e.q[0], e.q[1], e.r[0], e.r[1]])
         # 2. where do my rows land?  the consumer's recv offsets, in my send order
         def peer_offsets(recv_off, recv_rows, send_rows):
             out = torch.zeros(int(sum(send_rows)), dtype=torch.int64, device=dev)
@@ -452,26 +430,39 @@ class PeerPush:
         self.src_r_off, self.src_q_off = to(t["src_r_off"]), to(t["src_q_off"])
         self.n_r, self.n_q = len(p.send_r_len), len(p.send_q_len)
         self.dom = int(p.layout.uniform_dom)
-        self.token = torch.zeros(1, device=dev)
-        self.launches = 0
-        from .engine import PRECISIONS
-        self.prec = PRECISIONS[e.precision][0]
+        # 3. device-side barrier with the ranks I share cut edges with
+        peers = [b for b in range(W) if b != me and (p.send_r_rows[b] or p.send_q_rows[b]
+                                                    or p.recv_r_rows[b] or p.recv_q_rows[b])]
+        self.sync = PeerSync(self.pmap, peers)
+        plan = _cabi.FgHaloPlan()
+        plan.elem_bytes, plan.dom, plan.n_r, plan.n_q = elem, self.dom, self.n_r, self.n_q
+        plan.dev_src_r_off, plan.dev_src_q_off = self.src_r_off.data_ptr(), self.src_q_off.data_ptr()
+        for b in range(2):
+            plan.dev_dst_r[b], plan.dev_dst_q[b] = self.dst_r[b].data_ptr(), self.dst_q[b].data_ptr()
+        plan.dev_counter = self.sync.counter.data_ptr()
+        plan.sync = self.sync.struct
+        self._plan = plan
+        rc = e.lib.fg_maxsum_shard_attach(e._h, C.byref(plan))
+        if rc != 0:
+            raise RuntimeError(f"fg_maxsum_shard_attach failed rc={rc}: {e._last_error()}")
+        self.launches = 0      # counted inside the engine handle now
         dist.barrier(group=group)
 
-    def push(self, buf_index):
+    def step(self, n_cycles):
         e, torch = self.engine, self.torch
-        if self.n_r + self.n_q:
-            rc = e.lib.fg_halo_push(self.prec, C.c_void_p(e.r[buf_index].data_ptr()),
-                                    C.c_void_p(e.q[buf_index].data_ptr()),
-                                    C.c_void_p(self.src_r_off.data_ptr()), C.c_void_p(self.src_q_off.data_ptr()),
-                                    C.c_void_p(self.dst_r[buf_index].data_ptr()),
-                                    C.c_void_p(self.dst_q[buf_index].data_ptr()), self.n_r, self.n_q, self.dom,
-                                    C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
-            if rc != 0:
-                raise RuntimeError(f"fg_halo_push failed rc={rc}")
-            self.launches += 1
-        # every rank's stores are complete and visible once all ranks passed this point
-        self.dist.all_reduce(self.token, group=self.group)
+        with torch.cuda.device(e.device):
+            rc = e.lib.fg_maxsum_shard_step(e._h, int(n_cycles),
+                                            C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"fg_maxsum_shard_step failed rc={rc}: {e._last_error()}")
+
+    def phase(self, ph):
+        e, torch = self.engine, self.torch
+        with torch.cuda.device(e.device):
+            rc = e.lib.fg_maxsum_shard_phase(e._h, int(ph),
+                                             C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"fg_maxsum_shard_phase({ph}) failed rc={rc}: {e._last_error()}")
 
 
 class ShardedMaxSum:
@@ -555,21 +546,39 @@ class ShardedMaxSum:
 
     def step(self, n_cycles=1):
         e = self.engine
+        if self.peer is not None:       # whole cycles enqueued by one C call, closed on the device
+            self.peer.step(n_cycles)
+            return self
         for _ in range(int(n_cycles)):
             e.cycle_compute()
             nxt = e.cur ^ 1
-            if self.peer is not None:
-                self.peer.push(nxt)
-            else:
-                self.halo.exchange(e.q[nxt], e.r[nxt])
+            self.halo.exchange(e.q[nxt], e.r[nxt])
             e.cycle_commit()
         return self
 
+    def check(self):
+        """Raise if the device-side barrier timed out (synchronises the device)."""
+        if self.peer is not None:
+            self.peer.sync.check()
+
     def timed_breakdown(self, n_cycles=50):
-        """Device time (ms per cycle) of compute / pack / all_to_all / unpack, for tuning."""
+        """Device time (ms per cycle) of the phases of a cycle on this rank: peer push path ->
+        compute / push (+ release) / wait; NCCL path -> compute / pack / all_to_all / unpack."""
         import torch.distributed as dist
         torch, e, h = self.torch, self.engine, self.halo
         ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        if self.peer is not None:
+            acc = np.zeros(3)
+            for _ in range(n_cycles):
+                t = [ev() for _ in range(4)]
+                for ph in range(3):
+                    t[ph].record()
+                    self.peer.phase(ph)
+                t[3].record()
+                self.peer.phase(3)
+                torch.cuda.synchronize(self.device)
+                acc += [t[i].elapsed_time(t[i + 1]) for i in range(3)]
+            return dict(zip(("compute", "push", "wait"), (acc / n_cycles).tolist()))
         acc = np.zeros(4)
         for _ in range(n_cycles):
             t = [ev() for _ in range(5)]
@@ -591,7 +600,7 @@ class ShardedMaxSum:
 
     @property
     def launch_count(self):
-        return self.engine.launch_count + self.halo.launches + (self.peer.launches if self.peer else 0)
+        return self.engine.launch_count + self.halo.launches
 
     def local_values(self):
         """(global variable ids, value indices) of the variables this rank owns."""

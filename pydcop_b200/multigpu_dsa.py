@@ -8,8 +8,8 @@ unchanged:
   * the variables it owns, with ALL their constraints (so costs, `p_mode=arity` counts and the
     variant-B violation test see exactly what the single-GPU run sees);
   * a GHOST variable for every remote variable in the scope of one of those constraints.  Ghosts
-    are frozen (`DsaEngine(frozen=…)`: the kernels copy their value through) and their value is
-    overwritten by the owner's every cycle.
+    are frozen (`DsaEngine(frozen=…)`: the local kernels never write them) and their value is
+    supplied by the owner every cycle.
 Random draws are keyed by the GLOBAL variable id (`DsaEngine(var_global_id=…)`), so the sharded
 trajectory equals the single-GPU trajectory bit for bit, for any world size.
 
@@ -223,47 +223,24 @@ def value_push_tables(shard: DsaShard, base: np.ndarray, dst_idx):
 
 class ValuePeerPush:
     """Boundary values over NVLink peer memory, the DSA twin of multigpu.PeerPush: every rank maps
-    the peers' two value buffers (CUDA IPC) and ONE push kernel (fg_halo_push, rows of one 4-byte
-    element) stores each boundary value straight into the ghost entry of the consumer's `next`
-    buffer; an all-reduce closes the cycle.  Replaces pack -> all_to_all -> unpack."""
+    the peers' two value buffers (CUDA IPC) and ONE push kernel (rows of one 4-byte element) stores
+    each boundary value straight into the ghost entry of the consumer's `next` buffer; the cycle is
+    closed by the device-side epoch barrier (pydcop_b200/peer.py).  Ghost entries are written ONLY by
+    their owner's push (the local kernels skip them, has_nbr == 2), so a fast rank's push cannot be
+    overwritten by a slow rank's own kernel.  Whole cycles are enqueued by fg_dsa_shard_step."""
 
     def __init__(self, sharded, group=None):
         import torch
         import torch.distributed as dist
         from . import _cabi
+        from .peer import PeerMap, PeerSync
         self.torch, self.dist, self.group = torch, dist, group
-        e, sh, h = sharded.engine, sharded.shard, sharded.halo
+        e, sh = sharded.engine, sharded.shard
         self.engine = e
         dev = e.device
         W, me = sh.world, sh.rank
-        lib = e.lib
-        mine = []
-        for t in (e.value[0], e.value[1]):
-            hb = (C.c_ubyte * 64)()
-            off = C.c_int64()
-            rc = lib.fg_ipc_export(C.c_void_p(t.data_ptr()), C.cast(hb, C.c_void_p), C.byref(off))
-            if rc != 0:
-                raise RuntimeError(f"fg_ipc_export failed rc={rc}")
-            mine.append((bytes(hb), int(off.value)))
-        everyone = [None] * W
-        dist.all_gather_object(everyone, mine, group=group)
-        self._mapped = {}
-        base = np.zeros((W, 2), dtype=np.int64)
-        with torch.cuda.device(dev):
-            for rnk in range(W):
-                if rnk == me:
-                    base[rnk] = [e.value[0].data_ptr(), e.value[1].data_ptr()]
-                    continue
-                for i, (hbytes, off) in enumerate(everyone[rnk]):
-                    key = (rnk, hbytes)
-                    if key not in self._mapped:
-                        out = C.c_void_p()
-                        buf = (C.c_ubyte * 64).from_buffer_copy(hbytes)
-                        rc = lib.fg_ipc_import(C.cast(buf, C.c_void_p), C.byref(out))
-                        if rc != 0:
-                            raise RuntimeError(f"fg_ipc_import failed rc={rc} (rank {rnk})")
-                        self._mapped[key] = int(out.value)
-                    base[rnk, i] = self._mapped[key] + off
+        self.pmap = PeerMap(e.lib, dev, me, W, group)
+        base = self.pmap.map([e.value[0], e.value[1]])
         # where my values land: the consumers' ghost indices (internal order), in my send order
         perm = np.asarray(sh.layout.var_perm, dtype=np.int64)
         out = torch.zeros(len(sh.send_var), dtype=torch.int64, device=dev)
@@ -273,23 +250,29 @@ class ValuePeerPush:
         t = value_push_tables(sh, base, out.cpu().numpy())
         self.dst, self.src = [to(a) for a in t["dst"]], to(t["src"])
         self.n = len(sh.send_var)
-        self.token = torch.zeros(1, device=dev)
-        self.launches = 0
-        self.prec = _cabi.FG_F32     # 4-byte elements, moved bit for bit
+        peers = [b for b in range(W) if b != me and (sh.send_split[b] or sh.recv_split[b])]
+        self.sync = PeerSync(self.pmap, peers)
+        plan = _cabi.FgHaloPlan()
+        plan.elem_bytes, plan.dom, plan.n_r, plan.n_q = 4, 1, self.n, 0
+        plan.dev_src_r_off = self.src.data_ptr()
+        for b in range(2):
+            plan.dev_dst_r[b] = self.dst[b].data_ptr()
+        plan.dev_counter = self.sync.counter.data_ptr()
+        plan.sync = self.sync.struct
+        self._plan = plan
+        rc = e.lib.fg_dsa_shard_attach(e._h, C.byref(plan))
+        if rc != 0:
+            raise RuntimeError(f"fg_dsa_shard_attach failed rc={rc}: {e._last_error()}")
+        self.launches = 0      # counted inside the engine handle
         dist.barrier(group=group)
 
-    def push(self, buf_index):
+    def step(self, n_cycles):
         e, torch = self.engine, self.torch
-        if self.n:
-            v = C.c_void_p(e.value[buf_index].data_ptr())
-            d = C.c_void_p(self.dst[buf_index].data_ptr())
-            s = C.c_void_p(self.src.data_ptr())
-            rc = e.lib.fg_halo_push(self.prec, v, v, s, s, d, d, self.n, 0, 1,
-                                    C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
-            if rc != 0:
-                raise RuntimeError(f"fg_halo_push failed rc={rc}")
-            self.launches += 1
-        self.dist.all_reduce(self.token, group=self.group)
+        with torch.cuda.device(e.device):
+            rc = e.lib.fg_dsa_shard_step(e._h, int(n_cycles),
+                                         C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"fg_dsa_shard_step failed rc={rc}: {e._last_error()}")
 
 
 class ShardedDsa:
@@ -357,13 +340,13 @@ class ShardedDsa:
 
     def step(self, n_cycles=1):
         e = self.engine
+        if self.peer is not None:       # whole cycles enqueued by one C call, closed on the device
+            self.peer.step(n_cycles)
+            return self
         for _ in range(int(n_cycles)):
             before = e.cycle
             e.cycle_compute()
-            if self.peer is not None:
-                self.peer.push(e.cur ^ 1)
-            else:
-                self.halo.exchange(e.value[e.cur ^ 1])
+            self.halo.exchange(e.value[e.cur ^ 1])
             e.cycle_commit()
             if e.cycle == before:                 # stop_cycle reached: nothing moves any more
                 break
@@ -375,7 +358,12 @@ class ShardedDsa:
 
     @property
     def launch_count(self):
-        return self.engine.launch_count + self.halo.launches + (self.peer.launches if self.peer else 0)
+        return self.engine.launch_count + self.halo.launches
+
+    def check(self):
+        """Raise if the device-side barrier timed out (synchronises the device)."""
+        if self.peer is not None:
+            self.peer.sync.check()
 
     def local_values(self):
         """(global variable ids, value indices) of the variables this rank owns."""

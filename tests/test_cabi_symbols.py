@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     prog = r'''
 #include <stdio.h>
 #include "pydcop_b200.h"
-int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(fg_class_t), sizeof(fg_maxsum_desc_t), sizeof(fg_dsa_desc_t), sizeof(fg_mgm_desc_t), sizeof(fg_varclass_t));return 0;}
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(fg_class_t), sizeof(fg_maxsum_desc_t), sizeof(fg_dsa_desc_t), sizeof(fg_mgm_desc_t), sizeof(fg_varclass_t), sizeof(fg_peer_sync_t), sizeof(fg_halo_plan_t));return 0;}
 '''
     with tempfile.TemporaryDirectory() as td:
         src, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
@@ -45,7 +45,8 @@ int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(fg_class_t), sizeof(fg_max
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert [int(x) for x in out] == [C.sizeof(_cabi.FgClass), C.sizeof(_cabi.FgMaxSumDesc),
                                      C.sizeof(_cabi.FgDsaDesc), C.sizeof(_cabi.FgMgmDesc),
-                                     C.sizeof(_cabi.FgVarClass)]
+                                     C.sizeof(_cabi.FgVarClass), C.sizeof(_cabi.FgPeerSync),
+                                     C.sizeof(_cabi.FgHaloPlan)]
 
 
 def test_no_cpu_fallback_without_gpu():

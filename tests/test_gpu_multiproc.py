@@ -1,6 +1,10 @@
-"""GPU (>= 2 devices): the real multi-process path — one process per GPU, NCCL — in both halo modes
-(pack -> all_to_all -> unpack, and the direct NVLink peer push through CUDA IPC).  The all-gathered
-assignment must equal the single-GPU engine's, which the other tests tie to the oracle bit-exactly."""
+"""GPU (>= 2 devices): the real multi-process path — one process per GPU, NCCL for the plumbing — in
+both halo modes: pack -> all_to_all -> unpack, and the NVLink peer push through CUDA IPC closed by
+the DEVICE-SIDE epoch barrier (csrc/peer_sync.cuh, fg_maxsum_shard_step / fg_dsa_shard_step).  The
+all-gathered assignment must equal the single-GPU engine's, which the other tests tie to the oracle
+bit for bit.  Cases cover: several step() calls and a re-init on one engine (the epoch counter only
+grows), the split push (r rows behind the factor side, q rows behind the variable side), and a
+deliberately IMBALANCED partition — a fast rank's push must not be overwritten by a slow rank."""
 import os
 import socket
 
@@ -18,8 +22,21 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, mode, q):
+def _owner(case, n_vars, world):
+    """Partition argument of a case: a method name, or 'imbalanced' = rank 0 owns 85 % of the ids."""
+    part = case.get("partition", "blocks")
+    if part != "imbalanced":
+        return part
+    own = np.zeros(n_vars, dtype=np.int32)
+    tail = n_vars - int(n_vars * 0.85)
+    own[n_vars - tail:] = 1 + (np.arange(tail) % (world - 1))
+    return own
+
+
+def _maxsum_worker(rank, world, port, case, q):
     try:
+        for k, v in case.get("env", {}).items():
+            os.environ[k] = v
         import torch
         import torch.distributed as dist
         from pydcop_b200 import MaxSumEngine, build_layout
@@ -29,13 +46,25 @@ def _worker(rank, world, port, mode, q):
         torch.cuda.set_device(rank)
         dev = torch.device("cuda", rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-        inst = random_factor_graph(2000, 10, 4000, 2, seed=21)
-        sh = ShardedMaxSum(inst, rank, world, dev, precision="f32", halo=mode).init().step(9)
+        n = case.get("n_vars", 2000)
+        inst = random_factor_graph(n, 10, 2 * n, 2, seed=21)
+        sh = ShardedMaxSum(inst, rank, world, dev, precision=case.get("precision", "f32"), halo=case["mode"],
+                           partition=_owner(case, n, world)).init()
+        plan = case.get("steps", [9])
+        ok, got = True, None
+        for i, steps in enumerate(plan):
+            if steps == "init":
+                sh.init()
+                continue
+            sh.step(steps)
+        sh.check()
         got = sh.values()
         used = "p2p" if sh.peer is not None else "nccl"
-        ok = True
         if rank == 0:
-            ref = MaxSumEngine(build_layout(**inst), device=dev, precision="f32").init().step(9)
+            tot, cur = 0, 0
+            for s in plan:     # cycles since the last init
+                cur = 0 if s == "init" else cur + s
+            ref = MaxSumEngine(build_layout(**inst), device=dev, precision=case.get("precision", "f32")).init().step(cur)
             ok = bool(np.array_equal(got, ref.values()[0]))
         dist.barrier()
         dist.destroy_process_group()
@@ -45,29 +74,7 @@ def _worker(rank, world, port, mode, q):
         q.put((rank, "FAIL " + repr(e) + traceback.format_exc(), "?"))
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
-def test_two_process_sharded_matches_single_gpu(mode):
-    import torch
-    import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=90) for _ in procs]
-    for p in procs:
-        p.join(timeout=20)
-        if p.is_alive():
-            p.kill()
-    assert all(r[1] == "ok" for r in results), results
-    assert all(r[2] == mode for r in results), results
-
-
-def _dsa_worker(rank, world, port, mode, q):
+def _dsa_worker(rank, world, port, case, q):
     try:
         import torch
         import torch.distributed as dist
@@ -79,15 +86,19 @@ def _dsa_worker(rank, world, port, mode, q):
         torch.cuda.set_device(rank)
         dev = torch.device("cuda", rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-        inst = random_factor_graph(4000, 20, 12000, 2, seed=22, noise=0.0)
+        n = case.get("n_vars", 4000)
+        inst = random_factor_graph(n, 20, 3 * n, 2, seed=22, noise=0.0)
         inst["tables"] = np.floor(inst["tables"] / 3.0).astype(np.float32)
-        sh = ShardedDsa(inst, rank, world, dev, precision="f32", variant="B", seed=9, halo=mode,
-                        partition="multilevel").init().step(10)
+        kw = dict(precision="f32", variant="B", seed=9, stop_cycle=case.get("stop_cycle", 0))
+        sh = ShardedDsa(inst, rank, world, dev, halo=case["mode"], partition=_owner(case, n, world), **kw).init()
+        for steps in case.get("steps", [10]):
+            sh.step(steps)
+        sh.check()
         got = sh.values()
         used = "p2p" if sh.peer is not None else "nccl"
         ok = True
         if rank == 0:
-            ref = DsaEngine(build_layout(**inst), device=dev, precision="f32", variant="B", seed=9).init().step(10)
+            ref = DsaEngine(build_layout(**inst), device=dev, **kw).init().step(sum(case.get("steps", [10])))
             ok = bool(np.array_equal(got, ref.values()))
         dist.barrier()
         dist.destroy_process_group()
@@ -97,23 +108,56 @@ def _dsa_worker(rank, world, port, mode, q):
         q.put((rank, "FAIL " + repr(e) + traceback.format_exc(), "?"))
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
-def test_two_process_sharded_dsa_matches_single_gpu(mode):
+def _run(worker, world, case):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_dsa_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=90) for _ in procs]
-    for p in procs:
-        p.join(timeout=20)
-        if p.is_alive():
-            p.kill()
+    try:
+        results = [q.get(timeout=150) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
     assert all(r[1] == "ok" for r in results), results
-    assert all(r[2] == mode for r in results), results
+    assert all(r[2] == case["mode"] for r in results), results
+
+
+MAXSUM_CASES = {
+    "nccl": dict(mode="nccl"),
+    "p2p": dict(mode="p2p"),
+    "p2p-steps-reinit": dict(mode="p2p", steps=[1, 3, "init", 2, 5, 4]),
+    "p2p-split-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_SPLIT": "1"}, steps=[4, 5]),
+    "p2p-multilevel-f64": dict(mode="p2p", partition="multilevel", precision="f64"),
+    "p2p-imbalanced": dict(mode="p2p", partition="imbalanced", n_vars=20000, steps=[12]),
+}
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("name", sorted(MAXSUM_CASES))
+def test_sharded_maxsum_processes_match_single_gpu(name, world):
+    _run(_maxsum_worker, world, MAXSUM_CASES[name])
+
+
+DSA_CASES = {
+    "nccl": dict(mode="nccl", partition="multilevel"),
+    "p2p": dict(mode="p2p", partition="multilevel"),
+    "p2p-steps": dict(mode="p2p", steps=[1, 2, 7]),
+    "p2p-stop-cycle": dict(mode="p2p", stop_cycle=6, steps=[4, 4, 2]),
+    # rank 0 owns 85 % of the variables: the other ranks finish their kernel and push long before rank 0's
+    # kernel reaches its ghost entries (a local write of the ghost would overwrite the push)
+    "p2p-imbalanced": dict(mode="p2p", partition="imbalanced", n_vars=200000, steps=[12]),
+}
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("name", sorted(DSA_CASES))
+def test_sharded_dsa_processes_match_single_gpu(name, world):
+    _run(_dsa_worker, world, DSA_CASES[name])
