@@ -292,6 +292,16 @@ typedef struct {
   const int64_t *dev_dst_r[2], *dev_dst_q[2];
   uint32_t *dev_counter;              /* one zeroed uint32: last-block detection of the push kernel */
   fg_peer_sync_t sync;
+  /* Optional (NULL / 0 = one thread per 4/8/16-byte piece of a row): the push lists cut into RUNS of rows
+   * whose destinations are consecutive addresses — the rows one peer receives land in dense blocks of its
+   * buffers — so that the kernel can issue whole 16-byte aligned stores over NVLink whatever the row
+   * size (rows of 40 bytes would otherwise leave as 8-byte stores).  Per list and buffer index b:
+   * dev_runs[b] = int64 [n_runs][4] = (first destination address, index of the run's first row in the
+   * list, bytes in the run, index of the run's first 16-byte destination unit), units = total units.
+   * Needs row bytes % 8 == 0. */
+  const int64_t *dev_runs_r[2], *dev_runs_q[2];
+  int32_t n_runs_r[2], n_runs_q[2];
+  int64_t units_r[2], units_q[2];
 } fg_halo_plan_t;
 
 /* Attach a push plan to an engine (copied).  From then on fg_*_shard_step runs whole cycles on the
@@ -302,6 +312,11 @@ int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan);
 int fg_maxsum_shard_step(fg_maxsum_t h, int32_t n_cycles, void *stream);
 /* One phase of a cycle, for timing breakdowns: 0 compute, 1 push + signal, 2 wait, 3 commit. */
 int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream);
+/* Diagnostics: n_cycles whole cycles with CUDA timing events INSIDE the cycle (no host work between the
+ * kernels), averaged, microseconds: out_us[0] factor side, [1] push of the r rows (split mode),
+ * [2] variable side, [3] push of the q rows (split mode), [4] push / release after the join, [5] wait
+ * for the peers, [6] whole cycle.  Synchronises the stream after every cycle. */
+int fg_maxsum_shard_profile(fg_maxsum_t h, int32_t n_cycles, void *stream, double *out_us);
 int fg_dsa_shard_attach(fg_dsa_t h, const fg_halo_plan_t *plan);
 int fg_dsa_shard_step(fg_dsa_t h, int32_t n_cycles, void *stream);
 

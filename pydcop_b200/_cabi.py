@@ -94,7 +94,9 @@ class FgPeerSync(C.Structure):
 class FgHaloPlan(C.Structure):
     _fields_ = [("elem_bytes", C.c_int32), ("dom", C.c_int32), ("n_r", C.c_int64), ("n_q", C.c_int64),
                 ("dev_src_r_off", P), ("dev_src_q_off", P), ("dev_dst_r", P * 2), ("dev_dst_q", P * 2),
-                ("dev_counter", P), ("sync", FgPeerSync)]
+                ("dev_counter", P), ("sync", FgPeerSync),
+                ("dev_runs_r", P * 2), ("dev_runs_q", P * 2), ("n_runs_r", C.c_int32 * 2), ("n_runs_q", C.c_int32 * 2),
+                ("units_r", C.c_int64 * 2), ("units_q", C.c_int64 * 2)]
 
 
 # every symbol include/pydcop_b200.h declares: (restype, argtypes)
@@ -124,6 +126,7 @@ SYMBOLS = {
     "fg_maxsum_shard_attach": (C.c_int, [P, C.POINTER(FgHaloPlan)]),
     "fg_maxsum_shard_step": (C.c_int, [P, C.c_int32, P]),
     "fg_maxsum_shard_phase": (C.c_int, [P, C.c_int32, P]),
+    "fg_maxsum_shard_profile": (C.c_int, [P, C.c_int32, P, C.POINTER(C.c_double)]),
     "fg_dsa_shard_attach": (C.c_int, [P, C.POINTER(FgHaloPlan)]),
     "fg_dsa_shard_step": (C.c_int, [P, C.c_int32, P]),
     "fg_dsa_create": (C.c_int, [C.POINTER(FgDsaDesc), C.POINTER(P)]),

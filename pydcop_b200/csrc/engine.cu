@@ -10,6 +10,7 @@
 #include "dsa_generic.cuh"
 #include "maxsum_generic.cuh"
 #include "maxsum_fast.cuh"
+#include "maxsum_warp.cuh"
 #include "dsa_fast.cuh"
 #include "peer_sync.cuh"
 
@@ -28,6 +29,7 @@ struct fg_maxsum {
   std::vector<fg_class_t> classes;
   std::vector<fg_varclass_t> varclasses;
   MaxSumFastPlan fast;
+  MaxSumWarpPlan warp;   // warp-autonomous kernels (round 2) over the same classes
   bool fast_first = true;   // tiled kernels in cycle 1 as well (PYDCOP_B200_FAST_FIRST=0: generic kernels)
   int cur = 0;
   int64_t cycle = 0;
@@ -37,6 +39,7 @@ struct fg_maxsum {
   bool split_push = false;  // PYDCOP_B200_PUSH_SPLIT=1: r rows right behind the factor side, q rows on the side stream
   fg_halo_plan_t halo;
   uint64_t epoch = 0;
+  cudaEvent_t *prof = nullptr;   // fg_maxsum_shard_profile: 8 timing events recorded inside a cycle
   char err[512] = {0};
 };
 
@@ -107,6 +110,7 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
+  maxsum_warp_plan(h->d, h->varclasses, h->fast, h->warp);
   { const char *e = getenv("PYDCOP_B200_FAST_FIRST"); h->fast_first = !(e && e[0] == '0'); }
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -201,10 +205,12 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
                                                              d.dev_edge_qoff, d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
     ++h->launches;
   }
+  if (h->prof) cudaEventRecord(h->prof[1], st);
   if (push_split && h->halo.n_r > 0) {
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, h->halo.n_r, 0, 0, 0, st, h->launches);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (r rows) failed"); return rc; }
   }
+  if (h->prof) cudaEventRecord(h->prof[2], st);
   // variable -> factor (+ value selection).  Both sides only READ the current buffers and WRITE
   // disjoint next buffers (Jacobi), so from cycle 2 on the variable side runs on a second stream,
   // concurrently with the factor side: one is HBM-streaming, the other gather/latency-bound.
@@ -220,8 +226,12 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
         ++h->launches;
       }
     } else {
-      for (size_t li = 0; li < h->fast.v2f.size(); ++li) {
-        if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
+      if (h->warp.v2f_on) {
+        for (size_t li = 0; li < h->warp.v2f.size(); ++li)
+          if (dispatch_v2f_warp<T>(h->warp.v2f_dom[li], h->warp.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
+      } else {
+        for (size_t li = 0; li < h->fast.v2f.size(); ++li)
+          if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
       }
       for (int vi : h->fast.slow_varclasses) {
         const fg_varclass_t &vc = h->varclasses[vi];
@@ -232,10 +242,12 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
       }
     }
   }
+  if (h->prof) cudaEventRecord(h->prof[3], st);
   if (push_split && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, st, h->launches);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows) failed"); return rc; }
   }
+  if (h->prof) cudaEventRecord(h->prof[4], st);
   if (fork) {
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
     CUDA_TRY(h, cudaStreamWaitEvent(st_f, h->ev_join, 0));
@@ -334,6 +346,41 @@ extern "C" int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream)
     case 3: ++h->epoch; return fg_maxsum_cycle_commit(h);
   }
   return FG_ERR_ARG;
+}
+
+// Device-time profile of a sharded cycle (diagnostics; bench.py's `breakdown`): n_cycles cycles with timing
+// events inside, averaged, in microseconds:
+//   out[0] factor side   out[1] push of the r rows (split mode)   out[2] variable side (from the cycle start)
+//   out[3] push of the q rows (split mode)   out[4] join -> push (+ release) done   out[5] wait   out[6] whole cycle
+extern "C" int fg_maxsum_shard_profile(fg_maxsum_t h, int32_t n_cycles, void *stream, double *out_us) {
+  if (!h || !h->has_halo || !out_us || n_cycles < 1) return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev[8];
+  for (auto &e : ev) CUDA_TRY(h, cudaEventCreate(&e));
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  int rc = FG_OK;
+  for (int i = 0; i < n_cycles && rc == FG_OK; ++i) {
+    cudaEventRecord(ev[0], st);
+    h->prof = ev;
+    rc = fg_maxsum_shard_phase(h, 0, stream);
+    h->prof = nullptr;
+    cudaEventRecord(ev[5], st);
+    if (rc == FG_OK) rc = fg_maxsum_shard_phase(h, 1, stream);
+    cudaEventRecord(ev[6], st);
+    if (rc == FG_OK) rc = fg_maxsum_shard_phase(h, 2, stream);
+    cudaEventRecord(ev[7], st);
+    if (rc == FG_OK) rc = fg_maxsum_shard_phase(h, 3, stream);
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = FG_ERR_CUDA;
+    if (h->side_stream) cudaStreamSynchronize(h->side_stream);
+    if (rc != FG_OK) break;
+    auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return (double)t * 1e3; };
+    acc[0] += ms(0, 1); acc[1] += ms(1, 2); acc[2] += ms(0, 3); acc[3] += ms(3, 4);
+    acc[4] += ms(5, 6); acc[5] += ms(6, 7); acc[6] += ms(0, 7);
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  cudaGetLastError();
+  for (int k = 0; k < 7; ++k) out_us[k] = acc[k] / n_cycles;
+  return rc;
 }
 
 extern "C" int fg_maxsum_shard_step(fg_maxsum_t h, int32_t n_cycles, void *stream) {
@@ -548,6 +595,10 @@ extern "C" int fg_dsa_create(const fg_dsa_desc_t *desc, fg_dsa_t *out) {
   if (fg_device_count() <= 0) {
     snprintf(h->err, sizeof(h->err), "no CUDA device visible: pydcop_b200 has no CPU fallback");
     return FG_ERR_CUDA;
+  }
+  {  // experiment knob: L2 -> DRAM fetch granularity hint (32 | 64 | 128 bytes) for the sparse row reads
+    const int g = fg_env_int("PYDCOP_B200_L2_FETCH", 0);
+    if (g == 32 || g == 64 || g == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g); cudaGetLastError(); }
   }
   // the class table is the one device allocation the library owns (a few hundred bytes)
   size_t bytes = sizeof(fg_class_t) * (h->classes.empty() ? 1 : h->classes.size());

@@ -101,6 +101,52 @@ k_halo_push_sig(const unsigned char *__restrict__ arr_r, const unsigned char *__
   }
 }
 
+// Run-based push of ONE list: thread <-> one 16-byte aligned unit of a destination run; the two 8-byte
+// halves of a unit come from (possibly different) source rows.  A unit that sticks out of its run at
+// either end is stored as its inner 8-byte half.
+template <bool SIGNAL>
+__global__ void __launch_bounds__(256)
+k_halo_push_runs(const unsigned char *__restrict__ arr, const int64_t *__restrict__ src_off,
+                 const int64_t *__restrict__ runs, int n_runs, int64_t total_units, uint32_t row_bytes, int elem,
+                 uint32_t *__restrict__ counter, PeerSlots ps, uint64_t epoch) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total_units) {
+    int lo = 0, hi = n_runs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (runs[4 * mid + 3] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int64_t a0 = runs[4 * lo], row0 = runs[4 * lo + 1], len = runs[4 * lo + 2];
+    const int64_t unit = (a0 & ~(int64_t)15) + 16 * (t - runs[4 * lo + 3]);
+    uint2 v[2];
+    bool ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t b = unit + 8 * h - a0;  // byte offset inside the run
+      ok[h] = b >= 0 && b < len;
+      if (ok[h]) {
+        const uint32_t bb = (uint32_t)b, r = bb / row_bytes, c = bb - r * row_bytes;
+        v[h] = *reinterpret_cast<const uint2 *>(arr + src_off[row0 + r] * elem + c);
+      }
+    }
+    unsigned char *d = reinterpret_cast<unsigned char *>(unit);
+    if (ok[0] && ok[1]) *reinterpret_cast<uint4 *>(d) = make_uint4(v[0].x, v[0].y, v[1].x, v[1].y);
+    else if (ok[0]) *reinterpret_cast<uint2 *>(d) = v[0];
+    else if (ok[1]) *reinterpret_cast<uint2 *>(d + 8) = v[1];
+  }
+  if (SIGNAL) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(counter, 1u);
+      if (prev == gridDim.x - 1) {
+        *counter = 0;
+        peer_release_all(ps, epoch);
+      }
+    }
+  }
+}
+
 inline PeerSlots peer_slots_of(const fg_peer_sync_t &s) {
   PeerSlots ps;
   ps.n = s.n_peers;
@@ -124,6 +170,28 @@ inline int peer_sync_check(const fg_peer_sync_t *s) {
 inline int halo_push_launch(const fg_halo_plan_t &p, const void *arr_r, const void *arr_q, int b, int64_t n_r,
                             int64_t n_q, int signal, uint64_t epoch, cudaStream_t st, int64_t &launches) {
   const PeerSlots ps = peer_slots_of(p.sync);
+  // run tables present: one launch per list, 16-byte stores; the release rides on the last launch
+  const bool runs_r = n_r > 0 && p.dev_runs_r[b] && p.n_runs_r[b] > 0, runs_q = n_q > 0 && p.dev_runs_q[b] && p.n_runs_q[b] > 0;
+  if ((n_r <= 0 || runs_r) && (n_q <= 0 || runs_q) && (n_r > 0 || n_q > 0) && ((p.dom * p.elem_bytes) % 8 == 0)) {
+    const bool sig = signal && ps.n;
+    for (int list = 0; list < 2; ++list) {
+      const bool is_q = list == 1;
+      if (is_q ? !runs_q : !runs_r) continue;
+      const bool last = is_q || !runs_q;
+      const int64_t units = is_q ? p.units_q[b] : p.units_r[b];
+      const unsigned blocks = (unsigned)((units + 255) / 256);
+      const unsigned char *arr = (const unsigned char *)(is_q ? arr_q : arr_r);
+      const int64_t *off = is_q ? p.dev_src_q_off : p.dev_src_r_off;
+      const int64_t *runs = is_q ? p.dev_runs_q[b] : p.dev_runs_r[b];
+      const int nr = is_q ? p.n_runs_q[b] : p.n_runs_r[b];
+      if (sig && last)
+        k_halo_push_runs<true><<<blocks, 256, 0, st>>>(arr, off, runs, nr, units, (uint32_t)(p.dom * p.elem_bytes), p.elem_bytes, p.dev_counter, ps, epoch);
+      else
+        k_halo_push_runs<false><<<blocks, 256, 0, st>>>(arr, off, runs, nr, units, (uint32_t)(p.dom * p.elem_bytes), p.elem_bytes, p.dev_counter, ps, epoch);
+      ++launches;
+    }
+    return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+  }
   if (n_r + n_q <= 0) {
     if (signal && ps.n) { k_peer_signal<<<1, 32, 0, st>>>(ps, epoch); ++launches; }
     return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;

@@ -391,6 +391,25 @@ def push_tables(plan: ShardPlan, base: np.ndarray, dst_r_off, dst_q_off, elem: i
         src_q_off=np.asarray(plan.send_q_off, dtype=np.int64)[perm_q])
 
 
+def push_runs(dst_addr, row_bytes: int):
+    """Cut a push list (absolute destination address per row, in push order) into RUNS of rows whose
+    destinations are consecutive addresses.  Returns (int64 [n_runs, 4], total_units): per run the first
+    destination address, the index of its first row, its length in bytes, and the index of its first
+    16-byte aligned destination unit (the run-based push kernel maps one thread to one unit, fg_halo_plan_t)."""
+    dst = np.asarray(dst_addr, dtype=np.int64)
+    if not len(dst):
+        return np.zeros((0, 4), dtype=np.int64), 0
+    brk = np.ones(len(dst), dtype=bool)
+    brk[1:] = dst[1:] != dst[:-1] + row_bytes
+    first = np.nonzero(brk)[0]
+    n_rows = np.diff(np.concatenate([first, [len(dst)]]))
+    a0 = dst[first]
+    nbytes = n_rows * row_bytes
+    units = (a0 + nbytes + 15) // 16 - a0 // 16
+    first_unit = np.concatenate([[0], np.cumsum(units)[:-1]])
+    return np.ascontiguousarray(np.stack([a0, first, nbytes, first_unit], axis=1), dtype=np.int64), int(units.sum())
+
+
 class PeerPush:
     """Halo over NVLink peer memory: every rank maps the peers' message buffers (CUDA IPC) and its
     push kernel stores each boundary row straight into the consumer's `next` buffer.  The cycle is
@@ -441,6 +460,20 @@ class PeerPush:
             plan.dev_dst_r[b], plan.dev_dst_q[b] = self.dst_r[b].data_ptr(), self.dst_q[b].data_ptr()
         plan.dev_counter = self.sync.counter.data_ptr()
         plan.sync = self.sync.struct
+        # destination runs: whole 16-byte stores over NVLink whatever the row size (PYDCOP_B200_PUSH_RUNS=0: per row)
+        self.runs = []
+        import os
+        if (self.dom * elem) % 8 == 0 and os.environ.get("PYDCOP_B200_PUSH_RUNS", "1") != "0":
+            for b in range(2):
+                for name, dst in (("r", t["dst_r"][b]), ("q", t["dst_q"][b])):
+                    runs, units = push_runs(dst, self.dom * elem)
+                    rt = to(runs.reshape(-1)) if len(runs) else None
+                    self.runs.append(rt)
+                    if rt is not None:
+                        getattr(plan, "dev_runs_" + name)[b] = rt.data_ptr()
+                        getattr(plan, "n_runs_" + name)[b] = len(runs)
+                        getattr(plan, "units_" + name)[b] = units
+        self.n_runs = [int(plan.n_runs_r[0]), int(plan.n_runs_q[0])]
         self._plan = plan
         rc = e.lib.fg_maxsum_shard_attach(e._h, C.byref(plan))
         if rc != 0:
@@ -567,18 +600,14 @@ class ShardedMaxSum:
         import torch.distributed as dist
         torch, e, h = self.torch, self.engine, self.halo
         ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-        if self.peer is not None:
-            acc = np.zeros(3)
-            for _ in range(n_cycles):
-                t = [ev() for _ in range(4)]
-                for ph in range(3):
-                    t[ph].record()
-                    self.peer.phase(ph)
-                t[3].record()
-                self.peer.phase(3)
-                torch.cuda.synchronize(self.device)
-                acc += [t[i].elapsed_time(t[i + 1]) for i in range(3)]
-            return dict(zip(("compute", "push", "wait"), (acc / n_cycles).tolist()))
+        if self.peer is not None:   # timing events recorded inside the C cycle: no host time between the kernels
+            out = (C.c_double * 7)()
+            with torch.cuda.device(self.device):
+                rc = e.lib.fg_maxsum_shard_profile(e._h, int(n_cycles), e._stream(), out)
+            if rc != 0:
+                raise RuntimeError(f"fg_maxsum_shard_profile failed rc={rc}: {e._last_error()}")
+            keys = ("factor_side", "push_r", "variable_side", "push_q", "push_release", "wait", "cycle")
+            return {k: out[i] * 1e-3 for i, k in enumerate(keys)}
         acc = np.zeros(4)
         for _ in range(n_cycles):
             t = [ev() for _ in range(5)]

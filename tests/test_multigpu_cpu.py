@@ -329,3 +329,43 @@ def test_peer_push_tables_move_every_boundary_row_to_its_ghost_row(world, partit
     for r in range(world):
         for arr in (1, 3):
             assert np.array_equal(got[r][arr], want[r][arr]), (r, arr)
+
+
+@pytest.mark.parametrize("row_bytes", [40, 80, 16, 8])
+def test_push_runs_cover_every_destination_byte_exactly_once(row_bytes):
+    """multigpu.push_runs + the unit addressing of k_halo_push_runs (restated here in numpy): executing every
+    16-byte unit — full, or its inner 8-byte half at the ends of a run — writes exactly the bytes the per-row
+    push writes, from the same source bytes."""
+    from pydcop_b200.multigpu import push_runs
+    rng = np.random.default_rng(row_bytes)
+    # destination rows: a few dense blocks at 8-byte aligned bases, some single rows
+    dst = []
+    addr = 1 << 20
+    for n in (7, 1, 12, 1, 1, 30, 2):
+        addr += int(rng.integers(1, 50)) * 8 + n * row_bytes
+        dst += [addr + i * row_bytes for i in range(n)]
+        addr += n * row_bytes
+    dst = np.array(dst, dtype=np.int64)
+    n = len(dst)
+    src_off = rng.permutation(n * 3)[:n].astype(np.int64) * row_bytes      # byte offsets of the source rows
+    src = rng.integers(0, 255, size=3 * n * row_bytes + 64).astype(np.uint8)
+    want = {}
+    for i in range(n):
+        for k in range(row_bytes):
+            want[int(dst[i]) + k] = src[src_off[i] + k]
+    runs, units = push_runs(dst, row_bytes)
+    assert runs[:, 2].sum() == n * row_bytes and runs[0, 3] == 0
+    got = {}
+    for t in range(units):
+        lo = int(np.searchsorted(runs[:, 3], t, side="right") - 1)
+        a0, row0, ln, u0 = (int(x) for x in runs[lo])
+        unit = (a0 & ~15) + 16 * (t - u0)
+        for h in range(2):
+            b = unit + 8 * h - a0
+            if 0 <= b < ln:
+                r, c = divmod(b, row_bytes)
+                for k in range(8):
+                    key = unit + 8 * h + k
+                    assert key not in got
+                    got[key] = src[src_off[row0 + r] + c + k]
+    assert got == want
