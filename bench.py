@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--vars-per-gpu", type=int, default=100_000)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps: skip the end-to-end leg (line has no e2e key)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "target", "c4", "mgm"],
                     help="c2 (default, the driver's line) | c3 Ising 1024^2 | c5 arity-3 | target 1M vars "
                          "| c4 DSA 1M vars d=20 (variable updates/s) | mgm: MGM on the c4 instance")
@@ -388,7 +389,7 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = out_host.numel() * 4
     times = []
-    for it in range(3 + 5):
+    for it in range(0 if args.no_e2e else 3 + 5):
         flush.zero_()
         if world > 1:
             dist.barrier()
@@ -403,7 +404,7 @@ def main():
         torch.cuda.synchronize(dev)
         if it >= 3:
             times.append(a.elapsed_time(b))
-    e2e_ms = float(np.mean(times))
+    e2e_ms = float(np.mean(times)) if times else float("nan")
     if world > 1:
         t = torch.tensor([e2e_ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
         tm = t.clone()

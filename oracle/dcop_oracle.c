@@ -5,6 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #define MAX_ARITY 8
 #define MAX_DOM 256
 #define SAME_COUNT 4 /* maxsum.py:106 */
@@ -34,6 +38,18 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* OpenMP threads the parallel loops use: set (n > 0) / query.  torchrun exports OMP_NUM_THREADS=1; a
+ * timed baseline sets the count explicitly and reports what the runtime says. */
+int oracle_threads(int set_to) {
+#ifdef _OPENMP
+  if (set_to > 0) omp_set_num_threads(set_to);
+  return omp_get_max_threads();
+#else
+  (void)set_to;
+  return 1;
+#endif
 }
 
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,

@@ -180,18 +180,12 @@ void FN(maxsum_oracle_init)(const fg_t *g, const REAL *tables, const REAL *unary
   }
 }
 
-/* One synchronous cycle k >= 1 for every factor and variable (Jacobi: both sides read the state
- * at the end of cycle k-1, SynchronousComputationMixin, computations.py:633-642,755-788). */
-void FN(maxsum_oracle_step)(const fg_t *g, const REAL *tables, const REAL *unary, int mode_max,
-                            int damp_vars, int damp_factors, double damping, double stability,
-                            REAL *q, REAL *r, uint8_t *q_flags, uint8_t *r_flags, uint8_t *q_sent,
-                            uint8_t *r_sent, int32_t *value, REAL *value_cost) {
-  int64_t M = g->msg_off[g->E];
-  REAL lam = (REAL)damping, oml = (REAL)(1.0 - damping), stab = (REAL)stability;
-  REAL *q2 = (REAL *)malloc(sizeof(REAL) * (M ? M : 1));
-  REAL *r2 = (REAL *)malloc(sizeof(REAL) * (M ? M : 1));
-  uint8_t *qf2 = (uint8_t *)malloc(g->E ? g->E : 1);
-  uint8_t *rf2 = (uint8_t *)malloc(g->E ? g->E : 1);
+/* one cycle: reads (q, r, q_flags, r_flags), writes (q2, r2, qf2, rf2) */
+static void FN(maxsum_cycle_into)(const fg_t *g, const REAL *tables, const REAL *unary, int mode_max,
+                                  int damp_vars, int damp_factors, REAL lam, REAL oml, REAL stab,
+                                  const REAL *q, const REAL *r, const uint8_t *q_flags, const uint8_t *r_flags,
+                                  REAL *q2, REAL *r2, uint8_t *qf2, uint8_t *rf2, uint8_t *q_sent,
+                                  uint8_t *r_sent, int32_t *value, REAL *value_cost) {
 #pragma omp parallel
   {
     REAL cand[MAX_DOM];
@@ -220,11 +214,49 @@ void FN(maxsum_oracle_step)(const fg_t *g, const REAL *tables, const REAL *unary
       }
     }
   }
-  memcpy(q, q2, sizeof(REAL) * M);
-  memcpy(r, r2, sizeof(REAL) * M);
-  memcpy(q_flags, qf2, g->E);
-  memcpy(r_flags, rf2, g->E);
+}
+
+/* n synchronous cycles k >= 1 for every factor and variable (Jacobi: both sides read the state at the
+ * end of cycle k-1, SynchronousComputationMixin, computations.py:633-642,755-788).  The scratch
+ * buffers are allocated once per call and the two states swap roles between cycles, so a timed call
+ * with n >> 1 measures the arithmetic, not malloc / memcpy. */
+void FN(maxsum_oracle_steps)(const fg_t *g, const REAL *tables, const REAL *unary, int mode_max,
+                             int damp_vars, int damp_factors, double damping, double stability,
+                             REAL *q, REAL *r, uint8_t *q_flags, uint8_t *r_flags, uint8_t *q_sent,
+                             uint8_t *r_sent, int32_t *value, REAL *value_cost, int n) {
+  int64_t M = g->msg_off[g->E];
+  REAL lam = (REAL)damping, oml = (REAL)(1.0 - damping), stab = (REAL)stability;
+  REAL *q2 = (REAL *)malloc(sizeof(REAL) * (M ? M : 1));
+  REAL *r2 = (REAL *)malloc(sizeof(REAL) * (M ? M : 1));
+  uint8_t *qf2 = (uint8_t *)malloc(g->E ? g->E : 1);
+  uint8_t *rf2 = (uint8_t *)malloc(g->E ? g->E : 1);
+  REAL *qa = q, *ra = r, *qb = q2, *rb = r2;
+  uint8_t *qfa = q_flags, *rfa = r_flags, *qfb = qf2, *rfb = rf2;
+  for (int i = 0; i < n; ++i) {
+    FN(maxsum_cycle_into)(g, tables, unary, mode_max, damp_vars, damp_factors, lam, oml, stab, qa, ra, qfa,
+                          rfa, qb, rb, qfb, rfb, q_sent, r_sent, value, value_cost);
+    REAL *t;
+    uint8_t *u;
+    t = qa; qa = qb; qb = t;
+    t = ra; ra = rb; rb = t;
+    u = qfa; qfa = qfb; qfb = u;
+    u = rfa; rfa = rfb; rfb = u;
+  }
+  if (qa != q) { /* odd n: the current state sits in the scratch buffers */
+    memcpy(q, qa, sizeof(REAL) * M);
+    memcpy(r, ra, sizeof(REAL) * M);
+    memcpy(q_flags, qfa, g->E);
+    memcpy(r_flags, rfa, g->E);
+  }
   free(q2); free(r2); free(qf2); free(rf2);
+}
+
+void FN(maxsum_oracle_step)(const fg_t *g, const REAL *tables, const REAL *unary, int mode_max,
+                            int damp_vars, int damp_factors, double damping, double stability,
+                            REAL *q, REAL *r, uint8_t *q_flags, uint8_t *r_flags, uint8_t *q_sent,
+                            uint8_t *r_sent, int32_t *value, REAL *value_cost) {
+  FN(maxsum_oracle_steps)(g, tables, unary, mode_max, damp_vars, damp_factors, damping, stability, q, r,
+                          q_flags, r_flags, q_sent, r_sent, value, value_cost, 1);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -46,6 +46,13 @@ def _p(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def threads(set_to: int = 0) -> int:
+    """OpenMP threads of the oracle's parallel loops: set (set_to > 0) and / or query."""
+    fn = lib().oracle_threads
+    fn.restype, fn.argtypes = C.c_int, [C.c_int]
+    return int(fn(int(set_to)))
+
+
 class _Graph:
     """Flat factor-graph arrays shared by both oracles (same arrays as the engine front door)."""
 
@@ -117,13 +124,15 @@ class MaxSumOracle(_Graph):
         return self
 
     def step(self, n=1):
-        fn = getattr(lib(), "maxsum_oracle_step" + self.sfx)
-        for _ in range(n):
-            fn(C.byref(self.fg), _p(self.tables), _p(self.unary), self.mode_max, self.damp_vars,
-               self.damp_factors, C.c_double(self.damping), C.c_double(self.stability),
-               _p(self.q), _p(self.r), _p(self.q_flags), _p(self.r_flags), _p(self.q_sent),
-               _p(self.r_sent), _p(self.value), _p(self.value_cost))
-            self.cycle += 1
+        """n cycles in ONE C call (scratch allocated once, states swapped between cycles)."""
+        if n <= 0:
+            return self
+        fn = getattr(lib(), "maxsum_oracle_steps" + self.sfx)
+        fn(C.byref(self.fg), _p(self.tables), _p(self.unary), self.mode_max, self.damp_vars,
+           self.damp_factors, C.c_double(self.damping), C.c_double(self.stability),
+           _p(self.q), _p(self.r), _p(self.q_flags), _p(self.r_flags), _p(self.q_sent),
+           _p(self.r_sent), _p(self.value), _p(self.value_cost), C.c_int(int(n)))
+        self.cycle += int(n)
         return self
 
 

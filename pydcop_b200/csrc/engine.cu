@@ -111,6 +111,7 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
   maxsum_warp_plan(h->d, h->varclasses, h->fast, h->warp);
+  maxsum_warp_plan_f2v(h->d, h->classes, h->fast, h->warp);
   { const char *e = getenv("PYDCOP_B200_FAST_FIRST"); h->fast_first = !(e && e[0] == '0'); }
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -195,6 +196,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
   for (size_t ci = 0; ci < h->classes.size(); ++ci) {
     const fg_class_t &c = h->classes[ci];
     if (c.n_factors == 0 || (c.flags & FG_CLASS_GHOST)) continue;
+    if (!first && h->warp.f2v[ci] && dispatch_f2v_warp<T>(false, c, d, q_cur, r_cur, r_next, p, st)) { ++h->launches; continue; }
     if (!first && maxsum_fast_f2v<T>(h->fast, (int)ci, c, d, q_cur, r_cur, r_next, p, st, h->launches)) continue;
     const int64_t n = (int64_t)c.n_factors * c.arity;
     if (first)

@@ -131,45 +131,49 @@ __device__ __forceinline__ T v2f_lane_msg(const T *__restrict__ col, const T *__
 #define FG_V2FW_MINB 6   // register cap 65536 / (6 * 128) = 85: the factor side runs concurrently on the same SMs
 #endif
 
-template <typename T, int D>
+template <typename T, int D, int NS_>
 struct V2FWarpCfg {
   static constexpr int VR = V2FCfg<T, D>::VR;
   static constexpr int VR_BYTES = V2FCfg<T, D>::VR_BYTES;
   static constexpr int PIECES = D / VR;                     // async-copy pieces per row
   static constexpr int STAGE = 3 * 32 * D;                  // rrow | qio | un   (elements)
-  static constexpr size_t WARP_SMEM = (size_t)2 * STAGE * sizeof(T);
-  static constexpr size_t SMEM = FG_V2FW_WARPS * WARP_SMEM + FG_V2FW_WARPS * 2 * sizeof(uint64_t) + 16;
+  static constexpr int NS = NS_;
+  static constexpr size_t WARP_SMEM = (size_t)NS * STAGE * sizeof(T);
+  static constexpr size_t SMEM = FG_V2FW_WARPS * WARP_SMEM + FG_V2FW_WARPS * NS * sizeof(uint64_t) + 16;
+  static constexpr bool OK = SMEM <= FG_SMEM_LIMIT;
 };
 
-template <typename T, int D, typename OffT>
+template <typename T, int D, int NS_, typename OffT>
 __global__ void __launch_bounds__(FG_V2FW_WARPS * 32, FG_V2FW_MINB)
 k_v2f_warp(const WTileTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
            const T *__restrict__ r_cur, const T *__restrict__ q_cur, T *__restrict__ q_next,
            uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
            T *__restrict__ value_cost, MaxSumParams p) {
-  using C = V2FWarpCfg<T, D>;
-  constexpr int VR = C::VR, PIECES = C::PIECES;
+  using C = V2FWarpCfg<T, D, NS_>;
+  constexpr int VR = C::VR, PIECES = C::PIECES, NS = C::NS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   T *stage0 = reinterpret_cast<T *>(smem_raw + (size_t)wib * C::WARP_SMEM);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FG_V2FW_WARPS * C::WARP_SMEM) + 2 * wib;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FG_V2FW_WARPS * C::WARP_SMEM) + NS * wib;
   if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
   __syncwarp();
 
   const int gw = (int)blockIdx.x * FG_V2FW_WARPS + wib;       // global warp id
   const int nw = (int)gridDim.x * FG_V2FW_WARPS;
-  int cursor = 0;
-  auto tile_at = [&](int k) { return wtile_at(tab, gw + k * nw, D, cursor); };
+  // one forward-only cursor per role (compute, issue, gather-index loads, counter loads): each role
+  // visits this warp's tiles in ascending order
+  int cur_c = 0, cur_i = 0, cur_l = 0, cur_n = 0;
+  auto tile_at = [&](int k, int &cursor) { return wtile_at(tab, gw + k * nw, D, cursor); };
 
-  // per-lane gather index and gate counter of a tile (lane = slot)
-  auto load_regs = [&](const WTile &t, OffT &roff, uint8_t &cn) {
-    const bool act = t.valid && lane < t.nslots;
-    roff = act ? slot_roff[t.slot0 + lane] : (OffT)0;
-    cn = act ? q_cnt[t.slot0 + lane] : (uint8_t)0;
+  auto load_roff = [&](const WTile &t) -> OffT {
+    return (t.valid && lane < t.nslots) ? slot_roff[t.slot0 + lane] : (OffT)0;
+  };
+  auto load_cnt = [&](const WTile &t) -> uint8_t {
+    return (t.valid && lane < t.nslots) ? q_cnt[t.slot0 + lane] : (uint8_t)0;
   };
   // start every load of tile t into stage s (all lanes)
   auto issue = [&](int s, const WTile &t, OffT roff) {
@@ -206,30 +210,31 @@ k_v2f_warp(const WTileTable tab, const OffT *__restrict__ slot_roff, const T *__
   const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
 
-  WTile t_cur = tile_at(0), t_nxt = tile_at(1);
-  OffT roff;
-  uint8_t cnt;
-  load_regs(t_cur, roff, cnt);
-  issue(0, t_cur, roff);
-  OffT roff_n;
-  uint8_t cnt_n;
-  load_regs(t_nxt, roff_n, cnt_n);
+  // prologue: tiles 0 .. NS-2 in flight, gather indices of tile NS-1 and counters of tile 0 on their way
+#pragma unroll 1
+  for (int k = 0; k < NS - 1; ++k) {
+    const WTile t = tile_at(k, cur_i);
+    issue(k, t, load_roff(t));
+    cur_l = cur_i;
+  }
+  OffT roff_n = load_roff(tile_at(NS - 1, cur_l));
+  uint8_t cnt = load_cnt(tile_at(0, cur_n));
 
 #pragma unroll 1
-  for (int k = 0; t_cur.valid; ++k) {
-    const int s = k & 1;
-    // stage s^1 was the output of tile k-1: its bulk store must have finished READING it
+  for (int k = 0;; ++k) {
+    const WTile t = tile_at(k, cur_c);
+    if (!t.valid) break;
+    const int s = k % NS;
+    // tile k+NS-1 goes into the stage tile k-1 held: its bulk store must have finished READING it
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
-    issue(s ^ 1, t_nxt, roff_n);
-    OffT roff_n2;
-    uint8_t cnt_n2;
-    load_regs(tile_at(k + 2), roff_n2, cnt_n2);  // descriptor recomputed at the end of the trip: fewer live registers
-    cp_async_wait_group<1>();                       // my gathers of tile k have landed ...
-    mbar_wait(&bars[s], (uint32_t)((k >> 1) & 1));  // ... and so have its bulk copies
+    issue((k + NS - 1) % NS, tile_at(k + NS - 1, cur_i), roff_n);
+    const OffT roff_n2 = load_roff(tile_at(k + NS, cur_l));
+    const uint8_t cnt_n = load_cnt(tile_at(k + 1, cur_n));
+    cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
+    mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and so have its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
 
-    const WTile t = t_cur;
     const int K = t.K;
     T *rrow = stage0 + s * C::STAGE;
     T *qio = rrow + 32 * D;
@@ -274,11 +279,8 @@ k_v2f_warp(const WTileTable tab, const OffT *__restrict__ slot_roff, const T *__
       for (int i = lane; i < t.nslots * D; i += 32) q_next[t.qoff + i] = qio[i];
       __syncwarp();
     }
-    t_cur = t_nxt;
-    t_nxt = tile_at(k + 2);
     roff_n = roff_n2;
     cnt = cnt_n;
-    cnt_n = cnt_n2;
   }
   cp_async_wait_all();
   if (lane == 0) tma_store_wait_read();
@@ -318,11 +320,12 @@ inline void v2fw_build_tables(const std::vector<fg_varclass_t> &vcs, int D, size
   flush();
 }
 
-template <typename T, int D>
-inline void launch_v2f_warp(const WTileTable &tab, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
-                            const MaxSumParams &p, cudaStream_t st) {
-  using C = V2FWarpCfg<T, D>;
-  auto kern = k_v2f_warp<T, D, uint32_t>;
+template <typename T, int D, int NS_>
+inline bool launch_v2f_warp_ns(const WTileTable &tab, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
+                               const MaxSumParams &p, cudaStream_t st) {
+  using C = V2FWarpCfg<T, D, NS_>;
+  if constexpr (!C::OK) return false;
+  auto kern = k_v2f_warp<T, D, NS_, uint32_t>;
   static int per_sm = 0, n_sm = 0;  // one per instantiation
   if (!per_sm) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -331,13 +334,24 @@ inline void launch_v2f_warp(const WTileTable &tab, const fg_maxsum_desc_t &d, co
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2FW_WARPS * 32, C::SMEM);
     if (per_sm < 1) per_sm = 1;
-    const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 4);  // leaves room for the factor side (runs concurrently)
+    const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 2);  // leaves room for the factor side (runs concurrently)
     if (per_sm > cap) per_sm = cap;
   }
   const int need = (tab.total_tiles + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
   const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
   kern<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
                                                      d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+  return true;
+}
+
+// pipeline depth: PYDCOP_B200_V2FW_NS = 2 | 3 | 4 stages per warp (default 3)
+template <typename T, int D>
+inline void launch_v2f_warp(const WTileTable &tab, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
+                            const MaxSumParams &p, cudaStream_t st) {
+  static const int ns = fg_env_int("PYDCOP_B200_V2FW_NS", 3);
+  if (ns >= 4 && launch_v2f_warp_ns<T, D, 4>(tab, d, r_cur, q_cur, q_next, p, st)) return;
+  if (ns >= 3 && launch_v2f_warp_ns<T, D, 3>(tab, d, r_cur, q_cur, q_next, p, st)) return;
+  launch_v2f_warp_ns<T, D, 2>(tab, d, r_cur, q_cur, q_next, p, st);
 }
 
 template <typename T>
@@ -352,6 +366,7 @@ inline bool dispatch_v2f_warp(int D, const WTileTable &tab, const fg_maxsum_desc
 }
 
 struct MaxSumWarpPlan {
+  std::vector<uint8_t> f2v;          // per factor class: warp kernel available (PYDCOP_B200_F2V != pipe)
   bool v2f_on = false;               // PYDCOP_B200_V2F != pipe
   std::vector<WTileTable> v2f;       // launches over the regular variable classes
   std::vector<int> v2f_dom;
@@ -379,5 +394,287 @@ inline void maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_var
     std::vector<WTileTable> ts;
     v2fw_build_tables(same, D, elem, ts);
     for (auto &t : ts) { plan.v2f.push_back(t); plan.v2f_dom.push_back(D); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  k_f2v_warp<T,D>   factor -> variable, binary factors over one (even) domain size D.
+//      A tile = 16 factors = 32 directed edges, TWO LANES PER FACTOR: lane (f, h) owns the table rows
+//      x0 in [h*D/2, (h+1)*D/2) and walks them ONCE, producing from the same shared-memory read
+//        - its D/2 values of the marginal towards position 0 (row optimum of T[x0][.] + q1), and
+//        - partial optima over its rows of the marginal towards position 1 (T[.][x1] + q0[x0]),
+//      which the two lanes of a factor complete with D/2 shuffles (the optimum of a set of floats is
+//      exact, so the split changes no bit).  Round 1's kernel read every table twice (once per directed
+//      edge) and spent 31 % of its shared-memory wavefronts on bank conflicts; here the lanes of a
+//      half-warp read 16 distinct 8-byte bank pairs (factor stride D*D words, half stride D*D/2).
+//      HBM side per warp and stage: tables and previous r rows of the tile are contiguous (1-D bulk
+//      async copies on a per-warp mbarrier), the 32 q rows are gathered through edge_qoff with
+//      cp.async (lanes <-> (row, piece)), the produced r rows are written in place over the staged
+//      previous rows and leave with one bulk store.  NS stages: tile k computes while k+1 .. k+NS-1 load.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int D, int NS_>
+struct F2VWarpCfg {
+  static constexpr int S = D * D, HD = D / 2, NF = 16;
+  static constexpr int VR = V2FCfg<T, D>::VR;          // elements per row vector (row = D elements)
+  static constexpr int VR_BYTES = V2FCfg<T, D>::VR_BYTES;
+  static constexpr int PIECES = D / VR;
+  static constexpr int VH_BYTES = fg_gcd(16, HD * (int)sizeof(T));   // half rows
+  static constexpr int VH = VH_BYTES / (int)sizeof(T);
+  static constexpr int STAGE = NF * S + 2 * NF * 2 * D;              // tab | rt (in/out) | qt   (elements)
+  static constexpr int NS = NS_;
+  static constexpr size_t WARP_SMEM = (size_t)NS * STAGE * sizeof(T);
+  static constexpr size_t smem_for(int w) { return (size_t)w * WARP_SMEM + (size_t)w * NS * sizeof(uint64_t) + 16; }
+  // warps per CTA: the CTA is only a container of independent warps
+  static constexpr int WARPS = smem_for(2) <= FG_SMEM_LIMIT ? 2 : (smem_for(1) <= FG_SMEM_LIMIT ? 1 : 0);
+  static constexpr size_t SMEM = smem_for(WARPS > 0 ? WARPS : 1);
+  static constexpr bool OK = (D % 2 == 0) && D >= 4 && WARPS > 0;
+};
+
+template <typename T, int D, int NS_, typename OffT>
+__global__ void __launch_bounds__(F2VWarpCfg<T, D, NS_>::WARPS > 0 ? F2VWarpCfg<T, D, NS_>::WARPS * 32 : 32)
+k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict__ q_cur,
+           const T *__restrict__ r_cur, T *__restrict__ r_next, const OffT *__restrict__ edge_qoff,
+           uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
+  using C = F2VWarpCfg<T, D, NS_>;
+  constexpr int S = C::S, HD = C::HD, NF = C::NF, NS = C::NS, VR = C::VR, PIECES = C::PIECES, R = 2 * D;
+  constexpr int WARPS = C::WARPS > 0 ? C::WARPS : 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  T *stage0 = reinterpret_cast<T *>(smem_raw + (size_t)wib * C::WARP_SMEM);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * C::WARP_SMEM) + NS * wib;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  const int gw = (int)blockIdx.x * WARPS + wib;
+  const int nw = (int)gridDim.x * WARPS;
+  const int n_tiles = (c.n_factors + NF - 1) / NF;
+  const int n_my = gw < n_tiles ? (n_tiles - 1 - gw) / nw + 1 : 0;
+
+  // lane = local edge le = 2 f + j of my k-th tile: gather offset / gate counter
+  auto load_qo = [&](int k) -> OffT {
+    if (k < n_my) {
+      const int f0 = (gw + k * nw) * NF;
+      if (lane < 2 * min(NF, c.n_factors - f0)) return edge_qoff[c.first_edge + f0 * 2 + lane];
+    }
+    return (OffT)0;
+  };
+  auto load_cnt = [&](int k) -> uint8_t {
+    if (k < n_my) {
+      const int f0 = (gw + k * nw) * NF;
+      if (lane < 2 * min(NF, c.n_factors - f0)) return r_cnt[c.first_edge + f0 * 2 + lane];
+    }
+    return (uint8_t)0;
+  };
+  auto issue = [&](int k, OffT qo) {
+    if (k < n_my) {
+      const int s = k % NS;
+      const int f0 = (gw + k * nw) * NF;
+      const int nf = min(NF, c.n_factors - f0);
+      T *tab = stage0 + s * C::STAGE;
+      T *rt = tab + NF * S;
+      T *qt = rt + NF * R;
+      const T *gtab = tables + c.table_base + (int64_t)f0 * S;
+      const T *grow = r_cur + c.msg_base + (int64_t)f0 * R;
+      const uint32_t tb = (uint32_t)(nf * S) * (uint32_t)sizeof(T), rb = (uint32_t)(nf * R) * (uint32_t)sizeof(T);
+      const bool tma_t = (tb % 16 == 0), tma_r = (rb % 16 == 0);   // bases are 128-byte aligned, tiles 16 factors
+      if (lane == 0) {
+        mbar_expect_tx(&bars[s], (tma_t ? tb : 0u) + (tma_r ? rb : 0u));
+        if (tma_t) tma_load_1d(tab, gtab, tb, &bars[s]);
+        if (tma_r) tma_load_1d(rt, grow, rb, &bars[s]);
+      }
+      if (!tma_t) for (int i = lane; i < nf * S; i += 32) cp_async_b<(int)sizeof(T)>(tab + i, gtab + i);
+      if (!tma_r) for (int i = lane; i < nf * R; i += 32) cp_async_b<(int)sizeof(T)>(rt + i, grow + i);
+#pragma unroll
+      for (int it = 0; it < PIECES; ++it) {
+        const int pc = it * 32 + lane;
+        const int row = pc / PIECES, piece = pc - row * PIECES;
+        const OffT ro = __shfl_sync(0xffffffffu, qo, row & 31);
+        if (row < 2 * nf) cp_async_b<C::VR_BYTES>(qt + row * D + piece * VR, q_cur + (int64_t)ro + piece * VR);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const bool mx = p.mode_max != 0;
+  const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
+  const T init = mx ? -Inf<T>::pos() : Inf<T>::pos();
+  const int fl = lane >> 1, h = lane & 1;
+
+  // prologue: tiles 0 .. NS-2 in flight, gather offsets of tile NS-1 and counters of tile 0 on their way
+#pragma unroll 1
+  for (int k = 0; k < NS - 1; ++k) issue(k, load_qo(k));
+  OffT qo_next = load_qo(NS - 1);
+  uint8_t cnt = load_cnt(0);
+
+#pragma unroll 1
+  for (int k = 0; k < n_my; ++k) {
+    const int s = k % NS;
+    // tile k+NS-1 goes into the stage tile k-1 held: its bulk store must have finished reading it
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    issue(k + NS - 1, qo_next);
+    const OffT qo_n2 = load_qo(k + NS);
+    const uint8_t cnt_n = load_cnt(k + 1);
+    cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
+    mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and its bulk copies
+    __syncwarp();                                   // ... and every other lane's gathers
+
+    const int f0 = (gw + k * nw) * NF;
+    const int nf = min(NF, c.n_factors - f0);
+    T *tab = stage0 + s * C::STAGE;
+    T *rt = tab + NF * S;
+    const T *qt = rt + NF * R;
+    const bool act = fl < nf;
+    const uint8_t cnt_other = (uint8_t)__shfl_xor_sync(0xffffffffu, (unsigned)cnt, 1);
+    T cand0[HD], cand1[HD], prev0[HD], prev1[HD];
+    bool m0 = false, m1 = false;
+    uint8_t c0 = h == 0 ? cnt : cnt_other, c1 = h == 0 ? cnt_other : cnt;
+    {
+      const T *tf = tab + fl * S + h * HD * D;   // my HD rows
+      T q0[D], q1[D], part[D];
+      if (act) {
+        ld_row<T, D, VR>(qt + (2 * fl) * D, q0);
+        ld_row<T, D, VR>(qt + (2 * fl + 1) * D, q1);
+      }
+#pragma unroll
+      for (int x = 0; x < D; ++x) part[x] = init;
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) {
+          T row[D], a[D];
+          ld_row<T, D, VR>(tf + i * D, row);
+          const T qx = h == 0 ? q0[i] : q0[HD + i];   // static register indices
+#pragma unroll
+          for (int x1 = 0; x1 < D; ++x1) {
+            a[x1] = row[x1] + q1[x1];
+            part[x1] = fg_opt<T>(part[x1], row[x1] + qx, mx);
+          }
+          cand0[i] = opt_tree<T, D>(a, mx);
+        }
+      }
+      // complete position 1: I keep x1 in my half, the partner lane sends its partial optima for it
+#pragma unroll
+      for (int i = 0; i < HD; ++i) {
+        const T mine = h == 0 ? part[i] : part[HD + i];
+        const T give = h == 0 ? part[HD + i] : part[i];
+        const T got = __shfl_xor_sync(0xffffffffu, give, 1);
+        cand1[i] = fg_opt<T>(mine, got, mx);
+      }
+      if (act) {
+        ld_row<T, HD, C::VH>(rt + fl * R + h * HD, prev0);
+        ld_row<T, HD, C::VH>(rt + fl * R + D + h * HD, prev1);
+        m0 = damp_match_row<T, HD>(cand0, prev0, (c0 & 1) != 0, p.damp_factors != 0, lam, oml, stab);
+        m1 = damp_match_row<T, HD>(cand1, prev1, (c1 & 1) != 0, p.damp_factors != 0, lam, oml, stab);
+      }
+    }
+    const unsigned mm = (m0 ? 1u : 0u) | (m1 ? 2u : 0u);
+    const unsigned mo = __shfl_xor_sync(0xffffffffu, mm, 1);
+    if (act) {
+      const bool s0 = gate_decide((mm & mo & 1u) != 0, c0);
+      const bool s1 = gate_decide((mm & mo & 2u) != 0, c1);
+      if (!s0) {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) cand0[i] = prev0[i];
+      }
+      if (!s1) {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) cand1[i] = prev1[i];
+      }
+      st_row<T, HD, C::VH>(rt + fl * R + h * HD, cand0);
+      st_row<T, HD, C::VH>(rt + fl * R + D + h * HD, cand1);
+      const int e = c.first_edge + f0 * 2 + lane;   // edge (f, j = h)
+      r_cnt[e] = h == 0 ? c0 : c1;
+      if (r_sent) r_sent[e] = (h == 0 ? s0 : s1) ? 1 : 0;
+    }
+    const uint32_t ob = (uint32_t)(nf * R) * (uint32_t)sizeof(T);
+    T *gout = r_next + c.msg_base + (int64_t)f0 * R;
+    if (ob % 16 == 0) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_1d(gout, rt, ob);
+        tma_store_commit();
+      }
+    } else {
+      __syncwarp();
+      for (int i = lane; i < nf * R; i += 32) gout[i] = rt[i];
+      __syncwarp();
+    }
+    qo_next = qo_n2;
+    cnt = cnt_n;
+  }
+  cp_async_wait_all();
+  if (lane == 0) tma_store_wait_read();
+}
+
+template <typename T, int D, int NS_>
+inline bool launch_f2v_warp_ns(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
+                               T *r_next, const MaxSumParams &p, cudaStream_t st) {
+  using C = F2VWarpCfg<T, D, NS_>;
+  if constexpr (!C::OK) {
+    return false;
+  } else {
+    if (probe) return true;
+    auto kern = k_f2v_warp<T, D, NS_, uint32_t>;
+    static int per_sm = 0, n_sm = 0;  // one per instantiation
+    if (!per_sm) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::WARPS * 32, C::SMEM);
+      if (per_sm < 1) per_sm = 1;
+      const int cap = fg_env_int("PYDCOP_B200_F2VW_CPS", 2);  // CTAs of 2 warps; the variable side shares the SMs
+      if (per_sm > cap) per_sm = cap;
+    }
+    const int n_tiles = (c.n_factors + C::NF - 1) / C::NF;
+    const int need = (n_tiles + C::WARPS - 1) / C::WARPS;
+    const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
+    kern<<<blocks, C::WARPS * 32, C::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, d.dev_edge_qoff32,
+                                                d.dev_r_cnt, d.dev_r_sent, p);
+    return true;
+  }
+}
+
+// pipeline depth: PYDCOP_B200_F2VW_NS = 2 | 3 | 4 stages per warp (default 3), shallower when it does not fit
+template <typename T, int D>
+inline bool launch_f2v_warp(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
+                            T *r_next, const MaxSumParams &p, cudaStream_t st) {
+  static const int ns = fg_env_int("PYDCOP_B200_F2VW_NS", 3);
+  if (ns >= 4 && launch_f2v_warp_ns<T, D, 4>(probe, c, d, q_cur, r_cur, r_next, p, st)) return true;
+  if (ns >= 3 && launch_f2v_warp_ns<T, D, 3>(probe, c, d, q_cur, r_cur, r_next, p, st)) return true;
+  return launch_f2v_warp_ns<T, D, 2>(probe, c, d, q_cur, r_cur, r_next, p, st);
+}
+
+// binary classes over one even domain size; probe == true: only report whether the kernel exists
+template <typename T>
+inline bool dispatch_f2v_warp(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
+                              T *r_next, const MaxSumParams &p, cudaStream_t st) {
+  if (c.arity != 2 || c.dom[0] != c.dom[1]) return false;
+  switch (c.dom[0]) {
+#define X(n) case n: return launch_f2v_warp<T, n>(probe, c, d, q_cur, r_cur, r_next, p, st);
+    X(4) X(6) X(8) X(10) X(16) X(20)
+#undef X
+  }
+  return false;
+}
+
+// factor classes the warp kernel takes over from the round-1 pipelined kernel
+inline void maxsum_warp_plan_f2v(const fg_maxsum_desc_t &d, const std::vector<fg_class_t> &classes,
+                                 const MaxSumFastPlan &fast, MaxSumWarpPlan &plan) {
+  plan.f2v.assign(classes.size(), 0);
+  const char *e = getenv("PYDCOP_B200_F2V");
+  if (!fast.off32 || fg_fast_disabled() || (e && e[0] == 'p')) return;
+  MaxSumParams dummy{};
+  for (size_t i = 0; i < classes.size(); ++i) {
+    if (classes[i].flags & FG_CLASS_GHOST) continue;
+    const bool ok = d.precision == FG_F64
+                        ? dispatch_f2v_warp<double>(true, classes[i], d, nullptr, nullptr, nullptr, dummy, nullptr)
+                        : dispatch_f2v_warp<float>(true, classes[i], d, nullptr, nullptr, nullptr, dummy, nullptr);
+    if (ok) plan.f2v[i] = 1;
   }
 }
