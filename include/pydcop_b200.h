@@ -12,7 +12,8 @@
  *   - plain C, opaque handles, int return codes (0 = FG_OK), no exceptions, no torch types;
  *   - every `dev_*` pointer is CALLER-OWNED DEVICE memory (the Python host passes
  *     torch.Tensor.data_ptr()); the only device memory the library owns is the DSA handle's copy
- *     of the class table (a few hundred bytes), and a MaxSum handle owns one side stream + 2 events;
+ *     of the class table (a few hundred bytes) and a MaxSum handle's tile descriptors of the variable
+ *     side (32 bytes per 32 slots); a MaxSum handle also owns one side stream + 2 events;
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
  *   - all calls are asynchronous on `stream`; the caller synchronises;
  *   - value type T is float (precision = FG_F32) or double (FG_F64) for every cost/message array;
@@ -376,13 +377,21 @@ int fg_mgm_step(fg_mgm_t h, int32_t n_cycles, void *stream);
 int fg_mgm_current(fg_mgm_t h, int64_t *cycle, int32_t *finished);
 int64_t fg_mgm_launch_count(fg_mgm_t h);
 
-/* Solution cost (next-tier row §8f.1; pydcop/dcop/dcop.py:319-367): sum over factors of
- * table[value of scope] + sum over variables of unary[value]; one double in dev_out[0], number of
- * factors at +/-infinity ("violations") in dev_out[1]. */
+/* Solution cost (next-tier row §8f.1; pydcop/dcop/dcop.py:319-367 `solution_cost`, called by the
+ * orchestrator at the end of a run and at every metric tick, orchestrator.py:1229-1231): over the factors
+ * of every non-ghost class the table entry at the assignment, over the first n_vars variables
+ * dev_unary[unary_off[v] + value[v]]; an entry EQUAL to `infinity` (compared in the tables' precision) is
+ * counted as a violation, every other entry is summed: dev_out[0] = cost (double), dev_out[1] =
+ * violations.  dev_unary holds the variables' OWN costs in internal variable order (without MaxSum's
+ * noise, which is not part of the problem's cost); NULL skips the variable costs.  A shard counts only
+ * what it owns — n_vars leading variables, and the optional byte masks dev_factor_skip[internal factor]
+ * / dev_var_skip[internal variable] (non-zero = not mine; NULL = none) — and the caller all-reduces
+ * dev_out over the ranks. */
 int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_class_t *classes,
                      const void *dev_tables, const int32_t *dev_edge_var,
                      const int32_t *dev_value, const void *dev_unary,
-                     const int64_t *dev_unary_off, int32_t n_vars, double *dev_out, void *stream);
+                     const int64_t *dev_unary_off, int32_t n_vars, const uint8_t *dev_factor_skip,
+                     const uint8_t *dev_var_skip, double infinity, double *dev_out, void *stream);
 
 /* Diagnostic: evaluates the send-gate predicate approx_match (maxsum.py:688-710) on n pairs with
  * the division-free fast form used by the tiled kernels (out_fast) and the literal form

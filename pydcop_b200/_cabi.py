@@ -147,7 +147,7 @@ SYMBOLS = {
     "fg_mgm_current": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "fg_mgm_launch_count": (C.c_int64, [P]),
     "fg_solution_cost": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(FgClass), P, P, P, P, P,
-                                   C.c_int32, P, P]),
+                                   C.c_int32, P, P, C.c_double, P, P]),
 }
 
 _lib = None

@@ -77,11 +77,25 @@ class GpuSession:
     # -- registry ---------------------------------------------------------------------------
     @classmethod
     def get(cls, key: str, kind: str) -> "GpuSession":
+        """The session collecting the nodes of the CURRENT run under `key`.  A session that already runs
+        (worker started), has published a result, failed or was closed belongs to a PREVIOUS run — e.g.
+        pydcop.infrastructure.run.solve called twice in one process with the default session name — and
+        is replaced: all nodes of a run are built before any of them is started
+        (orchestrator.py:745-761, 932-944)."""
         with cls._lock:
             s = cls._sessions.get(key)
-            if s is None or s.closed:
+            if (s is None or s.closed or s.thread is not None or s.snapshot is not None
+                    or s.error is not None):
                 s = cls._sessions[key] = GpuSession(key, kind)
             return s
+
+    def _retire(self):
+        """The worker is done (finished, failed, or every member stopped): the proxies keep their
+        reference and the last snapshot, the registry forgets the session."""
+        self.closed = True
+        with type(self)._lock:
+            if type(self)._sessions.get(self.key) is self:
+                del type(self)._sessions[self.key]
 
     @classmethod
     def reset(cls):
@@ -266,6 +280,8 @@ class GpuSession:
             msg = f"pydcop_b200: {self.kind}_gpu session '{self.key}' failed: {e!r} (no CPU fallback)"
             logging.getLogger("pydcop_b200").critical(msg)
             print(msg, file=sys.stderr, flush=True)
+        finally:
+            self._retire()
 
     def _publish(self, engine, cycle, finished):
         out = engine.values()

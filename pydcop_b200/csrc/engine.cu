@@ -110,7 +110,10 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_fast_plan(h->d, h->classes, h->varclasses, h->fast);
-  maxsum_warp_plan(h->d, h->varclasses, h->fast, h->warp);
+  if (maxsum_warp_plan(h->d, h->varclasses, h->fast, h->warp) != FG_OK) {
+    snprintf(h->err, sizeof(h->err), "tile descriptors of the variable side: %s", cudaGetErrorString(cudaGetLastError()));
+    return FG_ERR_CUDA;
+  }
   maxsum_warp_plan_f2v(h->d, h->classes, h->fast, h->warp);
   { const char *e = getenv("PYDCOP_B200_FAST_FIRST"); h->fast_first = !(e && e[0] == '0'); }
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
@@ -126,6 +129,7 @@ extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->warp.dev_tiles) cudaFree(h->warp.dev_tiles);
   }
   delete h;
   return FG_OK;
@@ -229,8 +233,8 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
       }
     } else {
       if (h->warp.v2f_on) {
-        for (size_t li = 0; li < h->warp.v2f.size(); ++li)
-          if (dispatch_v2f_warp<T>(h->warp.v2f_dom[li], h->warp.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
+        for (const WTileRange &rg : h->warp.v2f)
+          if (dispatch_v2f_warp<T>(h->warp.dev_tiles, rg, d, r_cur, q_cur, q_next, p, st)) ++h->launches;
       } else {
         for (size_t li = 0; li < h->fast.v2f.size(); ++li)
           if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
@@ -733,19 +737,21 @@ extern "C" int fg_dsa_shard_step(fg_dsa_t h, int32_t n_cycles, void *stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// solution cost (dcop.py:319-367)
+// solution cost (dcop.py:319-367): costs equal to `infinity` are COUNTED, the others summed —
+// constraints and variable costs alike
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_cost_factors(const fg_class_t c, const T *__restrict__ tables, const int32_t *__restrict__ edge_var,
-                               const int32_t *__restrict__ value, double *__restrict__ out) {
+                               const int32_t *__restrict__ value, const uint8_t *__restrict__ skip, T infinity,
+                               double *__restrict__ out) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   double cst = 0.0, viol = 0.0;
-  if (f < c.n_factors) {
+  if (f < c.n_factors && !(skip && skip[c.first_factor + f])) {
     int64_t idx = 0, stride = 1;
     const int e0 = c.first_edge + f * c.arity;
     for (int i = c.arity - 1; i >= 0; --i) { idx += (int64_t)value[edge_var[e0 + i]] * stride; stride *= c.dom[i]; }
-    double t = (double)tables[c.table_base + (int64_t)f * c.table_size + idx];
-    if (isinf(t)) viol = 1.0; else cst = t;
+    const T t = tables[c.table_base + (int64_t)f * c.table_size + idx];
+    if (t != infinity) cst = (double)t; else viol = 1.0;   // `r_cost != infinity`, dcop.py:355
   }
   for (int o = 16; o; o >>= 1) { cst += __shfl_xor_sync(0xffffffffu, cst, o); viol += __shfl_xor_sync(0xffffffffu, viol, o); }
   if ((threadIdx.x & 31) == 0) { if (cst != 0.0) atomicAdd(out, cst); if (viol != 0.0) atomicAdd(out + 1, viol); }
@@ -753,27 +759,33 @@ __global__ void k_cost_factors(const fg_class_t c, const T *__restrict__ tables,
 
 template <typename T>
 __global__ void k_cost_unary(const T *__restrict__ unary, const int64_t *__restrict__ unary_off,
-                             const int32_t *__restrict__ value, int n_vars, double *__restrict__ out) {
+                             const int32_t *__restrict__ value, int n_vars, const uint8_t *__restrict__ skip,
+                             T infinity, double *__restrict__ out) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  double cst = (v < n_vars) ? (double)unary[unary_off[v] + value[v]] : 0.0;
-  for (int o = 16; o; o >>= 1) cst += __shfl_xor_sync(0xffffffffu, cst, o);
-  if ((threadIdx.x & 31) == 0 && cst != 0.0) atomicAdd(out, cst);
+  double cst = 0.0, viol = 0.0;
+  if (v < n_vars && !(skip && skip[v])) {
+    const T t = unary[unary_off[v] + value[v]];
+    if (t != infinity) cst = (double)t; else viol = 1.0;   // `cost_for_val != infinity`, dcop.py:363
+  }
+  for (int o = 16; o; o >>= 1) { cst += __shfl_xor_sync(0xffffffffu, cst, o); viol += __shfl_xor_sync(0xffffffffu, viol, o); }
+  if ((threadIdx.x & 31) == 0) { if (cst != 0.0) atomicAdd(out, cst); if (viol != 0.0) atomicAdd(out + 1, viol); }
 }
 
 extern "C" int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_class_t *classes, const void *dev_tables,
                                 const int32_t *dev_edge_var, const int32_t *dev_value, const void *dev_unary,
-                                const int64_t *dev_unary_off, int32_t n_vars, double *dev_out, void *stream) {
+                                const int64_t *dev_unary_off, int32_t n_vars, const uint8_t *dev_factor_skip,
+                                const uint8_t *dev_var_skip, double infinity, double *dev_out, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(dev_out, 0, 2 * sizeof(double), st) != cudaSuccess) return FG_ERR_CUDA;
   for (int i = 0; i < n_classes; ++i) {
     const fg_class_t &c = classes[i];
-    if (!c.n_factors) continue;
-    if (precision == FG_F64) k_cost_factors<double><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const double *)dev_tables, dev_edge_var, dev_value, dev_out);
-    else k_cost_factors<float><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const float *)dev_tables, dev_edge_var, dev_value, dev_out);
+    if (!c.n_factors || (c.flags & FG_CLASS_GHOST)) continue;   // halo stubs stand for another rank's factors
+    if (precision == FG_F64) k_cost_factors<double><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const double *)dev_tables, dev_edge_var, dev_value, dev_factor_skip, infinity, dev_out);
+    else k_cost_factors<float><<<blocks_for(c.n_factors, 128), 128, 0, st>>>(c, (const float *)dev_tables, dev_edge_var, dev_value, dev_factor_skip, (float)infinity, dev_out);
   }
   if (dev_unary && n_vars) {
-    if (precision == FG_F64) k_cost_unary<double><<<blocks_for(n_vars, 128), 128, 0, st>>>((const double *)dev_unary, dev_unary_off, dev_value, n_vars, dev_out);
-    else k_cost_unary<float><<<blocks_for(n_vars, 128), 128, 0, st>>>((const float *)dev_unary, dev_unary_off, dev_value, n_vars, dev_out);
+    if (precision == FG_F64) k_cost_unary<double><<<blocks_for(n_vars, 128), 128, 0, st>>>((const double *)dev_unary, dev_unary_off, dev_value, n_vars, dev_var_skip, infinity, dev_out);
+    else k_cost_unary<float><<<blocks_for(n_vars, 128), 128, 0, st>>>((const float *)dev_unary, dev_unary_off, dev_value, n_vars, dev_var_skip, (float)infinity, dev_out);
   }
   return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }

@@ -1,118 +1,53 @@
 // Warp-autonomous MaxSum kernels (round 2): every warp runs its OWN software pipeline over its own
 // tiles — its own shared-memory stages, its own mbarriers and cp.async groups — so there is no
-// block-wide barrier anywhere in the steady state (round 1's k_v2f_pipe spent 45 % of its issue
-// slots parked at __syncthreads, profiles/r01_final_ncu_v2f_pipe_c2.txt).
+// block-wide barrier anywhere (round 1's k_v2f_pipe spent 45 % of its issue slots parked at
+// __syncthreads, profiles/r01_final_ncu_v2f_pipe_c2.txt), and the arithmetic is written for the issue
+// slots it costs: ncu showed both sides of the cycle bounded by instruction issue (30-40 % issue
+// utilisation at 1-2 warps per scheduler, DRAM at 12-40 %, profiles/r02_ncu_*_warp_v1.txt), so
+//   * add chains run as packed fp32x2 instructions (FADD2 / FMUL2) and optima as 3-input FMNMX3
+//     (packed.cuh) — every element still gets the correctly rounded IEEE operation of the scalar code;
+//   * min / max is a template parameter, tile descriptors are precomputed on the host, lane -> (variable,
+//     slot) uses a reciprocal from the descriptor.
 //
-//  k_v2f_warp<T,D>   variable -> factor (+ select_value).  A tile = nv variables of one (D, K) class
+//  k_v2f_warp<T,D,NS,MX>   variable -> factor (+ select_value).  A tile = nv variables of one (D, K) class
 //      = nv*K <= 32 consecutive slots, ONE SLOT PER LANE.  HBM side: the previous q rows and the unary
 //      rows of a tile are contiguous (1-D bulk async copies, TMA, per-warp mbarrier), the K r rows of a
-//      variable are gathered through slot_roff with cp.async — lanes mapped (row, 8/16-byte piece) so
-//      one LDGSTS instruction touches ~7 rows instead of 32 — and the produced q rows leave with one
-//      bulk store per tile (written in place over the staged previous rows).  While tile k is computed
-//      the loads of tile k+1 are in flight.
-//      Arithmetic per lane (slot f of variable i): costs_for_factor (maxsum.py:623-676) with the
-//      reference's operand order — value-major, then factors in `links` order, the own factor skipped —
-//      fully unrolled for K = 1..8; the lane of the LAST slot also holds ur + r_0 + ... + r_{K-2}, so
-//      select_value (maxsum.py:584-620) costs it one more add per value.
+//      variable are gathered through slot_roff with cp.async — lanes mapped (row, 8/16-byte piece) so one
+//      LDGSTS instruction touches ~7 rows instead of 32 — and the produced q rows leave with one bulk
+//      store per tile (written in place over the staged previous rows).  NS stages per warp: tile k is
+//      computed while tiles k+1 .. k+NS-1 load.
+//      Arithmetic per lane (slot f of variable i): costs_for_factor (maxsum.py:623-676) in the
+//      reference's operand order — value-major, then the OTHER factors in `links` order (the own factor
+//      is skipped by addressing: row g = gg + (gg >= f), no select) — unrolled for K = 1..8; the lane of
+//      the LAST slot holds ur + r_0 + ... + r_{K-2}, so select_value (maxsum.py:584-620) costs one more
+//      add per value.
+//
+//  k_f2v_warp<T,D,NS,MX>   factor -> variable, binary factors over one even domain size (see below).
 //
 // Results are bit-identical to the generic kernels, the round-1 pipelined kernels and the CPU oracle
 // of the same precision.
 #pragma once
 #include "maxsum_fast.cuh"
+#include "packed.cuh"
 
-#define FG_WARP_MAX_ENTRIES 24
-
-struct WTileEntry {
-  fg_varclass_t vc;
-  int32_t tile_begin;  // first tile of this class in the launch
-  int32_t nv_tile;     // variables per tile (nv_tile * degree <= 32)
+// ------------------------------------------------------------------------------------------------
+// variable -> factor
+// ------------------------------------------------------------------------------------------------
+// one tile of the variable side (host-built, 32 bytes)
+struct WTileDesc {
+  int32_t slot0;   // first slot
+  int32_t pack;    // K | nv << 8 | nslots << 16
+  uint32_t qoff;   // element offset of the tile's q rows (slot order)
+  uint32_t uoff;   // element offset of the tile's unary rows
+  int32_t var0;    // first (internal) variable
+  int32_t kinv;    // ceil(65536 / K): lane / K == (lane * kinv) >> 16 for lane < 32
+  int32_t pad0, pad1;
 };
-struct WTileTable {
-  int32_t n;
-  int32_t total_tiles;
-  WTileEntry e[FG_WARP_MAX_ENTRIES];
+static_assert(sizeof(WTileDesc) == 32, "two 16-byte loads");
+
+struct WTileRange {   // one launch: the tiles of every regular variable class of one domain size
+  int32_t dom, first, count;
 };
-
-struct WTile {
-  int K, nv, nslots, slot0, var0, valid;
-  uint32_t qoff, uoff;  // element offsets (the fast plans require 32-bit message offsets)
-};
-
-// tile t of the launch; `ci` is a cursor that only moves forward (a warp visits its tiles in order)
-__device__ __forceinline__ WTile wtile_at(const WTileTable &tab, int t, int D, int &ci) {
-  WTile o;
-  o.valid = t < tab.total_tiles;
-  if (!o.valid) { o.K = 1; o.nv = o.nslots = o.slot0 = o.var0 = 0; o.qoff = o.uoff = 0; return o; }
-#pragma unroll 1
-  while (ci + 1 < tab.n && t >= tab.e[ci + 1].tile_begin) ++ci;
-  const WTileEntry &en = tab.e[ci];
-  o.K = en.vc.degree;
-  const int v0 = (t - en.tile_begin) * en.nv_tile;
-  o.nv = min(en.nv_tile, en.vc.n_vars - v0);
-  o.nslots = o.nv * o.K;
-  o.slot0 = en.vc.first_slot + v0 * o.K;
-  o.var0 = en.vc.first_var + v0;
-  o.qoff = (uint32_t)(en.vc.q_base + (int64_t)v0 * o.K * D);
-  o.uoff = (uint32_t)(en.vc.unary_base + (int64_t)v0 * D);
-  return o;
-}
-
-// One lane = one slot f of a variable whose K gathered r rows start at `col` (row g at col + g*D) and
-// whose own costs are `ur`.  cand <- un-normalised message (own factor skipped), returns sum_cost;
-// best / best_c <- select_value over ur + sum of ALL K rows, meaningful on the lane with f == K-1 only
-// (its message chain is exactly the first K-1 terms of that sum).
-// K > 0: compile-time degree; K == 0: run-time degree k_rt.
-template <typename T, int D, int K>
-__device__ __forceinline__ T v2f_lane_msg(const T *__restrict__ col, const T *__restrict__ ur, int f, int k_rt, bool mx,
-                                          T (&cand)[D], int &best, T &best_c) {
-  constexpr int VR = V2FCfg<T, D>::VR;
-  T sum_cost = (T)0;
-  best = 0;
-  best_c = (T)0;
-  if constexpr (K > 0) {
-#pragma unroll
-    for (int x0 = 0; x0 < D; x0 += VR) {
-      T u[VR], c[K][VR];
-      ld_row<T, VR, VR>(ur + x0, u);
-#pragma unroll
-      for (int g = 0; g < K; ++g) ld_row<T, VR, VR>(col + g * D + x0, c[g]);
-#pragma unroll
-      for (int xx = 0; xx < VR; ++xx) {
-        T m = u[xx];
-#pragma unroll
-        for (int g = 0; g < K; ++g) {
-          if (g != f) {
-            sum_cost += c[g][xx];
-            m += c[g][xx];
-          }
-        }
-        cand[x0 + xx] = m;
-        const T tot = m + c[K - 1][xx];  // lane f == K-1: ((ur + r_0) + ...) + r_{K-1}
-        const int x = x0 + xx;
-        if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-      }
-    }
-  } else {  // run-time degree (9..16): values unrolled, factors in a loop
-#pragma unroll
-    for (int x = 0; x < D; ++x) {
-      T m = ur[x];
-      T last = (T)0;
-#pragma unroll 1
-      for (int g = 0; g < k_rt; ++g) {
-        const T cst = col[g * D + x];
-        last = cst;
-        if (g != f) {
-          sum_cost += cst;
-          m += cst;
-        }
-      }
-      cand[x] = m;
-      const T tot = m + last;  // lane f == K-1 skipped exactly the last row
-      if (x == 0 || (mx ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
-    }
-  }
-  return sum_cost;
-}
 
 #define FG_WARP_K_SWITCH(K_, CALL)                 \
   switch (K_) {                                    \
@@ -126,9 +61,81 @@ __device__ __forceinline__ T v2f_lane_msg(const T *__restrict__ col, const T *__
     case 8: { constexpr int KK = 8; CALL; } break; \
   }
 
+// One lane = slot f of a variable whose K gathered r rows start at `col` (row g at col + g*D) and whose
+// own costs are `ur`.  cand <- un-normalised message, returns sum_cost; best / best_c <- select_value over
+// ur + ALL K rows, meaningful on the lane with f == K-1 only (its message chain is exactly the first
+// K-1 terms of that sum).  KK > 0: compile-time degree; KK == 0: run-time degree k_rt.
+template <typename T, int D, int KK, bool MX>
+__device__ __forceinline__ T v2f_lane_msg(const T *__restrict__ col, const T *__restrict__ ur, int f, int k_rt,
+                                          T (&cand)[D], int &best, T &best_c) {
+  constexpr int VR = V2FCfg<T, D>::VR;
+  using P = typename Pair<T>::type;
+  T sum_cost = (T)0;
+  best = 0;
+  best_c = (T)0;
+  if constexpr (KK > 0) {
+    constexpr int KO = KK > 1 ? KK - 1 : 1;
+    const T *rp[KO];   // the other factors' rows, in `links` order
+#pragma unroll
+    for (int gg = 0; gg < KK - 1; ++gg) rp[gg] = col + (gg + (gg >= f ? 1 : 0)) * D;
+    const T *lastp = col + (KK - 1) * D;
+#pragma unroll
+    for (int x0 = 0; x0 < D; x0 += VR) {
+      T u[VR], last[VR], c[KO][VR];
+      ld_row<T, VR, VR>(ur + x0, u);
+      ld_row<T, VR, VR>(lastp + x0, last);
+#pragma unroll
+      for (int gg = 0; gg < KK - 1; ++gg) ld_row<T, VR, VR>(rp[gg] + x0, c[gg]);
+#pragma unroll
+      for (int xx = 0; xx < VR; ++xx) {    // sum_cost: ONE chain, value-major then factor order
+#pragma unroll
+        for (int gg = 0; gg < KK - 1; ++gg) sum_cost += c[gg][xx];
+      }
+      if constexpr (VR % 2 == 0) {
+#pragma unroll
+        for (int xx = 0; xx < VR; xx += 2) {
+          P m = pmake<T>(u[xx], u[xx + 1]);
+#pragma unroll
+          for (int gg = 0; gg < KK - 1; ++gg) m = padd(m, pmake<T>(c[gg][xx], c[gg][xx + 1]));
+          cand[x0 + xx] = m.x;
+          cand[x0 + xx + 1] = m.y;
+          const P tot = padd(m, pmake<T>(last[xx], last[xx + 1]));   // lane f == K-1: ((ur + r_0) + ...) + r_{K-1}
+          if (x0 + xx == 0 || (MX ? (tot.x > best_c) : (tot.x < best_c))) { best = x0 + xx; best_c = tot.x; }
+          if (MX ? (tot.y > best_c) : (tot.y < best_c)) { best = x0 + xx + 1; best_c = tot.y; }
+        }
+      } else {
+#pragma unroll
+        for (int xx = 0; xx < VR; ++xx) {
+          T m = u[xx];
+#pragma unroll
+          for (int gg = 0; gg < KK - 1; ++gg) m += c[gg][xx];
+          cand[x0 + xx] = m;
+          const T tot = m + last[xx];
+          if (x0 + xx == 0 || (MX ? (tot > best_c) : (tot < best_c))) { best = x0 + xx; best_c = tot; }
+        }
+      }
+    }
+  } else {  // run-time degree (9..16): values unrolled, factors in a loop
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      T m = ur[x];
+#pragma unroll 1
+      for (int gg = 0; gg < k_rt - 1; ++gg) {
+        const T cst = col[(gg + (gg >= f ? 1 : 0)) * D + x];
+        sum_cost += cst;
+        m += cst;
+      }
+      cand[x] = m;
+      const T tot = m + col[(k_rt - 1) * D + x];
+      if (x == 0 || (MX ? (tot > best_c) : (tot < best_c))) { best = x; best_c = tot; }
+    }
+  }
+  return sum_cost;
+}
+
 #define FG_V2FW_WARPS 4   // warps per CTA (each warp is independent; the CTA is only a container)
 #ifndef FG_V2FW_MINB
-#define FG_V2FW_MINB 6   // register cap 65536 / (6 * 128) = 85: the factor side runs concurrently on the same SMs
+#define FG_V2FW_MINB 6   // register cap 65536 / (6 * 128) = 85
 #endif
 
 template <typename T, int D, int NS_>
@@ -143,12 +150,12 @@ struct V2FWarpCfg {
   static constexpr bool OK = SMEM <= FG_SMEM_LIMIT;
 };
 
-template <typename T, int D, int NS_, typename OffT>
+template <typename T, int D, int NS_, bool MX, typename OffT>
 __global__ void __launch_bounds__(FG_V2FW_WARPS * 32, FG_V2FW_MINB)
-k_v2f_warp(const WTileTable tab, const OffT *__restrict__ slot_roff, const T *__restrict__ unary,
-           const T *__restrict__ r_cur, const T *__restrict__ q_cur, T *__restrict__ q_next,
-           uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent, int32_t *__restrict__ value,
-           T *__restrict__ value_cost, MaxSumParams p) {
+k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__ slot_roff,
+           const T *__restrict__ unary, const T *__restrict__ r_cur, const T *__restrict__ q_cur,
+           T *__restrict__ q_next, uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent,
+           int32_t *__restrict__ value, T *__restrict__ value_cost, MaxSumParams p) {
   using C = V2FWarpCfg<T, D, NS_>;
   constexpr int VR = C::VR, PIECES = C::PIECES, NS = C::NS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -164,119 +171,138 @@ k_v2f_warp(const WTileTable tab, const OffT *__restrict__ slot_roff, const T *__
 
   const int gw = (int)blockIdx.x * FG_V2FW_WARPS + wib;       // global warp id
   const int nw = (int)gridDim.x * FG_V2FW_WARPS;
-  // one forward-only cursor per role (compute, issue, gather-index loads, counter loads): each role
-  // visits this warp's tiles in ascending order
-  int cur_c = 0, cur_i = 0, cur_l = 0, cur_n = 0;
-  auto tile_at = [&](int k, int &cursor) { return wtile_at(tab, gw + k * nw, D, cursor); };
-
-  auto load_roff = [&](const WTile &t) -> OffT {
-    return (t.valid && lane < t.nslots) ? slot_roff[t.slot0 + lane] : (OffT)0;
+  // first half of the descriptor of my k-th tile: (slot0, pack, qoff, uoff); pack == 0: no such tile
+  auto desc_a = [&](int k) -> int4 {
+    const int t = gw + k * nw;
+    return t < n_tiles ? tiles[2 * t] : make_int4(0, 0, 0, 0);
   };
-  auto load_cnt = [&](const WTile &t) -> uint8_t {
-    return (t.valid && lane < t.nslots) ? q_cnt[t.slot0 + lane] : (uint8_t)0;
+  auto load_roff = [&](const int4 &a) -> OffT {
+    return lane < (a.y >> 16) ? slot_roff[a.x + lane] : (OffT)0;
   };
-  // start every load of tile t into stage s (all lanes)
-  auto issue = [&](int s, const WTile &t, OffT roff) {
-    if (t.valid) {
+  auto load_cnt = [&](const int4 &a) -> uint8_t {
+    return lane < (a.y >> 16) ? q_cnt[a.x + lane] : (uint8_t)0;
+  };
+  // start every load of a tile into stage s (all lanes)
+  auto issue = [&](int s, const int4 &a, OffT roff) {
+    if (a.y) {
+      const int nslots = a.y >> 16, nv = (a.y >> 8) & 0xff;
+      const uint32_t qoff = (uint32_t)a.z, uoff = (uint32_t)a.w;
       T *rrow = stage0 + s * C::STAGE;
       T *qio = rrow + 32 * D;
       T *un = qio + 32 * D;
-      const uint32_t qbytes = (uint32_t)(t.nslots * D) * (uint32_t)sizeof(T);
-      const uint32_t ubytes = (uint32_t)(t.nv * D) * (uint32_t)sizeof(T);
-      const bool tma_q = (qbytes % 16 == 0) && ((((int64_t)t.qoff * (int64_t)sizeof(T)) & 15) == 0);
-      const bool tma_u = (ubytes % 16 == 0) && ((((int64_t)t.uoff * (int64_t)sizeof(T)) & 15) == 0);
+      const uint32_t qbytes = (uint32_t)(nslots * D) * (uint32_t)sizeof(T);
+      const uint32_t ubytes = (uint32_t)(nv * D) * (uint32_t)sizeof(T);
+      const bool tma_q = (qbytes % 16 == 0) && ((((int64_t)qoff * (int64_t)sizeof(T)) & 15) == 0);
+      const bool tma_u = (ubytes % 16 == 0) && ((((int64_t)uoff * (int64_t)sizeof(T)) & 15) == 0);
       if (lane == 0) {
         mbar_expect_tx(&bars[s], (tma_q ? qbytes : 0u) + (tma_u ? ubytes : 0u));
-        if (tma_q) tma_load_1d(qio, q_cur + t.qoff, qbytes, &bars[s]);
-        if (tma_u) tma_load_1d(un, unary + t.uoff, ubytes, &bars[s]);
+        if (tma_q) tma_load_1d(qio, q_cur + qoff, qbytes, &bars[s]);
+        if (tma_u) tma_load_1d(un, unary + uoff, ubytes, &bars[s]);
       }
       if (!tma_q)
-        for (int i = lane; i < t.nslots * D; i += 32) cp_async_b<(int)sizeof(T)>(qio + i, q_cur + t.qoff + i);
+        for (int i = lane; i < nslots * D; i += 32) cp_async_b<(int)sizeof(T)>(qio + i, q_cur + qoff + i);
       if (!tma_u)
-        for (int i = lane; i < t.nv * D; i += 32) cp_async_b<(int)sizeof(T)>(un + i, unary + t.uoff + i);
+        for (int i = lane; i < nv * D; i += 32) cp_async_b<(int)sizeof(T)>(un + i, unary + uoff + i);
       // r rows: lane <-> (row, piece), consecutive lanes on consecutive pieces of one row
 #pragma unroll
       for (int it = 0; it < PIECES; ++it) {
         const int pc = it * 32 + lane;
         const int row = pc / PIECES, piece = pc - row * PIECES;
         const OffT ro = __shfl_sync(0xffffffffu, roff, row & 31);
-        if (row < t.nslots)
-          cp_async_b<C::VR_BYTES>(rrow + row * D + piece * VR, r_cur + (int64_t)ro + piece * VR);
+        if (row < nslots) cp_async_b<C::VR_BYTES>(rrow + row * D + piece * VR, r_cur + (int64_t)ro + piece * VR);
       }
     }
     cp_async_commit();  // one group per tile, even when empty: uniform accounting
   };
 
-  const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
 
   // prologue: tiles 0 .. NS-2 in flight, gather indices of tile NS-1 and counters of tile 0 on their way
 #pragma unroll 1
   for (int k = 0; k < NS - 1; ++k) {
-    const WTile t = tile_at(k, cur_i);
-    issue(k, t, load_roff(t));
-    cur_l = cur_i;
+    const int4 a = desc_a(k);
+    issue(k, a, load_roff(a));
   }
-  OffT roff_n = load_roff(tile_at(NS - 1, cur_l));
-  uint8_t cnt = load_cnt(tile_at(0, cur_n));
+  OffT roff_n = load_roff(desc_a(NS - 1));
+  uint8_t cnt = load_cnt(desc_a(0));
 
 #pragma unroll 1
   for (int k = 0;; ++k) {
-    const WTile t = tile_at(k, cur_c);
-    if (!t.valid) break;
+    const int t_idx = gw + k * nw;
+    if (t_idx >= n_tiles) break;
+    const int4 a = tiles[2 * t_idx];
+    const int4 b = tiles[2 * t_idx + 1];
     const int s = k % NS;
     // tile k+NS-1 goes into the stage tile k-1 held: its bulk store must have finished READING it
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
-    issue((k + NS - 1) % NS, tile_at(k + NS - 1, cur_i), roff_n);
-    const OffT roff_n2 = load_roff(tile_at(k + NS, cur_l));
-    const uint8_t cnt_n = load_cnt(tile_at(k + 1, cur_n));
+    issue((k + NS - 1) % NS, desc_a(k + NS - 1), roff_n);
+    const OffT roff_n2 = load_roff(desc_a(k + NS));
+    const uint8_t cnt_n = load_cnt(desc_a(k + 1));
     cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
     mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and so have its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
 
-    const int K = t.K;
+    const int K = a.y & 0xff, nslots = a.y >> 16, slot0 = a.x;
+    const uint32_t qoff = (uint32_t)a.z;
     T *rrow = stage0 + s * C::STAGE;
     T *qio = rrow + 32 * D;
     const T *un = qio + 32 * D;
-    const bool act = lane < t.nslots;
-    if (act) {
-      const int i = lane / K, f = lane - i * K;
+    if (lane < nslots) {
+      const int i = (lane * b.y) >> 16, f = lane - i * K;
       const T *col = rrow + i * K * D;
       const T *ur = un + i * D;
       T cand[D], prev[D];
       int best = 0;
       T best_c = (T)0, sum_cost = (T)0;
       if (K <= 8) {
-        FG_WARP_K_SWITCH(K, (sum_cost = v2f_lane_msg<T, D, KK>(col, ur, f, K, mx, cand, best, best_c)))
+        FG_WARP_K_SWITCH(K, (sum_cost = v2f_lane_msg<T, D, KK, MX>(col, ur, f, K, cand, best, best_c)))
       } else {
-        sum_cost = v2f_lane_msg<T, D, 0>(col, ur, f, K, mx, cand, best, best_c);
+        sum_cost = v2f_lane_msg<T, D, 0, MX>(col, ur, f, K, cand, best, best_c);
       }
       const T avg = sum_cost / (T)D;
-#pragma unroll
-      for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg;
       ld_row<T, D, VR>(qio + lane * D, prev);
       uint8_t c8 = cnt;
-      const bool sent = damp_gate_row<T, D>(cand, prev, c8, p.damp_vars != 0, lam, oml, stab);
+      bool match;
+      if constexpr (D % 2 == 0) {
+        using P = typename Pair<T>::type;
+        const P avg2 = pmake<T>(avg, avg);
+#pragma unroll
+        for (int x = 0; x < D; x += 2) {
+          const P v = psub(pmake<T>(cand[x], cand[x + 1]), avg2);
+          cand[x] = v.x;
+          cand[x + 1] = v.y;
+        }
+        match = damp_match_pairs<T, D>(cand, prev, (c8 & 1) != 0, p.damp_vars != 0, lam, oml, stab);
+      } else {
+#pragma unroll
+        for (int x = 0; x < D; ++x) cand[x] = cand[x] - avg;
+        match = damp_match_row<T, D>(cand, prev, (c8 & 1) != 0, p.damp_vars != 0, lam, oml, stab);
+      }
+      const bool sent = gate_decide(match, c8);
+      if (!sent) {
+#pragma unroll
+        for (int x = 0; x < D; ++x) cand[x] = prev[x];
+      }
       st_row<T, D, VR>(qio + lane * D, cand);
-      q_cnt[t.slot0 + lane] = c8;
-      if (q_sent) q_sent[t.slot0 + lane] = sent ? 1 : 0;
+      q_cnt[slot0 + lane] = c8;
+      if (q_sent) q_sent[slot0 + lane] = sent ? 1 : 0;
       if (f == K - 1) {
-        value[t.var0 + i] = best;
-        value_cost[t.var0 + i] = best_c;
+        value[b.x + i] = best;
+        value_cost[b.x + i] = best_c;
       }
     }
-    const uint32_t obytes = (uint32_t)(t.nslots * D) * (uint32_t)sizeof(T);
-    if ((obytes % 16 == 0) && ((((int64_t)t.qoff * (int64_t)sizeof(T)) & 15) == 0)) {
+    const uint32_t obytes = (uint32_t)(nslots * D) * (uint32_t)sizeof(T);
+    if ((obytes % 16 == 0) && ((((int64_t)qoff * (int64_t)sizeof(T)) & 15) == 0)) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_1d(q_next + t.qoff, qio, obytes);
+        tma_store_1d(q_next + qoff, qio, obytes);
         tma_store_commit();
       }
     } else {
       __syncwarp();
-      for (int i = lane; i < t.nslots * D; i += 32) q_next[t.qoff + i] = qio[i];
+      for (int i = lane; i < nslots * D; i += 32) q_next[qoff + i] = qio[i];
       __syncwarp();
     }
     roff_n = roff_n2;
@@ -287,126 +313,140 @@ k_v2f_warp(const WTileTable tab, const OffT *__restrict__ slot_roff, const T *__
 }
 
 // ------------------------------------------------------------------------------------------------
-// host side
+// host side of the variable kernel
 // ------------------------------------------------------------------------------------------------
-// Regular variable classes (degree 1..16, one domain size D, not ghosts) -> tile tables of at most
-// FG_WARP_MAX_ENTRIES classes.  nv_tile: as many variables as fit 32 lanes, rounded down to the number
-// of rows that keeps every tile's q / unary offsets 16-byte aligned (bulk copies) when possible.
-inline void v2fw_build_tables(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<WTileTable> &out) {
-  WTileTable cur;
-  cur.n = 0;
-  cur.total_tiles = 0;
-  auto flush = [&]() {
-    if (cur.n) out.push_back(cur);
-    cur.n = 0;
-    cur.total_tiles = 0;
-  };
-  std::vector<fg_varclass_t> order(vcs);
+// Tiles of the regular variable classes (degree 1..16, not ghosts) of domain size D, costly (high-degree)
+// classes first.  nv per tile: as many variables as fit 32 lanes, rounded down to the number of rows that
+// keeps every tile's q / unary offsets 16-byte aligned (bulk copies) when possible.
+inline void v2fw_build_tiles(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<WTileDesc> &out) {
+  std::vector<fg_varclass_t> order;
+  for (const fg_varclass_t &vc : vcs)
+    if (vc.dom == D && vc.degree >= 1 && vc.degree <= 32 && vc.n_vars > 0 && !(vc.flags & FG_CLASS_GHOST)) order.push_back(vc);
   std::stable_sort(order.begin(), order.end(),
                    [](const fg_varclass_t &a, const fg_varclass_t &b) { return a.degree > b.degree; });
   const int unit = 16 / fg_gcd(16, D * (int)elem);  // rows per 16-byte multiple
   for (const fg_varclass_t &vc : order) {
-    if (vc.dom != D || vc.degree < 1 || vc.degree > 32 || vc.n_vars == 0) continue;
-    int nv = 32 / vc.degree;
+    const int K = vc.degree;
+    int nv = 32 / K;
     if (nv >= unit) nv = nv / unit * unit;
-    WTileEntry e;
-    e.vc = vc;
-    e.tile_begin = cur.total_tiles;
-    e.nv_tile = nv;
-    cur.e[cur.n++] = e;
-    cur.total_tiles += (vc.n_vars + nv - 1) / nv;
-    if (cur.n == FG_WARP_MAX_ENTRIES) flush();
+    for (int v0 = 0; v0 < vc.n_vars; v0 += nv) {
+      const int n = std::min(nv, vc.n_vars - v0);
+      WTileDesc t;
+      t.slot0 = vc.first_slot + v0 * K;
+      t.pack = K | (n << 8) | ((n * K) << 16);
+      t.qoff = (uint32_t)(vc.q_base + (int64_t)v0 * K * D);
+      t.uoff = (uint32_t)(vc.unary_base + (int64_t)v0 * D);
+      t.var0 = vc.first_var + v0;
+      t.kinv = (65536 + K - 1) / K;
+      t.pad0 = t.pad1 = 0;
+      out.push_back(t);
+    }
   }
-  flush();
 }
 
-template <typename T, int D, int NS_>
-inline bool launch_v2f_warp_ns(const WTileTable &tab, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
-                               const MaxSumParams &p, cudaStream_t st) {
+struct MaxSumWarpPlan {
+  std::vector<uint8_t> f2v;          // per factor class: warp kernel available (PYDCOP_B200_F2V != pipe)
+  bool v2f_on = false;               // PYDCOP_B200_V2F != pipe
+  std::vector<WTileRange> v2f;       // launches of the variable side
+  WTileDesc *dev_tiles = nullptr;    // library-owned: tile descriptors of every launch (32 bytes per tile)
+};
+
+template <typename T, int D, int NS_, bool MX>
+inline bool launch_v2f_warp_ns(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
+                               const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
   using C = V2FWarpCfg<T, D, NS_>;
-  if constexpr (!C::OK) return false;
-  auto kern = k_v2f_warp<T, D, NS_, uint32_t>;
-  static int per_sm = 0, n_sm = 0;  // one per instantiation
-  if (!per_sm) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2FW_WARPS * 32, C::SMEM);
-    if (per_sm < 1) per_sm = 1;
-    const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 2);  // leaves room for the factor side (runs concurrently)
-    if (per_sm > cap) per_sm = cap;
+  if constexpr (!C::OK) {
+    return false;
+  } else {
+    auto kern = k_v2f_warp<T, D, NS_, MX, uint32_t>;
+    static int per_sm = 0, n_sm = 0;  // one per instantiation
+    if (!per_sm) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2FW_WARPS * 32, C::SMEM);
+      if (per_sm < 1) per_sm = 1;
+      const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 2);  // leaves room for the factor side (runs concurrently)
+      if (per_sm > cap) per_sm = cap;
+    }
+    const int need = (rg.count + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
+    const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
+    kern<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(reinterpret_cast<const int4 *>(dev_tiles + rg.first), rg.count,
+                                                       d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
+                                                       d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
+    return true;
   }
-  const int need = (tab.total_tiles + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
-  const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
-  kern<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(tab, d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
-                                                     d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
-  return true;
 }
 
 // pipeline depth: PYDCOP_B200_V2FW_NS = 2 | 3 | 4 stages per warp (default 3)
 template <typename T, int D>
-inline void launch_v2f_warp(const WTileTable &tab, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur, T *q_next,
-                            const MaxSumParams &p, cudaStream_t st) {
+inline void launch_v2f_warp(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
+                            const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
   static const int ns = fg_env_int("PYDCOP_B200_V2FW_NS", 3);
-  if (ns >= 4 && launch_v2f_warp_ns<T, D, 4>(tab, d, r_cur, q_cur, q_next, p, st)) return;
-  if (ns >= 3 && launch_v2f_warp_ns<T, D, 3>(tab, d, r_cur, q_cur, q_next, p, st)) return;
-  launch_v2f_warp_ns<T, D, 2>(tab, d, r_cur, q_cur, q_next, p, st);
+#define FG_TRY(NS_)                                                                                              \
+  if (p.mode_max ? launch_v2f_warp_ns<T, D, NS_, true>(dev_tiles, rg, d, r_cur, q_cur, q_next, p, st)            \
+                 : launch_v2f_warp_ns<T, D, NS_, false>(dev_tiles, rg, d, r_cur, q_cur, q_next, p, st))          \
+    return;
+  if (ns >= 4) { FG_TRY(4) }
+  if (ns >= 3) { FG_TRY(3) }
+  FG_TRY(2)
+#undef FG_TRY
 }
 
 template <typename T>
-inline bool dispatch_v2f_warp(int D, const WTileTable &tab, const fg_maxsum_desc_t &d, const T *r_cur, const T *q_cur,
-                              T *q_next, const MaxSumParams &p, cudaStream_t st) {
-  switch (D) {
-#define X(n) case n: launch_v2f_warp<T, n>(tab, d, r_cur, q_cur, q_next, p, st); return true;
+inline bool dispatch_v2f_warp(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
+                              const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
+  switch (rg.dom) {
+#define X(n) case n: launch_v2f_warp<T, n>(dev_tiles, rg, d, r_cur, q_cur, q_next, p, st); return true;
     FG_FAST_DOMS(X)
 #undef X
   }
   return false;
 }
 
-struct MaxSumWarpPlan {
-  std::vector<uint8_t> f2v;          // per factor class: warp kernel available (PYDCOP_B200_F2V != pipe)
-  bool v2f_on = false;               // PYDCOP_B200_V2F != pipe
-  std::vector<WTileTable> v2f;       // launches over the regular variable classes
-  std::vector<int> v2f_dom;
-};
-
-// same class selection as maxsum_fast_plan (every regular class of a compiled domain size)
-inline void maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varclass_t> &vcs, const MaxSumFastPlan &fast,
-                             MaxSumWarpPlan &plan) {
+// same class selection as maxsum_fast_plan (every regular class of a compiled domain size); uploads the
+// tile descriptors (cudaMalloc: the device must be there)
+inline int maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varclass_t> &vcs, const MaxSumFastPlan &fast,
+                            MaxSumWarpPlan &plan) {
   plan.v2f.clear();
-  plan.v2f_dom.clear();
   const char *e = getenv("PYDCOP_B200_V2F");
   plan.v2f_on = fast.off32 && !fg_fast_disabled() && !(e && e[0] == 'p');
-  if (!plan.v2f_on) return;
+  if (!plan.v2f_on) return FG_OK;
   const size_t elem = d.precision == FG_F64 ? 8 : 4;
-  std::vector<uint8_t> taken(vcs.size(), 0);
-  for (size_t i = 0; i < vcs.size(); ++i) {
-    if (taken[i] || (vcs[i].flags & FG_CLASS_GHOST) || vcs[i].degree < 1 || !fg_fast_dom(vcs[i].dom)) continue;
-    const int D = vcs[i].dom;
-    std::vector<fg_varclass_t> same;
-    for (size_t j = i; j < vcs.size(); ++j)
-      if (!taken[j] && !(vcs[j].flags & FG_CLASS_GHOST) && vcs[j].dom == D && vcs[j].degree >= 1) {
-        same.push_back(vcs[j]);
-        taken[j] = 1;
-      }
-    std::vector<WTileTable> ts;
-    v2fw_build_tables(same, D, elem, ts);
-    for (auto &t : ts) { plan.v2f.push_back(t); plan.v2f_dom.push_back(D); }
+  std::vector<WTileDesc> all;
+  std::vector<int> doms;
+  for (const fg_varclass_t &vc : vcs)
+    if (!(vc.flags & FG_CLASS_GHOST) && vc.degree >= 1 && fg_fast_dom(vc.dom) &&
+        std::find(doms.begin(), doms.end(), vc.dom) == doms.end())
+      doms.push_back(vc.dom);
+  for (int D : doms) {
+    WTileRange rg;
+    rg.dom = D;
+    rg.first = (int32_t)all.size();
+    v2fw_build_tiles(vcs, D, elem, all);
+    rg.count = (int32_t)all.size() - rg.first;
+    if (rg.count) plan.v2f.push_back(rg);
   }
+  if (!all.empty()) {
+    if (cudaMalloc(reinterpret_cast<void **>(&plan.dev_tiles), all.size() * sizeof(WTileDesc)) != cudaSuccess) return FG_ERR_CUDA;
+    if (cudaMemcpy(plan.dev_tiles, all.data(), all.size() * sizeof(WTileDesc), cudaMemcpyHostToDevice) != cudaSuccess)
+      return FG_ERR_CUDA;
+  }
+  return FG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-//  k_f2v_warp<T,D>   factor -> variable, binary factors over one (even) domain size D.
-//      A tile = 16 factors = 32 directed edges, TWO LANES PER FACTOR: lane (f, h) owns the table rows
-//      x0 in [h*D/2, (h+1)*D/2) and walks them ONCE, producing from the same shared-memory read
+//  k_f2v_warp<T,D,NS,MX>   factor -> variable, binary factors over one (even) domain size D.
+//      A tile = 16 factors = 32 directed edges, TWO LANES PER FACTOR: lane (f, h) owns half of the table
+//      rows and walks them ONCE, producing from the same shared-memory read
 //        - its D/2 values of the marginal towards position 0 (row optimum of T[x0][.] + q1), and
 //        - partial optima over its rows of the marginal towards position 1 (T[.][x1] + q0[x0]),
 //      which the two lanes of a factor complete with D/2 shuffles (the optimum of a set of floats is
-//      exact, so the split changes no bit).  Round 1's kernel read every table twice (once per directed
-//      edge) and spent 31 % of its shared-memory wavefronts on bank conflicts; here the lanes of a
-//      half-warp read 16 distinct 8-byte bank pairs (factor stride D*D words, half stride D*D/2).
+//      exact, so the split changes no bit).  Rows are taken in PAIRS (two rows = 2*D contiguous elements,
+//      16-byte aligned: 128-bit shared-memory loads): for D/2 even lane h owns rows [h*D/2, (h+1)*D/2); for
+//      D/2 odd it owns the pairs [h*(D/2-1), (h+1)*(D/2-1)) and the single row D-2+h.  Adds are packed
+//      (FADD2), optima 3-input (FMNMX3).  Round 1's kernel read every table twice (once per directed edge).
 //      HBM side per warp and stage: tables and previous r rows of the tile are contiguous (1-D bulk
 //      async copies on a per-warp mbarrier), the 32 q rows are gathered through edge_qoff with
 //      cp.async (lanes <-> (row, piece)), the produced r rows are written in place over the staged
@@ -415,11 +455,13 @@ inline void maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_var
 template <typename T, int D, int NS_>
 struct F2VWarpCfg {
   static constexpr int S = D * D, HD = D / 2, NF = 16;
+  static constexpr int NPAIR = (HD % 2 == 0) ? HD / 2 : (HD - 1) / 2;   // row pairs per lane
+  static constexpr bool SINGLE = (HD % 2) != 0;                          // plus one single row
   static constexpr int VR = V2FCfg<T, D>::VR;          // elements per row vector (row = D elements)
   static constexpr int VR_BYTES = V2FCfg<T, D>::VR_BYTES;
   static constexpr int PIECES = D / VR;
-  static constexpr int VH_BYTES = fg_gcd(16, HD * (int)sizeof(T));   // half rows
-  static constexpr int VH = VH_BYTES / (int)sizeof(T);
+  static constexpr int V2_BYTES = fg_gcd(16, 2 * D * (int)sizeof(T));   // a pair of rows / a factor's 2 message rows
+  static constexpr int V2 = V2_BYTES / (int)sizeof(T);
   static constexpr int STAGE = NF * S + 2 * NF * 2 * D;              // tab | rt (in/out) | qt   (elements)
   static constexpr int NS = NS_;
   static constexpr size_t WARP_SMEM = (size_t)NS * STAGE * sizeof(T);
@@ -430,12 +472,19 @@ struct F2VWarpCfg {
   static constexpr bool OK = (D % 2 == 0) && D >= 4 && WARPS > 0;
 };
 
-template <typename T, int D, int NS_, typename OffT>
+// table row index of the i-th row lane h owns (i < D/2); see the kernel comment
+template <int D>
+__host__ __device__ constexpr int f2vw_row(int h, int i) {
+  return ((D / 2) % 2 == 0) ? h * (D / 2) + i : (i < D / 2 - 1 ? h * (D / 2 - 1) + i : 2 * (D / 2 - 1) + h);
+}
+
+template <typename T, int D, int NS_, bool MX, typename OffT>
 __global__ void __launch_bounds__(F2VWarpCfg<T, D, NS_>::WARPS > 0 ? F2VWarpCfg<T, D, NS_>::WARPS * 32 : 32)
 k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict__ q_cur,
            const T *__restrict__ r_cur, T *__restrict__ r_next, const OffT *__restrict__ edge_qoff,
            uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
   using C = F2VWarpCfg<T, D, NS_>;
+  using P = typename Pair<T>::type;
   constexpr int S = C::S, HD = C::HD, NF = C::NF, NS = C::NS, VR = C::VR, PIECES = C::PIECES, R = 2 * D;
   constexpr int WARPS = C::WARPS > 0 ? C::WARPS : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -499,9 +548,8 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     cp_async_commit();
   };
 
-  const bool mx = p.mode_max != 0;
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
-  const T init = mx ? -Inf<T>::pos() : Inf<T>::pos();
+  const T init = MX ? -Inf<T>::pos() : Inf<T>::pos();
   const int fl = lane >> 1, h = lane & 1;
 
   // prologue: tiles 0 .. NS-2 in flight, gather offsets of tile NS-1 and counters of tile 0 on their way
@@ -530,45 +578,96 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     const T *qt = rt + NF * R;
     const bool act = fl < nf;
     const uint8_t cnt_other = (uint8_t)__shfl_xor_sync(0xffffffffu, (unsigned)cnt, 1);
-    T cand0[HD], cand1[HD], prev0[HD], prev1[HD];
-    bool m0 = false, m1 = false;
     uint8_t c0 = h == 0 ? cnt : cnt_other, c1 = h == 0 ? cnt_other : cnt;
-    {
-      const T *tf = tab + fl * S + h * HD * D;   // my HD rows
-      T q0[D], q1[D], part[D];
-      if (act) {
-        ld_row<T, D, VR>(qt + (2 * fl) * D, q0);
-        ld_row<T, D, VR>(qt + (2 * fl + 1) * D, q1);
+    // cc / pp: [0, HD) = my values of the message towards position 0 (at my ROW indices), [HD, 2 HD) = my
+    // half of the message towards position 1
+    T cc[2 * HD], pp[2 * HD];
+    T part[D];   // optima over MY rows of T[x0][x1] + q0[x0], per x1
+#pragma unroll
+    for (int x = 0; x < D; ++x) part[x] = init;
+#pragma unroll
+    for (int i = 0; i < 2 * HD; ++i) { cc[i] = init; pp[i] = (T)0; }
+    if (act) {
+      const T *tf = tab + fl * S;
+      T q0[D], q1[D];
+      {
+        T qq[2 * D];
+        ld_row<T, 2 * D, C::V2>(qt + (2 * fl) * D, qq);   // the factor's two q rows are adjacent
+#pragma unroll
+        for (int x = 0; x < D; ++x) { q0[x] = qq[x]; q1[x] = qq[D + x]; }
       }
+      // pairs of rows: one vector read of 2*D elements, both marginals from it
 #pragma unroll
-      for (int x = 0; x < D; ++x) part[x] = init;
-      if (act) {
+      for (int pi = 0; pi < C::NPAIR; ++pi) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int ra = h == 0 ? f2vw_row<D>(0, 2 * pi) : f2vw_row<D>(1, 2 * pi);   // rows ra, ra + 1
+        T rows[2 * D];
+        ld_row<T, 2 * D, C::V2>(tf + ra * D, rows);
+        // q0[ra], q0[ra + 1] with static register indices: h selects between two compile-time candidates
+        const T qa = h == 0 ? q0[f2vw_row<D>(0, 2 * pi)] : q0[f2vw_row<D>(1, 2 * pi)];
+        const T qb = h == 0 ? q0[f2vw_row<D>(0, 2 * pi) + 1] : q0[f2vw_row<D>(1, 2 * pi) + 1];
+        const P qa2 = pmake<T>(qa, qa), qb2 = pmake<T>(qb, qb);
+        T a0[D], a1[D];
 #pragma unroll
-        for (int i = 0; i < HD; ++i) {
-          T row[D], a[D];
-          ld_row<T, D, VR>(tf + i * D, row);
-          const T qx = h == 0 ? q0[i] : q0[HD + i];   // static register indices
-#pragma unroll
-          for (int x1 = 0; x1 < D; ++x1) {
-            a[x1] = row[x1] + q1[x1];
-            part[x1] = fg_opt<T>(part[x1], row[x1] + qx, mx);
-          }
-          cand0[i] = opt_tree<T, D>(a, mx);
+        for (int x = 0; x < D; x += 2) {
+          const P ta = pmake<T>(rows[x], rows[x + 1]), tb2 = pmake<T>(rows[D + x], rows[D + x + 1]);
+          const P q1p = pmake<T>(q1[x], q1[x + 1]);
+          const P sa = padd(ta, q1p), sb = padd(tb2, q1p);     // towards position 0: T + q1[x1]
+          a0[x] = sa.x; a0[x + 1] = sa.y;
+          a1[x] = sb.x; a1[x + 1] = sb.y;
+          const P ua = padd(ta, qa2), ub = padd(tb2, qb2);     // towards position 1: T + q0[x0]
+          part[x] = opt3<MX>(part[x], ua.x, ub.x);
+          part[x + 1] = opt3<MX>(part[x + 1], ua.y, ub.y);
         }
+        cc[2 * pi] = opt_tree3<MX, T, D>(a0);
+        cc[2 * pi + 1] = opt_tree3<MX, T, D>(a1);
       }
-      // complete position 1: I keep x1 in my half, the partner lane sends its partial optima for it
+      if constexpr (C::SINGLE) {
+        const int ra = h == 0 ? f2vw_row<D>(0, HD - 1) : f2vw_row<D>(1, HD - 1);
+        T row[D], a0[D];
+        ld_row<T, D, VR>(tf + ra * D, row);
+        const T qa = h == 0 ? q0[f2vw_row<D>(0, HD - 1)] : q0[f2vw_row<D>(1, HD - 1)];
+        const P qa2 = pmake<T>(qa, qa);
+#pragma unroll
+        for (int x = 0; x < D; x += 2) {
+          const P ta = pmake<T>(row[x], row[x + 1]);
+          const P sa = padd(ta, pmake<T>(q1[x], q1[x + 1]));
+          a0[x] = sa.x; a0[x + 1] = sa.y;
+          const P ua = padd(ta, qa2);
+          part[x] = opt2<MX>(part[x], ua.x);
+          part[x + 1] = opt2<MX>(part[x + 1], ua.y);
+        }
+        cc[HD - 1] = opt_tree3<MX, T, D>(a0);
+      }
+    }
+    // complete position 1: I keep x1 in [h*HD, (h+1)*HD), the partner lane sends its partial optima for it
+#pragma unroll
+    for (int i = 0; i < HD; ++i) {
+      const T mine = h == 0 ? part[i] : part[HD + i];
+      const T give = h == 0 ? part[HD + i] : part[i];
+      const T got = __shfl_xor_sync(0xffffffffu, give, 1);
+      cc[HD + i] = opt2<MX>(mine, got);
+    }
+    bool m0 = false, m1 = false;
+    if (act) {
+      // previous messages: position 0 at my ROW indices, position 1 at my half
 #pragma unroll
       for (int i = 0; i < HD; ++i) {
-        const T mine = h == 0 ? part[i] : part[HD + i];
-        const T give = h == 0 ? part[HD + i] : part[i];
-        const T got = __shfl_xor_sync(0xffffffffu, give, 1);
-        cand1[i] = fg_opt<T>(mine, got, mx);
+        const int x0 = h == 0 ? f2vw_row<D>(0, i) : f2vw_row<D>(1, i);
+        pp[i] = rt[fl * R + x0];
+        pp[HD + i] = rt[fl * R + D + h * HD + i];
       }
-      if (act) {
-        ld_row<T, HD, C::VH>(rt + fl * R + h * HD, prev0);
-        ld_row<T, HD, C::VH>(rt + fl * R + D + h * HD, prev1);
-        m0 = damp_match_row<T, HD>(cand0, prev0, (c0 & 1) != 0, p.damp_factors != 0, lam, oml, stab);
-        m1 = damp_match_row<T, HD>(cand1, prev1, (c1 & 1) != 0, p.damp_factors != 0, lam, oml, stab);
+      if ((c0 & c1 & 1) != 0) {   // both edges hold a previous message (every cycle but the first ones)
+        damp_match_pairs2<T, 2 * HD, HD>(cc, pp, p.damp_factors != 0, lam, oml, stab, m0, m1);
+      } else {
+        T ca[HD], cb[HD], pa[HD], pb[HD];
+#pragma unroll
+        for (int i = 0; i < HD; ++i) { ca[i] = cc[i]; cb[i] = cc[HD + i]; pa[i] = pp[i]; pb[i] = pp[HD + i]; }
+        m0 = damp_match_row<T, HD>(ca, pa, (c0 & 1) != 0, p.damp_factors != 0, lam, oml, stab);
+        m1 = damp_match_row<T, HD>(cb, pb, (c1 & 1) != 0, p.damp_factors != 0, lam, oml, stab);
+#pragma unroll
+        for (int i = 0; i < HD; ++i) { cc[i] = ca[i]; cc[HD + i] = cb[i]; }
       }
     }
     const unsigned mm = (m0 ? 1u : 0u) | (m1 ? 2u : 0u);
@@ -576,16 +675,12 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     if (act) {
       const bool s0 = gate_decide((mm & mo & 1u) != 0, c0);
       const bool s1 = gate_decide((mm & mo & 2u) != 0, c1);
-      if (!s0) {
 #pragma unroll
-        for (int i = 0; i < HD; ++i) cand0[i] = prev0[i];
+      for (int i = 0; i < HD; ++i) {
+        const int x0 = h == 0 ? f2vw_row<D>(0, i) : f2vw_row<D>(1, i);
+        rt[fl * R + x0] = s0 ? cc[i] : pp[i];
+        rt[fl * R + D + h * HD + i] = s1 ? cc[HD + i] : pp[HD + i];
       }
-      if (!s1) {
-#pragma unroll
-        for (int i = 0; i < HD; ++i) cand1[i] = prev1[i];
-      }
-      st_row<T, HD, C::VH>(rt + fl * R + h * HD, cand0);
-      st_row<T, HD, C::VH>(rt + fl * R + D + h * HD, cand1);
       const int e = c.first_edge + f0 * 2 + lane;   // edge (f, j = h)
       r_cnt[e] = h == 0 ? c0 : c1;
       if (r_sent) r_sent[e] = (h == 0 ? s0 : s1) ? 1 : 0;
@@ -611,7 +706,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
   if (lane == 0) tma_store_wait_read();
 }
 
-template <typename T, int D, int NS_>
+template <typename T, int D, int NS_, bool MX>
 inline bool launch_f2v_warp_ns(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
                                T *r_next, const MaxSumParams &p, cudaStream_t st) {
   using C = F2VWarpCfg<T, D, NS_>;
@@ -619,7 +714,7 @@ inline bool launch_f2v_warp_ns(bool probe, const fg_class_t &c, const fg_maxsum_
     return false;
   } else {
     if (probe) return true;
-    auto kern = k_f2v_warp<T, D, NS_, uint32_t>;
+    auto kern = k_f2v_warp<T, D, NS_, MX, uint32_t>;
     static int per_sm = 0, n_sm = 0;  // one per instantiation
     if (!per_sm) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -645,9 +740,15 @@ template <typename T, int D>
 inline bool launch_f2v_warp(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
                             T *r_next, const MaxSumParams &p, cudaStream_t st) {
   static const int ns = fg_env_int("PYDCOP_B200_F2VW_NS", 3);
-  if (ns >= 4 && launch_f2v_warp_ns<T, D, 4>(probe, c, d, q_cur, r_cur, r_next, p, st)) return true;
-  if (ns >= 3 && launch_f2v_warp_ns<T, D, 3>(probe, c, d, q_cur, r_cur, r_next, p, st)) return true;
-  return launch_f2v_warp_ns<T, D, 2>(probe, c, d, q_cur, r_cur, r_next, p, st);
+#define FG_TRY(NS_)                                                                                      \
+  if (p.mode_max ? launch_f2v_warp_ns<T, D, NS_, true>(probe, c, d, q_cur, r_cur, r_next, p, st)        \
+                 : launch_f2v_warp_ns<T, D, NS_, false>(probe, c, d, q_cur, r_cur, r_next, p, st))      \
+    return true;
+  if (ns >= 4) { FG_TRY(4) }
+  if (ns >= 3) { FG_TRY(3) }
+  FG_TRY(2)
+#undef FG_TRY
+  return false;
 }
 
 // binary classes over one even domain size; probe == true: only report whether the kernel exists

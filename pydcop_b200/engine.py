@@ -78,6 +78,40 @@ class _EngineBase:
         if rc != _cabi.FG_OK:
             raise EngineError(f"{what} failed (rc={rc}): {self._last_error()}")
 
+    def _solution_cost(self, value_tensor, infinity=10000.0, unary=None, n_vars=None, factor_skip=None,
+                       var_skip=None):
+        """(cost, violations) of `value_tensor` (internal variable order) as LOCAL sums, on the device:
+        pydcop/dcop/dcop.py:319-367 — an entry equal to `infinity` is a violation, the others are
+        summed, constraints and variable costs alike.  `unary`: the variables' own costs in CANONICAL
+        order (default: none are added); n_vars: leading variables that count (a shard's own ones);
+        factor_skip / var_skip: uint8 device tensors in internal order, non-zero = owned by another rank."""
+        L = self.layout
+        prec = PRECISIONS[self.precision][0]
+        tdt = PRECISIONS[self.precision][1]
+        with torch.cuda.device(self.device):
+            if not hasattr(self, "_cost_out"):
+                self._edge_var_dev = self._dev(L.edge_var, torch.int32)
+                self._cost_out = torch.zeros(2, dtype=torch.float64, device=self.device)
+                self._cost_unary_off = self._dev(L.unary_off, torch.int64)
+            un = None
+            if unary is not None:   # canonical (variable-major) -> internal (class-major, padded bases)
+                un_host = np.zeros(max(int(L.unary_off[-1]), 1))
+                cu = np.asarray(unary, dtype=np.float64).reshape(-1)
+                dom = L.dom_size.astype(np.int64)
+                c_off = np.concatenate([[0], np.cumsum(dom[L.var_perm])])[:-1]   # canonical offsets
+                if len(cu):
+                    src = np.repeat(c_off[L.var_order], dom) + (np.arange(int(dom.sum())) - np.repeat(np.cumsum(dom) - dom, dom))
+                    dst = np.repeat(L.unary_off[:-1], dom) + (np.arange(int(dom.sum())) - np.repeat(np.cumsum(dom) - dom, dom))
+                    un_host[dst] = cu[src]
+                un = self._dev(un_host, tdt)
+            rc = self.lib.fg_solution_cost(
+                prec, len(L.classes), C.cast(self._classes, C.POINTER(FgClass)), _ptr(self.tables),
+                _ptr(self._edge_var_dev), _ptr(value_tensor), _ptr(un), _ptr(self._cost_unary_off),
+                int(L.n_vars if n_vars is None else n_vars), _ptr(factor_skip), _ptr(var_skip), float(infinity),
+                _ptr(self._cost_out), self._stream())
+            self._check(rc, "fg_solution_cost")
+            return self._cost_out
+
 
 class MaxSumEngine(_EngineBase):
     """All-edges-at-once synchronous MaxSum.
@@ -232,21 +266,11 @@ class MaxSumEngine(_EngineBase):
             out["r_sent"] = L.edges_to_canonical(self.r_sent.cpu().numpy()[:L.n_edges])
         return out
 
-    def solution_cost(self):
-        """(cost, violations) of the currently selected assignment, reduced on the device: sum of the
-        factors' table entries + the variables' own costs; factors at +/-inf count as violations
-        (pydcop/dcop/dcop.py:319-367 `solution_cost`)."""
-        L = self.layout
-        with torch.cuda.device(self.device):
-            if not hasattr(self, "_edge_var_dev"):
-                self._edge_var_dev = self._dev(L.edge_var, torch.int32)
-                self._cost_out = torch.zeros(2, dtype=torch.float64, device=self.device)
-            rc = self.lib.fg_solution_cost(
-                self._desc.precision, len(L.classes), C.cast(self._classes, C.POINTER(FgClass)),
-                _ptr(self.tables), _ptr(self._edge_var_dev), _ptr(self.value), _ptr(self.unary),
-                _ptr(self.unary_off), L.n_vars, _ptr(self._cost_out), self._stream())
-            self._check(rc, "fg_solution_cost")
-            out = self._cost_out.cpu().numpy()
+    def solution_cost(self, infinity=10000.0, unary=None):
+        """(cost, violations) of the currently selected assignment, reduced on the device
+        (pydcop/dcop/dcop.py:319-367; `infinity` as `pydcop solve -i`).  `unary`: the variables' own
+        costs in canonical order WITHOUT MaxSum's noise (default: variable costs are not added)."""
+        out = self._solution_cost(self.value, infinity, unary).cpu().numpy()
         return float(out[0]), int(out[1])
 
     def values(self):
@@ -297,6 +321,7 @@ class DsaEngine(_EngineBase):
         self.lib = _cabi.load()
         self.device = _require_cuda(device)
         self.layout = L = layout
+        self.precision = precision
         prec, tdt, self.np_dtype = PRECISIONS[precision]
         if variant not in _cabi.DSA_VARIANTS:
             raise ValueError(f"invalid variant {variant!r}")
@@ -420,6 +445,11 @@ class DsaEngine(_EngineBase):
     def launch_count(self):
         return int(self.lib.fg_dsa_launch_count(self._h))
 
+    def solution_cost(self, infinity=10000.0, unary=None):
+        """(cost, violations) of the current assignment on the device (dcop.py:319-367)."""
+        out = self._solution_cost(self.value[self.cur], infinity, unary).cpu().numpy()
+        return float(out[0]), int(out[1])
+
     def values(self):
         """Current value index per variable, canonical variable order."""
         L = self.layout
@@ -505,6 +535,7 @@ class MgmEngine(_EngineBase):
         self.lib = _cabi.load()
         self.device = _require_cuda(device)
         self.layout = L = layout
+        self.precision = precision
         prec, tdt, self.np_dtype = PRECISIONS[precision]
         if break_mode not in ("lexic", "random"):
             raise ValueError(f"invalid break_mode {break_mode!r}")
@@ -616,6 +647,11 @@ class MgmEngine(_EngineBase):
         cost = self.cost[:n].double().cpu().numpy()
         cost[self.has_cost[:n].cpu().numpy() == 0] = np.nan
         return L.vars_to_canonical(self.value[:n].cpu().numpy()), L.vars_to_canonical(cost)
+
+    def solution_cost(self, infinity=10000.0, unary=None):
+        """(cost, violations) of the current assignment on the device (dcop.py:319-367)."""
+        out = self._solution_cost(self.value, infinity, unary).cpu().numpy()
+        return float(out[0]), int(out[1])
 
     def gains(self):
         """(gain, intended value) of the last round per variable, canonical order."""

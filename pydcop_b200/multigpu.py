@@ -516,6 +516,7 @@ class ShardedMaxSum:
         prec, tdt, _ = PRECISIONS[precision]
         self.global_n_edges = int(len(np.asarray(inst["edge_var"])))
         self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
+        self.global_dom_size = np.asarray(inst["dom_size"], dtype=np.int32)
         self.peer = None
         if engine_factory is not None:
             self.engine = engine_factory(self.plan.layout, precision=precision, **params)
@@ -635,6 +636,27 @@ class ShardedMaxSum:
         """(global variable ids, value indices) of the variables this rank owns."""
         val, _ = self.engine.values()
         return self.plan.own_vars, val[:self.plan.n_own_vars]
+
+    def solution_cost(self, infinity=10000.0, unary=None):
+        """(cost, violations) of the current assignment of the WHOLE problem: every rank reduces its own
+        factors and variables on its device (fg_solution_cost skips the ghost classes), one NCCL
+        all-reduce of the two sums (pydcop/dcop/dcop.py:319-367, orchestrator.py:1229-1231).
+        `unary`: the variables' own costs of the whole problem, global canonical order, without noise."""
+        import torch.distributed as dist
+        p, e = self.plan, self.engine
+        local_unary = None
+        if unary is not None:
+            dom = np.asarray(self.global_dom_size, dtype=np.int64)
+            uoff = np.concatenate([[0], np.cumsum(dom)])
+            own = p.own_vars
+            n_ghost_el = int(np.asarray(p.local_inst["dom_size"], dtype=np.int64)[p.n_own_vars:].sum())
+            local_unary = np.concatenate([np.asarray(unary, dtype=np.float64)[_ranges(uoff[own], dom[own])],
+                                          np.zeros(n_ghost_el)])
+        n_own_internal = sum(c.n_vars for c in p.layout.var_classes if not c.tag)
+        out = e._solution_cost(e.value, infinity, local_unary, n_vars=n_own_internal)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.halo.group)
+        o = out.cpu().numpy()
+        return float(o[0]), int(round(o[1]))
 
     def values(self):
         """All-gathered assignment (every rank gets the full vector)."""

@@ -289,6 +289,7 @@ class ShardedDsa:
         self.shard = sh = build_dsa_shard(inst, rank, world, partition)
         self.rank, self.world = rank, world
         self.global_n_vars = int(len(np.asarray(inst["dom_size"])))
+        self.global_dom_size = np.asarray(inst["dom_size"], dtype=np.int32)
         iso = params.pop("isolated_value", None)
         if iso is not None:
             iso = np.asarray(iso, dtype=np.int32)[sh.local_global_id]
@@ -364,6 +365,35 @@ class ShardedDsa:
         """Raise if the device-side barrier timed out (synchronises the device)."""
         if self.peer is not None:
             self.peer.sync.check()
+
+    def solution_cost(self, infinity=10000.0, unary=None):
+        """(cost, violations) of the whole problem's current assignment.  A DSA shard keeps ALL constraints of
+        its variables, so a cut constraint lives on several ranks: a rank counts a constraint only if it
+        owns the constraint's FIRST scope variable (the MaxSum ownership rule) and a variable cost only for
+        the variables it owns; it reduces on its device and the ranks all-reduce the two sums
+        (pydcop/dcop/dcop.py:319-367)."""
+        import torch.distributed as dist
+        sh, e, torch = self.shard, self.engine, self.torch
+        L = sh.layout
+        if not hasattr(self, "_cost_masks"):
+            ghost_internal = np.zeros(L.n_vars, dtype=np.uint8)
+            ghost_internal[L.var_perm[np.nonzero(sh.frozen)[0]]] = 1
+            first_e = (np.concatenate([c.first_edge + np.arange(c.n_factors, dtype=np.int64) * c.arity
+                                       for c in L.classes]) if L.n_factors else np.zeros(0, np.int64))
+            fskip = ghost_internal[L.edge_var[first_e]] if L.n_factors else np.zeros(1, np.uint8)
+            self._cost_masks = (torch.from_numpy(np.ascontiguousarray(fskip, dtype=np.uint8)).to(e.device),
+                                torch.from_numpy(ghost_internal).to(e.device))
+        local_unary = None
+        if unary is not None:
+            dom = np.asarray(self.global_dom_size, dtype=np.int64)
+            uoff = np.concatenate([[0], np.cumsum(dom)])
+            gid = sh.local_global_id
+            local_unary = np.asarray(unary, dtype=np.float64)[_ranges(uoff[gid], dom[gid])]
+        out = e._solution_cost(e.value[e.cur], infinity, local_unary, factor_skip=self._cost_masks[0],
+                               var_skip=self._cost_masks[1])
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.halo.group)
+        o = out.cpu().numpy()
+        return float(o[0]), int(round(o[1]))
 
     def local_values(self):
         """(global variable ids, value indices) of the variables this rank owns."""

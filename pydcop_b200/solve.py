@@ -253,7 +253,10 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
         if on_cycle is not None:
             on_cycle(cycle, _indices(engine))
     idx = _indices(engine)
-    violation, cost = solution_cost(dcop, idx, infinity)
+    if hasattr(engine, "solution_cost"):   # reduced on the device(s); sharded engines all-reduce over NCCL
+        cost, violation = engine.solution_cost(infinity, dcop.arrays["unary"])
+    else:                                  # engine seam of the CPU tests
+        violation, cost = solution_cost(dcop, idx, infinity)
     return {"status": status, "assignment": dcop.assignment(idx), "cost": cost,
             "violation": violation, "time": time.perf_counter() - t0, "cycle": cycle,
             "msg_count": 0, "msg_size": 0,  # nothing crosses an agent boundary

@@ -59,13 +59,16 @@ def _maxsum_worker(rank, world, port, case, q):
             sh.step(steps)
         sh.check()
         got = sh.values()
+        cost = sh.solution_cost(9.0, inst["unary"])     # table entries equal to 9 count as violations
         used = "p2p" if sh.peer is not None else "nccl"
         if rank == 0:
-            tot, cur = 0, 0
+            cur = 0
             for s in plan:     # cycles since the last init
                 cur = 0 if s == "init" else cur + s
             ref = MaxSumEngine(build_layout(**inst), device=dev, precision=case.get("precision", "f32")).init().step(cur)
             ok = bool(np.array_equal(got, ref.values()[0]))
+            want = ref.solution_cost(9.0, inst["unary"])
+            ok = ok and cost[1] == want[1] and cost[1] > 0 and abs(cost[0] - want[0]) <= 1e-6 * abs(want[0])
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok" if ok else "MISMATCH", used))
@@ -95,11 +98,14 @@ def _dsa_worker(rank, world, port, case, q):
             sh.step(steps)
         sh.check()
         got = sh.values()
+        cost = sh.solution_cost(2.0, inst["unary"])     # table entries equal to 2 count as violations
         used = "p2p" if sh.peer is not None else "nccl"
         ok = True
         if rank == 0:
             ref = DsaEngine(build_layout(**inst), device=dev, **kw).init().step(sum(case.get("steps", [10])))
             ok = bool(np.array_equal(got, ref.values()))
+            want = ref.solution_cost(2.0, inst["unary"])
+            ok = ok and cost[1] == want[1] and cost[1] > 0 and abs(cost[0] - want[0]) <= 1e-6 * max(1.0, abs(want[0]))
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok" if ok else "MISMATCH", used))

@@ -86,7 +86,7 @@ def test_solution_cost_kernel(name):
     p = {k: v for k, v in meta["params"].items() if k != "noise"}
     eng = MaxSumEngine(layout_from_instance(inst), precision="f64", mode=meta["mode"], **p).init().step(15)
     val, _ = eng.values()
-    cost, viol = eng.solution_cost()
+    cost, viol = eng.solution_cost(infinity=1e300, unary=inst["unary"])
     expect = 0.0
     fp, ev, toff = inst["factor_ptr"], inst["edge_var"], inst["table_off"]
     for f in range(len(fp) - 1):

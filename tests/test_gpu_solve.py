@@ -51,3 +51,44 @@ def test_dsa_from_yaml_matches_oracle(variant):
                       seed=5).init().step(25)
     assert _index(d, res["assignment"]) == o.val.tolist()
     assert res["cycle"] == 25
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("kind", ["maxsum", "dsa", "mgm"])
+def test_device_solution_cost_equals_the_references_known_answers(kind, precision):
+    """fg_solution_cost (pydcop/dcop/dcop.py:319-367) against (violations, cost) computed by the UNMODIFIED
+    reference for assignments of problems whose tables AND variable costs hold entries equal to `infinity`
+    (tests/golden/solution_cost.json, oracle/make_golden_cost.py) — incl. the reference's own hard
+    graph-colouring instance with `-i 10000`."""
+    import json
+    import torch
+    from pydcop_b200 import build_layout
+    from pydcop_b200.engine import DsaEngine, MaxSumEngine, MgmEngine
+    probs = json.load(open(os.path.join(HERE, "golden", "solution_cost.json")))
+    n_viol = 0
+    for prob in probs:
+        inst = {k: np.asarray(prob[k]) for k in ("dom_size", "factor_ptr", "edge_var", "tables")}
+        L = build_layout(**inst)
+        eng = {"maxsum": MaxSumEngine, "dsa": DsaEngine, "mgm": MgmEngine}[kind](L, precision=precision)
+        for case in prob["cases"]:
+            idx = torch.from_numpy(np.asarray(case["value_index"], dtype=np.int32)[L.var_order]).to(eng.device)
+            out = eng._solution_cost(idx, prob["infinity"], np.asarray(prob["unary"])).cpu().numpy()
+            assert int(out[1]) == case["violation"], (prob["name"], case)
+            tol = 1e-12 if precision == "f64" else 2e-6
+            assert float(out[0]) == pytest.approx(case["cost"], rel=tol, abs=tol), (prob["name"], case)
+            n_viol += case["violation"]
+    assert n_viol > 50
+
+
+def test_solve_reports_device_cost_and_violations_on_a_hard_instance():
+    """solve() ends with the device reduction: a hard graph colouring (10000 if equal) solved by DSA —
+    cost / violation of the returned assignment equal the host evaluation of the same assignment."""
+    import json
+    prob = [p for p in json.load(open(os.path.join(HERE, "golden", "solution_cost.json")))
+            if p["name"].startswith("graph_coloring")][0]
+    arrays = {k: np.asarray(prob[k]) for k in ("dom_size", "factor_ptr", "edge_var", "tables", "unary")}
+    d = ingest.from_arrays(arrays)
+    for algo, params in (("dsa", {"stop_cycle": 3}), ("maxsum", {"stop_cycle": 2, "noise": 0}), ("mgm", {"stop_cycle": 3})):
+        res = S.solve(arrays, algo, params, precision="f64", seed=3, infinity=10000)
+        viol, cost = S.solution_cost(d, _index(d, res["assignment"]), 10000)
+        assert (res["violation"], res["cost"]) == (viol, pytest.approx(cost)), algo

@@ -195,3 +195,18 @@ def test_reference_cli_known_answers():
     inst, meta = orc.load_golden(os.path.join(HERE, "golden", "ms_secp_simple1.npz"))
     names = [str(n) for n in inst["var_names"]]
     assert dict(zip(names, inst["value"][-1].tolist())) == {"l1": 0, "l2": 3, "l3": 4, "m1": 3}
+
+
+def test_host_solution_cost_equals_the_references_known_answers():
+    """tests/golden/solution_cost.json holds (violations, cost) computed by the UNMODIFIED reference
+    (oracle/make_golden_cost.py; constraint tables and variable costs with entries equal to `infinity`):
+    the host evaluation used through the engine seam reproduces them; the device reduction is checked
+    against the same file in tests/test_gpu_solve.py."""
+    import json
+    from pydcop_b200 import ingest
+    for prob in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "solution_cost.json"))):
+        d = ingest.from_arrays({k: np.asarray(prob[k]) for k in ("dom_size", "factor_ptr", "edge_var", "tables", "unary")})
+        for case in prob["cases"]:
+            viol, cost = S.solution_cost(d, case["value_index"], prob["infinity"])
+            assert viol == case["violation"], prob["name"]
+            assert cost == pytest.approx(case["cost"], rel=1e-12, abs=1e-12), prob["name"]
