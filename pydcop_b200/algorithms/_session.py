@@ -48,6 +48,7 @@ class GpuSession:
 
     _lock = threading.Lock()
     _sessions: Dict[str, "GpuSession"] = {}
+    _retired: Dict[str, "GpuSession"] = {}    # most recent finished session per key (introspection / tests)
 
     #: engine factory, replaceable by tests: (kind, layout, params) -> engine with
     #: init() / step(n) / values()  (values() -> value indices, or (indices, costs))
@@ -96,6 +97,13 @@ class GpuSession:
         with type(self)._lock:
             if type(self)._sessions.get(self.key) is self:
                 del type(self)._sessions[self.key]
+            type(self)._retired[self.key] = self
+
+    @classmethod
+    def last(cls, key: str) -> Optional["GpuSession"]:
+        """The running session under `key`, else the most recent finished one (None if there was none)."""
+        with cls._lock:
+            return cls._sessions.get(key) or cls._retired.get(key)
 
     @classmethod
     def reset(cls):
@@ -103,6 +111,7 @@ class GpuSession:
             for s in cls._sessions.values():
                 s.closed = True
             cls._sessions.clear()
+            cls._retired.clear()
 
     # -- registration (called from build_computation, any thread) ------------------------------
     def add_variable(self, name, variable, constraint_names, constraints=None, params=None, mode="min"):

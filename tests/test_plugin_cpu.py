@@ -216,9 +216,10 @@ def test_no_gpu_means_loud_failure_not_fallback(pydcop_ready):
         comps.append(c)
     for c in comps:
         c.start()
-    s = GpuSession.get("maxsum:nogpu", "maxsum")
+    s = comps[0]._session        # the proxies keep their session; the registry forgets it once the worker ends
     s.thread.join(timeout=30)
     assert isinstance(s.error, EngineError)
+    assert GpuSession.get("maxsum:nogpu", "maxsum") is not s   # a later run under the same name starts afresh
     with pytest.raises(EngineError):
         comps[0]._poll()
     GpuSession.reset()
@@ -392,9 +393,27 @@ def test_without_stop_cycle_the_run_ends_at_the_timeout_and_the_worker_stops(ora
     with contextlib.redirect_stdout(io.StringIO()):
         res = solve(dcop, algo, "adhoc", timeout=2)
     assert res == {"v1": "R", "v2": "G", "v3": "R"}
-    session = oracle_seam.get("maxsum:no_stop", "maxsum")
+    session = oracle_seam.last("maxsum:no_stop")
     assert session.snapshot is not None and session.snapshot.cycle > 30 and not session.snapshot.finished
     deadline = time.time() + 10
     while session.thread.is_alive() and time.time() < deadline:
         time.sleep(0.05)
     assert not session.thread.is_alive()
+
+
+@retry_once
+def test_second_run_in_one_process_gets_a_fresh_session(oracle_seam):
+    """pydcop.infrastructure.run.solve twice in one process with the DEFAULT session name and NO reset in
+    between: the second run must not be handed the finished session of the first."""
+    from pydcop.algorithms import AlgorithmDef
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    d1 = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    algo = AlgorithmDef.build_with_default_param("dsa_gpu", {"stop_cycle": 40, "seed": 3}, mode=d1.objective)
+    a1 = solve(d1, algo, "oneagent", timeout=8)
+    d2 = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring_10_4_15_0.1.yml")])
+    algo = AlgorithmDef.build_with_default_param("dsa_gpu", {"stop_cycle": 40, "seed": 3}, mode=d2.objective)
+    a2 = solve(d2, algo, "oneagent", timeout=8)
+    assert set(a1) == set(d1.variables) and set(a2) == set(d2.variables)
+    assert a1 in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
+    assert not oracle_seam._sessions      # both workers retired their session
