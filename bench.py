@@ -103,24 +103,91 @@ def oracle_instance(inst, L):
                 table_off=np.concatenate([[0], np.cumsum(t)]))
 
 
-def cpu_baseline(inst, L, seconds=12.0, dtype=np.float32):
-    """The CPU oracle (C port of the reference algorithm, OpenMP over all host threads) timed on a
-    bounded number of cycles of the same workload."""
+def oracle_threads():
+    """OpenMP threads for the CPU arms, set EXPLICITLY (torchrun exports OMP_NUM_THREADS=1) and read back from
+    the OpenMP runtime: PYDCOP_B200_CPU_THREADS, else every logical CPU of the box."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
+    want = int(os.environ.get("PYDCOP_B200_CPU_THREADS", "0") or 0) or (os.cpu_count() or 1)
+    return orc.threads(want)
+
+
+def time_oracle_blocks(o, block, min_seconds=3.0, min_repeats=5, max_seconds=40.0):
+    """Median wall time of `block` cycles of the CPU oracle over >= min_repeats repeats and >= min_seconds of
+    measurement (one C call per block: scratch allocated once, no per-cycle malloc / memcpy)."""
+    times, t_start = [], time.perf_counter()
+    while ((len(times) < min_repeats or sum(times) < min_seconds)
+           and time.perf_counter() - t_start < max_seconds) or not times:
+        t0 = time.perf_counter()
+        o.step(block)
+        times.append(time.perf_counter() - t0)
+    return float(np.median(times)), len(times), times
+
+
+def cpu_baseline(inst, L, dtype=np.float32):
+    """The CPU oracle (C port of the reference algorithm, OpenMP) on the same instance: median of >= 5 blocks of
+    5 cycles, >= 8 s of measurement."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    nthreads = oracle_threads()
     o = orc.MaxSumOracle(oracle_instance(inst, L), dtype).init()
-    o.step(1)
-    t0 = time.perf_counter()
-    o.step(1)
-    one = time.perf_counter() - t0
-    n = int(max(2, min(200, seconds / max(one, 1e-6))))
-    t0 = time.perf_counter()
-    o.step(n)
-    dt = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
-    return {"value": 2.0 * L.n_edges * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} cycles of the same instance, oracle/dcop_oracle.c "
-                      f"{'f32' if dtype == np.float32 else 'f64'}, OpenMP {cores} threads, {dt:.1f}s"}
+    o.step(2)
+    block = 5
+    med, reps, times = time_oracle_blocks(o, block, min_seconds=8.0, max_seconds=30.0)
+    return {"value": 2.0 * L.n_edges * block / med, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"median of {reps} blocks of {block} cycles of the same instance ({sum(times):.1f}s), "
+                      f"oracle/dcop_oracle.c {'f32' if dtype == np.float32 else 'f64'}, OpenMP {nthreads} threads "
+                      f"(omp_get_max_threads), spread min/max {min(times) / block * 1e3:.1f}/{max(times) / block * 1e3:.1f} ms per cycle"}
+
+
+def reference_threadmode(seconds=10):
+    """The UNMODIFIED reference's own thread-mode solve (`pydcop -t T solve -a maxsum -d adhoc`, one Python thread
+    per agent: GIL-bound, effectively one core) timed on THIS box's host: BASELINE.md 3.1 (C1, the reference's
+    graph_coloring_10_4_15_0.1.yml) and 3.2 (a C2-family instance with V = 100).  Reference = baseline/_ref, the
+    pip-installed copy of the source tree (oracle/ref_shim.py adds three import shims, edits nothing).  Returns a
+    list of cpu_baseline entries (kind `reference-threadmode`); [] with a reason when the install is absent."""
+    import subprocess
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    if not ref_shim.reference_available():
+        return [{"kind": "reference-threadmode", "unavailable": f"no reference at {ref_shim.REFERENCE_ROOT}"}]
+    out = []
+    with tempfile.TemporaryDirectory() as td:
+        # C2-family instance, V = 100, d = 10, 200 binary constraints, tables as literal nested lists
+        rng = np.random.default_rng(0)
+        lines = ["name: c2_family_v100", "objective: min", "domains:", "  d: {values: [0,1,2,3,4,5,6,7,8,9]}",
+                 "variables:"]
+        lines += [f"  v{i:03d}: {{domain: d}}" for i in range(100)]
+        lines.append("constraints:")
+        for j in range(200):
+            a, b = rng.choice(100, size=2, replace=False)
+            t = rng.integers(0, 10, size=(10, 10)).tolist()
+            lines += [f"  c{j:03d}:", "    type: intention", f"    function: '{t}[v{a:03d}][v{b:03d}]'"]
+        lines += ["agents:"] + [f"  a{i:03d}: {{capacity: 1000}}" for i in range(300)]
+        c2f = os.path.join(td, "c2_family_v100.yaml")
+        open(c2f, "w").write("\n".join(lines) + "\n")
+        c1 = os.path.join(ref_shim.REFERENCE_ROOT, "tests", "instances", "graph_coloring_10_4_15_0.1.yml")
+        for name, path, n_edges, dist in (("C1 graph_coloring_10_4_15_0.1.yml", c1, 24, "adhoc"),
+                                          ("C2-family V=100 d=10 F=200", c2f, 400, "oneagent")):
+            code = ("import sys; sys.path[:0] = [%r]\nimport ref_shim; ref_shim.install()\n"
+                    "from pydcop.dcop_cli import main\n"
+                    "sys.argv = ['pydcop', '-t', %r, 'solve', '-a', 'maxsum', '-d', %r, %r]\nmain()\n"
+                    ) % (os.path.join(ROOT, "oracle"), str(seconds), dist, path)
+            try:
+                r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True,
+                                   timeout=seconds * 6 + 60, cwd=td)
+                txt = r.stdout
+                res = json.loads(txt[txt.index("{"):txt.rindex("}") + 1])
+                cyc, tm = int(res.get("cycle") or 0), float(res.get("time") or seconds)
+                out.append({"kind": "reference-threadmode", "value": 2.0 * n_edges * cyc / tm if cyc else 0.0,
+                            "unit": UNIT, "cores": 1,
+                            "sample": f"{name}: unmodified `pydcop -t {seconds} solve -a maxsum -d {dist}` in thread mode "
+                                      f"(GIL-bound), {cyc} cycles in {tm:.1f}s, status {res.get('status')}, "
+                                      f"msg_count {res.get('msg_count')}; host has {os.cpu_count()} logical CPUs"})
+            except Exception as ex:  # noqa: BLE001 — a baseline must not cost the measured line
+                out.append({"kind": "reference-threadmode", "unavailable": f"{name}: {ex!r}"[:300]})
+    return out
 
 
 def shared_partition(inst, world, rank, dev, part):

@@ -367,7 +367,7 @@ inline bool launch_v2f_warp_ns(const WTileDesc *dev_tiles, const WTileRange &rg,
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FG_V2FW_WARPS * 32, C::SMEM);
       if (per_sm < 1) per_sm = 1;
-      const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 2);  // leaves room for the factor side (runs concurrently)
+      const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 3);  // leaves room for the factor side (runs concurrently)
       if (per_sm > cap) per_sm = cap;
     }
     const int need = (rg.count + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
@@ -379,11 +379,12 @@ inline bool launch_v2f_warp_ns(const WTileDesc *dev_tiles, const WTileRange &rg,
   }
 }
 
-// pipeline depth: PYDCOP_B200_V2FW_NS = 2 | 3 | 4 stages per warp (default 3)
+// pipeline depth: PYDCOP_B200_V2FW_NS = 2 | 3 | 4 stages per warp (default 2: 12 warps x 2 stages per SM measured
+// faster on C2 than 8 x 3, profiles/r02_call5_sweep.txt)
 template <typename T, int D>
 inline void launch_v2f_warp(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
                             const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
-  static const int ns = fg_env_int("PYDCOP_B200_V2FW_NS", 3);
+  static const int ns = fg_env_int("PYDCOP_B200_V2FW_NS", 2);
 #define FG_TRY(NS_)                                                                                              \
   if (p.mode_max ? launch_v2f_warp_ns<T, D, NS_, true>(dev_tiles, rg, d, r_cur, q_cur, q_next, p, st)            \
                  : launch_v2f_warp_ns<T, D, NS_, false>(dev_tiles, rg, d, r_cur, q_cur, q_next, p, st))          \
@@ -723,7 +724,7 @@ inline bool launch_f2v_warp_ns(bool probe, const fg_class_t &c, const fg_maxsum_
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::WARPS * 32, C::SMEM);
       if (per_sm < 1) per_sm = 1;
-      const int cap = fg_env_int("PYDCOP_B200_F2VW_CPS", 2);  // CTAs of 2 warps; the variable side shares the SMs
+      const int cap = fg_env_int("PYDCOP_B200_F2VW_CPS", 3);  // CTAs of 2 warps; the variable side shares the SMs
       if (per_sm > cap) per_sm = cap;
     }
     const int n_tiles = (c.n_factors + C::NF - 1) / C::NF;
@@ -735,11 +736,11 @@ inline bool launch_f2v_warp_ns(bool probe, const fg_class_t &c, const fg_maxsum_
   }
 }
 
-// pipeline depth: PYDCOP_B200_F2VW_NS = 2 | 3 | 4 stages per warp (default 3), shallower when it does not fit
+// pipeline depth: PYDCOP_B200_F2VW_NS = 2 | 3 | 4 stages per warp (default 2), shallower when it does not fit
 template <typename T, int D>
 inline bool launch_f2v_warp(bool probe, const fg_class_t &c, const fg_maxsum_desc_t &d, const T *q_cur, const T *r_cur,
                             T *r_next, const MaxSumParams &p, cudaStream_t st) {
-  static const int ns = fg_env_int("PYDCOP_B200_F2VW_NS", 3);
+  static const int ns = fg_env_int("PYDCOP_B200_F2VW_NS", 2);
 #define FG_TRY(NS_)                                                                                      \
   if (p.mode_max ? launch_f2v_warp_ns<T, D, NS_, true>(probe, c, d, q_cur, r_cur, r_next, p, st)        \
                  : launch_f2v_warp_ns<T, D, NS_, false>(probe, c, d, q_cur, r_cur, r_next, p, st))      \

@@ -36,6 +36,13 @@ __device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 psub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
 
+// a + b with the two sums as SCALAR correctly-rounded adds (__fadd_rn is never contracted): ptxas fuses a
+// packed mul.rn.f32x2 feeding a packed add.rn.f32x2 into FFMA2 — one rounding instead of two, which broke bit
+// parity of the damping step for damping != 0.5 (seen on the B200, r02 call 5) — so wherever the inputs of
+// an add are products, the add must not be the packed form.
+__device__ __forceinline__ float2 padd_noncontract(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 padd_noncontract(double2 a, double2 b) { return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y)); }
+
 template <typename T> __device__ __forceinline__ typename Pair<T>::type pmake(T x, T y);
 template <> __device__ __forceinline__ float2 pmake<float>(float x, float y) { return make_float2(x, y); }
 template <> __device__ __forceinline__ double2 pmake<double>(double x, double y) { return make_double2(x, y); }
@@ -90,7 +97,7 @@ __device__ __forceinline__ bool damp_match_pairs(T (&cand)[N], const T (&prev)[N
   for (int i = 0; i < N / 2; ++i) {
     const P p = pmake<T>(prev[2 * i], prev[2 * i + 1]);
     P c = pmake<T>(cand[2 * i], cand[2 * i + 1]);
-    if (damp_side) c = padd(pmul(lam2, p), pmul(oml2, c));   // lam * prev + (1 - lam) * c, two roundings each
+    if (damp_side) c = padd_noncontract(pmul(lam2, p), pmul(oml2, c));   // lam * prev + (1 - lam) * c: three roundings
     cand[2 * i] = c.x;
     cand[2 * i + 1] = c.y;
     const P s = padd(p, c);
@@ -133,7 +140,7 @@ __device__ __forceinline__ void damp_match_pairs2(T (&cand)[N], const T (&prev)[
   for (int i = 0; i < N / 2; ++i) {
     const P p = pmake<T>(prev[2 * i], prev[2 * i + 1]);
     P c = pmake<T>(cand[2 * i], cand[2 * i + 1]);
-    if (damp_side) c = padd(pmul(lam2, p), pmul(oml2, c));
+    if (damp_side) c = padd_noncontract(pmul(lam2, p), pmul(oml2, c));
     cand[2 * i] = c.x;
     cand[2 * i + 1] = c.y;
     const P s = padd(p, c);

@@ -760,12 +760,30 @@ def load_instance(path: Union[str, os.PathLike], mmap: bool = True) -> DcopArray
 # --------------------------------------------------------------------------------------------
 # MaxSum noise (algorithm parameter, not part of the instance)
 # --------------------------------------------------------------------------------------------
+def stdlib_uniform_stream(n: int, seed: int) -> np.ndarray:
+    """The first n values of `random.Random(seed).random()` for an int seed, vectorised: CPython seeds its
+    MT19937 with init_by_array over the 32-bit words of abs(seed) and builds each double from two outputs
+    (a >> 5, b >> 6) exactly like numpy's legacy RandomState.random_sample, so the two streams are
+    bit-identical (checked against the stdlib in tests/test_ingest.py)."""
+    a, words = abs(int(seed)), []
+    while True:
+        words.append(a & 0xFFFFFFFF)
+        a >>= 32
+        if not a:
+            break
+    return np.random.RandomState(words).random_sample(int(n))     # a LIST: a 1-element array would be read as a scalar
+
+
 def add_noise(unary: np.ndarray, noise: float, seed: Optional[int] = None) -> np.ndarray:
     """MaxSum wraps every variable in VariableNoisyCostFunc(noise_level=noise) unless noise == 0
     (maxsum.py:474-483): cost + U(0, noise) per (variable, value), drawn in variable order then
-    value order from Python's `random` (objects.py:566-567).  `seed` makes the draws repeatable."""
+    value order from Python's `random` (objects.py:566-567): uniform(0, noise) = 0 + noise * random().
+    `seed` makes the draws repeatable — and equal to what `random.Random(seed)` would draw one by one."""
     if not noise:
         return np.asarray(unary, dtype=np.float64)
-    rnd = random.Random(seed) if seed is not None else random
-    return np.asarray(unary, dtype=np.float64) + np.array(
-        [rnd.uniform(0, noise) for _ in range(len(unary))])
+    n = len(unary)
+    if seed is not None:
+        draws = 0.0 + (float(noise) - 0.0) * stdlib_uniform_stream(n, seed)
+    else:
+        draws = np.array([random.uniform(0, noise) for _ in range(n)])
+    return np.asarray(unary, dtype=np.float64) + draws

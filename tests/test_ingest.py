@@ -363,3 +363,18 @@ def test_random_expressions_tabulate_like_the_reference():
     assert m, r.stdout[-500:]
     assert int(m.group(1)) >= 400 and int(m.group(2)) == 0, r.stdout[-1500:]
     assert "'vectorised': 0" not in m.group(3) and "'scalar': 0" not in m.group(3)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 11, 2 ** 31 + 5, 2 ** 40 + 3, -7, 123456789012345678901234567890])
+def test_vectorised_noise_stream_equals_the_stdlib_generator(seed):
+    """ingest.add_noise draws the MaxSum noise (objects.py:566-567) in one vectorised call; the values are the
+    ones `random.Random(seed).uniform(0, noise)` produces one at a time."""
+    import random
+    from pydcop_b200 import ingest
+    r = random.Random(seed)
+    want = np.array([r.uniform(0, 0.01) for _ in range(257)])
+    got = ingest.add_noise(np.zeros(257), 0.01, seed)
+    assert np.array_equal(got, want)
+    base = np.linspace(0, 3, 257)
+    r = random.Random(seed)
+    assert np.array_equal(ingest.add_noise(base, 0.5, seed), base + np.array([r.uniform(0, 0.5) for _ in range(257)]))
