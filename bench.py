@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "maxsum_edge_message_updates_per_s"
 UNIT = "updates/s"
-E2E_CYCLES = 30  # cycles per end-to-end solve (upload -> cycles -> read assignment)
+E2E_CYCLES = 200  # cycles per end-to-end solve() (ingestion -> layout -> upload -> cycles -> assignment + cost)
 PARITY_CYCLES = 12  # N > 1: sharded run vs one engine with the whole problem, outside the timed regions
 
 
@@ -248,6 +248,12 @@ def side_workload(args, dev):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     eng.step(max(3, args.warmup))
     torch.cuda.synchronize(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
     evs = []
     for _ in range(args.steps):
         flush.zero_()
@@ -257,6 +263,7 @@ def side_workload(args, dev):
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     parity = None
     if world > 1:
@@ -282,9 +289,11 @@ def side_workload(args, dev):
     peaks, kind = load_peaks()
     ach = alg / (ms * 1e-3) / 1e9
     line = {"metric": metric, "value": units / (ms * 1e-3), "unit": "updates/s", "n_gpus": world,
-            "steps": args.steps, "ms_per_step": ms, "dtype": args.precision,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "dtype": args.precision,
+            "higher_is_better": True, "data": "synthetic", "clocks": clocks,
             "scaling": "strong" if world > 1 else None,
-            "config": {"workload": w, "n_vars": L.n_vars, "n_factors": L.n_factors, "n_edges": L.n_edges},
+            "config": {"workload": w, "n_vars": L.n_vars, "n_factors": L.n_factors, "n_edges": L.n_edges,
+                       "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
                          "frac": ach / (peaks["hbm_gbs"] * world), "algorithmic_bytes_per_step": int(alg)}}
     if world > 1:
@@ -297,6 +306,19 @@ def side_workload(args, dev):
             line["config"]["cut_edges"] = int(eng.plan.n_cut_edges)
             line["config"]["halo"] = "peer push" if eng.peer is not None else "nccl all_to_all"
     print(json.dumps(line))
+
+
+def workload_config(n_vars, world):
+    """`config` of the main line: the workload and how it is measured — STATIC, so that the GPU arm and the
+    reference arm print the same dict at every N (what a run finds out goes under `run`)."""
+    return {"workload": f"random binary DCOP {n_vars} vars d=10 deg=4 (BASELINE configs[1] "
+                        f"{'x%d weak' % world if world > 1 else ''})".strip(),
+            "n_vars": n_vars, "n_factors": 2 * n_vars, "n_edges": 4 * n_vars, "d": 10,
+            "params": "damping 0.5 both, stability 0.1, noise 0.01, start_messages leafs",
+            "partition": (f"variable cut over {world} GPUs, method "
+                          f"{os.environ.get('PYDCOP_B200_PARTITION', 'auto')}" if world > 1 else "single GPU"),
+            "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
+            "step": "one synchronous MaxSum cycle over all edges"}
 
 
 def main():
@@ -323,37 +345,35 @@ def main():
     from pydcop_b200.generators import config_c2
 
     n_vars = args.vars_per_gpu * max(1, world)
-    config = {"workload": f"random binary DCOP {n_vars} vars d=10 deg=4 (BASELINE configs[1] "
-                          f"{'x%d weak' % world if world > 1 else ''})".strip(),
-              "n_vars": n_vars, "n_factors": 2 * n_vars, "n_edges": 4 * n_vars, "d": 10,
-              "params": "damping 0.5 both, stability 0.1, noise 0.01, start_messages leafs",
-              "partition": "variable-cut contiguous blocks" if world > 1 else "single GPU",
-              "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
-              "step": "one synchronous MaxSum cycle over all edges"}
+    config = workload_config(n_vars, world)
+    run_info = {}   # what this run found out (cut size, halo path ...): NOT part of `config`, which both arms share
 
     if args.impl == "reference":
+        # the reference's own algorithm for this path on the host cores (C port of the pure-Python reference,
+        # OpenMP): rank 0 only, same instance and `config` as the GPU arm at this N.  A "step" is one cycle; the
+        # line reports the MEDIAN over >= 5 blocks of `--steps` cycles and >= 3 s of measurement.
         if rank != 0:
             return
         inst = config_c2(seed=0, n_vars=n_vars)
         L = build_layout(**inst)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as orc
+        nthreads = oracle_threads()
         o = orc.MaxSumOracle(oracle_instance(inst, L), np.float32).init()
         o.step(max(1, args.warmup))
-        t0 = time.perf_counter()
-        o.step(args.steps)
-        dt = time.perf_counter() - t0
-        val = 2.0 * L.n_edges * args.steps / dt
-        cores = os.cpu_count() or 1
+        med, reps, times = time_oracle_blocks(o, max(1, args.steps), min_seconds=3.0, min_repeats=5, max_seconds=90.0)
+        val = 2.0 * L.n_edges * args.steps / med
+        sample = (f"median of {reps} blocks of {args.steps} cycles ({sum(times):.1f}s measured, min/max block "
+                  f"{min(times):.3f}/{max(times):.3f}s), oracle/dcop_oracle.c f32 (C port of the pure-Python "
+                  f"reference), OpenMP {nthreads} threads (omp_get_max_threads; OMP_NUM_THREADS in the environment: "
+                  f"{os.environ.get('OMP_NUM_THREADS', 'unset')}), host has {os.cpu_count()} logical CPUs")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "ms_per_step": 1e3 * med / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} cycles, oracle/dcop_oracle.c f32 (C port of "
-                                       f"the pure-Python reference), OpenMP {cores} threads"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -380,14 +400,14 @@ def main():
         part, part_owner, perr = shared_partition(inst, world, rank, dev,
                                                   os.environ.get("PYDCOP_B200_PARTITION", "auto"))
         if perr:
-            config["partition_error"] = perr
+            run_info["partition_error"] = perr
         runner = ShardedMaxSum(inst, rank, world, dev, precision=args.precision,
                                halo=os.environ.get("PYDCOP_B200_HALO", "auto"), partition=part_owner)
         L = None
-        config["cut_edges"] = runner.plan.n_cut_edges
-        config["partition"] = (f"{part}: the fewer-cut of contiguous blocks and a multilevel k-way split "
-                               f"(pydcop_b200/partition.py), {runner.plan.n_cut_edges} of {n_edges_global} edges cut"
-                               if part == "auto" else f"{part}, {runner.plan.n_cut_edges} of {n_edges_global} edges cut")
+        run_info["cut_edges"] = runner.plan.n_cut_edges
+        run_info["partition"] = (f"{part}: the fewer-cut of contiguous blocks and a multilevel k-way split "
+                                 f"(pydcop_b200/partition.py), {runner.plan.n_cut_edges} of {n_edges_global} edges cut"
+                                 if part == "auto" else f"{part}, {runner.plan.n_cut_edges} of {n_edges_global} edges cut")
     else:
         L = build_layout(**inst)
         runner = MaxSumEngine(L, device=dev, precision=args.precision, record_sent=True)
@@ -402,7 +422,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     runner.init()
     if world > 1:
-        config["halo"] = ("push kernel storing boundary rows straight into the peers' buffers over NVLink (CUDA "
+        run_info["halo"] = ("push kernel storing boundary rows straight into the peers' buffers over NVLink (CUDA "
                           "IPC), its last block releasing the cycle's epoch flag to the peers; device-side "
                           "acquire wait; whole cycle enqueued by one C call (fg_maxsum_shard_step)"
                           + ("; split push" if os.environ.get("PYDCOP_B200_PUSH_SPLIT", "0") not in ("", "0") else "")
@@ -443,47 +463,6 @@ def main():
         breakdown["unit"] = "us per cycle, rank 0"
         runner.check()
 
-    # end to end through the public API: pinned host arrays -> device, E2E_CYCLES cycles, values back
-    # (N > 1: every rank uploads its own shard; time = max over ranks)
-    eng = runner.engine if world > 1 else runner
-    Ls = eng.layout
-    npdt = np.float32 if vb == 4 else np.float64
-    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
-            (("tables", Ls.tables.astype(npdt)), ("unary", Ls.unary.astype(npdt)),
-             ("slot_roff", Ls.slot_roff), ("edge_qoff", Ls.edge_qoff),
-             ("slot_edge", Ls.slot_edge), ("slot_var", Ls.slot_var), ("var_ptr", Ls.var_ptr))}
-    out_host = torch.empty(Ls.n_vars, dtype=torch.int32).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in host.values())
-    d2h = out_host.numel() * 4
-    times = []
-    for it in range(0 if args.no_e2e else 3 + 5):
-        flush.zero_()
-        if world > 1:
-            dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for k, t in host.items():
-            getattr(eng, k).copy_(t, non_blocking=True)
-        runner.init()
-        runner.step(E2E_CYCLES)
-        out_host.copy_(eng.value[:Ls.n_vars], non_blocking=True)
-        b.record()
-        torch.cuda.synchronize(dev)
-        if it >= 3:
-            times.append(a.elapsed_time(b))
-    e2e_ms = float(np.mean(times)) if times else float("nan")
-    if world > 1:
-        t = torch.tensor([e2e_ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
-        tm = t.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_ms, h2d, d2h = float(tm[0].item()), int(t[1].item()), int(t[2].item())
-    e2e = {"value": updates_per_step * E2E_CYCLES / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "solve": f"upload tables+unary+CSR from pinned host, init + {E2E_CYCLES} cycles, "
-                    f"assignment back to host; {e2e_ms:.3f} ms per solve"
-                    + (" (max over ranks; bytes summed over ranks)" if world > 1 else "")}
-
     parity = None
     if world > 1:
         # outside every timed region: the sharded run (halo path as timed) against ONE engine holding the
@@ -504,6 +483,47 @@ def main():
             except Exception as ex:  # noqa: BLE001 — the check must not cost the measured line
                 parity = {"cycles": PARITY_CYCLES, "error": repr(ex)}
         dist.barrier()
+    # end to end through the PUBLIC API, pydcop_b200.solve.solve(): host arrays in, result dict out.  Inside the timed
+    # region, every repeat: ingestion of the arrays, noise draws, layout packing (host), engine construction
+    # (device allocations, host -> device copies of tables / unary / CSR from pageable host memory), init,
+    # E2E_CYCLES cycles, device -> host copy of the assignment, cost / violation reduction on the device, the
+    # name -> value dict.  N > 1: every rank calls solve() (the partition is given: computing it is the
+    # partitioner's cost, reported separately), time = max over ranks.  Wall clock between device synchronisations.
+    from pydcop_b200 import solve as S
+    times, h2d, d2h = [], 0, 0
+    if not args.no_e2e:
+        del runner
+        torch.cuda.empty_cache()
+        for it in range(1 + 3):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            res = S.solve(inst, "maxsum", {"stop_cycle": E2E_CYCLES}, precision=args.precision, device=dev, seed=0,
+                          partition=part_owner if world > 1 else "auto",
+                          halo=os.environ.get("PYDCOP_B200_HALO", "auto"))
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            assert res["status"] == "FINISHED" and res["cycle"] == E2E_CYCLES
+            h2d, d2h = res["h2d_bytes"], res["d2h_bytes"]
+            if it >= 1:
+                times.append(dt * 1e3)
+    e2e_ms = float(np.median(times)) if times else float("nan")
+    if world > 1:
+        t = torch.tensor([e2e_ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_ms, h2d, d2h = float(tm[0].item()), int(t[1].item()), int(t[2].item())
+    e2e = {"value": updates_per_step * E2E_CYCLES / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "solve": f"pydcop_b200.solve.solve(arrays, 'maxsum', stop_cycle={E2E_CYCLES}): ingestion + layout packing on "
+                    f"the host, engine construction + uploads, init, {E2E_CYCLES} cycles, assignment + device cost "
+                    f"reduction back; median of 3 solves after 1 warm-up: {e2e_ms:.1f} ms per solve"
+                    + (" (max over ranks; bytes summed over ranks)" if world > 1 else "")}
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -522,6 +542,9 @@ def main():
         "config": config, "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": ("constant from the committed ncu --set full capture named in profiles/ (dram__bytes_read + "
+                                        "dram__bytes_write of one launch of each kernel), not a measurement of this run"
+                                        if traffic is not None else None),
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                      "algorithmic_bytes_per_step": int(per_gpu_bytes),
                      "bytes_per_update": alg_bytes / updates_per_step,
@@ -529,12 +552,16 @@ def main():
                                "profiles/)"},
         "e2e": e2e,
     }
+    if run_info:
+        line["run"] = run_info
     if parity is not None:
         line["parity"] = parity
     if breakdown is not None:
         line["breakdown"] = breakdown
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(inst, L)
+        # the UNMODIFIED reference's thread-mode solve on this host: reported next to the port
+        line["cpu_baseline_reference_threadmode"] = reference_threadmode(int(os.environ.get("PYDCOP_B200_REF_SECONDS", "10")))
     print(json.dumps(line))
 
 

@@ -68,8 +68,9 @@ class _EngineBase:
         a = np.ascontiguousarray(a)
         if not a.flags.writeable:      # e.g. a read-only memory map of the binary container
             a = a.copy()
-        t = torch.from_numpy(a)
-        return t.to(device=self.device, dtype=dtype)
+        t = torch.from_numpy(a).to(device=self.device, dtype=dtype)
+        self.h2d_bytes = getattr(self, "h2d_bytes", 0) + t.numel() * t.element_size()   # what crossed PCIe / C2C
+        return t
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -159,7 +159,10 @@ def _sharded_engine(kind, inst, dcop, params, mode, precision, device, seed, par
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
                                              if torch.cuda.is_available() and "engine_factory" not in kw
                                              else torch.device("cpu"))
-    owner, err = broadcast_owner(inst, world, rank, dev, partition)
+    if isinstance(partition, str):
+        owner, err = broadcast_owner(inst, world, rank, dev, partition)
+    else:                                  # an owner array every rank already holds
+        owner, err = np.asarray(partition, dtype=np.int32), None
     if kind == "maxsum":
         eng = ShardedMaxSum(inst, rank, world, dev, precision=precision, halo=halo, partition=owner, mode=mode,
                             damping=params["damping"], damping_nodes=params["damping_nodes"],
@@ -261,7 +264,10 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
             "violation": violation, "time": time.perf_counter() - t0, "cycle": cycle,
             "msg_count": 0, "msg_size": 0,  # nothing crosses an agent boundary
             "algo": kind, "precision": precision, "n_gpus": n_gpus,
-            "ingest_time": t_packed - t0}
+            "ingest_time": t_packed - t0,
+            # bytes this process moved host -> device (problem arrays) and device -> host (assignment, costs)
+            "h2d_bytes": int(getattr(getattr(engine, "engine", engine), "h2d_bytes", 0)),
+            "d2h_bytes": int(len(idx) * 12 + 16)}
 
 
 def _indices(engine) -> np.ndarray:

@@ -44,3 +44,19 @@ def test_gpu_arm_refuses_to_run_without_a_device():
         return
     r = _run(["--steps", "1", "--warmup", "1"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_sets_its_threads_explicitly_and_shares_the_gpu_arms_config():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must not inherit it silently (it printed
+    "128 threads" while running one), and its `config` is the dict the GPU arm prints at the same N."""
+    import bench
+    r = _run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--vars-per-gpu", "1000", "--gpus", "2"],
+             env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1",
+                  "PYDCOP_B200_CPU_THREADS": "3"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == 3 and "OpenMP 3 threads" in d["cpu_baseline"]["sample"]
+    assert "median of" in d["cpu_baseline"]["sample"]
+    os.environ.pop("PYDCOP_B200_PARTITION", None)
+    assert d["config"] == bench.workload_config(2000, 2)
+    assert d["n_gpus"] == 2 and d["config"]["n_vars"] == 2000
