@@ -79,7 +79,7 @@ class _EngineBase:
         if rc != _cabi.FG_OK:
             raise EngineError(f"{what} failed (rc={rc}): {self._last_error()}")
 
-    def _solution_cost(self, value_tensor, infinity=10000.0, unary=None, n_vars=None, factor_skip=None,
+    def _solution_cost(self, value_tensor, infinity=float("inf"), unary=None, n_vars=None, factor_skip=None,
                        var_skip=None):
         """(cost, violations) of `value_tensor` (internal variable order) as LOCAL sums, on the device:
         pydcop/dcop/dcop.py:319-367 — an entry equal to `infinity` is a violation, the others are
@@ -267,7 +267,7 @@ class MaxSumEngine(_EngineBase):
             out["r_sent"] = L.edges_to_canonical(self.r_sent.cpu().numpy()[:L.n_edges])
         return out
 
-    def solution_cost(self, infinity=10000.0, unary=None):
+    def solution_cost(self, infinity=float("inf"), unary=None):
         """(cost, violations) of the currently selected assignment, reduced on the device
         (pydcop/dcop/dcop.py:319-367; `infinity` as `pydcop solve -i`).  `unary`: the variables' own
         costs in canonical order WITHOUT MaxSum's noise (default: variable costs are not added)."""
@@ -446,7 +446,7 @@ class DsaEngine(_EngineBase):
     def launch_count(self):
         return int(self.lib.fg_dsa_launch_count(self._h))
 
-    def solution_cost(self, infinity=10000.0, unary=None):
+    def solution_cost(self, infinity=float("inf"), unary=None):
         """(cost, violations) of the current assignment on the device (dcop.py:319-367)."""
         out = self._solution_cost(self.value[self.cur], infinity, unary).cpu().numpy()
         return float(out[0]), int(out[1])
@@ -649,7 +649,7 @@ class MgmEngine(_EngineBase):
         cost[self.has_cost[:n].cpu().numpy() == 0] = np.nan
         return L.vars_to_canonical(self.value[:n].cpu().numpy()), L.vars_to_canonical(cost)
 
-    def solution_cost(self, infinity=10000.0, unary=None):
+    def solution_cost(self, infinity=float("inf"), unary=None):
         """(cost, violations) of the current assignment on the device (dcop.py:319-367)."""
         out = self._solution_cost(self.value, infinity, unary).cpu().numpy()
         return float(out[0]), int(out[1])

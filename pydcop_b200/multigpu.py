@@ -637,7 +637,7 @@ class ShardedMaxSum:
         val, _ = self.engine.values()
         return self.plan.own_vars, val[:self.plan.n_own_vars]
 
-    def solution_cost(self, infinity=10000.0, unary=None):
+    def solution_cost(self, infinity=float("inf"), unary=None):
         """(cost, violations) of the current assignment of the WHOLE problem: every rank reduces its own
         factors and variables on its device (fg_solution_cost skips the ghost classes), one NCCL
         all-reduce of the two sums (pydcop/dcop/dcop.py:319-367, orchestrator.py:1229-1231).

@@ -366,7 +366,7 @@ class ShardedDsa:
         if self.peer is not None:
             self.peer.sync.check()
 
-    def solution_cost(self, infinity=10000.0, unary=None):
+    def solution_cost(self, infinity=float("inf"), unary=None):
         """(cost, violations) of the whole problem's current assignment.  A DSA shard keeps ALL constraints of
         its variables, so a cut constraint lives on several ranks: a rank counts a constraint only if it
         owns the constraint's FIRST scope variable (the MaxSum ownership rule) and a variable cost only for

@@ -98,9 +98,9 @@ def isolated_values(dcop: ingest.DcopArrays, mode: str) -> np.ndarray:
     return out
 
 
-def solution_cost(dcop: ingest.DcopArrays, value_index, infinity: float = 10000.0):
+def solution_cost(dcop: ingest.DcopArrays, value_index, infinity: float = float("inf")):
     """(violation, cost): constraints and variable costs equal to `infinity` are counted, the
-    others summed (pydcop/dcop/dcop.py:319-367; `infinity` default as commands/solve.py `-i`)."""
+    others summed (pydcop/dcop/dcop.py:319-367; `infinity` default as commands/solve.py `-i`: float("inf"))."""
     a = dcop.arrays
     idx = np.asarray(value_index, dtype=np.int64)
     fp, ev = a["factor_ptr"].astype(np.int64), a["edge_var"].astype(np.int64)
@@ -179,7 +179,7 @@ def _sharded_engine(kind, inst, dcop, params, mode, precision, device, seed, par
 
 def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] = None,
           timeout: Optional[float] = None, precision: str = "f32", device=None,
-          seed: Optional[int] = None, infinity: float = 10000.0, chunk: int = 50,
+          seed: Optional[int] = None, infinity: float = float("inf"), chunk: int = 50,
           on_cycle: Optional[Callable[[int, np.ndarray], None]] = None,
           engine_factory: Optional[Callable] = None, distributed: Optional[bool] = None,
           partition="auto", halo: str = "auto", sharded_kwargs: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
@@ -287,7 +287,9 @@ def main(argv=None):
     ap.add_argument("-t", "--timeout", type=float, default=None)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--seed", type=int, default=None)
-    ap.add_argument("-i", "--infinity", type=float, default=10000.0)
+    ap.add_argument("-i", "--infinity", type=float, default=float("inf"),
+                    help="cost that marks a violated hard constraint; like `pydcop solve -i` it defaults to inf "
+                         "(commands/solve.py:315-324: the help text there says 10 000, the default is float('inf'))")
     ap.add_argument("--no-assignment", action="store_true",
                     help="omit the assignment from the output (10^6 variables)")
     ap.add_argument("--save", metavar="FILE", help="also write the instance as a binary container")

@@ -50,7 +50,7 @@ def test_pydcop_solve_maxsum_gpu_real_engine_under_the_reference_orchestrator(tm
     want = {n: d.values_of(i)[int(o.value[i])] for i, n in enumerate(d.var_names)}
     assert res["assignment"] == want
     from pydcop_b200 import solve as S
-    viol, cost = S.solution_cost(d, o.value, 10000)     # the CLI's default `-i 10000` (commands/solve.py)
+    viol, cost = S.solution_cost(d, o.value)     # the CLI's default `-i` is float("inf") (commands/solve.py:315-324)
     assert res["violation"] == viol and res["cost"] == pytest.approx(cost)
 
 

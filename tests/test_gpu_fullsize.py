@@ -72,3 +72,69 @@ def test_dsa_100k_vars_d20_exact_vs_oracle():
         o.step()
         eng.step()
         assert np.array_equal(eng.values(), o.val), k
+
+
+def _assert_state_equals_oracle(eng, o):
+    q, r = eng.messages()
+    assert np.array_equal(q, o.q.astype(np.float64)), "q"
+    assert np.array_equal(r, o.r.astype(np.float64)), "r"
+    val, cost = eng.values()
+    assert np.array_equal(val, o.value), "value"
+    assert np.array_equal(cost, o.value_cost.astype(np.float64)), "value_cost"
+    fl = eng.flags()
+    assert np.array_equal(fl["q_sent"], o.q_sent) and np.array_equal(fl["r_sent"], o.r_sent), "sent"
+
+
+def test_c3_ising_1024x1024_full_size_bit_exact_vs_oracle():
+    """BASELINE configs[2] at its full size (1 048 576 variables, d=2, 2 097 152 binary + 1 048 576 unary factors,
+    E = 5 242 880): three cycles, every message / send decision / value against the CPU oracle."""
+    from pydcop_b200 import MaxSumEngine, build_layout
+    from pydcop_b200.generators import config_c3
+    inst = config_c3(seed=0)
+    L = build_layout(**inst)
+    assert L.n_vars == 1024 * 1024 and L.n_edges == 5 * 1024 * 1024
+    o = orc.MaxSumOracle(oracle_instance(inst, L), np.float32).init().step(3)
+    eng = MaxSumEngine(L, precision="f32").init().step(3)
+    _assert_state_equals_oracle(eng, o)
+
+
+def test_c5_arity3_50k_d8_full_size_bit_exact_vs_oracle():
+    """BASELINE configs[4] at its full size (50 000 ternary factors over d=8: 512-entry tables)."""
+    from pydcop_b200 import MaxSumEngine, build_layout
+    from pydcop_b200.generators import config_c5
+    inst = config_c5(seed=0)
+    L = build_layout(**inst)
+    assert L.n_factors == 50_000 and L.n_edges == 150_000
+    o = orc.MaxSumOracle(oracle_instance(inst, L), np.float32).init().step(4)
+    eng = MaxSumEngine(L, precision="f32").init().step(4)
+    _assert_state_equals_oracle(eng, o)
+
+
+def test_target_1m_vars_d10_full_size_bit_exact_vs_oracle():
+    """The north-star instance (1M variables, d=10, 2M binary factors) for two cycles."""
+    from pydcop_b200 import MaxSumEngine, build_layout
+    from pydcop_b200.generators import config_target
+    inst = config_target(seed=0)
+    L = build_layout(**inst)
+    assert L.n_vars == 1_000_000 and L.n_edges == 4_000_000
+    o = orc.MaxSumOracle(oracle_instance(inst, L), np.float32).init().step(2)
+    eng = MaxSumEngine(L, precision="f32").init().step(2)
+    _assert_state_equals_oracle(eng, o)
+
+
+def test_c4_dsa_1m_vars_d20_full_size_exact_vs_oracle():
+    """BASELINE configs[3] at its full size (1M variables, d=20, 3M binary constraints): two DSA-B cycles."""
+    from pydcop_b200 import DsaEngine, build_layout
+    from pydcop_b200.generators import config_c4
+    inst = config_c4(seed=0)
+    L = build_layout(**inst)
+    assert L.n_vars == 1_000_000 and L.n_factors == 3_000_000
+    o = orc.DsaOracle(oracle_instance(inst, L), np.float32, seed=1).init()
+    eng = DsaEngine(L, precision="f32", seed=1).init()
+    assert np.array_equal(eng.values(), o.val)
+    for k in range(2):
+        o.step()
+        eng.step()
+        assert np.array_equal(eng.values(), o.val), k
+    moved = int((eng.values() != DsaEngine(L, precision="f32", seed=1).init().values()).sum())
+    assert moved > 100_000

@@ -133,8 +133,9 @@ def test_infinity_counts_as_violation():
             "constraints:\n  ne: {type: intention, function: 10000 if a == b else 0}\n"
             "  pa: {type: intention, function: 10000 if a == 0 else 1}\n")
     d = ingest.loads_yaml(text)
-    assert S.solution_cost(d, [0, 0]) == (2, 0.0)
-    assert S.solution_cost(d, [1, 0]) == (0, 1.0)
+    assert S.solution_cost(d, [0, 0], infinity=10000) == (2, 0.0)
+    assert S.solution_cost(d, [1, 0], infinity=10000) == (0, 1.0)
+    assert S.solution_cost(d, [0, 0]) == (0, 20000.0)         # `pydcop solve` default: -i inf
     assert S.solution_cost(d, [1, 1], infinity=10000) == (1, 1.0)
     assert S.solution_cost(d, [0, 0], infinity=float("inf")) == (0, 20000.0)
 
