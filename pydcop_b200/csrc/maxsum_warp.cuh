@@ -169,12 +169,17 @@ k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__
   }
   __syncwarp();
 
+  // A warp owns a CONTIGUOUS run of tiles: its descriptors are adjacent (4 per 128-byte line: after the first
+  // miss they come from L1, the strided assignment of the first version paid an L2 / DRAM round trip per
+  // descriptor on the critical path of every trip, 18 % of the stall samples) and so are its q / unary rows.
   const int gw = (int)blockIdx.x * FG_V2FW_WARPS + wib;       // global warp id
   const int nw = (int)gridDim.x * FG_V2FW_WARPS;
+  const int per = (n_tiles + nw - 1) / nw;
+  const int t_begin = min(gw * per, n_tiles), t_end = min(t_begin + per, n_tiles);
   // first half of the descriptor of my k-th tile: (slot0, pack, qoff, uoff); pack == 0: no such tile
   auto desc_a = [&](int k) -> int4 {
-    const int t = gw + k * nw;
-    return t < n_tiles ? tiles[2 * t] : make_int4(0, 0, 0, 0);
+    const int t = t_begin + k;
+    return t < t_end ? __ldg(&tiles[2 * t]) : make_int4(0, 0, 0, 0);
   };
   auto load_roff = [&](const int4 &a) -> OffT {
     return lane < (a.y >> 16) ? slot_roff[a.x + lane] : (OffT)0;
@@ -228,10 +233,10 @@ k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__
 
 #pragma unroll 1
   for (int k = 0;; ++k) {
-    const int t_idx = gw + k * nw;
-    if (t_idx >= n_tiles) break;
-    const int4 a = tiles[2 * t_idx];
-    const int4 b = tiles[2 * t_idx + 1];
+    const int t_idx = t_begin + k;
+    if (t_idx >= t_end) break;
+    const int4 a = __ldg(&tiles[2 * t_idx]);
+    const int4 b = __ldg(&tiles[2 * t_idx + 1]);
     const int s = k % NS;
     // tile k+NS-1 goes into the stage tile k-1 held: its bulk store must have finished READING it
     if (lane == 0) tma_store_wait_read();
@@ -463,9 +468,10 @@ struct F2VWarpCfg {
   static constexpr int PIECES = D / VR;
   static constexpr int V2_BYTES = fg_gcd(16, 2 * D * (int)sizeof(T));   // a pair of rows / a factor's 2 message rows
   static constexpr int V2 = V2_BYTES / (int)sizeof(T);
-  static constexpr int STAGE = NF * S + 2 * NF * 2 * D;              // tab | rt (in/out) | qt   (elements)
+  static constexpr int STAGE = NF * S + 2 * NF * 2 * D;              // tab | rt (previous r rows) | qt   (elements)
+  static constexpr int OUT = NF * 2 * D;                             // produced r rows, double-buffered per warp
   static constexpr int NS = NS_;
-  static constexpr size_t WARP_SMEM = (size_t)NS * STAGE * sizeof(T);
+  static constexpr size_t WARP_SMEM = (size_t)(NS * STAGE + 2 * OUT) * sizeof(T);
   static constexpr size_t smem_for(int w) { return (size_t)w * WARP_SMEM + (size_t)w * NS * sizeof(uint64_t) + 16; }
   // warps per CTA: the CTA is only a container of independent warps
   static constexpr int WARPS = smem_for(2) <= FG_SMEM_LIMIT ? 2 : (smem_for(1) <= FG_SMEM_LIMIT ? 1 : 0);
@@ -551,7 +557,11 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 
   const T lam = (T)p.damping, oml = (T)p.one_minus_damping, stab = (T)p.stability;
   const T init = MX ? -Inf<T>::pos() : Inf<T>::pos();
-  const int fl = lane >> 1, h = lane & 1;
+  // lane -> (factor, half): the 16 lanes of a half-warp walk 16 different factors, whose stride (D*D elements = an
+  // odd number of 16-byte units for D = 6, 10) spreads a quarter-warp's 128-bit reads over all 32 banks; the first
+  // mapping (half in the low lane bit) had 43 % conflict wavefronts.  The partner of a lane is lane ^ 16.
+  const int fl = lane & 15, h = lane >> 4;
+  T *out0 = stage0 + NS * C::STAGE;
 
   // prologue: tiles 0 .. NS-2 in flight, gather offsets of tile NS-1 and counters of tile 0 on their way
 #pragma unroll 1
@@ -562,8 +572,9 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
 #pragma unroll 1
   for (int k = 0; k < n_my; ++k) {
     const int s = k % NS;
-    // tile k+NS-1 goes into the stage tile k-1 held: its bulk store must have finished reading it
-    if (lane == 0) tma_store_wait_read();
+    // tile k+NS-1 goes into the stage tile k-1 held (all lanes are past its reads: they met at the __syncwarp
+    // before its store); the OUTPUT buffer of this trip was last used by tile k-2: at most one store pending
+    if (lane == 0) tma_store_wait_read1();
     __syncwarp();
     issue(k + NS - 1, qo_next);
     const OffT qo_n2 = load_qo(k + NS);
@@ -578,8 +589,9 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     T *rt = tab + NF * S;
     const T *qt = rt + NF * R;
     const bool act = fl < nf;
-    const uint8_t cnt_other = (uint8_t)__shfl_xor_sync(0xffffffffu, (unsigned)cnt, 1);
-    uint8_t c0 = h == 0 ? cnt : cnt_other, c1 = h == 0 ? cnt_other : cnt;
+    // counters were loaded lane = edge index (2 f + j): fetch both edges of my factor
+    uint8_t c0 = (uint8_t)__shfl_sync(0xffffffffu, (unsigned)cnt, 2 * fl);
+    uint8_t c1 = (uint8_t)__shfl_sync(0xffffffffu, (unsigned)cnt, 2 * fl + 1);
     // cc / pp: [0, HD) = my values of the message towards position 0 (at my ROW indices), [HD, 2 HD) = my
     // half of the message towards position 1
     T cc[2 * HD], pp[2 * HD];
@@ -647,7 +659,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     for (int i = 0; i < HD; ++i) {
       const T mine = h == 0 ? part[i] : part[HD + i];
       const T give = h == 0 ? part[HD + i] : part[i];
-      const T got = __shfl_xor_sync(0xffffffffu, give, 1);
+      const T got = __shfl_xor_sync(0xffffffffu, give, 16);
       cc[HD + i] = opt2<MX>(mine, got);
     }
     bool m0 = false, m1 = false;
@@ -672,17 +684,18 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
       }
     }
     const unsigned mm = (m0 ? 1u : 0u) | (m1 ? 2u : 0u);
-    const unsigned mo = __shfl_xor_sync(0xffffffffu, mm, 1);
+    const unsigned mo = __shfl_xor_sync(0xffffffffu, mm, 16);
+    T *ot = out0 + (k & 1) * C::OUT;   // the bulk store of tile k-2 has finished reading it (waited above: <= 1 pending)
     if (act) {
       const bool s0 = gate_decide((mm & mo & 1u) != 0, c0);
       const bool s1 = gate_decide((mm & mo & 2u) != 0, c1);
 #pragma unroll
       for (int i = 0; i < HD; ++i) {
         const int x0 = h == 0 ? f2vw_row<D>(0, i) : f2vw_row<D>(1, i);
-        rt[fl * R + x0] = s0 ? cc[i] : pp[i];
-        rt[fl * R + D + h * HD + i] = s1 ? cc[HD + i] : pp[HD + i];
+        ot[fl * R + x0] = s0 ? cc[i] : pp[i];
+        ot[fl * R + D + h * HD + i] = s1 ? cc[HD + i] : pp[HD + i];
       }
-      const int e = c.first_edge + f0 * 2 + lane;   // edge (f, j = h)
+      const int e = c.first_edge + f0 * 2 + 2 * fl + h;   // edge (f, j = h)
       r_cnt[e] = h == 0 ? c0 : c1;
       if (r_sent) r_sent[e] = (h == 0 ? s0 : s1) ? 1 : 0;
     }
@@ -692,12 +705,12 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_1d(gout, rt, ob);
+        tma_store_1d(gout, ot, ob);
         tma_store_commit();
       }
     } else {
       __syncwarp();
-      for (int i = lane; i < nf * R; i += 32) gout[i] = rt[i];
+      for (int i = lane; i < nf * R; i += 32) gout[i] = ot[i];
       __syncwarp();
     }
     qo_next = qo_n2;

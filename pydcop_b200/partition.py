@@ -57,27 +57,37 @@ def block_owner(n_vars: int, world: int) -> np.ndarray:
 
 def _match(A, w, max_w, rng, rounds=3):
     """Heavy-edge handshake matching: every unmatched vertex proposes to its heaviest unmatched
-    neighbour (random tie break); mutual proposals are matched.  Returns coarse ids."""
+    neighbour (random tie break); mutual proposals are matched.  Returns coarse ids.
+    Linear in the number of edges per round: the best neighbour of a row is a segmented maximum over the
+    CSR entries (np.maximum.reduceat), not a sort."""
     import scipy.sparse as sp
+    A = A.tocsr()
     n = A.shape[0]
+    indptr, indices, data = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data
+    deg = np.diff(indptr)
+    row = np.repeat(np.arange(n, dtype=np.int64), deg)
+    nonempty = np.nonzero(deg > 0)[0]
     mate = np.full(n, -1, dtype=np.int64)
+    wsum_ok = (w[row] + w[indices]) <= max_w
     for _ in range(rounds):
         free = mate < 0
-        if free.sum() < 2:
+        if free.sum() < 2 or not len(indices):
             break
         # restrict to edges between free vertices whose merged weight stays bounded
-        B = A.tocoo()
-        ok = free[B.row] & free[B.col] & (w[B.row] + w[B.col] <= max_w)
+        ok = free[row] & free[indices] & wsum_ok
         if not ok.any():
             break
-        r, c = B.row[ok], B.col[ok]
-        score = B.data[ok] + rng.random(ok.sum()) * 0.5          # heavy edge first, random ties
-        order = np.lexsort((score, r))                             # last entry of each row = best
-        r_s, c_s = r[order], c[order]
-        last = np.ones(len(r_s), dtype=bool)
-        last[:-1] = r_s[1:] != r_s[:-1]
+        score = np.where(ok, data + rng.random(len(data)) * 0.5, -1.0)     # heavy edge first, random ties
+        rowmax = np.full(n, -1.0)
+        rowmax[nonempty] = np.maximum.reduceat(score, indptr[:-1][nonempty])
+        pos = np.flatnonzero(ok & (score == rowmax[row]))                    # sorted by row
+        if not len(pos):
+            break
+        r = row[pos]
+        first = np.ones(len(pos), dtype=bool)
+        first[1:] = r[1:] != r[:-1]
         prop = np.full(n, -1, dtype=np.int64)
-        prop[r_s[last]] = c_s[last]
+        prop[r[first]] = indices[pos[first]]
         v = np.nonzero(prop >= 0)[0]
         mutual = v[prop[prop[v]] == v]
         mate[mutual] = prop[mutual]
