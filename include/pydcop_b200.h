@@ -12,8 +12,8 @@
  *   - plain C, opaque handles, int return codes (0 = FG_OK), no exceptions, no torch types;
  *   - every `dev_*` pointer is CALLER-OWNED DEVICE memory (the Python host passes
  *     torch.Tensor.data_ptr()); the only device memory the library owns is the DSA handle's copy
- *     of the class table (a few hundred bytes) and a MaxSum handle's tile descriptors of the variable
- *     side (32 bytes per 32 slots); a MaxSum handle also owns one side stream + 2 events;
+ *     of the class table (a few hundred bytes) and a MaxSum handle's class table of the variable side
+ *     (48 bytes per (domain, degree) class); a MaxSum handle also owns one side stream + 2 events;
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
  *   - all calls are asynchronous on `stream`; the caller synchronises;
  *   - value type T is float (precision = FG_F32) or double (FG_F64) for every cost/message array;
@@ -237,6 +237,11 @@ typedef struct {
   int32_t mode_max, variant;     /* FG_DSA_* */
   int32_t stop_cycle;            /* 0 = never (dsa.py:134,352) */
   uint64_t seed;
+  /* A-DSA (pydcop/algorithms/adsa.py:344-377): non-NULL = the variables' own costs T[sum dom] (internal variable
+   * order, row of v at dev_unary_off[v]) are added to every CANDIDATE's cost; the current cost (adsa.py:262) and
+   * DSA itself (the variable-cost branch of find_optimal is dead code, relations.py:1630) do not use them. */
+  const void *dev_var_cost;
+  const int64_t *dev_unary_off;  /* [n_vars+1] */
 } fg_dsa_desc_t;
 
 typedef struct fg_dsa *fg_dsa_t;

@@ -294,11 +294,13 @@ static REAL FN(con_value)(const fg_t *g, const REAL *tables, const int32_t *val,
 /* One evaluate_cycle (dsa.py:320-357) for every variable with >=1 neighbour.
  * variant: 0 A, 1 B, 2 C.  prob[v] is the per-variable threshold (p_mode, dsa.py:257-263).
  * edge_fac[e] = factor owning edge e.  has_nbr[v] = variable has at least one neighbour. */
+/* var_cost != NULL: A-DSA (adsa.py:344-377 find_best_values adds the variable's own cost to every candidate;
+ * current_cost, adsa.py:262, does not).  NULL: DSA (the variable-cost branch of find_optimal is dead code). */
 void FN(dsa_oracle_step)(const fg_t *g, const REAL *tables, const int32_t *edge_fac,
                          const uint8_t *has_nbr, const REAL *con_opt, const double *prob,
                          int mode_max, int variant, uint64_t seed, uint32_t cycle,
                          const int32_t *var_id, const int32_t *val, int32_t *val_next,
-                         REAL *val_cost) {
+                         REAL *val_cost, const REAL *var_cost) {
 #pragma omp parallel
   {
     REAL cost[MAX_DOM];
@@ -320,6 +322,7 @@ void FN(dsa_oracle_step)(const fg_t *g, const REAL *tables, const int32_t *edge_
           c += FN(con_value)(g, tables, val, f, e - g->factor_ptr[f], x);
         }
         cost[x] = c;
+        if (var_cost) c += var_cost[g->unary_off[v] + x];
         if (c == best_cost) {
           best[nbest++] = x;
         } else if (mode_max ? (c > best_cost) : (c < best_cost)) {

@@ -140,14 +140,16 @@ class DsaOracle(_Graph):
     """Lock-step DSA with injected Philox draws (oracle/philox.py)."""
 
     def __init__(self, inst, dtype=np.float64, mode="min", probability=0.7, p_mode="fixed",
-                 variant="B", stop_cycle=0, seed=0, var_id=None, frozen=None, **_ignored):
+                 variant="B", stop_cycle=0, seed=0, var_id=None, frozen=None, var_costs=False, **_ignored):
         """var_id: Philox counter per variable (default: its index); frozen: variables that are
-        never evaluated (ghosts of a partition, pydcop_b200/multigpu_dsa.py)."""
+        never evaluated (ghosts of a partition, pydcop_b200/multigpu_dsa.py); var_costs: A-DSA's
+        decision (adsa.py:344-377: candidates carry the variable's own cost, the current cost does not)."""
         if "var_edge" not in inst:  # DSA fixtures carry var_con (constraint ids), derive edges
             inst = dict(inst)
             inst["var_edge"] = var_con_to_edges(inst)
         super().__init__(inst, dtype)
         self.unary = np.ascontiguousarray(inst["unary"], dtype=np.float64)
+        self.var_cost = np.ascontiguousarray(inst["unary"], dtype=self.dtype) if var_costs else None
         self.mode_max = int(mode == "max")
         self.variant = VARIANTS[variant]
         self.stop_cycle = int(stop_cycle)
@@ -196,7 +198,8 @@ class DsaOracle(_Graph):
             C.byref(self.fg), _p(self.tables), _p(self.edge_fac), _p(self.has_nbr),
             _p(self.con_opt), _p(self.prob), self.mode_max, self.variant,
             C.c_uint64(self.seed), C.c_uint32(self.cycle), self._vid(), _p(self.val),
-            _p(self.val_next), _p(self.val_cost))
+            _p(self.val_next), _p(self.val_cost),
+            _p(self.var_cost) if self.var_cost is not None else C.c_void_p(0))
         return self
 
     def commit(self):

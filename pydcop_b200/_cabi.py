@@ -65,7 +65,7 @@ class FgDsaDesc(C.Structure):
                 ("dev_slot_opt", P), ("fast_dom", C.c_int32), ("reserved1", C.c_int32),
                 ("dev_value", P * 2), ("dev_value_cost", P),
                 ("mode_max", C.c_int32), ("variant", C.c_int32), ("stop_cycle", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("dev_var_cost", P), ("dev_unary_off", P)]
 
 
 class FgMgmDesc(C.Structure):

@@ -1,13 +1,15 @@
 // DSA fast path: every constraint binary over one domain size D (BASELINE config C4).
 // One thread per variable; per incident constraint it reads ONE contiguous row of D costs from the
 // table oriented towards the variable (the transposed copy for scope position 0), so the table
-// traffic is 4*D bytes per incidence instead of D strided sectors.
+// traffic is 4*D bytes per incidence instead of D strided sectors; rows are stored with the stride of
+// row_load.cuh::fg_row_stride so that a row never straddles a line it does not have to.
 #pragma once
 #include <vector>
 
 #include "common.cuh"
 #include "maxsum_fast.cuh"
 #include "philox.cuh"
+#include "row_load.cuh"
 
 template <typename T, int D>
 __global__ void __launch_bounds__(128)
@@ -16,8 +18,9 @@ k_dsa_step_bin(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t *_
                const T *__restrict__ tables_or, const uint8_t *__restrict__ has_nbr,
                const double *__restrict__ prob, const int32_t *__restrict__ var_id,
                const int32_t *__restrict__ val, int32_t *__restrict__ val_next, T *__restrict__ val_cost,
-               int mode_max, int variant, uint64_t seed, uint32_t cycle) {
-  constexpr int VR = V2FCfg<T, D>::VR;
+               int mode_max, int variant, uint64_t seed, uint32_t cycle, const T *__restrict__ var_cost,
+               const int64_t *__restrict__ unary_off) {
+  constexpr int RS = fg_row_stride<T, D>();   // rows on their own line slots
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vars) return;
   const int cur = val[v];
@@ -33,21 +36,29 @@ k_dsa_step_bin(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t *_
   const int s1 = var_ptr[v + 1];
   for (int s = var_ptr[v]; s < s1; ++s) {
     const int y = val[slot_nbr[s]];
-    const T *row = tables_or + slot_tab[s] + (int64_t)y * D;
+    const T *row = tables_or + slot_tab[s] + (int64_t)y * RS;
     T r[D];
-    ld_row<T, D, VR>(row, r);
+    fg_load_row_padded<T, D>(row, r);
 #pragma unroll
     for (int x = 0; x < D; ++x) cost[x] += r[x];  // assignment_cost, relations.py:1479-1532
     if (variant == FG_DSA_B && row[cur] != slot_opt[s]) violated = true;  // dsa.py:419-431
   }
+  // A-DSA (adsa.py:344-377): the candidates carry the variable's own cost, the current cost (adsa.py:262) does not
+  T cur_cost = (T)0;
+#pragma unroll
+  for (int x = 0; x < D; ++x)
+    if (x == cur) cur_cost = cost[x];
+  if (var_cost) {
+    const T *vc = var_cost + unary_off[v];
+#pragma unroll
+    for (int x = 0; x < D; ++x) cost[x] += vc[x];
+  }
   // find_optimal (relations.py:1594-1638)
   T best_cost = mode_max ? -Inf<T>::pos() : Inf<T>::pos();
   int nbest = 0;
-  T cur_cost = (T)0;
 #pragma unroll
   for (int x = 0; x < D; ++x) {
     const T c = cost[x];
-    if (x == cur) cur_cost = c;
     if (c == best_cost) ++nbest;
     else if (mode_max ? (c > best_cost) : (c < best_cost)) { best_cost = c; nbest = 1; }
   }
@@ -93,7 +104,8 @@ inline bool dsa_fast_step(const fg_dsa_desc_t &d, const std::vector<fg_class_t> 
     k_dsa_step_bin<T, n><<<blocks, 128, 0, st>>>(d.n_vars, d.dev_var_ptr, d.dev_slot_nbr, d.dev_slot_tab,   \
                                                  (const T *)d.dev_slot_opt, (const T *)d.dev_tables_or,     \
                                                  d.dev_has_nbr, d.dev_prob, d.dev_var_id, val, val_next,    \
-                                                 (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed, cycle); \
+                                                 (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed, cycle, \
+                                                 (const T *)d.dev_var_cost, d.dev_unary_off);               \
     ++launches;                                                                                            \
     return true;
     FG_FAST_DOMS(X)

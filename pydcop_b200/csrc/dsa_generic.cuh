@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(128)
 k_dsa_step_generic(DsaSide g, int n_vars, const T *__restrict__ tables,
                    const T *__restrict__ con_opt, const int32_t *__restrict__ val,
                    int32_t *__restrict__ val_next, T *__restrict__ val_cost, int mode_max,
-                   int variant, uint64_t seed, uint32_t cycle) {
+                   int variant, uint64_t seed, uint32_t cycle, const T *__restrict__ var_cost = nullptr,
+                   const int64_t *__restrict__ unary_off = nullptr) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vars) return;
   const int cur = val[v];
@@ -69,6 +70,12 @@ k_dsa_step_generic(DsaSide g, int n_vars, const T *__restrict__ tables,
     for (int x = 0; x < d; ++x) cost[x] += t[x * stride_j];  // assignment_cost, relations.py:1479
     if (variant == FG_DSA_B && t[cur * stride_j] != con_opt[c.first_factor + f]) violated = true;
   }
+  // A-DSA (adsa.py:344-377): the candidates carry the variable's own cost, the current cost (adsa.py:262) does not
+  const T cur_cost = cost[cur];
+  if (var_cost) {
+    const T *vc = var_cost + unary_off[v];
+    for (int x = 0; x < d; ++x) cost[x] += vc[x];
+  }
   // find_optimal (relations.py:1594-1638): all values whose cost == best, in domain order
   T best_cost = mode_max ? -Inf<T>::pos() : Inf<T>::pos();
   int nbest = 0;
@@ -77,7 +84,7 @@ k_dsa_step_generic(DsaSide g, int n_vars, const T *__restrict__ tables,
     if (c == best_cost) ++nbest;
     else if (mode_max ? (c > best_cost) : (c < best_cost)) { best_cost = c; nbest = 1; }
   }
-  const T delta = fg_abs<T>(cost[cur] - best_cost);
+  const T delta = fg_abs<T>(cur_cost - best_cost);
   bool attempt = false, drop_cur = false;
   if (delta > (T)0) {
     attempt = true;

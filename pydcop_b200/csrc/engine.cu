@@ -129,7 +129,7 @@ extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
-    if (h->warp.dev_tiles) cudaFree(h->warp.dev_tiles);
+    if (h->warp.dev_classes) cudaFree(h->warp.dev_classes);
   }
   delete h;
   return FG_OK;
@@ -234,7 +234,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
     } else {
       if (h->warp.v2f_on) {
         for (const WTileRange &rg : h->warp.v2f)
-          if (dispatch_v2f_warp<T>(h->warp.dev_tiles, rg, d, r_cur, q_cur, q_next, p, st)) ++h->launches;
+          if (dispatch_v2f_warp<T>(h->warp.dev_classes, rg, d, r_cur, q_cur, q_next, p, st)) ++h->launches;
       } else {
         for (size_t li = 0; li < h->fast.v2f.size(); ++li)
           if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
@@ -662,7 +662,8 @@ static int dsa_compute_t(fg_dsa *h, cudaStream_t st) {
   if (!dsa_fast_step<T>(h->d, h->classes, val, val_next, (uint32_t)h->cycle, st, h->launches)) {
     k_dsa_step_generic<T><<<blocks_for(d.n_vars, 128), 128, 0, st>>>(
         dsa_side(h), d.n_vars, (const T *)d.dev_tables, (const T *)d.dev_con_opt, val, val_next,
-        (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed, (uint32_t)h->cycle);
+        (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed, (uint32_t)h->cycle, (const T *)d.dev_var_cost,
+        d.dev_unary_off);
     ++h->launches;
   }
   CUDA_TRY(h, cudaGetLastError());

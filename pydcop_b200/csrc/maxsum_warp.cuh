@@ -6,8 +6,9 @@
 // utilisation at 1-2 warps per scheduler, DRAM at 12-40 %, profiles/r02_ncu_*_warp_v1.txt), so
 //   * add chains run as packed fp32x2 instructions (FADD2 / FMUL2) and optima as 3-input FMNMX3
 //     (packed.cuh) — every element still gets the correctly rounded IEEE operation of the scalar code;
-//   * min / max is a template parameter, tile descriptors are precomputed on the host, lane -> (variable,
-//     slot) uses a reciprocal from the descriptor.
+//   * min / max is a template parameter, tile descriptors are arithmetic from a per-class table staged in
+//     shared memory (no dependent global load on the critical path), lane -> (variable, slot) uses a
+//     reciprocal from that table.
 //
 //  k_v2f_warp<T,D,NS,MX>   variable -> factor (+ select_value).  A tile = nv variables of one (D, K) class
 //      = nv*K <= 32 consecutive slots, ONE SLOT PER LANE.  HBM side: the previous q rows and the unary
@@ -33,21 +34,48 @@
 // ------------------------------------------------------------------------------------------------
 // variable -> factor
 // ------------------------------------------------------------------------------------------------
-// one tile of the variable side (host-built, 32 bytes)
-struct WTileDesc {
-  int32_t slot0;   // first slot
-  int32_t pack;    // K | nv << 8 | nslots << 16
-  uint32_t qoff;   // element offset of the tile's q rows (slot order)
-  uint32_t uoff;   // element offset of the tile's unary rows
-  int32_t var0;    // first (internal) variable
-  int32_t kinv;    // ceil(65536 / K): lane / K == (lane * kinv) >> 16 for lane < 32
+// one class of the variable side as the kernel sees it (host-built, 48 bytes, staged in shared memory): tile t
+// of the launch belongs to the entry with tile_begin <= t < tile_end; everything of the tile is affine in it
+struct WClassEntry {
+  int32_t tile_begin, tile_end;
+  int32_t nv_tile;   // variables per tile (nv_tile * K <= 32)
+  int32_t K;         // degree
+  int32_t n_vars, first_slot, first_var;
+  int32_t kinv;      // ceil(65536 / K): lane / K == (lane * kinv) >> 16 for lane < 32
+  uint32_t q_base, unary_base;   // element offsets (the fast plans require 32-bit message offsets)
   int32_t pad0, pad1;
 };
-static_assert(sizeof(WTileDesc) == 32, "two 16-byte loads");
+static_assert(sizeof(WClassEntry) == 48, "three 16-byte loads");
+#define FG_WARP_MAX_CLASSES 40   // degrees 1..16 x (own | other tags) of one domain size
 
-struct WTileRange {   // one launch: the tiles of every regular variable class of one domain size
-  int32_t dom, first, count;
+struct WTileRange {   // one launch: the regular variable classes of one domain size
+  int32_t dom, first, count;   // entries [first, first + count) of the plan's class table
+  int32_t n_tiles;
 };
+
+struct WTile {
+  int valid, K, nv, nslots, slot0, var0, kinv;
+  uint32_t qoff, uoff;
+};
+
+// tile t; `ci` is a forward-only cursor of the calling ROLE (a warp visits its tiles in ascending order)
+__device__ __forceinline__ WTile wtile_at(const WClassEntry *__restrict__ cls, int n_tiles, int t, int D, int &ci) {
+  WTile o;
+  o.valid = t < n_tiles;
+  if (!o.valid) { o.K = 1; o.nv = o.nslots = o.slot0 = o.var0 = 0; o.kinv = 65536; o.qoff = o.uoff = 0; return o; }
+  while (t >= cls[ci].tile_end) ++ci;
+  const WClassEntry &e = cls[ci];
+  const int v0 = (t - e.tile_begin) * e.nv_tile;
+  o.K = e.K;
+  o.kinv = e.kinv;
+  o.nv = min(e.nv_tile, e.n_vars - v0);
+  o.nslots = o.nv * e.K;
+  o.slot0 = e.first_slot + v0 * e.K;
+  o.var0 = e.first_var + v0;
+  o.qoff = e.q_base + (uint32_t)(v0 * e.K * D);
+  o.uoff = e.unary_base + (uint32_t)(v0 * D);
+  return o;
+}
 
 #define FG_WARP_K_SWITCH(K_, CALL)                 \
   switch (K_) {                                    \
@@ -146,13 +174,14 @@ struct V2FWarpCfg {
   static constexpr int STAGE = 3 * 32 * D;                  // rrow | qio | un   (elements)
   static constexpr int NS = NS_;
   static constexpr size_t WARP_SMEM = (size_t)NS * STAGE * sizeof(T);
-  static constexpr size_t SMEM = FG_V2FW_WARPS * WARP_SMEM + FG_V2FW_WARPS * NS * sizeof(uint64_t) + 16;
+  static constexpr size_t SMEM = FG_V2FW_WARPS * WARP_SMEM + FG_V2FW_WARPS * NS * sizeof(uint64_t) +
+                                 FG_WARP_MAX_CLASSES * sizeof(WClassEntry) + 16;
   static constexpr bool OK = SMEM <= FG_SMEM_LIMIT;
 };
 
 template <typename T, int D, int NS_, bool MX, typename OffT>
 __global__ void __launch_bounds__(FG_V2FW_WARPS * 32, FG_V2FW_MINB)
-k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__ slot_roff,
+k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, const OffT *__restrict__ slot_roff,
            const T *__restrict__ unary, const T *__restrict__ r_cur, const T *__restrict__ q_cur,
            T *__restrict__ q_next, uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent,
            int32_t *__restrict__ value, T *__restrict__ value_cost, MaxSumParams p) {
@@ -162,36 +191,36 @@ k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   T *stage0 = reinterpret_cast<T *>(smem_raw + (size_t)wib * C::WARP_SMEM);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FG_V2FW_WARPS * C::WARP_SMEM) + NS * wib;
+  // the class table of the launch, staged once per CTA: tile descriptors are arithmetic from it, so no trip of
+  // the loop waits for a descriptor to come from L2 (the first versions did: 18 % of the stall samples)
+  WClassEntry *cls = reinterpret_cast<WClassEntry *>(smem_raw + (size_t)FG_V2FW_WARPS * C::WARP_SMEM +
+                                                     FG_V2FW_WARPS * NS * sizeof(uint64_t));
+  for (int i = threadIdx.x; i < n_classes * (int)(sizeof(WClassEntry) / 16); i += blockDim.x)
+    reinterpret_cast<int4 *>(cls)[i] = reinterpret_cast<const int4 *>(classes)[i];
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
-  __syncwarp();
+  __syncthreads();   // the only block-wide barrier: the class table is in place
 
-  // A warp owns a CONTIGUOUS run of tiles: its descriptors are adjacent (4 per 128-byte line: after the first
-  // miss they come from L1, the strided assignment of the first version paid an L2 / DRAM round trip per
-  // descriptor on the critical path of every trip, 18 % of the stall samples) and so are its q / unary rows.
+  // tiles are strided over the warps (t = gw + k * nw): the costly high-degree tiles come first in the order and
+  // spread evenly (a contiguous run per warp left the first CTAs with all of them: 2x slower, r02 call 8)
   const int gw = (int)blockIdx.x * FG_V2FW_WARPS + wib;       // global warp id
   const int nw = (int)gridDim.x * FG_V2FW_WARPS;
-  const int per = (n_tiles + nw - 1) / nw;
-  const int t_begin = min(gw * per, n_tiles), t_end = min(t_begin + per, n_tiles);
-  // first half of the descriptor of my k-th tile: (slot0, pack, qoff, uoff); pack == 0: no such tile
-  auto desc_a = [&](int k) -> int4 {
-    const int t = t_begin + k;
-    return t < t_end ? __ldg(&tiles[2 * t]) : make_int4(0, 0, 0, 0);
+  int cur_c = 0, cur_i = 0, cur_l = 0, cur_n = 0;   // one forward-only cursor per role
+  auto tile_at = [&](int k, int &cursor) { return wtile_at(cls, n_tiles, gw + k * nw, D, cursor); };
+  auto load_roff = [&](const WTile &t) -> OffT {
+    return lane < t.nslots ? slot_roff[t.slot0 + lane] : (OffT)0;
   };
-  auto load_roff = [&](const int4 &a) -> OffT {
-    return lane < (a.y >> 16) ? slot_roff[a.x + lane] : (OffT)0;
-  };
-  auto load_cnt = [&](const int4 &a) -> uint8_t {
-    return lane < (a.y >> 16) ? q_cnt[a.x + lane] : (uint8_t)0;
+  auto load_cnt = [&](const WTile &t) -> uint8_t {
+    return lane < t.nslots ? q_cnt[t.slot0 + lane] : (uint8_t)0;
   };
   // start every load of a tile into stage s (all lanes)
-  auto issue = [&](int s, const int4 &a, OffT roff) {
-    if (a.y) {
-      const int nslots = a.y >> 16, nv = (a.y >> 8) & 0xff;
-      const uint32_t qoff = (uint32_t)a.z, uoff = (uint32_t)a.w;
+  auto issue = [&](int s, const WTile &t, OffT roff) {
+    if (t.valid) {
+      const int nslots = t.nslots, nv = t.nv;
+      const uint32_t qoff = t.qoff, uoff = t.uoff;
       T *rrow = stage0 + s * C::STAGE;
       T *qio = rrow + 32 * D;
       T *un = qio + 32 * D;
@@ -225,36 +254,35 @@ k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__
   // prologue: tiles 0 .. NS-2 in flight, gather indices of tile NS-1 and counters of tile 0 on their way
 #pragma unroll 1
   for (int k = 0; k < NS - 1; ++k) {
-    const int4 a = desc_a(k);
-    issue(k, a, load_roff(a));
+    const WTile t = tile_at(k, cur_i);
+    issue(k, t, load_roff(t));
+    cur_l = cur_i;
   }
-  OffT roff_n = load_roff(desc_a(NS - 1));
-  uint8_t cnt = load_cnt(desc_a(0));
+  OffT roff_n = load_roff(tile_at(NS - 1, cur_l));
+  uint8_t cnt = load_cnt(tile_at(0, cur_n));
 
 #pragma unroll 1
   for (int k = 0;; ++k) {
-    const int t_idx = t_begin + k;
-    if (t_idx >= t_end) break;
-    const int4 a = __ldg(&tiles[2 * t_idx]);
-    const int4 b = __ldg(&tiles[2 * t_idx + 1]);
+    const WTile t = tile_at(k, cur_c);
+    if (!t.valid) break;
     const int s = k % NS;
     // tile k+NS-1 goes into the stage tile k-1 held: its bulk store must have finished READING it
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
-    issue((k + NS - 1) % NS, desc_a(k + NS - 1), roff_n);
-    const OffT roff_n2 = load_roff(desc_a(k + NS));
-    const uint8_t cnt_n = load_cnt(desc_a(k + 1));
+    issue((k + NS - 1) % NS, tile_at(k + NS - 1, cur_i), roff_n);
+    const OffT roff_n2 = load_roff(tile_at(k + NS, cur_l));
+    const uint8_t cnt_n = load_cnt(tile_at(k + 1, cur_n));
     cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
     mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and so have its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
 
-    const int K = a.y & 0xff, nslots = a.y >> 16, slot0 = a.x;
-    const uint32_t qoff = (uint32_t)a.z;
+    const int K = t.K, nslots = t.nslots, slot0 = t.slot0;
+    const uint32_t qoff = t.qoff;
     T *rrow = stage0 + s * C::STAGE;
     T *qio = rrow + 32 * D;
     const T *un = qio + 32 * D;
     if (lane < nslots) {
-      const int i = (lane * b.y) >> 16, f = lane - i * K;
+      const int i = (lane * t.kinv) >> 16, f = lane - i * K;
       const T *col = rrow + i * K * D;
       const T *ur = un + i * D;
       T cand[D], prev[D];
@@ -293,8 +321,8 @@ k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__
       q_cnt[slot0 + lane] = c8;
       if (q_sent) q_sent[slot0 + lane] = sent ? 1 : 0;
       if (f == K - 1) {
-        value[b.x + i] = best;
-        value_cost[b.x + i] = best_c;
+        value[t.var0 + i] = best;
+        value_cost[t.var0 + i] = best_c;
       }
     }
     const uint32_t obytes = (uint32_t)(nslots * D) * (uint32_t)sizeof(T);
@@ -320,44 +348,48 @@ k_v2f_warp(const int4 *__restrict__ tiles, int n_tiles, const OffT *__restrict__
 // ------------------------------------------------------------------------------------------------
 // host side of the variable kernel
 // ------------------------------------------------------------------------------------------------
-// Tiles of the regular variable classes (degree 1..16, not ghosts) of domain size D, costly (high-degree)
+// Class entries of the regular variable classes (degree 1..16, not ghosts) of domain size D, costly (high-degree)
 // classes first.  nv per tile: as many variables as fit 32 lanes, rounded down to the number of rows that
-// keeps every tile's q / unary offsets 16-byte aligned (bulk copies) when possible.
-inline void v2fw_build_tiles(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<WTileDesc> &out) {
+// keeps every tile's q / unary offsets 16-byte aligned (bulk copies) when possible.  Returns the tile count.
+inline int v2fw_build_classes(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<WClassEntry> &out) {
   std::vector<fg_varclass_t> order;
   for (const fg_varclass_t &vc : vcs)
     if (vc.dom == D && vc.degree >= 1 && vc.degree <= 32 && vc.n_vars > 0 && !(vc.flags & FG_CLASS_GHOST)) order.push_back(vc);
   std::stable_sort(order.begin(), order.end(),
                    [](const fg_varclass_t &a, const fg_varclass_t &b) { return a.degree > b.degree; });
   const int unit = 16 / fg_gcd(16, D * (int)elem);  // rows per 16-byte multiple
+  int tiles = 0;
   for (const fg_varclass_t &vc : order) {
     const int K = vc.degree;
     int nv = 32 / K;
     if (nv >= unit) nv = nv / unit * unit;
-    for (int v0 = 0; v0 < vc.n_vars; v0 += nv) {
-      const int n = std::min(nv, vc.n_vars - v0);
-      WTileDesc t;
-      t.slot0 = vc.first_slot + v0 * K;
-      t.pack = K | (n << 8) | ((n * K) << 16);
-      t.qoff = (uint32_t)(vc.q_base + (int64_t)v0 * K * D);
-      t.uoff = (uint32_t)(vc.unary_base + (int64_t)v0 * D);
-      t.var0 = vc.first_var + v0;
-      t.kinv = (65536 + K - 1) / K;
-      t.pad0 = t.pad1 = 0;
-      out.push_back(t);
-    }
+    WClassEntry e;
+    e.tile_begin = tiles;
+    tiles += (vc.n_vars + nv - 1) / nv;
+    e.tile_end = tiles;
+    e.nv_tile = nv;
+    e.K = K;
+    e.n_vars = vc.n_vars;
+    e.first_slot = vc.first_slot;
+    e.first_var = vc.first_var;
+    e.kinv = (65536 + K - 1) / K;
+    e.q_base = (uint32_t)vc.q_base;
+    e.unary_base = (uint32_t)vc.unary_base;
+    e.pad0 = e.pad1 = 0;
+    out.push_back(e);
   }
+  return tiles;
 }
 
 struct MaxSumWarpPlan {
   std::vector<uint8_t> f2v;          // per factor class: warp kernel available (PYDCOP_B200_F2V != pipe)
   bool v2f_on = false;               // PYDCOP_B200_V2F != pipe
   std::vector<WTileRange> v2f;       // launches of the variable side
-  WTileDesc *dev_tiles = nullptr;    // library-owned: tile descriptors of every launch (32 bytes per tile)
+  WClassEntry *dev_classes = nullptr;   // library-owned: class table of every launch (48 bytes per class)
 };
 
 template <typename T, int D, int NS_, bool MX>
-inline bool launch_v2f_warp_ns(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
+inline bool launch_v2f_warp_ns(const WClassEntry *dev_classes, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
                                const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
   using C = V2FWarpCfg<T, D, NS_>;
   if constexpr (!C::OK) {
@@ -375,9 +407,9 @@ inline bool launch_v2f_warp_ns(const WTileDesc *dev_tiles, const WTileRange &rg,
       const int cap = fg_env_int("PYDCOP_B200_V2FW_CPS", 3);  // leaves room for the factor side (runs concurrently)
       if (per_sm > cap) per_sm = cap;
     }
-    const int need = (rg.count + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
+    const int need = (rg.n_tiles + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
     const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
-    kern<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(reinterpret_cast<const int4 *>(dev_tiles + rg.first), rg.count,
+    kern<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(dev_classes + rg.first, rg.count, rg.n_tiles,
                                                        d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
                                                        d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
     return true;
@@ -387,7 +419,7 @@ inline bool launch_v2f_warp_ns(const WTileDesc *dev_tiles, const WTileRange &rg,
 // pipeline depth: PYDCOP_B200_V2FW_NS = 2 | 3 | 4 stages per warp (default 2: 12 warps x 2 stages per SM measured
 // faster on C2 than 8 x 3, profiles/r02_call5_sweep.txt)
 template <typename T, int D>
-inline void launch_v2f_warp(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
+inline void launch_v2f_warp(const WClassEntry *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
                             const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
   static const int ns = fg_env_int("PYDCOP_B200_V2FW_NS", 2);
 #define FG_TRY(NS_)                                                                                              \
@@ -401,7 +433,7 @@ inline void launch_v2f_warp(const WTileDesc *dev_tiles, const WTileRange &rg, co
 }
 
 template <typename T>
-inline bool dispatch_v2f_warp(const WTileDesc *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
+inline bool dispatch_v2f_warp(const WClassEntry *dev_tiles, const WTileRange &rg, const fg_maxsum_desc_t &d, const T *r_cur,
                               const T *q_cur, T *q_next, const MaxSumParams &p, cudaStream_t st) {
   switch (rg.dom) {
 #define X(n) case n: launch_v2f_warp<T, n>(dev_tiles, rg, d, r_cur, q_cur, q_next, p, st); return true;
@@ -420,7 +452,7 @@ inline int maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varc
   plan.v2f_on = fast.off32 && !fg_fast_disabled() && !(e && e[0] == 'p');
   if (!plan.v2f_on) return FG_OK;
   const size_t elem = d.precision == FG_F64 ? 8 : 4;
-  std::vector<WTileDesc> all;
+  std::vector<WClassEntry> all;
   std::vector<int> doms;
   for (const fg_varclass_t &vc : vcs)
     if (!(vc.flags & FG_CLASS_GHOST) && vc.degree >= 1 && fg_fast_dom(vc.dom) &&
@@ -430,13 +462,14 @@ inline int maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varc
     WTileRange rg;
     rg.dom = D;
     rg.first = (int32_t)all.size();
-    v2fw_build_tiles(vcs, D, elem, all);
+    rg.n_tiles = v2fw_build_classes(vcs, D, elem, all);
     rg.count = (int32_t)all.size() - rg.first;
+    if (rg.count > FG_WARP_MAX_CLASSES) { all.resize(rg.first); continue; }   // (cannot happen: <= 16 degrees x 2 tags)
     if (rg.count) plan.v2f.push_back(rg);
   }
   if (!all.empty()) {
-    if (cudaMalloc(reinterpret_cast<void **>(&plan.dev_tiles), all.size() * sizeof(WTileDesc)) != cudaSuccess) return FG_ERR_CUDA;
-    if (cudaMemcpy(plan.dev_tiles, all.data(), all.size() * sizeof(WTileDesc), cudaMemcpyHostToDevice) != cudaSuccess)
+    if (cudaMalloc(reinterpret_cast<void **>(&plan.dev_classes), all.size() * sizeof(WClassEntry)) != cudaSuccess) return FG_ERR_CUDA;
+    if (cudaMemcpy(plan.dev_classes, all.data(), all.size() * sizeof(WClassEntry), cudaMemcpyHostToDevice) != cudaSuccess)
       return FG_ERR_CUDA;
   }
   return FG_OK;

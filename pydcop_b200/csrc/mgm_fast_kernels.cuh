@@ -43,7 +43,7 @@ k_mgm_gain_bin(MgmSide g, int n_vars, const int32_t *__restrict__ slot_nbr, cons
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       T r[D];
-      fg_load_row<T, D>(tables_or + tb[i] + (int64_t)y[i] * D, r);
+      fg_load_row_padded<T, D>(tables_or + tb[i] + (int64_t)y[i] * fg_row_stride<T, D>(), r);
       const bool first = (s + i == s0);   // ((f1 + f2) + f3)...: the first constraint starts the sum (mgm.py:443)
 #pragma unroll
       for (int x = 0; x < D; ++x) {

@@ -282,11 +282,23 @@ class MaxSumEngine(_EngineBase):
                 L.vars_to_canonical(self.value_cost[:n].double().cpu().numpy()))
 
 
+def dsa_row_stride(d: int, elem: int) -> int:
+    """Elements between two rows of an oriented table: the next power of two >= d, whole 128-byte lines above 128
+    bytes (csrc/row_load.cuh::fg_row_stride, the same rule): the one row a slot reads per cycle then costs one or two
+    whole DRAM lines."""
+    p2 = 1
+    while p2 < d:
+        p2 *= 2
+    line = 128 // elem
+    return -(-d // line) * line if p2 * elem > 128 else p2
+
+
 def dsa_fast_arrays(layout: FactorGraphLayout, tables: torch.Tensor, mode="min"):
     """Arrays of the DSA fast path, or None when the instance does not qualify (every constraint
     binary over ONE domain size).  Per slot (variable v, incident constraint c, neighbour u) the
     table of c is read ORIENTED so that row y = value of u is contiguous over v's values: slots at
-    scope position 1 read the table as stored, slots at position 0 read a transposed copy.
+    scope position 1 read the table as stored, slots at position 0 read a transposed copy; rows are
+    stored with stride dsa_row_stride (each row on its own cache-line slot).
     Returns (tables_or, slot_tab, slot_nbr, slot_opt, D) as tensors on `tables.device`."""
     L = layout
     if not (len(L.classes) == 1 and L.classes[0].arity == 2 and L.classes[0].dom[0] == L.classes[0].dom[1]
@@ -298,12 +310,17 @@ def dsa_fast_arrays(layout: FactorGraphLayout, tables: torch.Tensor, mode="min")
     S = D * D
     nF = c0.n_factors
     t = tables[c0.table_base:c0.table_base + nF * S].view(nF, D, D)
-    tables_or = torch.cat([t.reshape(-1), t.transpose(1, 2).contiguous().reshape(-1)])
+    RS = dsa_row_stride(D, t.element_size())
+    SP = D * RS                                     # elements per padded table
+    tables_or = torch.zeros(2 * nF * SP, dtype=t.dtype, device=dev)
+    tv = tables_or.view(2, nF, D, RS)
+    tv[0, :, :, :D] = t
+    tv[1, :, :, :D] = t.transpose(1, 2)
     opt = (t.reshape(nF, S).max(dim=1).values if mode == "max" else t.reshape(nF, S).min(dim=1).values)
     e = L.slot_edge.astype(np.int64) - c0.first_edge
     f, j = e // 2, e % 2
     # position 1 (me second): T[y][x] is already row-contiguous; position 0: transposed copy
-    slot_tab = np.where(j == 1, f * S, nF * S + f * S).astype(np.int64)
+    slot_tab = np.where(j == 1, f * SP, nF * SP + f * SP).astype(np.int64)
     slot_nbr = L.edge_var[c0.first_edge + f * 2 + (1 - j)].astype(np.int32)
     return (tables_or, torch.from_numpy(np.ascontiguousarray(slot_tab)).to(dev),
             torch.from_numpy(np.ascontiguousarray(slot_nbr)).to(dev),
@@ -315,8 +332,10 @@ class DsaEngine(_EngineBase):
 
     def __init__(self, layout: FactorGraphLayout, device=None, precision="f32", mode="min",
                  probability=0.7, p_mode="fixed", variant="B", stop_cycle=0, seed=0,
-                 isolated_value=None, var_global_id=None, frozen=None):
-        """var_global_id / frozen (canonical order) serve the multi-GPU partition
+                 isolated_value=None, var_global_id=None, frozen=None, var_costs=False):
+        """var_costs: A-DSA's decision (pydcop/algorithms/adsa.py:344-377: every candidate value carries the
+        variable's own cost, the current cost does not); False: DSA.
+        var_global_id / frozen (canonical order) serve the multi-GPU partition
         (pydcop_b200/multigpu_dsa.py): the Philox counter of each variable when the layout is a
         shard of a larger problem, and the ghost variables whose value is only copied through."""
         self.lib = _cabi.load()
@@ -369,6 +388,8 @@ class DsaEngine(_EngineBase):
             self.value = [self._dev(isolated_value, torch.int32) if L.n_vars else z(1, torch.int32),
                           z(L.n_vars, torch.int32)]
             self.value_cost = z(L.n_vars, tdt)
+            self.var_cost = self._dev(L.unary, tdt) if var_costs else None
+            self.unary_off = self._dev(L.unary_off, torch.int64) if var_costs else None
         # fast path: every constraint binary over ONE domain size -> oriented tables, one contiguous
         # row per incidence (transposed copy for scope position 0)
         self.tables_or = self.slot_nbr = self.slot_tab = self.slot_opt = None
@@ -394,6 +415,7 @@ class DsaEngine(_EngineBase):
         d.fast_dom = fast_dom
         d.mode_max, d.variant = int(mode == "max"), _cabi.DSA_VARIANTS[variant]
         d.stop_cycle, d.seed = int(stop_cycle), int(seed) & (2 ** 64 - 1)
+        d.dev_var_cost, d.dev_unary_off = _ptr(self.var_cost), _ptr(self.unary_off)
         self._desc = d
         self._h = C.c_void_p()
         self._check(self.lib.fg_dsa_create(C.byref(d), C.byref(self._h)), "fg_dsa_create")

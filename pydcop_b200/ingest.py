@@ -63,6 +63,35 @@ ARRAY_KEYS = ("dom_size", "factor_ptr", "edge_var", "table_off", "tables", "unar
               "var_edge", "init_value")
 
 
+class GeneratedNames(Sequence):
+    """Names <prefix>0 .. <prefix>{n-1} without materialising n strings (array front door at 10^5..10^6 nodes)."""
+
+    def __init__(self, prefix: str, n: int):
+        self.prefix, self.n = prefix, int(n)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [f"{self.prefix}{k}" for k in range(*i.indices(self.n))]
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        return f"{self.prefix}{i}"
+
+    def index(self, name, *a):
+        if isinstance(name, str) and name.startswith(self.prefix) and name[len(self.prefix):].isdigit():
+            k = int(name[len(self.prefix):])
+            if k < self.n and f"{self.prefix}{k}" == name:
+                return k
+        raise ValueError(name)
+
+    def __eq__(self, other):
+        return len(other) == self.n and all(a == b for a, b in zip(self, other))
+
+
 @dataclass
 class DcopArrays:
     """A DCOP as flat arrays plus the names needed to report a solution."""
@@ -93,8 +122,12 @@ class DcopArrays:
 
     def assignment(self, value_index: Sequence[int]) -> Dict[str, Any]:
         """{variable name: domain value} from per-variable value indices (engine.values())."""
+        idx = np.asarray(value_index).astype(np.int64).tolist()
+        if len(self.domain_values) == 1:      # one shared domain: no per-variable lookup
+            dom = next(iter(self.domain_values.values()))
+            return {n: dom[k] for n, k in zip(self.var_names, idx)}
         doms = [self.domain_values[d] for d in self.var_domain]
-        return {n: doms[i][int(value_index[i])] for i, n in enumerate(self.var_names)}
+        return {n: doms[i][k] for i, (n, k) in enumerate(zip(self.var_names, idx))}
 
     def cost(self, value_index: Sequence[int]) -> float:
         """Sum of constraint and variable costs of an assignment (DCOP.solution_cost,
@@ -638,8 +671,11 @@ def from_arrays(inst: Dict[str, np.ndarray], name="dcop", objective="min") -> Dc
     fp = np.asarray(a["factor_ptr"], dtype=np.int64)
     ev = np.asarray(a["edge_var"], dtype=np.int32)
     if a.get("table_off") is None:
-        ts = np.ones(len(fp) - 1, dtype=np.int64)
-        np.multiply.at(ts, np.repeat(np.arange(len(fp) - 1), np.diff(fp)), dom[ev].astype(np.int64))
+        if len(fp) > 1 and (np.diff(fp) > 0).all():
+            ts = np.multiply.reduceat(dom[ev].astype(np.int64), fp[:-1])
+        else:
+            ts = np.ones(len(fp) - 1, dtype=np.int64)
+            np.multiply.at(ts, np.repeat(np.arange(len(fp) - 1), np.diff(fp)), dom[ev].astype(np.int64))
         a["table_off"] = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
     if a.get("unary") is None:
         a["unary"] = np.zeros(int(dom.sum()))
@@ -653,10 +689,9 @@ def from_arrays(inst: Dict[str, np.ndarray], name="dcop", objective="min") -> Dc
     a["dom_size"], a["factor_ptr"], a["edge_var"] = dom, fp, ev
     sizes = sorted(set(int(d) for d in dom))
     return DcopArrays(name=name, objective=objective, arrays={k: a[k] for k in ARRAY_KEYS},
-                      var_names=[f"v{i}" for i in range(len(dom))],
-                      con_names=[f"c{i}" for i in range(len(fp) - 1)],
+                      var_names=GeneratedNames("v", len(dom)), con_names=GeneratedNames("c", len(fp) - 1),
                       domain_values={f"d{d}": list(range(d)) for d in sizes},
-                      var_domain=[f"d{int(d)}" for d in dom])
+                      var_domain=([f"d{sizes[0]}"] * len(dom) if len(sizes) == 1 else [f"d{int(d)}" for d in dom]))
 
 
 # --------------------------------------------------------------------------------------------
@@ -688,7 +723,7 @@ def save_instance(path: Union[str, os.PathLike], dcop: DcopArrays, table_dtype=n
     didx = {d: i for i, d in enumerate(doms)}
     arrs["var_domain_id"] = np.array([didx[d] for d in dcop.var_domain], dtype=np.int32)
     if names:
-        header["var_names"], header["con_names"] = dcop.var_names, dcop.con_names
+        header["var_names"], header["con_names"] = list(dcop.var_names), list(dcop.con_names)
 
     def layout(base):
         off = base
@@ -751,8 +786,8 @@ def load_instance(path: Union[str, os.PathLike], mmap: bool = True) -> DcopArray
     nv, nc = header["n_vars"], header["n_constraints"]
     return DcopArrays(name=header["name"], objective=header["objective"],
                       arrays={k: arrs[k] for k in ARRAY_KEYS},
-                      var_names=header.get("var_names") or [f"v{i}" for i in range(nv)],
-                      con_names=header.get("con_names") or [f"c{i}" for i in range(nc)],
+                      var_names=header.get("var_names") or GeneratedNames("v", nv),
+                      con_names=header.get("con_names") or GeneratedNames("c", nc),
                       domain_values=header["domain_values"], var_domain=var_domain,
                       meta=header.get("meta", {}))
 

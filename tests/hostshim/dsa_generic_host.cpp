@@ -36,6 +36,8 @@ struct dsa_host {
   int32_t *value[2];
   void *value_cost;
   uint64_t seed;
+  const void *var_cost;        // A-DSA: the variables' own costs (NULL: DSA)
+  const int64_t *unary_off;
 };
 }
 
@@ -58,7 +60,8 @@ template <typename T>
 static void step_t(const dsa_host *h, int cur, uint32_t cycle) {
   launch(h->n_vars, [&] {
     k_dsa_step_generic<T>(side(h), h->n_vars, (const T *)h->tables, (const T *)h->con_opt, h->value[cur],
-                          h->value[cur ^ 1], (T *)h->value_cost, h->mode_max, h->variant, h->seed, cycle);
+                          h->value[cur ^ 1], (T *)h->value_cost, h->mode_max, h->variant, h->seed, cycle,
+                          (const T *)h->var_cost, h->unary_off);
   });
 }
 

@@ -14,6 +14,7 @@ static thread_local Dim3 blockIdx, blockDim, threadIdx;
 #define __launch_bounds__(n)
 
 struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
 struct double2 { double x, y; };
 #include "../../pydcop_b200/csrc/mgm_kernels.cuh"
 #include "../../pydcop_b200/csrc/mgm_fast_kernels.cuh"

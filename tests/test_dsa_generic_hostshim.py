@@ -29,7 +29,8 @@ class _Host(C.Structure):
     _fields_ = [("classes", P), ("n_classes", C.c_int32), ("n_vars", C.c_int32), ("precision", C.c_int32),
                 ("mode_max", C.c_int32), ("variant", C.c_int32), ("tables", P), ("dom_size", P), ("var_id", P),
                 ("edge_var", P), ("edge_class", P), ("var_ptr", P), ("slot_edge", P), ("has_nbr", P), ("prob", P),
-                ("con_opt", P), ("value", P * 2), ("value_cost", P), ("seed", C.c_uint64)]
+                ("con_opt", P), ("value", P * 2), ("value_cost", P), ("seed", C.c_uint64), ("var_cost", P),
+                ("unary_off", P)]
 
 
 def _lib():
@@ -46,7 +47,7 @@ class HostDsa:
     """What DsaEngine prepares on the host (generic path), stepped by the host-shimmed kernels."""
 
     def __init__(self, inst, precision="f64", mode="min", probability=0.7, p_mode="fixed", variant="B",
-                 stop_cycle=0, seed=0, var_global_id=None, frozen=None, **_):
+                 stop_cycle=0, seed=0, var_global_id=None, frozen=None, var_costs=False, **_):
         self.lib = _lib()
         self.L = L = layout_from_instance(inst)
         dt = np.float64 if precision == "f64" else np.float32
@@ -71,7 +72,8 @@ class HostDsa:
                          edge_class=c(L.edge_class, np.int32), var_ptr=c(L.var_ptr, np.int32),
                          slot_edge=c(L.slot_edge, np.int32), has_nbr=c(has_nbr, np.uint8), prob=c(prob, np.float64),
                          con_opt=np.zeros(max(L.n_factors, 1), dt), v0=c(np.resize(iso, n), np.int32),
-                         v1=np.zeros(n, np.int32), value_cost=np.zeros(n, dt))
+                         v1=np.zeros(n, np.int32), value_cost=np.zeros(n, dt),
+                         var_cost=c(L.unary, dt), unary_off=c(L.unary_off, np.int64))
         h = _Host()
         k = self.keep
         for name in ("tables", "dom_size", "var_id", "edge_var", "edge_class", "var_ptr", "slot_edge", "has_nbr",
@@ -82,6 +84,8 @@ class HostDsa:
         h.n_classes, h.n_vars = len(L.classes), L.n_vars
         h.precision = _cabi.FG_F64 if precision == "f64" else _cabi.FG_F32
         h.mode_max, h.variant, h.seed = int(mode == "max"), _cabi.DSA_VARIANTS[variant], int(seed)
+        if var_costs:      # A-DSA (adsa.py:344-377)
+            h.var_cost, h.unary_off = P(k["var_cost"].ctypes.data), P(k["unary_off"].ctypes.data)
         self.h, self.cur, self.cycle, self.stop_cycle = h, 0, 0, int(stop_cycle)
 
     def init(self):
@@ -138,3 +142,18 @@ def test_generic_dsa_kernel_source_fuzz(seed, n_vars, variant, mode, p_mode, sha
         o.step()
         e.step()
         assert np.array_equal(e.values(), o.val), k
+
+
+@pytest.mark.parametrize("name", golden_names("adsa_"))
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_generic_kernel_source_with_variable_costs_matches_reference_adsa(name, precision):
+    """A-DSA = the DSA kernel with the variables' own costs added to the candidates (adsa.py:344-377): the
+    trajectories recorded from the UNMODIFIED ADsaComputation under aligned ticks (oracle/make_golden_adsa.py)."""
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    p = meta["params"]
+    e = HostDsa(inst, precision, mode=meta["mode"], seed=meta["seed"], probability=p["probability"],
+                variant=p["variant"], var_costs=True).init()
+    for k in range(meta["n_cycles"] + 1):
+        if k:
+            e.step()
+        assert np.array_equal(e.values(), inst["value"][k]), k

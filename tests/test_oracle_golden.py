@@ -174,3 +174,17 @@ def test_reference_unit_test_vectors():
                 var_ptr=[0, 0], var_edge=[], unary=[(4 - v) / 10 for v in (1, 2, 3)])
     o = orc.MaxSumOracle(inst).init()
     assert o.value[0] == 2 and o.value_cost[0] == 0.1
+
+
+@pytest.mark.parametrize("name", golden_names("adsa_"))
+def test_adsa_oracle_matches_reference_trajectory(name):
+    """The DSA oracle with var_costs=True reproduces, tick by tick, the values of the UNMODIFIED
+    ADsaComputation (pydcop/algorithms/adsa.py) recorded by oracle/make_golden_adsa.py."""
+    inst, meta = orc.load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    p = meta["params"]
+    o = orc.DsaOracle(inst, np.float64, mode=meta["mode"], probability=p["probability"], variant=p["variant"],
+                      seed=meta["seed"], var_costs=True).init()
+    assert np.array_equal(o.val, inst["value"][0])
+    for k in range(1, meta["n_cycles"] + 1):
+        o.step()
+        assert np.array_equal(o.val, inst["value"][k]), k
