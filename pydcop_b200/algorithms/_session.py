@@ -248,7 +248,8 @@ class GpuSession:
         return DsaEngine(layout, precision=precision, mode=self.mode,
                          probability=p.get("probability", 0.7), p_mode=p.get("p_mode", "fixed"),
                          variant=p.get("variant", "B"), stop_cycle=p.get("stop_cycle", 0),
-                         seed=p.get("seed", 0), isolated_value=inst.get("isolated_value"))
+                         seed=p.get("seed", 0), isolated_value=inst.get("isolated_value"),
+                         var_costs=(self.kind == "adsa"))   # A-DSA: candidates carry the variable's own cost
 
     def _run(self):
         try:

@@ -1,4 +1,5 @@
-"""Direct solve: a DCOP file (or arrays, or a pyDcop DCOP object) -> GPU engine -> result dict.
+"""Direct solve: a DCOP file (or arrays, or a pyDcop DCOP object) -> GPU engine -> result dict
+(algorithms: maxsum, dsa, adsa, mgm).
 
 The plugin modules (pydcop_b200/algorithms/) keep pyDcop's orchestrator, agents and one Python
 computation object per graph node around the engine — that is the drop-in path, and it is what
@@ -31,14 +32,15 @@ from .layout import build_layout
 MAXSUM_DEFAULTS = {"damping": 0.5, "damping_nodes": "both", "stability": 0.1, "noise": 0.01,
                    "start_messages": "leafs", "stop_cycle": 0}
 DSA_DEFAULTS = {"probability": 0.7, "p_mode": "fixed", "variant": "B", "stop_cycle": 0}
+ADSA_DEFAULTS = {"period": 0.5, "probability": 0.7, "variant": "B", "stop_cycle": 0}   # adsa.py:121-125 + stop_cycle
 MGM_DEFAULTS = {"break_mode": "lexic", "stop_cycle": 0}
-DEFAULTS = {"maxsum": MAXSUM_DEFAULTS, "dsa": DSA_DEFAULTS, "mgm": MGM_DEFAULTS}
+DEFAULTS = {"maxsum": MAXSUM_DEFAULTS, "dsa": DSA_DEFAULTS, "mgm": MGM_DEFAULTS, "adsa": ADSA_DEFAULTS}
 _CHOICES = {"damping_nodes": ("vars", "factors", "both", "none"),
             "start_messages": ("leafs", "leafs_vars", "all"),
             "p_mode": ("fixed", "arity"), "variant": ("A", "B", "C"),
             "break_mode": ("lexic", "random")}
 ALGOS = {"maxsum": "maxsum", "maxsum_gpu": "maxsum", "dsa": "dsa", "dsa_gpu": "dsa",
-         "mgm": "mgm", "mgm_gpu": "mgm"}
+         "mgm": "mgm", "mgm_gpu": "mgm", "adsa": "adsa", "adsa_gpu": "adsa"}
 
 
 def check_params(kind: str, params: Optional[Dict[str, Any]]) -> Dict[str, Any]:
@@ -81,12 +83,17 @@ def load(problem, seed: Optional[int] = None) -> ingest.DcopArrays:
 
 
 def isolated_values(dcop: ingest.DcopArrays, mode: str) -> np.ndarray:
-    """DSA start value of a variable without neighbours: argopt of (own cost, value) in Python
-    tuple order over the real domain values (dsa.py:278-289).  Only degree-0 variables matter."""
+    """DSA start value of a variable without NEIGHBOURS — no constraint at all, or only unary ones (the engines
+    treat both as isolated and take this value verbatim): argopt of (own cost, value) in Python tuple order over
+    the real domain values (dsa.py:278-289, relations.py:1641-1669)."""
     a = dcop.arrays
     out = np.zeros(dcop.n_vars, dtype=np.int32)
     uoff = np.concatenate([[0], np.cumsum(a["dom_size"].astype(np.int64))])
-    for i in np.nonzero(np.diff(a["var_ptr"]) == 0)[0]:
+    fp, ev = np.asarray(a["factor_ptr"], dtype=np.int64), np.asarray(a["edge_var"], dtype=np.int64)
+    n_nbr = np.zeros(dcop.n_vars, dtype=np.int64)
+    if len(ev):
+        np.add.at(n_nbr, ev, np.repeat(np.diff(fp) - 1, np.diff(fp)))
+    for i in np.nonzero(n_nbr == 0)[0]:
         dom = dcop.values_of(int(i))
         pairs = [(float(a["unary"][uoff[i] + k]), x) for k, x in enumerate(dom)]
         try:
@@ -139,9 +146,9 @@ def _default_engine(kind, layout, dcop, params, mode, precision, device, seed):
                             stability=params["stability"], start_messages=params["start_messages"],
                             record_sent=False)
     return DsaEngine(layout, device=device, precision=precision, mode=mode,
-                     probability=params["probability"], p_mode=params["p_mode"],
+                     probability=params["probability"], p_mode=params.get("p_mode", "fixed"),
                      variant=params["variant"], stop_cycle=params["stop_cycle"], seed=seed or 0,
-                     isolated_value=isolated_values(dcop, mode))
+                     isolated_value=isolated_values(dcop, mode), var_costs=(kind == "adsa"))
 
 
 def _sharded_engine(kind, inst, dcop, params, mode, precision, device, seed, partition, halo, sharded_kwargs):
@@ -170,9 +177,9 @@ def _sharded_engine(kind, inst, dcop, params, mode, precision, device, seed, par
                             **dict({"record_sent": False} if "engine_factory" not in kw else {}, **kw))
     else:
         eng = ShardedDsa(inst, rank, world, dev, precision=precision, halo=halo, partition=owner, mode=mode,
-                         probability=params["probability"], p_mode=params["p_mode"], variant=params["variant"],
-                         stop_cycle=params["stop_cycle"], seed=seed or 0,
-                         isolated_value=isolated_values(dcop, mode), **kw)
+                         probability=params["probability"], p_mode=params.get("p_mode", "fixed"),
+                         variant=params["variant"], stop_cycle=params["stop_cycle"], seed=seed or 0,
+                         isolated_value=isolated_values(dcop, mode), var_costs=(kind == "adsa"), **kw)
     eng.partition_error = err
     return eng
 

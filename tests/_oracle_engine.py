@@ -18,7 +18,7 @@ class OracleEngine:
                                    **{k: params[k] for k in keys if k in params})
         else:
             keys = ("probability", "p_mode", "variant", "stop_cycle", "seed")
-            self.o = orc.DsaOracle(dict(inst), np.float64, mode=params["mode"],
+            self.o = orc.DsaOracle(dict(inst), np.float64, mode=params["mode"], var_costs=(kind == "adsa"),
                                    **{k: params[k] for k in keys if k in params})
 
     def init(self):

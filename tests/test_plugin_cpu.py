@@ -417,3 +417,22 @@ def test_second_run_in_one_process_gets_a_fresh_session(oracle_seam):
     assert set(a1) == set(d1.variables) and set(a2) == set(d2.variables)
     assert a1 in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
     assert not oracle_seam._sessions      # both workers retired their session
+
+
+@retry_once
+def test_solve_api_adsa_gpu(oracle_seam):
+    """`adsa_gpu` through the unmodified orchestrator (engine seam: the A-DSA oracle): a proper colouring of the
+    3-variable chain; the module lists the reference's parameters (adsa.py:121-125)."""
+    from pydcop.algorithms import AlgorithmDef, load_algorithm_module
+    from pydcop.dcop.yamldcop import load_dcop_from_file
+    from pydcop.infrastructure.run import solve
+    import pydcop.algorithms.adsa as ref
+    mod = load_algorithm_module("adsa_gpu")
+    ours = {p.name: (p.type, p.default_value) for p in mod.algo_params}
+    for p in ref.algo_params:
+        assert ours[p.name] == (p.type, p.default_value), p.name
+    assert mod.GRAPH_TYPE == ref.GRAPH_TYPE
+    dcop = load_dcop_from_file([os.path.join(INSTANCES, "graph_coloring1.yaml")])
+    algo = AlgorithmDef.build_with_default_param("adsa_gpu", {"stop_cycle": 40, "seed": 3}, mode=dcop.objective)
+    assignment = solve(dcop, algo, "oneagent", timeout=8)
+    assert assignment in ({"v1": "R", "v2": "G", "v3": "R"}, {"v1": "G", "v2": "R", "v3": "G"})
