@@ -444,7 +444,8 @@ def main():
         run_info["halo"] = ("push kernel storing boundary rows straight into the peers' buffers over NVLink (CUDA "
                           "IPC), its last block releasing the cycle's epoch flag to the peers; device-side "
                           "acquire wait; whole cycle enqueued by one C call (fg_maxsum_shard_step)"
-                          + ("; split push" if os.environ.get("PYDCOP_B200_PUSH_SPLIT", "0") not in ("", "0") else "")
+                          + ("; rows pushed right behind each side (split), 16-byte destination runs"
+                             if os.environ.get("PYDCOP_B200_PUSH_SPLIT", "1") != "0" else "; one push after both sides")
                           if runner.peer is not None else
                           "pack kernel + ONE NCCL all_to_all (q and r rows together) + unpack kernel per cycle")
     for _ in range(max(3, args.warmup)):

@@ -269,9 +269,12 @@ def tabulate_expression(func, names: Sequence[str], domains: Sequence[list],
     the layout NAryMatrixRelation stores (relations.py:716-733).
 
     One vectorised evaluation on broadcast axes; accepted only if the result has a numeric dtype,
-    broadcasts to the table shape and equals the scalar evaluation on `n_check` sampled entries
-    (plus the two corners) bit for bit.  Anything else — an exception, an object result, a
-    mismatch — falls back to one scalar call per entry, i.e. what the reference does."""
+    broadcasts to the table shape and equals the scalar evaluation bit for bit — on EVERY entry of a
+    table of up to 2048 entries, on `n_check` sampled entries plus the two corners of a larger one — and,
+    when an axis holds integers, equals a second vectorised evaluation on float64 axes (numpy integers
+    wrap silently on overflow where Python's grow: a wrapped `x ** k` cannot survive that comparison).
+    Anything else — an exception, an object result, a mismatch — falls back to one scalar call per
+    entry, i.e. what the reference does."""
     shape = tuple(len(d) for d in domains)
     size = int(np.prod(shape)) if shape else 1
     if not names:
@@ -289,11 +292,18 @@ def tabulate_expression(func, names: Sequence[str], domains: Sequence[list],
             out = np.asarray(out)
             if out.dtype.kind in "biuf":
                 table = np.ascontiguousarray(np.broadcast_to(out, shape), dtype=np.float64)
+                if any(a.dtype.kind in "iu" for a in axes):      # integer overflow guard
+                    fout = np.asarray(func(**dict(zip(names, [a.astype(np.float64) if a.dtype.kind in "iu" else a
+                                                               for a in axes]))))
+                    ftab = np.broadcast_to(fout, shape).astype(np.float64)
+                    if not np.array_equal(table, ftab, equal_nan=True):
+                        table = None
         except Exception:  # noqa: BLE001 — any failure means "numpy semantics differ": fall back
             table = None
         if table is not None:
             rng = np.random.default_rng(size)
-            picks = {0, size - 1} | set(int(x) for x in rng.integers(0, size, min(n_check, size)))
+            picks = (range(size) if size <= 2048 else
+                     {0, size - 1} | set(int(x) for x in rng.integers(0, size, min(n_check, size))))
             flat = table.reshape(-1)
             for p in picks:
                 idx = np.unravel_index(p, shape)
@@ -701,18 +711,19 @@ MAGIC = b"PDCOPFG1"
 _ALIGN = 4096
 
 
-def save_instance(path: Union[str, os.PathLike], dcop: DcopArrays, table_dtype=np.float32,
+def save_instance(path: Union[str, os.PathLike], dcop: DcopArrays, table_dtype=None,
                   names: bool = True) -> int:
     """Write `dcop` as: MAGIC, u64 header length, JSON header, then every array raw at a
     4 KiB-aligned offset (so `load_instance` can memory-map it and a reader can `cudaMemcpy`
-    straight from the page cache).  Tables are stored as `table_dtype` (float32 by default: the
-    engine's f32 path reads them as is; pass float64 to keep non-representable costs exact).
+    straight from the page cache).  Tables are stored as `table_dtype`; the default keeps the source
+    dtype (float64 for YAML input: a later f64 solve then sees the costs the YAML solve sees; pass
+    float32 to halve the file when every cost is representable).
     `names=False` drops variable / constraint names (they dominate the header at 10^6 scale;
     `load_instance` regenerates v<i> / c<i>).  Returns the file size."""
     arrs = {}
     for k in ARRAY_KEYS:
         a = np.ascontiguousarray(dcop.arrays[k])
-        if k == "tables":
+        if k == "tables" and table_dtype is not None:
             a = np.ascontiguousarray(a, dtype=table_dtype)
         arrs[k] = a
     header = {"format": 1, "name": dcop.name, "objective": dcop.objective,

@@ -3,7 +3,8 @@ both halo modes: pack -> all_to_all -> unpack, and the NVLink peer push through 
 the DEVICE-SIDE epoch barrier (csrc/peer_sync.cuh, fg_maxsum_shard_step / fg_dsa_shard_step).  The
 all-gathered assignment must equal the single-GPU engine's, which the other tests tie to the oracle
 bit for bit.  Cases cover: several step() calls and a re-init on one engine (the epoch counter only
-grows), the split push (r rows behind the factor side, q rows behind the variable side), and a
+grows), the joined push (one launch after both sides instead of r rows behind the factor side / q rows behind
+the variable side), the per-row push (no destination runs), and a
 deliberately IMBALANCED partition — a fast rank's push must not be overwritten by a slow rank."""
 import os
 import socket
@@ -140,7 +141,8 @@ MAXSUM_CASES = {
     "nccl": dict(mode="nccl"),
     "p2p": dict(mode="p2p"),
     "p2p-steps-reinit": dict(mode="p2p", steps=[1, 3, "init", 2, 5, 4]),
-    "p2p-split-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_SPLIT": "1"}, steps=[4, 5]),
+    "p2p-joined-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_SPLIT": "0"}, steps=[4, 5]),
+    "p2p-per-row-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_RUNS": "0"}, steps=[4, 5]),
     "p2p-multilevel-f64": dict(mode="p2p", partition="multilevel", precision="f64"),
     "p2p-imbalanced": dict(mode="p2p", partition="imbalanced", n_vars=20000, steps=[12]),
 }
