@@ -227,7 +227,7 @@ def side_workload(args, dev):
     from pydcop_b200.engine import DsaEngine, MaxSumEngine, MgmEngine
     w = args.workload
     inst = {"c3": G.config_c3, "c5": G.config_c5, "target": G.config_target, "c4": G.config_c4,
-            "mgm": G.config_c4}[w]()
+            "mgm": G.config_c4, "mixed": G.config_mixed}[w]()
     L = build_layout(**inst)
     vb = 4 if args.precision == "f32" else 8
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps: skip the end-to-end leg (line has no e2e key)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "target", "c4", "mgm"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "target", "c4", "mgm", "mixed"],
                     help="c2 (default, the driver's line) | c3 Ising 1024^2 | c5 arity-3 | target 1M vars "
                          "| c4 DSA 1M vars d=20 (variable updates/s) | mgm: MGM on the c4 instance")
     ap.add_argument("--profile", action="store_true",

@@ -160,6 +160,11 @@ int fg_maxsum_cycle_commit(fg_maxsum_t h);
 int fg_maxsum_current(fg_maxsum_t h, int32_t *buf_index, int64_t *cycle);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t fg_maxsum_launch_count(fg_maxsum_t h);
+/* Which kernel family computes each factor class from cycle 2 on (diagnostic; -1 = ghost class, never computed):
+ * generic one-thread-per-edge, round-1 CTA-pipelined (compile-time shape), warp-autonomous (binary, even domain),
+ * runtime-dimension tiled (any other shape whose table fits shared memory). */
+enum { FG_KERNEL_GENERIC = 0, FG_KERNEL_PIPE = 1, FG_KERNEL_WARP = 2, FG_KERNEL_TILED_RT = 3 };
+int fg_maxsum_kernel_plan(fg_maxsum_t h, int32_t *family, int32_t n_classes);
 
 /* Gather / scatter of boundary message rows for the halo exchange (replaces
  * Messaging.post_msg for cut edges, pydcop/infrastructure/communication.py:588-698).

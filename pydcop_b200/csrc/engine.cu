@@ -11,6 +11,7 @@
 #include "maxsum_generic.cuh"
 #include "maxsum_fast.cuh"
 #include "maxsum_warp.cuh"
+#include "maxsum_tiled_rt.cuh"
 #include "dsa_fast.cuh"
 #include "peer_sync.cuh"
 
@@ -30,6 +31,7 @@ struct fg_maxsum {
   std::vector<fg_varclass_t> varclasses;
   MaxSumFastPlan fast;
   MaxSumWarpPlan warp;   // warp-autonomous kernels (round 2) over the same classes
+  TiledRtPlan tiled_rt;  // factor classes of other shapes on the runtime-dimension tiled kernel (maxsum_tiled_rt.cuh)
   bool fast_first = true;   // tiled kernels in cycle 1 as well (PYDCOP_B200_FAST_FIRST=0: generic kernels)
   int cur = 0;
   int64_t cycle = 0;
@@ -115,6 +117,14 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
     return FG_ERR_CUDA;
   }
   maxsum_warp_plan_f2v(h->d, h->classes, h->fast, h->warp);
+  {
+    std::vector<uint8_t> skip(h->classes.size(), 0);
+    for (size_t i = 0; i < h->classes.size(); ++i) skip[i] = h->fast.f2v[i] || h->warp.f2v[i];
+    if (tiled_rt_plan(h->d, h->classes, skip, !fg_fast_disabled() && fg_env_int("PYDCOP_B200_TILED_RT", 1), h->tiled_rt) != FG_OK) {
+      snprintf(h->err, sizeof(h->err), "tile table of the runtime-dimension factor kernel: %s", cudaGetErrorString(cudaGetLastError()));
+      return FG_ERR_CUDA;
+    }
+  }
   { const char *e = getenv("PYDCOP_B200_FAST_FIRST"); h->fast_first = !(e && e[0] == '0'); }
   if (!fg_env_int("PYDCOP_B200_SERIAL", 0)) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -130,6 +140,7 @@ extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->warp.dev_classes) cudaFree(h->warp.dev_classes);
+    tiled_rt_free(h->tiled_rt);
   }
   delete h;
   return FG_OK;
@@ -202,6 +213,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
     if (c.n_factors == 0 || (c.flags & FG_CLASS_GHOST)) continue;
     if (!first && h->warp.f2v[ci] && dispatch_f2v_warp<T>(false, c, d, q_cur, r_cur, r_next, p, st)) { ++h->launches; continue; }
     if (!first && maxsum_fast_f2v<T>(h->fast, (int)ci, c, d, q_cur, r_cur, r_next, p, st, h->launches)) continue;
+    if (!first && h->tiled_rt.on[ci]) continue;   // below, one launch per arity
     const int64_t n = (int64_t)c.n_factors * c.arity;
     if (first)
       k_f2v_generic<T, 1><<<blocks_for(n, 128), 128, 0, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next,
@@ -211,6 +223,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
                                                              d.dev_edge_qoff, d.dev_q_valid, d.dev_r_cnt, d.dev_r_sent, p);
     ++h->launches;
   }
+  if (!first) h->launches += dispatch_f2v_tiled_rt<T>(h->tiled_rt, d, q_cur, r_cur, r_next, p, st);
   if (h->prof) cudaEventRecord(h->prof[1], st);
   if (push_split && h->halo.n_r > 0) {
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, h->halo.n_r, 0, 0, 0, st, h->launches);
@@ -298,6 +311,16 @@ extern "C" int fg_maxsum_current(fg_maxsum_t h, int32_t *buf_index, int64_t *cyc
 }
 
 extern "C" int64_t fg_maxsum_launch_count(fg_maxsum_t h) { return h ? h->launches : -1; }
+
+extern "C" int fg_maxsum_kernel_plan(fg_maxsum_t h, int32_t *family, int32_t n_classes) {
+  if (!h || !family || n_classes != (int32_t)h->classes.size()) return FG_ERR_ARG;
+  for (int32_t i = 0; i < n_classes; ++i) {
+    const fg_class_t &c = h->classes[i];
+    family[i] = (c.flags & FG_CLASS_GHOST) ? -1 : h->warp.f2v[i] ? FG_KERNEL_WARP : h->fast.f2v[i] ? FG_KERNEL_PIPE
+              : h->tiled_rt.on[i] ? FG_KERNEL_TILED_RT : FG_KERNEL_GENERIC;
+  }
+  return FG_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // multi-GPU cycle on the device: compute -> peer push (+ release) -> wait -> commit

@@ -245,6 +245,17 @@ class MaxSumEngine(_EngineBase):
     def launch_count(self):
         return int(self.lib.fg_maxsum_launch_count(self._h))
 
+    KERNEL_FAMILIES = {-1: "ghost", 0: "generic", 1: "pipe", 2: "warp", 3: "tiled_rt"}
+
+    def kernel_plan(self):
+        """Kernel family of every factor class (fg_maxsum_kernel_plan), as a list of names."""
+        n = len(self.layout.classes)
+        out = (C.c_int32 * max(n, 1))()
+        rc = self.lib.fg_maxsum_kernel_plan(self._h, out, n)
+        if rc != 0:
+            raise EngineError(f"fg_maxsum_kernel_plan rc={rc}")
+        return [self.KERNEL_FAMILIES[int(out[i])] for i in range(n)]
+
     # -- readback (canonical edge order) -----------------------------------------------------
     def messages(self):
         """(q, r) receiver-side message state as float64 numpy arrays in canonical edge order."""

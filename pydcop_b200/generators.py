@@ -35,6 +35,31 @@ def random_factor_graph(n_vars, d, n_factors, arity=2, seed=0, noise=0.01, int_t
                 edge_var=scopes.reshape(-1), tables=tables, unary=unary)
 
 
+def mixed_shape_graph(n_vars, doms, shapes, seed=0, noise=0.01, int_tables=False):
+    """Variables with domain sizes drawn from `doms`, factors of several arities: `shapes` is a list of
+    (arity, n_factors).  Tables follow the scopes' domain sizes (mixed-domain classes, the SECP /
+    meeting-scheduling kind of problem).  Factors are stored arity by arity."""
+    rng = np.random.default_rng(seed)
+    dom = rng.choice(np.asarray(doms, dtype=np.int32), size=n_vars).astype(np.int32)
+    ev, ptr, tabs = [], [0], []
+    for arity, n_f in shapes:
+        sc = _distinct_scopes(rng, n_vars, n_f, arity) if arity > 1 else rng.integers(0, n_vars, (n_f, 1)).astype(np.int32)
+        ev.append(sc.reshape(-1))
+        ptr.extend((ptr[-1] + arity * np.arange(1, n_f + 1)).tolist())
+        size = int(np.prod(dom[sc].astype(np.int64), axis=1).sum())
+        tabs.append(rng.integers(0, 10, size).astype(np.float32) if int_tables else rng.uniform(0, 10, size).astype(np.float32))
+    n_un = int(dom.sum())
+    unary = rng.uniform(0, noise, n_un) if noise else np.zeros(n_un)
+    return dict(dom_size=dom, factor_ptr=np.asarray(ptr, dtype=np.int64), edge_var=np.concatenate(ev).astype(np.int32),
+                tables=np.concatenate(tabs), unary=unary)
+
+
+def config_mixed(seed=0, n_vars=200_000):
+    """side workload for the runtime-dimension kernels: domains {3, 5, 7, 12}, binary + ternary + arity-4 factors."""
+    return mixed_shape_graph(n_vars, (3, 5, 7, 12), [(2, n_vars * 3 // 2), (3, n_vars // 4), (4, n_vars // 16)], seed,
+                             int_tables=True)
+
+
 def config_c2(seed=0, n_vars=100_000):
     """random binary DCOP 100k vars d=10 deg=4 (F = V*deg/2)."""
     return random_factor_graph(n_vars, 10, n_vars * 2, 2, seed)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 O=gpurun_out/r02_call9
 : > $O.txt
 run() { echo "== $*" | tee -a $O.txt; "$@" 2>&1 | tail -n 6 | cut -c1-500 | tee -a $O.txt; }
-run timeout 900 python -m pytest tests/test_gpu_warp_kernels.py tests/test_gpu_fast.py tests/test_gpu_parity.py tests/test_gpu_zz_mgm.py tests/test_gpu_zz_mgm_fast.py tests/test_gpu_zz_sharded_dsa.py tests/test_gpu_fullsize.py tests/test_gpu_adsa.py tests/test_gpu_solve.py -q -p no:cacheprovider
+run timeout 900 python -m pytest tests/test_gpu_tiled_rt.py tests/test_gpu_warp_kernels.py tests/test_gpu_fast.py tests/test_gpu_parity.py tests/test_gpu_zz_mgm.py tests/test_gpu_zz_mgm_fast.py tests/test_gpu_zz_sharded_dsa.py tests/test_gpu_fullsize.py tests/test_gpu_adsa.py tests/test_gpu_solve.py -q -p no:cacheprovider
 B="python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-e2e"
 run timeout 200 $B
 for cfg in "2 3 2 4" "2 2 2 4" "3 2 2 3" "2 3 2 3" "2 2 2 5"; do
@@ -28,6 +28,8 @@ for r in rows:
 print('   per-kernel us:', {k: round(sum(v)/len(v)/1e3,2) for k,v in acc.items()})
 P
 done
+run timeout 300 python bench.py --workload mixed --steps 50 --warmup 5
+run env PYDCOP_B200_TILED_RT=0 timeout 300 python bench.py --workload mixed --steps 20 --warmup 5
 run timeout 300 python bench.py --workload c4 --steps 100 --warmup 5
 run timeout 300 python bench.py --workload mgm --steps 100 --warmup 5
 run timeout 300 python bench.py --workload c3 --steps 100 --warmup 5
