@@ -263,7 +263,7 @@ def solve(problem, algo: str = "maxsum", algo_params: Optional[Dict[str, Any]] =
         if on_cycle is not None:
             on_cycle(cycle, _indices(engine))
     idx = _indices(engine)
-    if hasattr(engine, "solution_cost"):   # reduced on the device(s); sharded engines all-reduce over NCCL
+    if hasattr(getattr(engine, "engine", engine), "_solution_cost"):   # reduced on the device(s); sharded engines all-reduce over NCCL
         cost, violation = engine.solution_cost(infinity, dcop.arrays["unary"])
     else:                                  # engine seam of the CPU tests
         violation, cost = solution_cost(dcop, idx, infinity)
