@@ -61,7 +61,7 @@ typedef struct {
   int32_t arity;                 /* 1..FG_MAX_ARITY */
   int32_t dom[FG_MAX_ARITY];     /* domain size per scope position */
   int32_t row_off[FG_MAX_ARITY]; /* offset of position j's message row inside a factor's rows */
-  int32_t row_total;             /* sum(dom) */
+  int32_t row_total;             /* elements of one factor's rows: sum(dom), or with every row padded to 4 elements when the scope mixes domain sizes */
   int32_t n_factors;
   int32_t flags;                 /* FG_CLASS_GHOST: rows exist but the class is never computed
                                     (multi-GPU halo stubs, filled by the exchange) */
@@ -247,6 +247,11 @@ typedef struct {
    * DSA itself (the variable-cost branch of find_optimal is dead code, relations.py:1630) do not use them. */
   const void *dev_var_cost;
   const int64_t *dev_unary_off;  /* [n_vars+1] */
+  /* optional, fast path only (csrc/dsa_cached.cuh): the row each slot read last, slot-major T[n_edges * fast_dom],
+   * and the neighbour value it belongs to (0xFF = none yet; reset by fg_dsa_init).  A cycle streams these rows and
+   * goes to the oriented tables only for the slots whose neighbour changed; results are identical. */
+  void *dev_row_cache;
+  uint8_t *dev_slot_last;        /* [n_edges] */
 } fg_dsa_desc_t;
 
 typedef struct fg_dsa *fg_dsa_t;
@@ -409,6 +414,13 @@ int fg_solution_cost(int32_t precision, int32_t n_classes, const fg_class_t *cla
 int fg_selftest_approx_match(int32_t precision, int64_t n, const void *dev_c, const void *dev_prev,
                              double stability, uint8_t *dev_out_fast, uint8_t *dev_out_exact,
                              void *stream);
+
+/* Diagnostic: HBM throughput of the DSA / MGM table access pattern alone — `n_threads` threads each read
+ * `rows_per_thread` (1, 2, 3 or 6) rows of `row_bytes` (multiple of 16) at pseudo-random multiples of `stride_bytes`
+ * inside [dev_base, dev_base + region_bytes), all loads independent; dev_out[n_threads] receives a checksum.
+ * Timed by the caller (tools/gather_peak.py): the ceiling those kernels are measured against in DESIGN.md. */
+int fg_selftest_gather(const void *dev_base, int64_t region_bytes, int32_t row_bytes, int32_t stride_bytes,
+                       int64_t n_threads, int32_t rows_per_thread, float *dev_out, void *stream);
 
 #ifdef __cplusplus
 }

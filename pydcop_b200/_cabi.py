@@ -65,7 +65,8 @@ class FgDsaDesc(C.Structure):
                 ("dev_slot_opt", P), ("fast_dom", C.c_int32), ("reserved1", C.c_int32),
                 ("dev_value", P * 2), ("dev_value_cost", P),
                 ("mode_max", C.c_int32), ("variant", C.c_int32), ("stop_cycle", C.c_int32),
-                ("seed", C.c_uint64), ("dev_var_cost", P), ("dev_unary_off", P)]
+                ("seed", C.c_uint64), ("dev_var_cost", P), ("dev_unary_off", P),
+                ("dev_row_cache", P), ("dev_slot_last", P)]
 
 
 class FgMgmDesc(C.Structure):
@@ -140,6 +141,7 @@ SYMBOLS = {
     "fg_dsa_current": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fg_dsa_launch_count": (C.c_int64, [P]),
     "fg_selftest_approx_match": (C.c_int, [C.c_int32, C.c_int64, P, P, C.c_double, P, P, P]),
+    "fg_selftest_gather": (C.c_int, [P, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, P, P]),
     "fg_mgm_create": (C.c_int, [C.POINTER(FgMgmDesc), C.POINTER(P)]),
     "fg_mgm_destroy": (C.c_int, [P]),
     "fg_mgm_last_error": (C.c_char_p, [P]),

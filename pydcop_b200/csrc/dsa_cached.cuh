@@ -1,0 +1,187 @@
+// DSA fast path with an ACTIVE-ROW array (binary constraints over one domain size D, BASELINE config C4).
+//
+// evaluate_cycle (dsa.py:320-357) needs, per incident constraint, ONE row of D costs of the table oriented
+// towards the variable: the row of the neighbour's current value.  Read from the oriented tables
+// (dsa_fast.cuh) that is one random 128-byte line per incidence — ncu on C4: DRAM at 33 % of peak with 6 %
+// issue utilisation; tools/gather_peak.py shows that this is what random lines reach on HBM3e with nothing
+// else going on.  But a neighbour's value changes rarely once DSA has taken its first steps, and the row is
+// a function of that value alone.  So the engine keeps, per slot, the row it read last in a slot-major array
+// (`row_cache`, the rows of one variable contiguous, variables in kernel order) next to the neighbour value
+// it belongs to (`slot_last`); a cycle
+//   1. streams the block's run of cached rows into shared memory (coalesced, every byte used),
+//   2. compares each slot's neighbour value with `slot_last`; ONLY where it changed it fetches the new row
+//      from the oriented table and replaces it in shared memory and in the array,
+//   3. sums the rows per (variable, value) in slot order — the same adds in the same order as
+//      k_dsa_step_bin, so the result is bit-identical — and runs the decision rule per variable.
+// The bytes that cross HBM per cycle are the algorithmic ones (one row per incidence), now
+// sequential; a cycle in which EVERY neighbour changed costs what the uncached kernel costs plus the
+// write-back.  slot_last = 0xFF (fg_dsa_init) marks a row as not yet read.
+#pragma once
+#include "dsa_fast.cuh"
+
+template <typename T, int D>
+struct DsaCachedCfg {
+  static constexpr int THREADS = 256;
+  static constexpr int NV = 32;          // variables per CTA
+  static constexpr int CH = THREADS;     // slots per chunk: one slot per thread in the refresh phase
+  static constexpr int CS = D + 1;       // stride of the per-variable cost rows (conflict-free column reads)
+  static constexpr bool VEC = (D * sizeof(T)) % 16 == 0;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(DsaCachedCfg<T, D>::THREADS)
+k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t *__restrict__ slot_nbr,
+                  const int64_t *__restrict__ slot_tab, const T *__restrict__ slot_opt, const T *__restrict__ tables_or,
+                  const uint8_t *__restrict__ has_nbr, const double *__restrict__ prob, const int32_t *__restrict__ var_id,
+                  const int32_t *__restrict__ val, int32_t *__restrict__ val_next, T *__restrict__ val_cost, int mode_max,
+                  int variant, uint64_t seed, uint32_t cycle, const T *__restrict__ var_cost,
+                  const int64_t *__restrict__ unary_off, T *row_cache, uint8_t *slot_last) {
+  using Cfg = DsaCachedCfg<T, D>;
+  constexpr int RS = fg_row_stride<T, D>();
+  constexpr int NV = Cfg::NV, CH = Cfg::CH, CS = Cfg::CS, NT = Cfg::THREADS;
+  __shared__ __align__(16) T rows[CH * D];
+  __shared__ T cost[NV * CS];
+  __shared__ int sptr[NV + 1];
+  __shared__ int scur[NV];
+  __shared__ int sviol[NV];
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * NV;
+  const int nv = min(NV, n_vars - v0);
+  if (tid <= nv) sptr[tid] = var_ptr[v0 + tid];
+  if (tid < nv) { scur[tid] = val[v0 + tid]; sviol[tid] = 0; }
+  for (int i = tid; i < NV * CS; i += NT) cost[i] = (T)0;
+  __syncthreads();
+  const int sb = sptr[0], se = sptr[nv];
+  for (int c0 = sb; c0 < se; c0 += CH) {
+    const int n = min(CH, se - c0);
+    // refresh candidates first: the index / value gathers are in flight while the rows stream in
+    const int s = c0 + tid;
+    int y = 0;
+    bool changed = false;
+    int64_t tab = 0;
+    if (tid < n) {
+      y = val[slot_nbr[s]];
+      changed = slot_last[s] != (uint8_t)y;
+      tab = slot_tab[s];
+    }
+    // 1. cached rows of the chunk: contiguous
+    if constexpr (Cfg::VEC) {
+      constexpr int V = 16 / (int)sizeof(T);
+      const float4 *src = reinterpret_cast<const float4 *>(row_cache + (int64_t)c0 * D);
+      float4 *dst = reinterpret_cast<float4 *>(rows);
+      const int nvec = n * D / V;
+      for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
+    } else {
+      const T *src = row_cache + (int64_t)c0 * D;
+      for (int i = tid; i < n * D; i += NT) rows[i] = src[i];
+    }
+    T fresh[D];
+    if (changed) fg_load_row_padded<T, D>(tables_or + tab + (int64_t)y * RS, fresh);
+    __syncthreads();
+    // 2. replace the rows whose neighbour moved
+    if (changed) {
+      T *rc = row_cache + (int64_t)s * D;
+#pragma unroll
+      for (int x = 0; x < D; ++x) { rows[tid * D + x] = fresh[x]; rc[x] = fresh[x]; }
+      slot_last[s] = (uint8_t)y;
+    }
+    __syncthreads();
+    // 3. cost[v][x] += row_s[x] for the variable's slots inside the chunk, in slot order
+    for (int it = tid; it < nv * D; it += NT) {
+      const int v = it / D, x = it - v * D;
+      const int a = max(sptr[v], c0), b = min(sptr[v + 1], c0 + n);
+      T acc = cost[v * CS + x];
+      for (int t = a; t < b; ++t) acc += rows[(t - c0) * D + x];   // assignment_cost, relations.py:1479-1532
+      cost[v * CS + x] = acc;
+    }
+    if (variant == FG_DSA_B && tid < n) {   // exists_violated_constraint, dsa.py:419-431
+      // owner of slot s: binary search over the NV + 1 slot pointers
+      int lo = 0, hi = nv;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sptr[mid] <= s) lo = mid; else hi = mid; }
+      if (rows[tid * D + scur[lo]] != slot_opt[s]) sviol[lo] = 1;
+    }
+    __syncthreads();
+  }
+  if (tid >= nv) return;
+  const int v = v0 + tid;
+  const int cur = scur[tid];
+  const uint8_t hn = has_nbr[v];   // 0 isolated (value carried over), 1 active, 2 ghost (never written here)
+  if (hn != 1) {
+    if (hn == 0) val_next[v] = cur;
+    return;
+  }
+  T c[D];
+#pragma unroll
+  for (int x = 0; x < D; ++x) c[x] = cost[tid * CS + x];
+  const bool violated = sviol[tid] != 0;
+  T cur_cost = (T)0;   // A-DSA (adsa.py:344-377): candidates carry the variable's own cost, the current cost does not
+#pragma unroll
+  for (int x = 0; x < D; ++x)
+    if (x == cur) cur_cost = c[x];
+  if (var_cost) {
+    const T *vc = var_cost + unary_off[v];
+#pragma unroll
+    for (int x = 0; x < D; ++x) c[x] += vc[x];
+  }
+  T best_cost = mode_max ? -Inf<T>::pos() : Inf<T>::pos();   // find_optimal (relations.py:1594-1638)
+  int nbest = 0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) {
+    const T cx = c[x];
+    if (cx == best_cost) ++nbest;
+    else if (mode_max ? (cx > best_cost) : (cx < best_cost)) { best_cost = cx; nbest = 1; }
+  }
+  const T delta = fg_abs<T>(cur_cost - best_cost);
+  bool attempt = false, drop_cur = false;
+  if (delta > (T)0) {
+    attempt = true;
+  } else if (delta == (T)0) {
+    if (variant == FG_DSA_C || (variant == FG_DSA_B && violated)) {
+      attempt = true;
+      drop_cur = nbest > 1;
+    }
+  }
+  int nvv = cur;
+  if (attempt) {  // probabilistic_change, dsa.py:407-417
+    uint32_t b[4];
+    philox4x32_10((uint32_t)var_id[v], cycle, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+    if (prob[v] > philox_u53(b)) {
+      int pick = philox_choice(b, drop_cur ? nbest - 1 : nbest);
+      bool done = false;
+#pragma unroll
+      for (int x = 0; x < D; ++x) {
+        if (!done && c[x] == best_cost && !(drop_cur && x == cur)) {
+          if (pick == 0) { nvv = x; done = true; }
+          --pick;
+        }
+      }
+      val_cost[v] = best_cost;
+    }
+  }
+  val_next[v] = nvv;
+}
+
+template <typename T>
+inline bool dsa_cached_step(const fg_dsa_desc_t &d, const int32_t *val, int32_t *val_next, uint32_t cycle, cudaStream_t st,
+                            int64_t &launches) {
+  if (!d.dev_row_cache || !d.dev_slot_last || !d.dev_tables_or || !d.dev_slot_nbr || !d.dev_slot_tab || !d.dev_slot_opt ||
+      d.fast_dom <= 0 || d.fast_dom > 254)
+    return false;
+  if (fg_fast_disabled() || fg_env_is("PYDCOP_B200_DSA_CACHE", '0')) return false;
+  switch (d.fast_dom) {
+#define X(n)                                                                                                          \
+  case n: {                                                                                                           \
+    using Cfg = DsaCachedCfg<T, n>;                                                                                   \
+    const unsigned blocks = (unsigned)((d.n_vars + Cfg::NV - 1) / Cfg::NV);                                           \
+    k_dsa_step_cached<T, n><<<blocks, Cfg::THREADS, 0, st>>>(                                                         \
+        d.n_vars, d.dev_var_ptr, d.dev_slot_nbr, d.dev_slot_tab, (const T *)d.dev_slot_opt, (const T *)d.dev_tables_or, \
+        d.dev_has_nbr, d.dev_prob, d.dev_var_id, val, val_next, (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed,   \
+        cycle, (const T *)d.dev_var_cost, d.dev_unary_off, (T *)d.dev_row_cache, d.dev_slot_last);                     \
+    ++launches;                                                                                                       \
+    return true;                                                                                                      \
+  }
+    FG_FAST_DOMS(X)
+#undef X
+  }
+  return false;
+}

@@ -12,7 +12,9 @@
 #include "maxsum_fast.cuh"
 #include "maxsum_warp.cuh"
 #include "maxsum_tiled_rt.cuh"
+#include "selftest.cuh"
 #include "dsa_fast.cuh"
+#include "dsa_cached.cuh"
 #include "peer_sync.cuh"
 
 namespace {
@@ -120,7 +122,7 @@ extern "C" int fg_maxsum_create(const fg_maxsum_desc_t *desc, fg_maxsum_t *out) 
   {
     std::vector<uint8_t> skip(h->classes.size(), 0);
     for (size_t i = 0; i < h->classes.size(); ++i) skip[i] = h->fast.f2v[i] || h->warp.f2v[i];
-    if (tiled_rt_plan(h->d, h->classes, skip, !fg_fast_disabled() && fg_env_int("PYDCOP_B200_TILED_RT", 1), h->tiled_rt) != FG_OK) {
+    if (tiled_rt_plan(h->d, h->classes, skip, !fg_fast_disabled() && !fg_env_is("PYDCOP_B200_TILED_RT", '0'), h->tiled_rt) != FG_OK) {
       snprintf(h->err, sizeof(h->err), "tile table of the runtime-dimension factor kernel: %s", cudaGetErrorString(cudaGetLastError()));
       return FG_ERR_CUDA;
     }
@@ -664,6 +666,8 @@ static int dsa_init_t(fg_dsa *h, cudaStream_t st) {
     ++h->launches;
     CUDA_TRY(h, cudaMemcpyAsync(d.dev_value[1], d.dev_value[0], sizeof(int32_t) * (size_t)d.n_vars, cudaMemcpyDeviceToDevice, st));
   }
+  if (d.dev_slot_last && d.n_edges)   // active-row array (dsa_cached.cuh): no row has been read yet
+    CUDA_TRY(h, cudaMemsetAsync(d.dev_slot_last, 0xFF, (size_t)d.n_edges, st));
   CUDA_TRY(h, cudaGetLastError());
   h->cur = 0;
   h->cycle = 0;
@@ -682,7 +686,8 @@ static int dsa_compute_t(fg_dsa *h, cudaStream_t st) {
   if (!d.n_vars) return FG_OK;
   const int32_t *val = d.dev_value[h->cur];
   int32_t *val_next = d.dev_value[h->cur ^ 1];
-  if (!dsa_fast_step<T>(h->d, h->classes, val, val_next, (uint32_t)h->cycle, st, h->launches)) {
+  if (dsa_cached_step<T>(h->d, val, val_next, (uint32_t)h->cycle, st, h->launches)) {
+  } else if (!dsa_fast_step<T>(h->d, h->classes, val, val_next, (uint32_t)h->cycle, st, h->launches)) {
     k_dsa_step_generic<T><<<blocks_for(d.n_vars, 128), 128, 0, st>>>(
         dsa_side(h), d.n_vars, (const T *)d.dev_tables, (const T *)d.dev_con_opt, val, val_next,
         (T *)d.dev_value_cost, d.mode_max, d.variant, d.seed, (uint32_t)h->cycle, (const T *)d.dev_var_cost,
@@ -834,5 +839,22 @@ extern "C" int fg_selftest_approx_match(int32_t precision, int64_t n, const void
     k_selftest_match<double><<<blocks_for(n, 256), 256, 0, st>>>(n, (const double *)dev_c, (const double *)dev_prev, stability, dev_out_fast, dev_out_exact);
   else
     k_selftest_match<float><<<blocks_for(n, 256), 256, 0, st>>>(n, (const float *)dev_c, (const float *)dev_prev, (float)stability, dev_out_fast, dev_out_exact);
+  return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
+}
+
+extern "C" int fg_selftest_gather(const void *dev_base, int64_t region_bytes, int32_t row_bytes, int32_t stride_bytes,
+                                  int64_t n_threads, int32_t rows_per_thread, float *dev_out, void *stream) {
+  if (!dev_base || !dev_out || row_bytes <= 0 || row_bytes % 16 || stride_bytes < row_bytes || stride_bytes % 16 ||
+      region_bytes < stride_bytes || n_threads <= 0)
+    return FG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t n_slots = (uint64_t)(region_bytes / stride_bytes);
+  const unsigned blocks = blocks_for(n_threads, 128);
+  switch (rows_per_thread) {
+#define X(n) case n: k_selftest_gather<n><<<blocks, 128, 0, st>>>((const uint8_t *)dev_base, n_slots, row_bytes, stride_bytes, n_threads, dev_out); break;
+    X(1) X(2) X(3) X(6)
+#undef X
+    default: return FG_ERR_ARG;
+  }
   return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }

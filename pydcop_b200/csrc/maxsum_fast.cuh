@@ -825,6 +825,11 @@ inline int fg_env_int(const char *name, int dflt) {
   return v > 0 ? v : dflt;
 }
 
+inline bool fg_env_is(const char *name, char first) {
+  const char *e = getenv(name);
+  return e && e[0] == first;
+}
+
 inline bool fg_fast_disabled() {
   const char *e = getenv("PYDCOP_B200_NO_FAST");
   return e && e[0] == '1';

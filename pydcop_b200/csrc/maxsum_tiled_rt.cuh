@@ -10,6 +10,7 @@
 // OUTPUT VALUE — one item = (factor, scope position j, value x_j), a minimum over the table slice —
 // so a class of few large tables keeps a whole CTA busy as well as a class of many small ones.
 //
+// Message rows may be padded (fg_class_t::row_off is aligned, row_total >= sum(dom)): padding elements are carried over.
 // Arithmetic is the generic kernel's, operand for operand: sum = 0, += q_i[x_i] for i != j in scope
 // order, table + sum, strict optimum; damping / approx_match / send gate per edge.  Bit-identical to
 // k_f2v_generic and to the oracle (tests/test_gpu_tiled_rt.py).
@@ -138,7 +139,11 @@ k_f2v_tiled_rt(const fg_class_t *__restrict__ classes, const RtTile *__restrict_
 #pragma unroll
       for (int t = 1; t < A; ++t)
         if (k >= roff[t]) { j = t; ro = roff[t]; }
-      qs[i] = q_cur[qo[f * A + j] + (k - ro)];
+      int dj = dom[0];
+#pragma unroll
+      for (int t = 1; t < A; ++t)
+        if (j == t) dj = dom[t];
+      qs[i] = (k - ro) < dj ? q_cur[qo[f * A + j] + (k - ro)] : (T)0;   // rows may be padded (row_off is aligned)
     }
   }
   __syncthreads();
@@ -153,6 +158,11 @@ k_f2v_tiled_rt(const fg_class_t *__restrict__ classes, const RtTile *__restrict_
       for (int t = 1; t < A; ++t)
         if (k >= roff[t]) { j = t; ro = roff[t]; }
       const int xv = k - ro;
+      int dj = dom[0];
+#pragma unroll
+      for (int t = 1; t < A; ++t)
+        if (j == t) dj = dom[t];
+      if (xv >= dj) { cand[it] = prev[it]; continue; }   // padding between rows: carried over
       const T *tf = tab + f * sp;
       const T *qf = qs + f * RT;
       int x[A];

@@ -407,8 +407,12 @@ class DsaEngine(_EngineBase):
         fast_dom = 0
         with torch.cuda.device(self.device):
             fast = dsa_fast_arrays(L, self.tables, mode)
+        self.row_cache = self.slot_last = None
         if fast is not None:
             self.tables_or, self.slot_tab, self.slot_nbr, self.slot_opt, fast_dom = fast
+            with torch.cuda.device(self.device):   # active-row array (csrc/dsa_cached.cuh): L.n_edges rows of fast_dom costs
+                self.row_cache = torch.zeros(max(L.n_edges * fast_dom, 4), dtype=tdt, device=self.device)
+                self.slot_last = torch.full((max(L.n_edges, 1),), 255, dtype=torch.uint8, device=self.device)
         self._classes = _class_array(L)
         d = FgDsaDesc()
         d.abi_version, d.precision = _cabi.FG_ABI_VERSION, prec
@@ -427,6 +431,7 @@ class DsaEngine(_EngineBase):
         d.mode_max, d.variant = int(mode == "max"), _cabi.DSA_VARIANTS[variant]
         d.stop_cycle, d.seed = int(stop_cycle), int(seed) & (2 ** 64 - 1)
         d.dev_var_cost, d.dev_unary_off = _ptr(self.var_cost), _ptr(self.unary_off)
+        d.dev_row_cache, d.dev_slot_last = _ptr(self.row_cache), _ptr(self.slot_last)
         self._desc = d
         self._h = C.c_void_p()
         self._check(self.lib.fg_dsa_create(C.byref(d), C.byref(self._h)), "fg_dsa_create")
