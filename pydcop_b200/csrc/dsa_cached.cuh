@@ -11,8 +11,10 @@
 //   1. streams the block's run of cached rows into shared memory (coalesced, every byte used),
 //   2. compares each slot's neighbour value with `slot_last`; ONLY where it changed it fetches the new row
 //      from the oriented table and replaces it in shared memory and in the array,
-//   3. sums the rows per (variable, value) in slot order — the same adds in the same order as
-//      k_dsa_step_bin, so the result is bit-identical — and runs the decision rule per variable.
+//   3. sums the rows per variable in slot order, one thread per variable with its D costs in registers —
+//      the same adds in the same order as k_dsa_step_bin, so the result is bit-identical — and runs the
+//      decision rule.  (A first version summed per (variable, value) item: 130 M instructions per cycle on
+//      C4, 398 us; profiles/r02_call11_*.)
 // The bytes that cross HBM per cycle are the algorithmic ones (one row per incidence), now
 // sequential; a cycle in which EVERY neighbour changed costs what the uncached kernel costs plus the
 // write-back.  slot_last = 0xFF (fg_dsa_init) marks a row as not yet read.
@@ -21,10 +23,10 @@
 
 template <typename T, int D>
 struct DsaCachedCfg {
-  static constexpr int THREADS = 256;
-  static constexpr int NV = 32;          // variables per CTA
-  static constexpr int CH = THREADS;     // slots per chunk: one slot per thread in the refresh phase
-  static constexpr int CS = D + 1;       // stride of the per-variable cost rows (conflict-free column reads)
+  static constexpr int THREADS = 128;    // one thread per variable in the summing phase
+  static constexpr int NV = THREADS;     // variables per CTA
+  static constexpr int SPT = (D * sizeof(T) <= 32) ? 8 : (D * sizeof(T) <= 80 ? 4 : 2);   // slots per thread and chunk
+  static constexpr int CH = THREADS * SPT;   // slots per chunk (<= 40 KB of rows)
   static constexpr bool VEC = (D * sizeof(T)) % 16 == 0;
 };
 
@@ -38,96 +40,106 @@ k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t
                   const int64_t *__restrict__ unary_off, T *row_cache, uint8_t *slot_last) {
   using Cfg = DsaCachedCfg<T, D>;
   constexpr int RS = fg_row_stride<T, D>();
-  constexpr int NV = Cfg::NV, CH = Cfg::CH, CS = Cfg::CS, NT = Cfg::THREADS;
+  constexpr int NV = Cfg::NV, CH = Cfg::CH, NT = Cfg::THREADS, SPT = Cfg::SPT;
   __shared__ __align__(16) T rows[CH * D];
-  __shared__ T cost[NV * CS];
+  __shared__ T sopt[CH];          // optimum of the slot's constraint (variant B)
+  __shared__ int16_t snew[CH];    // neighbour value when it differs from the one the cached row belongs to, else -1
   __shared__ int sptr[NV + 1];
-  __shared__ int scur[NV];
-  __shared__ int sviol[NV];
   const int tid = threadIdx.x;
   const int v0 = blockIdx.x * NV;
   const int nv = min(NV, n_vars - v0);
   if (tid <= nv) sptr[tid] = var_ptr[v0 + tid];
-  if (tid < nv) { scur[tid] = val[v0 + tid]; sviol[tid] = 0; }
-  for (int i = tid; i < NV * CS; i += NT) cost[i] = (T)0;
+  const int v = v0 + tid;
+  const bool mine = tid < nv;
+  const int cur = mine ? val[v] : 0;
   __syncthreads();
   const int sb = sptr[0], se = sptr[nv];
+  const int my_a = mine ? sptr[tid] : 0, my_b = mine ? sptr[tid + 1] : 0;
+  T cost[D];
+#pragma unroll
+  for (int x = 0; x < D; ++x) cost[x] = (T)0;
+  bool violated = false;
   for (int c0 = sb; c0 < se; c0 += CH) {
     const int n = min(CH, se - c0);
-    // refresh candidates first: the index / value gathers are in flight while the rows stream in
-    const int s = c0 + tid;
-    int y = 0;
-    bool changed = false;
-    int64_t tab = 0;
-    if (tid < n) {
-      y = val[slot_nbr[s]];
-      changed = slot_last[s] != (uint8_t)y;
-      tab = slot_tab[s];
+    // A. per-slot metadata, slot-ordered (coalesced); the value gathers are in flight while the rows stream in
+    int yv[SPT], lastv[SPT];
+    T optv[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int i = tid + k * NT;
+      yv[k] = 0; lastv[k] = 0; optv[k] = (T)0;
+      if (i < n) {
+        yv[k] = val[slot_nbr[c0 + i]];
+        lastv[k] = slot_last[c0 + i];
+        optv[k] = slot_opt[c0 + i];
+      }
     }
-    // 1. cached rows of the chunk: contiguous
+    // B. cached rows of the chunk: contiguous
     if constexpr (Cfg::VEC) {
       constexpr int V = 16 / (int)sizeof(T);
       const float4 *src = reinterpret_cast<const float4 *>(row_cache + (int64_t)c0 * D);
       float4 *dst = reinterpret_cast<float4 *>(rows);
       const int nvec = n * D / V;
+#pragma unroll 4
       for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
     } else {
       const T *src = row_cache + (int64_t)c0 * D;
+#pragma unroll 4
       for (int i = tid; i < n * D; i += NT) rows[i] = src[i];
     }
-    T fresh[D];
-    if (changed) fg_load_row_padded<T, D>(tables_or + tab + (int64_t)y * RS, fresh);
-    __syncthreads();
-    // 2. replace the rows whose neighbour moved
-    if (changed) {
-      T *rc = row_cache + (int64_t)s * D;
 #pragma unroll
-      for (int x = 0; x < D; ++x) { rows[tid * D + x] = fresh[x]; rc[x] = fresh[x]; }
-      slot_last[s] = (uint8_t)y;
+    for (int k = 0; k < SPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < n) { sopt[i] = optv[k]; snew[i] = (int16_t)(yv[k] != lastv[k] ? yv[k] : -1); }
     }
     __syncthreads();
-    // 3. cost[v][x] += row_s[x] for the variable's slots inside the chunk, in slot order
-    for (int it = tid; it < nv * D; it += NT) {
-      const int v = it / D, x = it - v * D;
-      const int a = max(sptr[v], c0), b = min(sptr[v + 1], c0 + n);
-      T acc = cost[v * CS + x];
-      for (int t = a; t < b; ++t) acc += rows[(t - c0) * D + x];   // assignment_cost, relations.py:1479-1532
-      cost[v * CS + x] = acc;
+    // C. rows whose neighbour moved: from the oriented table, into shared memory and back into the array
+#pragma unroll 1
+    for (int i = tid; i < n; i += NT) {
+      const int y = snew[i];
+      if (y < 0) continue;
+      T fresh[D];
+      fg_load_row_padded<T, D>(tables_or + slot_tab[c0 + i] + (int64_t)y * RS, fresh);
+      T *rc = row_cache + (int64_t)(c0 + i) * D;
+#pragma unroll
+      for (int x = 0; x < D; ++x) { rows[i * D + x] = fresh[x]; rc[x] = fresh[x]; }
+      slot_last[c0 + i] = (uint8_t)y;
     }
-    if (variant == FG_DSA_B && tid < n) {   // exists_violated_constraint, dsa.py:419-431
-      // owner of slot s: binary search over the NV + 1 slot pointers
-      int lo = 0, hi = nv;
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sptr[mid] <= s) lo = mid; else hi = mid; }
-      if (rows[tid * D + scur[lo]] != slot_opt[s]) sviol[lo] = 1;
+    __syncthreads();
+    // D. cost[x] += row_s[x] over the variable's slots inside the chunk, in slot order (assignment_cost,
+    //    relations.py:1479-1532); exists_violated_constraint (dsa.py:419-431) for variant B
+    {
+      const int a = max(my_a, c0), b = min(my_b, c0 + n);
+      for (int t = a; t < b; ++t) {
+        T r[D];
+        fg_load_row<T, D>(rows + (t - c0) * D, r);
+#pragma unroll
+        for (int x = 0; x < D; ++x) cost[x] += r[x];
+        if (variant == FG_DSA_B && rows[(t - c0) * D + cur] != sopt[t - c0]) violated = true;
+      }
     }
     __syncthreads();
   }
-  if (tid >= nv) return;
-  const int v = v0 + tid;
-  const int cur = scur[tid];
+  if (!mine) return;
   const uint8_t hn = has_nbr[v];   // 0 isolated (value carried over), 1 active, 2 ghost (never written here)
   if (hn != 1) {
     if (hn == 0) val_next[v] = cur;
     return;
   }
-  T c[D];
-#pragma unroll
-  for (int x = 0; x < D; ++x) c[x] = cost[tid * CS + x];
-  const bool violated = sviol[tid] != 0;
   T cur_cost = (T)0;   // A-DSA (adsa.py:344-377): candidates carry the variable's own cost, the current cost does not
 #pragma unroll
   for (int x = 0; x < D; ++x)
-    if (x == cur) cur_cost = c[x];
+    if (x == cur) cur_cost = cost[x];
   if (var_cost) {
     const T *vc = var_cost + unary_off[v];
 #pragma unroll
-    for (int x = 0; x < D; ++x) c[x] += vc[x];
+    for (int x = 0; x < D; ++x) cost[x] += vc[x];
   }
   T best_cost = mode_max ? -Inf<T>::pos() : Inf<T>::pos();   // find_optimal (relations.py:1594-1638)
   int nbest = 0;
 #pragma unroll
   for (int x = 0; x < D; ++x) {
-    const T cx = c[x];
+    const T cx = cost[x];
     if (cx == best_cost) ++nbest;
     else if (mode_max ? (cx > best_cost) : (cx < best_cost)) { best_cost = cx; nbest = 1; }
   }
@@ -150,7 +162,7 @@ k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t
       bool done = false;
 #pragma unroll
       for (int x = 0; x < D; ++x) {
-        if (!done && c[x] == best_cost && !(drop_cur && x == cur)) {
+        if (!done && cost[x] == best_cost && !(drop_cur && x == cur)) {
           if (pick == 0) { nvv = x; done = true; }
           --pick;
         }
@@ -172,6 +184,7 @@ inline bool dsa_cached_step(const fg_dsa_desc_t &d, const int32_t *val, int32_t 
 #define X(n)                                                                                                          \
   case n: {                                                                                                           \
     using Cfg = DsaCachedCfg<T, n>;                                                                                   \
+    static_assert(sizeof(T) * Cfg::CH * (n + 1) + 2 * Cfg::CH + 4 * (Cfg::NV + 1) <= 48 * 1024, "static shared memory");    \
     const unsigned blocks = (unsigned)((d.n_vars + Cfg::NV - 1) / Cfg::NV);                                           \
     k_dsa_step_cached<T, n><<<blocks, Cfg::THREADS, 0, st>>>(                                                         \
         d.n_vars, d.dev_var_ptr, d.dev_slot_nbr, d.dev_slot_tab, (const T *)d.dev_slot_opt, (const T *)d.dev_tables_or, \
