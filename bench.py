@@ -441,13 +441,19 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     runner.init()
     if world > 1:
-        run_info["halo"] = ("push kernel storing boundary rows straight into the peers' buffers over NVLink (CUDA "
-                          "IPC), its last block releasing the cycle's epoch flag to the peers; device-side "
-                          "acquire wait; whole cycle enqueued by one C call (fg_maxsum_shard_step)"
-                          + ("; rows pushed right behind each side (split), 16-byte destination runs"
-                             if os.environ.get("PYDCOP_B200_PUSH_SPLIT", "1") != "0" else "; one push after both sides")
-                          if runner.peer is not None else
-                          "pack kernel + ONE NCCL all_to_all (q and r rows together) + unpack kernel per cycle")
+        if runner.peer is None:
+            run_info["halo"] = "pack kernel + ONE NCCL all_to_all (q and r rows together) + unpack kernel per cycle"
+        elif getattr(runner.peer, "fused", False):
+            run_info["halo"] = ("FUSED: the factor-side and variable-side kernels store every boundary row into its "
+                                "consumer's buffer over NVLink (CUDA IPC) from the lane that produced it; one release "
+                                "kernel publishes the cycle's epoch flag to the peers, device-side acquire wait; whole "
+                                "cycle enqueued by one C call (fg_maxsum_shard_step)")
+        else:
+            run_info["halo"] = ("push kernel storing boundary rows straight into the peers' buffers over NVLink (CUDA "
+                                "IPC), its last block releasing the cycle's epoch flag to the peers; device-side "
+                                "acquire wait; whole cycle enqueued by one C call (fg_maxsum_shard_step)"
+                                + ("; rows pushed right behind each side (split), 16-byte destination runs"
+                                   if os.environ.get("PYDCOP_B200_PUSH_SPLIT", "1") != "0" else "; one push after both sides"))
     for _ in range(max(3, args.warmup)):
         runner.step(1)
     torch.cuda.synchronize(dev)

@@ -318,6 +318,13 @@ typedef struct {
   const int64_t *dev_runs_r[2], *dev_runs_q[2];
   int32_t n_runs_r[2], n_runs_q[2];
   int64_t units_r[2], units_q[2];
+  /* Optional, MaxSum only (NULL = off): FUSED halo.  Per buffer index b, for every edge (class-major order) the
+   * address in its consumer's r[b] of the f->v row the factor side produces, and for every slot the address in
+   * its consumer's q[b] of the v->f row the variable side produces; 0 = the row stays on this GPU.  When every
+   * non-ghost class of the shard runs on the warp-autonomous kernels (csrc/maxsum_warp.cuh), those kernels store
+   * each boundary row to its peer from the lane that produced it — the transfer overlaps the rest of the cycle's
+   * arithmetic tile by tile and the two push launches disappear; otherwise the push kernels above are used. */
+  const int64_t *dev_edge_dst_r[2], *dev_slot_dst_q[2];
 } fg_halo_plan_t;
 
 /* Attach a push plan to an engine (copied).  From then on fg_*_shard_step runs whole cycles on the
@@ -325,6 +332,8 @@ typedef struct {
  * block of the push kernel releasing epoch+1 -> wait for every peer's epoch+1 -> commit.  The epoch
  * counter only grows (it survives fg_*_init), so every rank must run the same number of cycles. */
 int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan);
+/* 1 when the attached plan runs in FUSED mode (boundary rows stored by the warp kernels), else 0. */
+int fg_maxsum_shard_fused(fg_maxsum_t h);
 int fg_maxsum_shard_step(fg_maxsum_t h, int32_t n_cycles, void *stream);
 /* One phase of a cycle, for timing breakdowns: 0 compute, 1 push + signal, 2 wait, 3 commit. */
 int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream);

@@ -97,7 +97,8 @@ class FgHaloPlan(C.Structure):
                 ("dev_src_r_off", P), ("dev_src_q_off", P), ("dev_dst_r", P * 2), ("dev_dst_q", P * 2),
                 ("dev_counter", P), ("sync", FgPeerSync),
                 ("dev_runs_r", P * 2), ("dev_runs_q", P * 2), ("n_runs_r", C.c_int32 * 2), ("n_runs_q", C.c_int32 * 2),
-                ("units_r", C.c_int64 * 2), ("units_q", C.c_int64 * 2)]
+                ("units_r", C.c_int64 * 2), ("units_q", C.c_int64 * 2),
+                ("dev_edge_dst_r", P * 2), ("dev_slot_dst_q", P * 2)]
 
 
 # every symbol include/pydcop_b200.h declares: (restype, argtypes)
@@ -114,6 +115,7 @@ SYMBOLS = {
     "fg_maxsum_current": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fg_maxsum_launch_count": (C.c_int64, [P]),
     "fg_maxsum_kernel_plan": (C.c_int, [P, P, C.c_int32]),
+    "fg_maxsum_shard_fused": (C.c_int, [P]),
     "fg_halo_pack": (C.c_int, [C.c_int32, P, P, P, P, P, C.c_int64, P]),
     "fg_halo_unpack": (C.c_int, [C.c_int32, P, P, P, P, P, C.c_int64, P]),
     "fg_halo_rows_uniform": (C.c_int, [C.c_int32, C.c_int32, P, P, P, P, P, C.c_int64, C.c_int64,

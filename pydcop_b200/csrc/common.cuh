@@ -54,6 +54,9 @@ __device__ __forceinline__ bool gate_decide(bool match, uint8_t &cnt_byte) {
 struct MaxSumParams {
   int mode_max, damp_vars, damp_factors;
   double damping, one_minus_damping, stability;
+  // multi-GPU, fused halo (warp kernels only; null = no peer stores): per edge / per slot the address in the consumer's
+  // `next` buffer of the row this cycle produces, 0 for interior rows (fg_halo_plan_t::dev_edge_dst_r / dev_slot_dst_q)
+  const int64_t *edge_dst, *slot_dst;
 };
 
 #define CUDA_TRY(h, expr)                                                          \

@@ -48,7 +48,7 @@ k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t
   const int tid = threadIdx.x;
   const int v0 = blockIdx.x * NV;
   const int nv = min(NV, n_vars - v0);
-  if (tid <= nv) sptr[tid] = var_ptr[v0 + tid];
+  for (int i = tid; i <= nv; i += NT) sptr[i] = var_ptr[v0 + i];
   const int v = v0 + tid;
   const bool mine = tid < nv;
   const int cur = mine ? val[v] : 0;

@@ -41,6 +41,7 @@ struct fg_maxsum {
   // multi-GPU: push plan + device-side barrier (fg_maxsum_shard_*)
   bool has_halo = false;
   bool split_push = true;   // r rows right behind the factor side, q rows on the side stream (PYDCOP_B200_PUSH_SPLIT=0: one push after the join)
+  bool fused_push = false;  // boundary rows stored to the peers by the warp kernels themselves (fg_halo_plan_t::dev_edge_dst_r)
   fg_halo_plan_t halo;
   uint64_t epoch = 0;
   cudaEvent_t *prof = nullptr;   // fg_maxsum_shard_profile: 8 timing events recorded inside a cycle
@@ -199,7 +200,9 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
   // B200 against the generic kernels and the oracle, tests/test_gpu_zz_fast_first.py).
   const bool first = (h->cycle == 0) && !h->fast_first;
   const bool first_cycle = (h->cycle == 0);
-  MaxSumParams p{d.mode_max, d.damp_vars, d.damp_factors, d.damping, 1.0 - d.damping, d.stability};
+  MaxSumParams p{d.mode_max, d.damp_vars, d.damp_factors, d.damping, 1.0 - d.damping, d.stability, nullptr, nullptr};
+  const bool fused = push_split && h->fused_push && !first;   // the warp kernels store the boundary rows themselves
+  if (fused) { p.edge_dst = h->halo.dev_edge_dst_r[nxt]; p.slot_dst = h->halo.dev_slot_dst_q[nxt]; }
   const T *q_cur = (const T *)d.dev_q[cur], *r_cur = (const T *)d.dev_r[cur];
   T *q_next = (T *)d.dev_q[nxt], *r_next = (T *)d.dev_r[nxt];
   // fork BEFORE anything of this cycle is enqueued, so the side stream only waits for the past
@@ -227,7 +230,7 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
   }
   if (!first) h->launches += dispatch_f2v_tiled_rt<T>(h->tiled_rt, d, q_cur, r_cur, r_next, p, st);
   if (h->prof) cudaEventRecord(h->prof[1], st);
-  if (push_split && h->halo.n_r > 0) {
+  if (push_split && !fused && h->halo.n_r > 0) {
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, h->halo.n_r, 0, 0, 0, st, h->launches);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (r rows) failed"); return rc; }
   }
@@ -254,17 +257,24 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
         for (size_t li = 0; li < h->fast.v2f.size(); ++li)
           if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
       }
-      for (int vi : h->fast.slow_varclasses) {
-        const fg_varclass_t &vc = h->varclasses[vi];
-        k_v2f_generic<T, 0><<<blocks_for(vc.n_slots, 128), 128, 0, st>>>(
-            g, vc.first_slot, vc.n_slots, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
+      // classes without a tiled kernel: one launch per RUN of adjacent slot ranges (the kernel works per slot)
+      for (size_t k = 0; k < h->fast.slow_varclasses.size();) {
+        const fg_varclass_t &vc = h->varclasses[h->fast.slow_varclasses[k]];
+        int64_t begin = vc.first_slot, n = vc.n_slots;
+        for (++k; k < h->fast.slow_varclasses.size(); ++k) {
+          const fg_varclass_t &nx = h->varclasses[h->fast.slow_varclasses[k]];
+          if (nx.first_slot != begin + n) break;
+          n += nx.n_slots;
+        }
+        k_v2f_generic<T, 0><<<blocks_for(n, 128), 128, 0, st>>>(
+            g, (int)begin, (int)n, (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_r_valid, d.dev_q_cnt,
             d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
         ++h->launches;
       }
     }
   }
   if (h->prof) cudaEventRecord(h->prof[3], st);
-  if (push_split && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
+  if (push_split && !fused && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, st, h->launches);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows) failed"); return rc; }
   }
@@ -356,8 +366,16 @@ extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan)
   h->has_halo = true;
   h->epoch = 0;
   { const char *e = getenv("PYDCOP_B200_PUSH_SPLIT"); h->split_push = !(e && e[0] == '0'); }   // default on: 102 vs 177 us at N=2
+  // fused halo: every class that produces rows must run on a warp kernel (they carry the peer stores)
+  bool all_warp = plan->dev_edge_dst_r[0] && plan->dev_edge_dst_r[1] && plan->dev_slot_dst_q[0] && plan->dev_slot_dst_q[1] &&
+                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && !fg_env_is("PYDCOP_B200_PUSH_FUSED", '0');
+  for (size_t i = 0; all_warp && i < h->classes.size(); ++i)
+    if (h->classes[i].n_factors && !(h->classes[i].flags & FG_CLASS_GHOST) && !h->warp.f2v[i]) all_warp = false;
+  h->fused_push = all_warp;
   return FG_OK;
 }
+
+extern "C" int fg_maxsum_shard_fused(fg_maxsum_t h) { return (h && h->has_halo && h->fused_push) ? 1 : 0; }
 
 extern "C" int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream) {
   if (!h || !h->has_halo) return FG_ERR_ARG;
@@ -365,11 +383,11 @@ extern "C" int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream)
   const int nxt = h->cur ^ 1;
   switch (phase) {
     case 0: {
-      const bool split = h->split_push && h->cycle > 0;
+      const bool split = (h->split_push || h->fused_push) && h->cycle > 0;
       return h->d.precision == FG_F64 ? maxsum_compute_t<double>(h, st, split) : maxsum_compute_t<float>(h, st, split);
     }
     case 1: {
-      const bool split = h->split_push && h->cycle > 0;   // rows already on their way: release only
+      const bool split = (h->split_push || h->fused_push) && h->cycle > 0;   // rows already on their way: release only
       return halo_push_launch(h->halo, h->d.dev_r[nxt], h->d.dev_q[nxt], nxt, split ? 0 : h->halo.n_r,
                               split ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches);
     }

@@ -179,6 +179,26 @@ struct V2FWarpCfg {
   static constexpr bool OK = SMEM <= FG_SMEM_LIMIT;
 };
 
+
+// Fused halo (multi-GPU): a boundary row leaves for its consumer's buffer — an IPC-mapped address of another
+// GPU, reached over NVLink — from the lane that produced it, while the rest of the tile is still being
+// computed; interior rows have destination 0.  8-byte stores when the row size allows (rows are 8-byte
+// aligned at both ends for even D), else element stores.
+template <typename T, int D>
+__device__ __forceinline__ void peer_store_row(int64_t dst, const T *row) {
+  if (dst == 0) return;
+  if constexpr ((D * sizeof(T)) % 8 == 0) {
+    uint64_t *d = reinterpret_cast<uint64_t *>(dst);
+    const uint64_t *s = reinterpret_cast<const uint64_t *>(row);
+#pragma unroll
+    for (int i = 0; i < (int)(D * sizeof(T) / 8); ++i) d[i] = s[i];
+  } else {
+    T *d = reinterpret_cast<T *>(dst);
+#pragma unroll
+    for (int i = 0; i < D; ++i) d[i] = row[i];
+  }
+}
+
 template <typename T, int D, int NS_, bool MX, typename OffT>
 __global__ void __launch_bounds__(FG_V2FW_WARPS * 32, FG_V2FW_MINB)
 k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, const OffT *__restrict__ slot_roff,
@@ -186,6 +206,7 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
            T *__restrict__ q_next, uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent,
            int32_t *__restrict__ value, T *__restrict__ value_cost, MaxSumParams p) {
   using C = V2FWarpCfg<T, D, NS_>;
+  const int64_t *__restrict__ slot_dst = p.slot_dst;   // per slot: peer address of its q row this cycle, 0 = interior; may be null
   constexpr int VR = C::VR, PIECES = C::PIECES, NS = C::NS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -215,6 +236,9 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
   };
   auto load_cnt = [&](const WTile &t) -> uint8_t {
     return lane < t.nslots ? q_cnt[t.slot0 + lane] : (uint8_t)0;
+  };
+  auto load_dst = [&](const WTile &t) -> int64_t {
+    return (slot_dst != nullptr && lane < t.nslots) ? slot_dst[t.slot0 + lane] : (int64_t)0;
   };
   // start every load of a tile into stage s (all lanes)
   auto issue = [&](int s, const WTile &t, OffT roff) {
@@ -259,7 +283,9 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
     cur_l = cur_i;
   }
   OffT roff_n = load_roff(tile_at(NS - 1, cur_l));
+  int cur_d = 0;
   uint8_t cnt = load_cnt(tile_at(0, cur_n));
+  int64_t pdst = load_dst(tile_at(0, cur_d));
 
 #pragma unroll 1
   for (int k = 0;; ++k) {
@@ -272,6 +298,7 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
     issue((k + NS - 1) % NS, tile_at(k + NS - 1, cur_i), roff_n);
     const OffT roff_n2 = load_roff(tile_at(k + NS, cur_l));
     const uint8_t cnt_n = load_cnt(tile_at(k + 1, cur_n));
+    const int64_t pdst_n = load_dst(tile_at(k + 1, cur_d));
     cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
     mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and so have its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
@@ -318,6 +345,7 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
         for (int x = 0; x < D; ++x) cand[x] = prev[x];
       }
       st_row<T, D, VR>(qio + lane * D, cand);
+      peer_store_row<T, D>(pdst, cand);
       q_cnt[slot0 + lane] = c8;
       if (q_sent) q_sent[slot0 + lane] = sent ? 1 : 0;
       if (f == K - 1) {
@@ -340,6 +368,7 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
     }
     roff_n = roff_n2;
     cnt = cnt_n;
+    pdst = pdst_n;
   }
   cp_async_wait_all();
   if (lane == 0) tma_store_wait_read();
@@ -524,6 +553,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
            const T *__restrict__ r_cur, T *__restrict__ r_next, const OffT *__restrict__ edge_qoff,
            uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
   using C = F2VWarpCfg<T, D, NS_>;
+  const int64_t *__restrict__ edge_dst = p.edge_dst;   // per edge: peer address of its r row this cycle, 0 = interior; may be null
   using P = typename Pair<T>::type;
   constexpr int S = C::S, HD = C::HD, NF = C::NF, NS = C::NS, VR = C::VR, PIECES = C::PIECES, R = 2 * D;
   constexpr int WARPS = C::WARPS > 0 ? C::WARPS : 1;
@@ -557,6 +587,13 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
       if (lane < 2 * min(NF, c.n_factors - f0)) return r_cnt[c.first_edge + f0 * 2 + lane];
     }
     return (uint8_t)0;
+  };
+  auto load_dst = [&](int k) -> int64_t {   // lane = local edge 2 f + j
+    if (edge_dst != nullptr && k < n_my) {
+      const int f0 = (gw + k * nw) * NF;
+      if (lane < 2 * min(NF, c.n_factors - f0)) return edge_dst[c.first_edge + f0 * 2 + lane];
+    }
+    return (int64_t)0;
   };
   auto issue = [&](int k, OffT qo) {
     if (k < n_my) {
@@ -601,6 +638,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
   for (int k = 0; k < NS - 1; ++k) issue(k, load_qo(k));
   OffT qo_next = load_qo(NS - 1);
   uint8_t cnt = load_cnt(0);
+  int64_t pdst = load_dst(0);
 
 #pragma unroll 1
   for (int k = 0; k < n_my; ++k) {
@@ -612,6 +650,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     issue(k + NS - 1, qo_next);
     const OffT qo_n2 = load_qo(k + NS);
     const uint8_t cnt_n = load_cnt(k + 1);
+    const int64_t pdst_n = load_dst(k + 1);
     cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
     mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
@@ -746,8 +785,10 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
       for (int i = lane; i < nf * R; i += 32) gout[i] = ot[i];
       __syncwarp();
     }
+    peer_store_row<T, D>(pdst, ot + lane * D);   // lane = local edge 2 f + j: its finished row (all lanes met above)
     qo_next = qo_n2;
     cnt = cnt_n;
+    pdst = pdst_n;
   }
   cp_async_wait_all();
   if (lane == 0) tma_store_wait_read();

@@ -565,9 +565,8 @@ def _assemble(dom_size, factor_ptr, edge_var, tables, unary, init_value):
     flat = np.concatenate(tables) if len(tables) else np.zeros(0, dtype=np.float64)
     V = len(dom_size)
     # incident edges of every variable in constraint (= edge id) order, factor_graph.py:277-280
-    order = np.argsort(edge_var, kind="stable").astype(np.int32)
-    var_ptr = np.zeros(V + 1, dtype=np.int32)
-    np.cumsum(np.bincount(edge_var, minlength=V), out=var_ptr[1:])
+    from .layout import stable_group_order
+    order, var_ptr = stable_group_order(edge_var, V)
     return dict(dom_size=np.asarray(dom_size, dtype=np.int32), factor_ptr=factor_ptr,
                 edge_var=edge_var, table_off=table_off, tables=flat,
                 unary=np.asarray(unary, dtype=np.float64), var_ptr=var_ptr, var_edge=order,
@@ -690,10 +689,8 @@ def from_arrays(inst: Dict[str, np.ndarray], name="dcop", objective="min") -> Dc
     if a.get("unary") is None:
         a["unary"] = np.zeros(int(dom.sum()))
     if a.get("var_ptr") is None or a.get("var_edge") is None:
-        a["var_edge"] = np.argsort(ev, kind="stable").astype(np.int32)
-        vp = np.zeros(len(dom) + 1, dtype=np.int32)
-        np.cumsum(np.bincount(ev, minlength=len(dom)), out=vp[1:])
-        a["var_ptr"] = vp
+        from .layout import stable_group_order
+        a["var_edge"], a["var_ptr"] = stable_group_order(ev, len(dom))
     if a.get("init_value") is None:
         a["init_value"] = np.full(len(dom), -1, dtype=np.int32)
     a["dom_size"], a["factor_ptr"], a["edge_var"] = dom, fp, ev

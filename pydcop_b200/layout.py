@@ -206,13 +206,36 @@ def _gather_tables(tables, starts, size):
     return tables[idx.reshape(-1)]
 
 
+def stable_group_order(keys, n_groups=None):
+    """np.argsort(keys, kind="stable") for small non-negative integer keys, plus the group pointer array:
+    a counting sort (scipy's COO -> CSR kernel, O(n)) instead of a comparison sort — the packing of a
+    10^5-variable problem spent a third of its time in three such sorts.  Returns (order int32, ptr int32)."""
+    keys = np.ascontiguousarray(keys)
+    n = len(keys)
+    if n_groups is None:
+        n_groups = int(keys.max()) + 1 if n else 0
+    if n and n < 2 ** 31 - 1 and n_groups < 2 ** 31 - 1:
+        try:
+            from scipy.sparse import _sparsetools
+            k32 = keys.astype(np.int32, copy=False)
+            ptr = np.empty(n_groups + 1, dtype=np.int32)
+            order = np.empty(n, dtype=np.int32)
+            junk = np.empty(n, dtype=np.int8)
+            _sparsetools.coo_tocsr(n_groups, n, n, k32, np.arange(n, dtype=np.int32), np.zeros(n, dtype=np.int8),
+                                   ptr, order, junk)
+            return order, ptr
+        except Exception:  # noqa: BLE001 — scipy missing or its private kernel moved: comparison sort below
+            pass
+    order = np.argsort(keys, kind="stable").astype(np.int32)
+    ptr = np.zeros(n_groups + 1, dtype=np.int32)
+    if n:
+        np.cumsum(np.bincount(keys, minlength=n_groups), out=ptr[1:])
+    return order, ptr
+
+
 def default_var_csr(n_vars, edge_var):
     """Incident edges per variable in ascending (canonical) edge id == constraint order."""
-    edge_var = _as(edge_var, np.int64)
-    order = np.argsort(edge_var, kind="stable").astype(np.int32)
-    deg = np.bincount(edge_var, minlength=n_vars)
-    var_ptr = np.zeros(n_vars + 1, dtype=np.int32)
-    np.cumsum(deg, out=var_ptr[1:])
+    order, var_ptr = stable_group_order(_as(edge_var, np.int32), n_vars)
     return var_ptr, order
 
 
@@ -262,7 +285,7 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
         uniq, cls_of_factor = _unique_rows(key)
     else:
         uniq, cls_of_factor = np.zeros((0, MAX_ARITY + 1), np.int32), np.zeros(0, np.int64)
-    order = np.argsort(cls_of_factor, kind="stable")          # internal factor -> canonical factor
+    order = stable_group_order(cls_of_factor, len(uniq))[0].astype(np.int64)   # internal factor -> canonical factor
     factor_perm = np.empty(F, dtype=np.int32)
     factor_perm[order] = np.arange(F, dtype=np.int32)          # canonical -> internal
     counts = np.bincount(cls_of_factor, minlength=len(uniq)) if F else np.zeros(0, np.int64)
@@ -334,7 +357,8 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     vkey = dom_size.astype(np.int64) * (MAX_CLASS_DEGREE + 2) + kdeg
     vtag = np.zeros(V, dtype=np.int64) if var_tag is None else _as(var_tag, np.int64)
     vkey = vkey + vtag * ((MAX_DOM + 1) * (MAX_CLASS_DEGREE + 2))
-    var_order = np.argsort(vkey, kind="stable").astype(np.int32)   # internal -> canonical
+    _, vk_inv = np.unique(vkey, return_inverse=True)               # dense class index, same order as the keys
+    var_order = stable_group_order(vk_inv.reshape(-1))[0]           # internal -> canonical
     var_perm = np.empty(V, dtype=np.int32)
     var_perm[var_order] = np.arange(V, dtype=np.int32)              # canonical -> internal
     i_dom = dom_size[var_order]

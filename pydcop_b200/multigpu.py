@@ -40,6 +40,7 @@ class ShardPlan:
     layout: FactorGraphLayout
     own_vars: np.ndarray            # global ids of the variables this rank owns (ascending)
     n_own_vars: int
+    ghost_vars: np.ndarray          # global ids of the other ranks' variables in the scopes of this rank's factors
     # halo, one entry per cut edge touching this rank, grouped by peer in ascending global edge id
     send_r_off: np.ndarray          # int64 element offsets into r (rows this rank produces)
     send_q_off: np.ndarray          # int64 element offsets into q
@@ -224,6 +225,7 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int, partition="b
     rr_split, rr_rows = sq_split, sq_rows
     return ShardPlan(
         rank=rank, world=world, layout=L, own_vars=own_v.astype(np.int64), n_own_vars=n_own,
+        ghost_vars=np.asarray(ghost_vars, dtype=np.int64),
         send_r_off=fr, send_q_off=vq, recv_r_off=vr, recv_q_off=fq,
         send_r_len=fl, send_q_len=vl, recv_r_len=vl, recv_q_len=fl,
         send_r_edge=fe, send_q_edge=ve, recv_r_edge=ve, recv_q_edge=fe,
@@ -391,6 +393,29 @@ def push_tables(plan: ShardPlan, base: np.ndarray, dst_r_off, dst_q_off, elem: i
         src_q_off=np.asarray(plan.send_q_off, dtype=np.int64)[perm_q])
 
 
+def fused_destinations(plan: ShardPlan, base: np.ndarray, dst_r_off, dst_q_off, elem: int):
+    """Per-edge / per-slot destination addresses of the FUSED halo (fg_halo_plan_t::dev_edge_dst_r / dev_slot_dst_q):
+    for buffer index b, edge_dst[b][e] = address in the consumer's r[b] of the row edge e's factor produces (internal,
+    class-major edge ids), slot_dst[b][s] = address in the consumer's q[b] of slot s's row; 0 = the row stays here.
+    Same inputs as push_tables.  Pure function (tested on CPU)."""
+    L, W = plan.layout, plan.world
+    peer_of_r = np.repeat(np.arange(W), np.asarray(plan.send_r_rows, dtype=np.int64))
+    peer_of_q = np.repeat(np.arange(W), np.asarray(plan.send_q_rows, dtype=np.int64))
+    dst_r_off = np.asarray(dst_r_off, dtype=np.int64)
+    dst_q_off = np.asarray(dst_q_off, dtype=np.int64)
+    slot_of_edge = np.empty(L.n_edges, dtype=np.int64)
+    slot_of_edge[np.asarray(L.slot_edge, dtype=np.int64)] = np.arange(L.n_edges)
+    edge_dst, slot_dst = [], []
+    for b in range(2):
+        er = np.zeros(max(L.n_edges, 1), dtype=np.int64)
+        er[np.asarray(plan.send_r_edge, dtype=np.int64)] = base[peer_of_r, 2 + b] + dst_r_off * elem
+        sq = np.zeros(max(L.n_edges, 1), dtype=np.int64)
+        sq[slot_of_edge[np.asarray(plan.send_q_edge, dtype=np.int64)]] = base[peer_of_q, 0 + b] + dst_q_off * elem
+        edge_dst.append(er)
+        slot_dst.append(sq)
+    return edge_dst, slot_dst
+
+
 def push_runs(dst_addr, row_bytes: int):
     """Cut a push list (absolute destination address per row, in push order) into RUNS of rows whose
     destinations are consecutive addresses.  Returns (int64 [n_runs, 4], total_units): per run the first
@@ -474,11 +499,18 @@ class PeerPush:
                         getattr(plan, "n_runs_" + name)[b] = len(runs)
                         getattr(plan, "units_" + name)[b] = units
         self.n_runs = [int(plan.n_runs_r[0]), int(plan.n_runs_q[0])]
+        # fused halo: the warp kernels store each boundary row from the lane that produced it (the engine decides at
+        # attach time whether every class of this shard runs on them; PYDCOP_B200_PUSH_FUSED=0 keeps the push kernels)
+        ed, sd = fused_destinations(p, base, dst_r_off, dst_q_off, elem)
+        self.edge_dst, self.slot_dst = [to(a) for a in ed], [to(a) for a in sd]
+        for b in range(2):
+            plan.dev_edge_dst_r[b], plan.dev_slot_dst_q[b] = self.edge_dst[b].data_ptr(), self.slot_dst[b].data_ptr()
         self._plan = plan
         rc = e.lib.fg_maxsum_shard_attach(e._h, C.byref(plan))
         if rc != 0:
             raise RuntimeError(f"fg_maxsum_shard_attach failed rc={rc}: {e._last_error()}")
         self.launches = 0      # counted inside the engine handle now
+        self.fused = bool(e.lib.fg_maxsum_shard_fused(e._h))
         dist.barrier(group=group)
 
     def step(self, n_cycles):
@@ -653,7 +685,13 @@ class ShardedMaxSum:
             local_unary = np.concatenate([np.asarray(unary, dtype=np.float64)[_ranges(uoff[own], dom[own])],
                                           np.zeros(n_ghost_el)])
         n_own_internal = sum(c.n_vars for c in p.layout.var_classes if not c.tag)
-        out = e._solution_cost(e.value, infinity, local_unary, n_vars=n_own_internal)
+        # a cut factor's entry needs the value of a variable another rank owns, and ghost variables are never
+        # evaluated here: take them from the all-gathered assignment (local canonical order = own, then ghosts)
+        full = self.values()
+        L = p.layout
+        local = np.concatenate([full[p.own_vars], full[p.ghost_vars]]).astype(np.int32)
+        val = self.torch.from_numpy(np.ascontiguousarray(local[L.var_order])).to(e.value.device)
+        out = e._solution_cost(val, infinity, local_unary, n_vars=n_own_internal)
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.halo.group)
         o = out.cpu().numpy()
         return float(o[0]), int(round(o[1]))

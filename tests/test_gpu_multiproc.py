@@ -1,5 +1,6 @@
 """GPU (>= 2 devices): the real multi-process path — one process per GPU, NCCL for the plumbing — in
-both halo modes: pack -> all_to_all -> unpack, and the NVLink peer push through CUDA IPC closed by
+both halo modes: pack -> all_to_all -> unpack, and the NVLink peer stores through CUDA IPC (FUSED into the
+factor-side / variable-side kernels by default; the separate push kernels behind PYDCOP_B200_PUSH_FUSED=0) closed by
 the DEVICE-SIDE epoch barrier (csrc/peer_sync.cuh, fg_maxsum_shard_step / fg_dsa_shard_step).  The
 all-gathered assignment must equal the single-GPU engine's, which the other tests tie to the oracle
 bit for bit.  Cases cover: several step() calls and a re-init on one engine (the epoch counter only
@@ -62,6 +63,9 @@ def _maxsum_worker(rank, world, port, case, q):
         got = sh.values()
         cost = sh.solution_cost(9.0, inst["unary"])     # table entries equal to 9 count as violations
         used = "p2p" if sh.peer is not None else "nccl"
+        if sh.peer is not None and case.get("partition", "blocks") != "imbalanced":
+            # default: the warp kernels store the boundary rows themselves (all classes binary d=10, degrees <= 16)
+            assert sh.peer.fused == case.get("fused", True), sh.peer.fused
         if rank == 0:
             cur = 0
             for s in plan:     # cycles since the last init
@@ -141,8 +145,9 @@ MAXSUM_CASES = {
     "nccl": dict(mode="nccl"),
     "p2p": dict(mode="p2p"),
     "p2p-steps-reinit": dict(mode="p2p", steps=[1, 3, "init", 2, 5, 4]),
-    "p2p-joined-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_SPLIT": "0"}, steps=[4, 5]),
-    "p2p-per-row-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_RUNS": "0"}, steps=[4, 5]),
+    "p2p-split-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "0"}, steps=[4, 5], fused=False),
+    "p2p-joined-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "0", "PYDCOP_B200_PUSH_SPLIT": "0"}, steps=[4, 5], fused=False),
+    "p2p-per-row-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "0", "PYDCOP_B200_PUSH_RUNS": "0"}, steps=[4, 5], fused=False),
     "p2p-multilevel-f64": dict(mode="p2p", partition="multilevel", precision="f64"),
     "p2p-imbalanced": dict(mode="p2p", partition="imbalanced", n_vars=20000, steps=[12]),
 }

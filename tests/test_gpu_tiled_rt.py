@@ -40,17 +40,19 @@ def test_parameter_sweep(params):
     _run_pair(inst, "f32", 11, **params)
 
 
-def test_large_table_one_factor_per_cta():
-    """arity 3, d = 20: one 32 KB table per CTA (f32); f64 leaves one table per CTA as well"""
-    inst = random_factor_graph(60, 20, 50, 3, seed=2, int_tables=False)
+def test_large_tables():
+    """one table per CTA: 54 KB (f32, 72 KB launch), 108 KB (f64, 200 KB launch), and tables that do not fit
+    shared memory at all and are read in place (arity 4 over 16 values: 256 KB in f32)"""
+    inst = random_factor_graph(60, 24, 40, 3, seed=2, int_tables=False)     # 13 824 entries
     for prec in ("f32", "f64"):
         eng = _run_pair(inst, prec, 4)
-        assert set(eng.kernel_plan()) == {"pipe"} or set(eng.kernel_plan()) == {"tiled_rt"}
-    inst = random_factor_graph(60, 24, 40, 3, seed=2, int_tables=False)     # 13 824 entries: 54 KB in f32
-    eng = _run_pair(inst, "f32", 4)
+        assert set(eng.kernel_plan()) == {"tiled_rt"}
+    inst = random_factor_graph(40, 16, 12, 4, seed=6, int_tables=False)     # 65 536 entries
+    eng = _run_pair(inst, "f32", 3)
     assert set(eng.kernel_plan()) == {"tiled_rt"}
-    eng = _run_pair(inst, "f64", 4)                                          # 108 KB: does not fit, generic kernel
-    assert set(eng.kernel_plan()) == {"generic"}
+    inst = mixed_shape_graph(50, (12, 33), [(4, 10), (2, 40)], seed=4)      # last dimension wider than a warp
+    eng = _run_pair(inst, "f32", 3)
+    assert "generic" not in eng.kernel_plan()
 
 
 def test_tiled_rt_and_generic_agree(monkeypatch):

@@ -315,6 +315,18 @@ def test_peer_push_tables_move_every_boundary_row_to_its_ghost_row(world, partit
             dst_r.append(np.asarray(pb.recv_r_off[ro_r[a]:ro_r[a + 1]], dtype=np.int64))
             dst_q.append(np.asarray(pb.recv_q_off[ro_q[a]:ro_q[a + 1]], dtype=np.int64))
         t = push_tables(pa, base, np.concatenate(dst_r), np.concatenate(dst_q), elem)
+        # the FUSED halo's per-edge / per-slot destinations describe the same set of (source row -> address) moves:
+        # edge e's r row sits at edge_msg_off[e], slot s's q row at edge_qoff[slot_edge[s]]
+        from pydcop_b200.multigpu import fused_destinations
+        ed, sd = fused_destinations(pa, base, np.concatenate(dst_r), np.concatenate(dst_q), elem)
+        La = pa.layout
+        for b in range(2):
+            e_idx = np.nonzero(ed[b])[0]
+            assert sorted(zip(La.edge_msg_off[e_idx].tolist(), ed[b][e_idx].tolist())) == \
+                sorted(zip(np.asarray(t["src_r_off"]).tolist(), np.asarray(t["dst_r"][b]).tolist()))
+            s_idx = np.nonzero(sd[b])[0]
+            assert sorted(zip(La.edge_qoff[La.slot_edge[s_idx]].tolist(), sd[b][s_idx].tolist())) == \
+                sorted(zip(np.asarray(t["src_q_off"]).tolist(), np.asarray(t["dst_q"][b]).tolist()))
         for src, dst, arr in ((t["src_r_off"], t["dst_r"][1], 3), (t["src_q_off"], t["dst_q"][1], 1)):
             assert len(src) == len(dst)
             for s, addr in zip(src, dst):

@@ -36,8 +36,46 @@ class HostEngine(HostMaxSum):
         self.launch_count = 0
         self.layout = layout
 
+        self.value = torch.from_numpy(k["value"])
+
     def cycle_compute(self):
         self.lib.ms_host_cycle(C.byref(self.h), self.cur, int(self.cycle == 0))
+
+    def _solution_cost(self, value_tensor, infinity=float("inf"), unary=None, n_vars=None, factor_skip=None,
+                       var_skip=None):
+        """Host restatement of fg_solution_cost's contract (same arguments as _EngineBase._solution_cost):
+        non-ghost classes, the first n_vars internal variables, entries equal to `infinity` counted."""
+        L = self.layout
+        val = value_tensor.numpy().astype(np.int64)
+        ev = np.asarray(L.edge_var, dtype=np.int64)
+        tdt = np.asarray(self.keep["tables"]).dtype
+        inf_t = np.array(infinity).astype(tdt)
+        cost, viol = 0.0, 0
+        for c in L.classes:
+            if c.tag or not c.n_factors:
+                continue
+            a, S = c.arity, c.table_size
+            scope = ev[c.first_edge:c.first_edge + c.n_factors * a].reshape(c.n_factors, a)
+            idx = np.zeros(c.n_factors, dtype=np.int64)
+            for j in range(a):
+                idx = idx * c.dom[j] + val[scope[:, j]]
+            ent = np.asarray(self.keep["tables"])[c.table_base + np.arange(c.n_factors) * S + idx]
+            bad = ent == inf_t
+            viol += int(bad.sum())
+            cost += float(ent[~bad].astype(np.float64).sum())
+        if unary is not None:
+            n = L.n_vars if n_vars is None else n_vars
+            cu = np.asarray(unary, dtype=np.float64)
+            dom = L.dom_size.astype(np.int64)               # internal order
+            c_dom = dom[L.var_perm]                         # canonical order
+            c_off = np.concatenate([[0], np.cumsum(c_dom)])[:-1]
+            for v in range(n):                               # internal variable v = canonical L.var_order[v]
+                u = cu[c_off[L.var_order[v]] + val[v]].astype(tdt)
+                if u == inf_t:
+                    viol += 1
+                else:
+                    cost += float(u)
+        return torch.tensor([cost, float(viol)], dtype=torch.float64)
 
     def cycle_commit(self):
         self.cur ^= 1
@@ -67,6 +105,11 @@ def _instance(kind):
     return inst
 
 
+def _cost_infinity(inst):
+    """a table value that occurs: entries equal to it count as violations (dcop.py:355-367)"""
+    return float(np.asarray(inst["tables"]).reshape(-1)[3])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -86,9 +129,11 @@ def _worker(rank, world, port, kind, params, partition, n_cycles, q):
         for _ in range(n_cycles):
             sm.step()
             traj.append(sm.values())
+        inst = _instance(kind)
+        cost = sm.solution_cost(_cost_infinity(inst), inst["unary"])
         dist.barrier()
         dist.destroy_process_group()
-        q.put((rank, "ok", np.stack(traj)))
+        q.put((rank, "ok", (np.stack(traj), cost)))
     except Exception as e:  # noqa: BLE001
         import traceback
         q.put((rank, "FAIL " + repr(e) + traceback.format_exc(), None))
@@ -119,7 +164,12 @@ def test_sharded_maxsum_class_over_gloo_with_the_kernel_source(kind, world, para
     res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=30)
-    for rank, status, traj in res:
+    from pydcop_b200 import ingest, solve as S
+    dcop = ingest.from_arrays(inst)
+    viol, cost = S.solution_cost(dcop, want[-1], _cost_infinity(inst))
+    for rank, status, out in res:
         assert status == "ok", (rank, status)
+        traj, got = out
         assert np.array_equal(traj, want), rank
+        assert got[1] == viol and viol > 0 and abs(got[0] - cost) <= 1e-9 * max(1.0, abs(cost)), (got, cost, viol)
     assert (np.diff(want, axis=0) != 0).any()
