@@ -285,6 +285,10 @@ def side_workload(args, dev):
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     parity = None
+    breakdown = None
+    if world > 1 and getattr(eng, "peer", None) is not None and hasattr(eng, "timed_breakdown"):
+        breakdown = {k: round(1e3 * v, 2) for k, v in eng.timed_breakdown(30).items()}   # every rank takes part
+        breakdown["unit"] = "us per cycle, rank 0"
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -318,6 +322,8 @@ def side_workload(args, dev):
     if world > 1:
         line["parity"] = parity
         line["config"]["partition"] = part
+        if breakdown is not None:
+            line["breakdown"] = breakdown
         if w == "c4":
             line["config"]["boundary_values"] = int(eng.shard.n_boundary)
             line["config"]["halo"] = "peer push" if eng.peer is not None else "nccl all_to_all"

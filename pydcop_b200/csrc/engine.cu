@@ -42,6 +42,10 @@ struct fg_maxsum {
   bool has_halo = false;
   bool split_push = true;   // r rows right behind the factor side, q rows on the side stream (PYDCOP_B200_PUSH_SPLIT=0: one push after the join)
   bool fused_push = false;  // boundary rows stored to the peers by the warp kernels themselves (fg_halo_plan_t::dev_edge_dst_r)
+  bool chain_push = true;   // split mode: the q push waits for the r push, then releases the epoch AND waits for the peers'
+                            // releases in its last block — no separate release / wait kernels (PYDCOP_B200_PUSH_CHAIN=0: off)
+  bool chained_now = false; // the cycle being enqueued was closed inside phase 0
+  cudaEvent_t ev_r = nullptr;
   fg_halo_plan_t halo;
   uint64_t epoch = 0;
   cudaEvent_t *prof = nullptr;   // fg_maxsum_shard_profile: 8 timing events recorded inside a cycle
@@ -141,6 +145,7 @@ extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
   if (h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_r) cudaEventDestroy(h->ev_r);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->warp.dev_classes) cudaFree(h->warp.dev_classes);
     tiled_rt_free(h->tiled_rt);
@@ -234,6 +239,9 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, h->halo.n_r, 0, 0, 0, st, h->launches);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (r rows) failed"); return rc; }
   }
+  const bool chain = push_split && h->chain_push && fork;   // the side stream's last launch closes the cycle
+  h->chained_now = chain;
+  if (chain) CUDA_TRY(h, cudaEventRecord(h->ev_r, st));
   if (h->prof) cudaEventRecord(h->prof[2], st);
   // variable -> factor (+ value selection).  Both sides only READ the current buffers and WRITE
   // disjoint next buffers (Jacobi), so from cycle 2 on the variable side runs on a second stream,
@@ -274,7 +282,11 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
     }
   }
   if (h->prof) cudaEventRecord(h->prof[3], st);
-  if (push_split && !fused && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
+  if (chain) {   // everything this rank sends in this cycle is on its way once the r push is done as well
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_r, 0));
+    int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, fused ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches, 1);
+    if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, release, wait) failed"); return rc; }
+  } else if (push_split && !fused && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, st, h->launches);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows) failed"); return rc; }
   }
@@ -368,10 +380,13 @@ extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan)
   { const char *e = getenv("PYDCOP_B200_PUSH_SPLIT"); h->split_push = !(e && e[0] == '0'); }   // default on: 102 vs 177 us at N=2
   // fused halo: every class that produces rows must run on a warp kernel (they carry the peer stores)
   bool all_warp = plan->dev_edge_dst_r[0] && plan->dev_edge_dst_r[1] && plan->dev_slot_dst_q[0] && plan->dev_slot_dst_q[1] &&
-                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && !fg_env_is("PYDCOP_B200_PUSH_FUSED", '0');
+                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && fg_env_is("PYDCOP_B200_PUSH_FUSED", '1') &&
+                  fg_env_int("PYDCOP_B200_F2VW_NS", 2) == 2 && fg_env_int("PYDCOP_B200_V2FW_NS", 2) == 2;   // opt-in: measured slower
   for (size_t i = 0; all_warp && i < h->classes.size(); ++i)
     if (h->classes[i].n_factors && !(h->classes[i].flags & FG_CLASS_GHOST) && !h->warp.f2v[i]) all_warp = false;
   h->fused_push = all_warp;
+  h->chain_push = !fg_env_is("PYDCOP_B200_PUSH_CHAIN", '0') && h->side_stream != nullptr;
+  if (h->chain_push && !h->ev_r) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_r, cudaEventDisableTiming));
   return FG_OK;
 }
 
@@ -387,12 +402,13 @@ extern "C" int fg_maxsum_shard_phase(fg_maxsum_t h, int32_t phase, void *stream)
       return h->d.precision == FG_F64 ? maxsum_compute_t<double>(h, st, split) : maxsum_compute_t<float>(h, st, split);
     }
     case 1: {
+      if (h->chained_now) return FG_OK;   // released (and waited) by the q push of phase 0
       const bool split = (h->split_push || h->fused_push) && h->cycle > 0;   // rows already on their way: release only
       return halo_push_launch(h->halo, h->d.dev_r[nxt], h->d.dev_q[nxt], nxt, split ? 0 : h->halo.n_r,
                               split ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches);
     }
-    case 2: return peer_wait_launch(h->halo.sync, h->epoch + 1, st, h->launches);
-    case 3: ++h->epoch; return fg_maxsum_cycle_commit(h);
+    case 2: return h->chained_now ? FG_OK : peer_wait_launch(h->halo.sync, h->epoch + 1, st, h->launches);
+    case 3: ++h->epoch; h->chained_now = false; return fg_maxsum_cycle_commit(h);
   }
   return FG_ERR_ARG;
 }

@@ -199,14 +199,15 @@ __device__ __forceinline__ void peer_store_row(int64_t dst, const T *row) {
   }
 }
 
-template <typename T, int D, int NS_, bool MX, typename OffT>
+template <typename T, int D, int NS_, bool MX, typename OffT, bool PEER = false>
 __global__ void __launch_bounds__(FG_V2FW_WARPS * 32, FG_V2FW_MINB)
 k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, const OffT *__restrict__ slot_roff,
            const T *__restrict__ unary, const T *__restrict__ r_cur, const T *__restrict__ q_cur,
            T *__restrict__ q_next, uint8_t *__restrict__ q_cnt, uint8_t *__restrict__ q_sent,
            int32_t *__restrict__ value, T *__restrict__ value_cost, MaxSumParams p) {
   using C = V2FWarpCfg<T, D, NS_>;
-  const int64_t *__restrict__ slot_dst = p.slot_dst;   // per slot: peer address of its q row this cycle, 0 = interior; may be null
+  // PEER (opt-in fused halo): per slot the peer address of its q row this cycle, 0 = interior
+  const int64_t *__restrict__ slot_dst = PEER ? p.slot_dst : nullptr;
   constexpr int VR = C::VR, PIECES = C::PIECES, NS = C::NS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -238,6 +239,7 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
     return lane < t.nslots ? q_cnt[t.slot0 + lane] : (uint8_t)0;
   };
   auto load_dst = [&](const WTile &t) -> int64_t {
+    if constexpr (!PEER) return (int64_t)0;
     return (slot_dst != nullptr && lane < t.nslots) ? slot_dst[t.slot0 + lane] : (int64_t)0;
   };
   // start every load of a tile into stage s (all lanes)
@@ -285,7 +287,8 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
   OffT roff_n = load_roff(tile_at(NS - 1, cur_l));
   int cur_d = 0;
   uint8_t cnt = load_cnt(tile_at(0, cur_n));
-  int64_t pdst = load_dst(tile_at(0, cur_d));
+  int64_t pdst = 0;
+  if constexpr (PEER) pdst = load_dst(tile_at(0, cur_d));
 
 #pragma unroll 1
   for (int k = 0;; ++k) {
@@ -298,7 +301,8 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
     issue((k + NS - 1) % NS, tile_at(k + NS - 1, cur_i), roff_n);
     const OffT roff_n2 = load_roff(tile_at(k + NS, cur_l));
     const uint8_t cnt_n = load_cnt(tile_at(k + 1, cur_n));
-    const int64_t pdst_n = load_dst(tile_at(k + 1, cur_d));
+    int64_t pdst_n = 0;
+    if constexpr (PEER) pdst_n = load_dst(tile_at(k + 1, cur_d));
     cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
     mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and so have its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
@@ -345,7 +349,7 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
         for (int x = 0; x < D; ++x) cand[x] = prev[x];
       }
       st_row<T, D, VR>(qio + lane * D, cand);
-      peer_store_row<T, D>(pdst, cand);
+      if constexpr (PEER) peer_store_row<T, D>(pdst, cand);
       q_cnt[slot0 + lane] = c8;
       if (q_sent) q_sent[slot0 + lane] = sent ? 1 : 0;
       if (f == K - 1) {
@@ -438,6 +442,17 @@ inline bool launch_v2f_warp_ns(const WClassEntry *dev_classes, const WTileRange 
     }
     const int need = (rg.n_tiles + FG_V2FW_WARPS - 1) / FG_V2FW_WARPS;
     const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
+    if constexpr (NS_ == 2) {   // fused halo: same kernel with the peer stores compiled in (default depth only)
+      if (p.slot_dst != nullptr) {
+        auto kp = k_v2f_warp<T, D, NS_, MX, uint32_t, true>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr = true; }
+        kp<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(dev_classes + rg.first, rg.count, rg.n_tiles, d.dev_slot_roff32,
+                                                        (const T *)d.dev_unary, r_cur, q_cur, q_next, d.dev_q_cnt, d.dev_q_sent,
+                                                        d.dev_value, (T *)d.dev_value_cost, p);
+        return true;
+      }
+    }
     kern<<<blocks, FG_V2FW_WARPS * 32, C::SMEM, st>>>(dev_classes + rg.first, rg.count, rg.n_tiles,
                                                        d.dev_slot_roff32, (const T *)d.dev_unary, r_cur, q_cur, q_next,
                                                        d.dev_q_cnt, d.dev_q_sent, d.dev_value, (T *)d.dev_value_cost, p);
@@ -547,13 +562,14 @@ __host__ __device__ constexpr int f2vw_row(int h, int i) {
   return ((D / 2) % 2 == 0) ? h * (D / 2) + i : (i < D / 2 - 1 ? h * (D / 2 - 1) + i : 2 * (D / 2 - 1) + h);
 }
 
-template <typename T, int D, int NS_, bool MX, typename OffT>
+template <typename T, int D, int NS_, bool MX, typename OffT, bool PEER = false>
 __global__ void __launch_bounds__(F2VWarpCfg<T, D, NS_>::WARPS > 0 ? F2VWarpCfg<T, D, NS_>::WARPS * 32 : 32)
 k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict__ q_cur,
            const T *__restrict__ r_cur, T *__restrict__ r_next, const OffT *__restrict__ edge_qoff,
            uint8_t *__restrict__ r_cnt, uint8_t *__restrict__ r_sent, MaxSumParams p) {
   using C = F2VWarpCfg<T, D, NS_>;
-  const int64_t *__restrict__ edge_dst = p.edge_dst;   // per edge: peer address of its r row this cycle, 0 = interior; may be null
+  // PEER (opt-in fused halo): per edge the peer address of its r row this cycle, 0 = interior
+  const int64_t *__restrict__ edge_dst = PEER ? p.edge_dst : nullptr;
   using P = typename Pair<T>::type;
   constexpr int S = C::S, HD = C::HD, NF = C::NF, NS = C::NS, VR = C::VR, PIECES = C::PIECES, R = 2 * D;
   constexpr int WARPS = C::WARPS > 0 ? C::WARPS : 1;
@@ -589,6 +605,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     return (uint8_t)0;
   };
   auto load_dst = [&](int k) -> int64_t {   // lane = local edge 2 f + j
+    if constexpr (!PEER) return (int64_t)0;
     if (edge_dst != nullptr && k < n_my) {
       const int f0 = (gw + k * nw) * NF;
       if (lane < 2 * min(NF, c.n_factors - f0)) return edge_dst[c.first_edge + f0 * 2 + lane];
@@ -638,7 +655,8 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
   for (int k = 0; k < NS - 1; ++k) issue(k, load_qo(k));
   OffT qo_next = load_qo(NS - 1);
   uint8_t cnt = load_cnt(0);
-  int64_t pdst = load_dst(0);
+  int64_t pdst = 0;
+  if constexpr (PEER) pdst = load_dst(0);
 
 #pragma unroll 1
   for (int k = 0; k < n_my; ++k) {
@@ -650,7 +668,8 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
     issue(k + NS - 1, qo_next);
     const OffT qo_n2 = load_qo(k + NS);
     const uint8_t cnt_n = load_cnt(k + 1);
-    const int64_t pdst_n = load_dst(k + 1);
+    int64_t pdst_n = 0;
+    if constexpr (PEER) pdst_n = load_dst(k + 1);
     cp_async_wait_group<NS - 1>();                  // my gathers of tile k have landed ...
     mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));  // ... and its bulk copies
     __syncwarp();                                   // ... and every other lane's gathers
@@ -785,7 +804,7 @@ k_f2v_warp(const fg_class_t c, const T *__restrict__ tables, const T *__restrict
       for (int i = lane; i < nf * R; i += 32) gout[i] = ot[i];
       __syncwarp();
     }
-    peer_store_row<T, D>(pdst, ot + lane * D);   // lane = local edge 2 f + j: its finished row (all lanes met above)
+    if constexpr (PEER) peer_store_row<T, D>(pdst, ot + lane * D);   // lane = local edge 2 f + j: its finished row (all lanes met above)
     qo_next = qo_n2;
     cnt = cnt_n;
     pdst = pdst_n;
@@ -817,6 +836,16 @@ inline bool launch_f2v_warp_ns(bool probe, const fg_class_t &c, const fg_maxsum_
     const int n_tiles = (c.n_factors + C::NF - 1) / C::NF;
     const int need = (n_tiles + C::WARPS - 1) / C::WARPS;
     const unsigned blocks = (unsigned)std::min(need, n_sm * per_sm);
+    if constexpr (NS_ == 2) {   // fused halo: same kernel with the peer stores compiled in (default depth only)
+      if (p.edge_dst != nullptr) {
+        auto kp = k_f2v_warp<T, D, NS_, MX, uint32_t, true>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr = true; }
+        kp<<<blocks, C::WARPS * 32, C::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, d.dev_edge_qoff32,
+                                                  d.dev_r_cnt, d.dev_r_sent, p);
+        return true;
+      }
+    }
     kern<<<blocks, C::WARPS * 32, C::SMEM, st>>>(c, (const T *)d.dev_tables, q_cur, r_cur, r_next, d.dev_edge_qoff32,
                                                 d.dev_r_cnt, d.dev_r_sent, p);
     return true;

@@ -45,6 +45,37 @@ __device__ __forceinline__ void peer_release_all(const PeerSlots &ps, uint64_t e
   for (int i = 0; i < ps.n; ++i) st_release_sys_u64(ps.slot[i], epoch);
 }
 
+// ONE thread: wait until every peer's slot in MY flag array holds >= epoch (ld.acquire.sys), with a timeout
+__device__ __forceinline__ void peer_wait_all(const uint64_t *__restrict__ flags, const PeerSlots &ps, uint64_t epoch,
+                                              uint64_t timeout_ns, int32_t *__restrict__ err) {
+  const uint64_t t0 = global_timer_ns();
+  for (int i = 0; i < ps.n; ++i) {
+    const uint64_t *f = flags + ps.rank[i];
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(f) < epoch) {
+      if ((++spins & 255u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+        atomicCAS(err, 0, ps.rank[i] + 1);
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// what the releasing thread does after the release when the launch also closes the cycle (null flags = nothing)
+struct PeerWait {
+  const uint64_t *flags;
+  uint64_t timeout_ns;
+  int32_t *err;
+};
+
+__global__ void k_peer_signal_wait(PeerSlots ps, uint64_t epoch, PeerWait w) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    peer_release_all(ps, epoch);
+    if (w.flags) peer_wait_all(w.flags, ps, epoch, w.timeout_ns, w.err);
+  }
+}
+
 __global__ void k_peer_signal(PeerSlots ps, uint64_t epoch) {
   if (threadIdx.x == 0 && blockIdx.x == 0) peer_release_all(ps, epoch);
 }
@@ -75,7 +106,7 @@ __global__ void __launch_bounds__(256)
 k_halo_push_sig(const unsigned char *__restrict__ arr_r, const unsigned char *__restrict__ arr_q,
                 const int64_t *__restrict__ off_r, const int64_t *__restrict__ off_q,
                 const int64_t *__restrict__ dst_r, const int64_t *__restrict__ dst_q, int64_t n_r, int64_t n_q,
-                int row_bytes, int elem, uint32_t *__restrict__ counter, PeerSlots ps, uint64_t epoch) {
+                int row_bytes, int elem, uint32_t *__restrict__ counter, PeerSlots ps, uint64_t epoch, PeerWait w) {
   const int ppr = row_bytes / PB;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = t / ppr;
@@ -96,6 +127,7 @@ k_halo_push_sig(const unsigned char *__restrict__ arr_r, const unsigned char *__
       if (prev == gridDim.x - 1) {
         *counter = 0;          // ready for the next launch (stream-ordered)
         peer_release_all(ps, epoch);
+        if (w.flags) peer_wait_all(w.flags, ps, epoch, w.timeout_ns, w.err);
       }
     }
   }
@@ -108,7 +140,7 @@ template <bool SIGNAL>
 __global__ void __launch_bounds__(256)
 k_halo_push_runs(const unsigned char *__restrict__ arr, const int64_t *__restrict__ src_off,
                  const int64_t *__restrict__ runs, int n_runs, int64_t total_units, uint32_t row_bytes, int elem,
-                 uint32_t *__restrict__ counter, PeerSlots ps, uint64_t epoch) {
+                 uint32_t *__restrict__ counter, PeerSlots ps, uint64_t epoch, PeerWait w) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < total_units) {
     int lo = 0, hi = n_runs - 1;
@@ -142,6 +174,7 @@ k_halo_push_runs(const unsigned char *__restrict__ arr, const int64_t *__restric
       if (prev == gridDim.x - 1) {
         *counter = 0;
         peer_release_all(ps, epoch);
+        if (w.flags) peer_wait_all(w.flags, ps, epoch, w.timeout_ns, w.err);   // chained mode: this launch closes the cycle
       }
     }
   }
@@ -167,9 +200,13 @@ inline int peer_sync_check(const fg_peer_sync_t *s) {
 
 // push rows [r_lo, r_lo + n_r) of list r and [q_lo, q_lo + n_q) of list q of `plan` for buffer b;
 // signal != 0: release `epoch` from the last block (or from a one-thread kernel when there is no row)
+// wait != 0 (with signal): the releasing thread then waits for every peer's release of the same epoch — the launch
+// closes the cycle (chained mode), no separate release / wait kernels
 inline int halo_push_launch(const fg_halo_plan_t &p, const void *arr_r, const void *arr_q, int b, int64_t n_r,
-                            int64_t n_q, int signal, uint64_t epoch, cudaStream_t st, int64_t &launches) {
+                            int64_t n_q, int signal, uint64_t epoch, cudaStream_t st, int64_t &launches, int wait = 0) {
   const PeerSlots ps = peer_slots_of(p.sync);
+  PeerWait w{nullptr, 0, nullptr};
+  if (wait && signal && ps.n) w = PeerWait{p.sync.dev_flags, p.sync.timeout_ns ? p.sync.timeout_ns : 20000000000ull, p.sync.dev_error};
   // run tables present: one launch per list, 16-byte stores; the release rides on the last launch
   const bool runs_r = n_r > 0 && p.dev_runs_r[b] && p.n_runs_r[b] > 0, runs_q = n_q > 0 && p.dev_runs_q[b] && p.n_runs_q[b] > 0;
   if ((n_r <= 0 || runs_r) && (n_q <= 0 || runs_q) && (n_r > 0 || n_q > 0) && ((p.dom * p.elem_bytes) % 8 == 0)) {
@@ -185,15 +222,15 @@ inline int halo_push_launch(const fg_halo_plan_t &p, const void *arr_r, const vo
       const int64_t *runs = is_q ? p.dev_runs_q[b] : p.dev_runs_r[b];
       const int nr = is_q ? p.n_runs_q[b] : p.n_runs_r[b];
       if (sig && last)
-        k_halo_push_runs<true><<<blocks, 256, 0, st>>>(arr, off, runs, nr, units, (uint32_t)(p.dom * p.elem_bytes), p.elem_bytes, p.dev_counter, ps, epoch);
+        k_halo_push_runs<true><<<blocks, 256, 0, st>>>(arr, off, runs, nr, units, (uint32_t)(p.dom * p.elem_bytes), p.elem_bytes, p.dev_counter, ps, epoch, w);
       else
-        k_halo_push_runs<false><<<blocks, 256, 0, st>>>(arr, off, runs, nr, units, (uint32_t)(p.dom * p.elem_bytes), p.elem_bytes, p.dev_counter, ps, epoch);
+        k_halo_push_runs<false><<<blocks, 256, 0, st>>>(arr, off, runs, nr, units, (uint32_t)(p.dom * p.elem_bytes), p.elem_bytes, p.dev_counter, ps, epoch, w);
       ++launches;
     }
     return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
   }
   if (n_r + n_q <= 0) {
-    if (signal && ps.n) { k_peer_signal<<<1, 32, 0, st>>>(ps, epoch); ++launches; }
+    if (signal && ps.n) { k_peer_signal_wait<<<1, 32, 0, st>>>(ps, epoch, w); ++launches; }
     return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
   }
   const int row_bytes = p.dom * p.elem_bytes;
@@ -204,7 +241,7 @@ inline int halo_push_launch(const fg_halo_plan_t &p, const void *arr_r, const vo
 #define FG_PUSH(PB_, SIG_)                                                                                       \
   k_halo_push_sig<PB_, SIG_><<<blocks, 256, 0, st>>>(r, q, p.dev_src_r_off, p.dev_src_q_off, p.dev_dst_r[b],     \
                                                      p.dev_dst_q[b], n_r, n_q, row_bytes, p.elem_bytes,          \
-                                                     p.dev_counter, ps, epoch)
+                                                     p.dev_counter, ps, epoch, w)
   if (signal && ps.n) {
     if (pb == 16) FG_PUSH(16, true); else if (pb == 8) FG_PUSH(8, true); else FG_PUSH(4, true);
   } else {
