@@ -20,6 +20,7 @@
 // write-back.  slot_last = 0xFF (fg_dsa_init) marks a row as not yet read.
 #pragma once
 #include "dsa_fast.cuh"
+#include "tma.cuh"
 
 template <typename T, int D>
 struct DsaCachedCfg {
@@ -45,7 +46,10 @@ k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t
   __shared__ T sopt[CH];          // optimum of the slot's constraint (variant B)
   __shared__ int16_t snew[CH];    // neighbour value when it differs from the one the cached row belongs to, else -1
   __shared__ int sptr[NV + 1];
+  __shared__ __align__(8) uint64_t bar;
+  uint32_t phase = 0;
   const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   const int v0 = blockIdx.x * NV;
   const int nv = min(NV, n_vars - v0);
   for (int i = tid; i <= nv; i += NT) sptr[i] = var_ptr[v0 + i];
@@ -61,7 +65,19 @@ k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t
   bool violated = false;
   for (int c0 = sb; c0 < se; c0 += CH) {
     const int n = min(CH, se - c0);
-    // A. per-slot metadata, slot-ordered (coalesced); the value gathers are in flight while the rows stream in
+    // B. cached rows of the chunk: one contiguous run -> 1-D bulk async copies (TMA) on an mbarrier, issued first
+    //    so that the row stream and the gathers of step A are in flight together
+    if constexpr (Cfg::VEC) {
+      if (tid == 0) {
+        fence_proxy_async_smem();   // the previous chunk's generic-proxy writes to `rows` are ordered before the copy
+        const uint32_t bytes = (uint32_t)(n * D) * (uint32_t)sizeof(T);
+        mbar_expect_tx(&bar, bytes);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(row_cache + (int64_t)c0 * D);
+        unsigned char *dst = reinterpret_cast<unsigned char *>(rows);
+        for (uint32_t o = 0; o < bytes; o += 16384u) tma_load_1d(dst + o, src + o, min(16384u, bytes - o), &bar);
+      }
+    }
+    // A. per-slot metadata, slot-ordered (coalesced)
     int yv[SPT], lastv[SPT];
     T optv[SPT];
 #pragma unroll
@@ -74,23 +90,19 @@ k_dsa_step_cached(int n_vars, const int32_t *__restrict__ var_ptr, const int32_t
         optv[k] = slot_opt[c0 + i];
       }
     }
-    // B. cached rows of the chunk: contiguous
-    if constexpr (Cfg::VEC) {
-      constexpr int V = 16 / (int)sizeof(T);
-      const float4 *src = reinterpret_cast<const float4 *>(row_cache + (int64_t)c0 * D);
-      float4 *dst = reinterpret_cast<float4 *>(rows);
-      const int nvec = n * D / V;
-#pragma unroll 4
-      for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
-    } else {
+    if constexpr (!Cfg::VEC) {
       const T *src = row_cache + (int64_t)c0 * D;
-#pragma unroll 4
+#pragma unroll 8
       for (int i = tid; i < n * D; i += NT) rows[i] = src[i];
     }
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const int i = tid + k * NT;
       if (i < n) { sopt[i] = optv[k]; snew[i] = (int16_t)(yv[k] != lastv[k] ? yv[k] : -1); }
+    }
+    if constexpr (Cfg::VEC) {
+      mbar_wait(&bar, phase & 1u);
+      ++phase;
     }
     __syncthreads();
     // C. rows whose neighbour moved: from the oriented table, into shared memory and back into the array

@@ -380,8 +380,8 @@ extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan)
   { const char *e = getenv("PYDCOP_B200_PUSH_SPLIT"); h->split_push = !(e && e[0] == '0'); }   // default on: 102 vs 177 us at N=2
   // fused halo: every class that produces rows must run on a warp kernel (they carry the peer stores)
   bool all_warp = plan->dev_edge_dst_r[0] && plan->dev_edge_dst_r[1] && plan->dev_slot_dst_q[0] && plan->dev_slot_dst_q[1] &&
-                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && fg_env_is("PYDCOP_B200_PUSH_FUSED", '1') &&
-                  fg_env_int("PYDCOP_B200_F2VW_NS", 2) == 2 && fg_env_int("PYDCOP_B200_V2FW_NS", 2) == 2;   // opt-in: measured slower
+                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && !fg_env_is("PYDCOP_B200_PUSH_FUSED", '0') &&
+                  fg_env_int("PYDCOP_B200_F2VW_NS", 2) == 2 && fg_env_int("PYDCOP_B200_V2FW_NS", 2) == 2;   // peer variants exist at the default depth
   for (size_t i = 0; all_warp && i < h->classes.size(); ++i)
     if (h->classes[i].n_factors && !(h->classes[i].flags & FG_CLASS_GHOST) && !h->warp.f2v[i]) all_warp = false;
   h->fused_push = all_warp;
