@@ -387,6 +387,11 @@ typedef struct {
   const int32_t *dev_slot_nbr;    /* [n_edges] */
   const int64_t *dev_slot_tab;    /* [n_edges] */
   int32_t fast_dom, fast_chunk;
+  /* optional with the fast shape (csrc/mgm_cached_kernels.cuh): the row each slot read last, slot-major
+   * T[n_edges * fast_dom], and the neighbour value it belongs to (0xFF = none yet; reset by fg_mgm_init): the value
+   * phase streams these rows and reads the oriented tables only where a neighbour moved; results are identical. */
+  void *dev_row_cache;
+  uint8_t *dev_slot_last;         /* [n_edges] */
 } fg_mgm_desc_t;
 
 typedef struct fg_mgm *fg_mgm_t;

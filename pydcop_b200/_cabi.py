@@ -80,7 +80,8 @@ class FgMgmDesc(C.Structure):
                 ("dev_gain", P), ("dev_new_value", P),
                 ("mode_max", C.c_int32), ("stop_cycle", C.c_int32), ("seed", C.c_uint64),
                 ("dev_tables_or", P), ("dev_slot_nbr", P), ("dev_slot_tab", P),
-                ("fast_dom", C.c_int32), ("fast_chunk", C.c_int32)]
+                ("fast_dom", C.c_int32), ("fast_chunk", C.c_int32),
+                ("dev_row_cache", P), ("dev_slot_last", P)]
 
 
 FG_MAX_PEERS = 16

@@ -45,6 +45,10 @@ struct TiledRtCfg {
 };
 
 inline int tiled_rt_pow2_ge(int d) { int g = 1; while (g < d && g < 32) g *= 2; return g; }
+// tables up to this many entries: one lane per output value walks its whole slice (the lane-group / parts split
+// costs more in index arithmetic and shuffles than the bank conflicts of a small table; B200, mixed-shape side
+// workload: arity 2 197 -> 344 us, arity 3 279 -> 425 us with the split, arity 4 1019 -> 437 us)
+constexpr int64_t FG_TILED_RT_WIDE = 2048;
 
 inline TiledRtCfg tiled_rt_cfg(const fg_class_t &c, size_t elem) {
   TiledRtCfg r;
@@ -52,11 +56,12 @@ inline TiledRtCfg tiled_rt_cfg(const fg_class_t &c, size_t elem) {
   const int64_t S = c.table_size, RT = c.row_total;
   if (S <= 0 || a < 1) return r;
   const int d_last = c.dom[a - 1];
-  const int64_t parts = a >= 3 ? (int64_t)c.dom[0] * d_last : 0;   // partial optima of the j == A-1 outputs
+  const bool wide = S > FG_TILED_RT_WIDE;
+  const int64_t parts = (wide && a >= 3) ? (int64_t)c.dom[0] * d_last : 0;   // partial optima of the j == A-1 outputs
   const int64_t rows = (3 * RT + parts) * (int64_t)elem;
   const int64_t sp = S | 1;       // odd: neighbouring factors start in different banks
-  int64_t threads = (a >= 3 ? (int64_t)c.dom[0] : 1) * d_last;     // lanes a factor keeps busy
-  for (int j = 0; j + 1 < a; ++j) threads += (int64_t)c.dom[j] * tiled_rt_pow2_ge(d_last);
+  int64_t threads = ((wide && a >= 3) ? (int64_t)c.dom[0] : 1) * d_last;     // lanes a factor keeps busy
+  for (int j = 0; j + 1 < a; ++j) threads += (int64_t)c.dom[j] * (wide ? tiled_rt_pow2_ge(d_last) : 1);
   const int64_t want = std::max<int64_t>(1, (2 * FG_TILED_RT_THREADS + threads - 1) / threads);
   const int64_t spread = std::max<int64_t>(1, c.n_factors / (148 * 6));
   const int64_t target = std::max(want, std::min<int64_t>(spread, 4 * want));
@@ -144,9 +149,10 @@ k_f2v_tiled_rt(const fg_class_t *__restrict__ classes, const RtTile *__restrict_
     for (int i = A - 1; i >= 0; --i) { dom[i] = c.dom[i]; roff[i] = c.row_off[i]; stride[i] = s; s *= c.dom[i]; }
   }
   const int d_last = dom[A - 1];
-  const int P = A >= 3 ? dom[0] : 1;   // parts of a j == A-1 output
-  int G = 1, logG = 0;                 // lanes per j < A-1 output
-  while (G < d_last && G < 32) { G *= 2; ++logG; }
+  const bool wide = S > (int)FG_TILED_RT_WIDE;       // small tables: one lane per output, no split
+  const int P = (wide && A >= 3) ? dom[0] : 1;       // parts of a j == A-1 output
+  int G = 1, logG = 0;                               // lanes per j < A-1 output
+  while (wide && G < d_last && G < 32) { G *= 2; ++logG; }
   T *tab = reinterpret_cast<T *>(fg_tiled_rt_smem);   // nf x sp (staged tables)
   T *qs = tab + (staged ? (size_t)nf * sp : 0);       // nf x RT   incoming v->f rows, scope order
   T *cand = qs + (size_t)nf * RT;                     // nf x RT   new f->v rows
@@ -221,7 +227,7 @@ k_f2v_tiled_rt(const fg_class_t *__restrict__ classes, const RtTile *__restrict_
       if (valid) {
         const T *tf = staged ? tab + f * sp : gtab + (int64_t)f * S;
         const T *qf = qs + f * RT;
-        const bool fix0 = last_pos && A >= 3;   // x_0 = part_id, not walked
+        const bool fix0 = last_pos && P > 1;    // x_0 = part_id, not walked
         int x[A];
 #pragma unroll
         for (int i = 0; i < A; ++i) x[i] = 0;
@@ -250,15 +256,17 @@ k_f2v_tiled_rt(const fg_class_t *__restrict__ classes, const RtTile *__restrict_
           if (!more) break;
         }
       }
-      // combine the G lanes of an output (all 32 lanes take part in the shuffles)
+      // combine the G lanes of an output (all 32 lanes take part in the shuffles; G is uniform over the CTA)
+      if (G > 1) {
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        const T other = __shfl_xor_sync(0xffffffffu, opt, m);
-        if (!last_pos && m < G) opt_update(opt, other, mx);
+        for (int m = 16; m >= 1; m >>= 1) {
+          const T other = __shfl_xor_sync(0xffffffffu, opt, m);
+          if (!last_pos && m < G) opt_update(opt, other, mx);
+        }
       }
       if (valid) {
         if (last_pos) {
-          if (A >= 3) part[(f * d_last + xv) * P + part_id] = opt;
+          if (P > 1) part[(f * d_last + xv) * P + part_id] = opt;
           else cand[f * RT + roff[A - 1] + xv] = opt;
         } else if (g == 0) {
           int ro = roff[0];
@@ -285,7 +293,7 @@ k_f2v_tiled_rt(const fg_class_t *__restrict__ classes, const RtTile *__restrict_
         if (j == t) { d = dom[t]; ro = roff[t]; }
       T *cr = cand + f * RT + ro;
       const T *pr = prev + f * RT + ro;
-      const bool parts = A >= 3 && j == A - 1;
+      const bool parts = P > 1 && j == A - 1;
       uint8_t cnt = r_cnt[e];
       const bool has_prev = cnt & 1;
       const bool damp = p.damp_factors && has_prev;

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "mgm_kernels.cuh"
 #include "mgm_fast_kernels.cuh"
+#include "mgm_cached_kernels.cuh"
 
 struct fg_mgm {
   fg_mgm_desc_t d;
@@ -98,6 +99,8 @@ extern "C" int fg_mgm_init(fg_mgm_t h, void *stream) {
                                                           d.dev_has_cost);
     ++h->launches;
   }
+  if (d.dev_slot_last && d.n_edges)   // active-row array: no row has been read yet
+    CUDA_TRY(h, cudaMemsetAsync(d.dev_slot_last, 0xFF, (size_t)d.n_edges, st));
   CUDA_TRY(h, cudaGetLastError());
   h->cycle = 0;
   return FG_OK;
@@ -114,11 +117,30 @@ static void mgm_gain_fast_launch(fg_mgm *h, cudaStream_t st) {
       (uint32_t)(h->cycle + 1));
 }
 
-// the fast value-phase kernel when the descriptor carries the oriented tables (opt-in), else false
+template <typename T, int D>
+static void mgm_gain_cached_launch(fg_mgm *h, cudaStream_t st) {
+  const fg_mgm_desc_t &d = h->d;
+  using Cfg = MgmCachedCfg<T, D>;
+  static_assert(sizeof(T) * Cfg::CH * D + 2 * Cfg::CH + 4 * (Cfg::NV + 1) + 16 <= 48 * 1024, "static shared memory");
+  k_mgm_gain_cached<T, D><<<mgm_blocks(d.n_vars, Cfg::NV), Cfg::THREADS, 0, st>>>(
+      mgm_side(h), d.n_vars, d.dev_slot_nbr, d.dev_slot_tab, (const T *)d.dev_tables_or, (const T *)d.dev_unary, d.dev_value,
+      (T *)d.dev_cost, d.dev_has_cost, (T *)d.dev_gain, d.dev_new_value, d.mode_max, d.seed, (uint32_t)(h->cycle + 1),
+      (T *)d.dev_row_cache, d.dev_slot_last);
+}
+
+// the fast value-phase kernel when the descriptor carries the oriented tables, else false; with the active-row array
+// (dev_row_cache) the streaming variant
 template <typename T>
 static bool mgm_gain_fast(fg_mgm *h, cudaStream_t st) {
   const fg_mgm_desc_t &d = h->d;
   if (!d.dev_tables_or || !d.dev_slot_nbr || !d.dev_slot_tab || (d.fast_chunk != 2 && d.fast_chunk != 4)) return false;
+  if (d.dev_row_cache && d.dev_slot_last) {
+    switch (d.fast_dom) {
+#define FG_MGM_CC(n) case n: mgm_gain_cached_launch<T, n>(h, st); return true;
+      FG_MGM_CC(4) FG_MGM_CC(8) FG_MGM_CC(10) FG_MGM_CC(16) FG_MGM_CC(20)
+#undef FG_MGM_CC
+    }
+  }
 #define FG_MGM_CASE(n)                                                              \
   case n:                                                                           \
     if (d.fast_chunk == 2) mgm_gain_fast_launch<T, n, 2>(h, st);                    \

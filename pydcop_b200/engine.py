@@ -633,6 +633,12 @@ class MgmEngine(_EngineBase):
                                                                    _ptr(self.slot_tab))
                 d.fast_dom, d.fast_chunk = fast_dom, chunk
                 self.fast_chunk = chunk
+                self.row_cache = self.slot_last = None
+                if os.environ.get("PYDCOP_B200_MGM_CACHE", "1") != "0":   # active-row array (csrc/mgm_cached_kernels.cuh)
+                    with torch.cuda.device(self.device):
+                        self.row_cache = torch.zeros(max(L.n_edges * fast_dom, 4), dtype=tdt, device=self.device)
+                        self.slot_last = torch.full((max(L.n_edges, 1),), 255, dtype=torch.uint8, device=self.device)
+                    d.dev_row_cache, d.dev_slot_last = _ptr(self.row_cache), _ptr(self.slot_last)
         self._desc = d
         self._h = C.c_void_p()
         self._check(self.lib.fg_mgm_create(C.byref(d), C.byref(self._h)), "fg_mgm_create")
