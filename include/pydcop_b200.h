@@ -54,7 +54,7 @@ enum { FG_OK = 0, FG_ERR_ARG = 1, FG_ERR_CUDA = 2, FG_ERR_UNSUPPORTED = 3 };
 enum { FG_F32 = 0, FG_F64 = 1 };
 enum { FG_START_LEAFS = 0, FG_START_LEAFS_VARS = 1, FG_START_ALL = 2 }; /* maxsum.py:219 */
 enum { FG_DSA_A = 0, FG_DSA_B = 1, FG_DSA_C = 2 };                      /* dsa.py:133 */
-enum { FG_CLASS_GHOST = 1 };
+enum { FG_CLASS_GHOST = 1, FG_CLASS_BOUNDARY = 2 };
 
 /* One class of same-shaped factors (constraints). */
 typedef struct {

@@ -46,6 +46,11 @@ struct fg_maxsum {
                             // releases in its last block — no separate release / wait kernels (PYDCOP_B200_PUSH_CHAIN=0: off)
   bool chained_now = false; // the cycle being enqueued was closed inside phase 0
   cudaEvent_t ev_r = nullptr;
+  // early q push: the variable classes with a remote factor (FG_CLASS_BOUNDARY) are launched first and their rows leave on
+  // a third stream while the interior classes are still being computed (PYDCOP_B200_PUSH_EARLY=0: off)
+  bool early_q = false;
+  cudaStream_t push_stream = nullptr;
+  cudaEvent_t ev_vb = nullptr, ev_q = nullptr;
   fg_halo_plan_t halo;
   uint64_t epoch = 0;
   cudaEvent_t *prof = nullptr;   // fg_maxsum_shard_profile: 8 timing events recorded inside a cycle
@@ -146,6 +151,9 @@ extern "C" int fg_maxsum_destroy(fg_maxsum_t h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_r) cudaEventDestroy(h->ev_r);
+    if (h->ev_vb) cudaEventDestroy(h->ev_vb);
+    if (h->ev_q) cudaEventDestroy(h->ev_q);
+    if (h->push_stream) cudaStreamDestroy(h->push_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->warp.dev_classes) cudaFree(h->warp.dev_classes);
     tiled_rt_free(h->tiled_rt);
@@ -242,6 +250,8 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
   const bool chain = push_split && h->chain_push && fork;   // the side stream's last launch closes the cycle
   h->chained_now = chain;
   if (chain) CUDA_TRY(h, cudaEventRecord(h->ev_r, st));
+  const bool early = chain && h->early_q && !fused;         // q rows of the boundary classes leave on the push stream
+  bool early_done = false;
   if (h->prof) cudaEventRecord(h->prof[2], st);
   // variable -> factor (+ value selection).  Both sides only READ the current buffers and WRITE
   // disjoint next buffers (Jacobi), so from cycle 2 on the variable side runs on a second stream,
@@ -259,8 +269,27 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
       }
     } else {
       if (h->warp.v2f_on) {
-        for (const WTileRange &rg : h->warp.v2f)
+        bool in_boundary = true;
+        for (const WTileRange &rg : h->warp.v2f) {
+          if (early && in_boundary && !rg.boundary) {   // every boundary class is enqueued: their q rows may leave now
+            in_boundary = false;
+            CUDA_TRY(h, cudaEventRecord(h->ev_vb, st));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->push_stream, h->ev_vb, 0));
+            int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, h->push_stream, h->launches);
+            if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, early) failed"); return rc; }
+            CUDA_TRY(h, cudaEventRecord(h->ev_q, h->push_stream));
+            early_done = true;
+          }
           if (dispatch_v2f_warp<T>(h->warp.dev_classes, rg, d, r_cur, q_cur, q_next, p, st)) ++h->launches;
+        }
+        if (early && !early_done) {   // no interior range followed: push behind the last boundary launch
+          CUDA_TRY(h, cudaEventRecord(h->ev_vb, st));
+          CUDA_TRY(h, cudaStreamWaitEvent(h->push_stream, h->ev_vb, 0));
+          int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, h->push_stream, h->launches);
+          if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, early) failed"); return rc; }
+          CUDA_TRY(h, cudaEventRecord(h->ev_q, h->push_stream));
+          early_done = true;
+        }
       } else {
         for (size_t li = 0; li < h->fast.v2f.size(); ++li)
           if (dispatch_v2f_classes<T>(h->fast.v2f_dom[li], h->fast.v2f[li], d, r_cur, q_cur, q_next, p, st)) ++h->launches;
@@ -284,7 +313,8 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
   if (h->prof) cudaEventRecord(h->prof[3], st);
   if (chain) {   // everything this rank sends in this cycle is on its way once the r push is done as well
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_r, 0));
-    int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, fused ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches, 1);
+    if (early_done) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_q, 0));
+    int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, (fused || early_done) ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches, 1);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, release, wait) failed"); return rc; }
   } else if (push_split && !fused && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, st, h->launches);
@@ -380,13 +410,29 @@ extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan)
   { const char *e = getenv("PYDCOP_B200_PUSH_SPLIT"); h->split_push = !(e && e[0] == '0'); }   // default on: 102 vs 177 us at N=2
   // fused halo: every class that produces rows must run on a warp kernel (they carry the peer stores)
   bool all_warp = plan->dev_edge_dst_r[0] && plan->dev_edge_dst_r[1] && plan->dev_slot_dst_q[0] && plan->dev_slot_dst_q[1] &&
-                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && !fg_env_is("PYDCOP_B200_PUSH_FUSED", '0') &&
-                  fg_env_int("PYDCOP_B200_F2VW_NS", 2) == 2 && fg_env_int("PYDCOP_B200_V2FW_NS", 2) == 2;   // peer variants exist at the default depth
+                  h->warp.v2f_on && h->fast.slow_varclasses.empty() && fg_env_is("PYDCOP_B200_PUSH_FUSED", '1') &&
+                  fg_env_int("PYDCOP_B200_F2VW_NS", 2) == 2 && fg_env_int("PYDCOP_B200_V2FW_NS", 2) == 2;   // opt-in: faster at N = 2
+                  // (82 vs 89 us) but the stores stall the compute kernels once the cut grows (N = 8: 157 vs 123 us)
   for (size_t i = 0; all_warp && i < h->classes.size(); ++i)
     if (h->classes[i].n_factors && !(h->classes[i].flags & FG_CLASS_GHOST) && !h->warp.f2v[i]) all_warp = false;
   h->fused_push = all_warp;
   h->chain_push = !fg_env_is("PYDCOP_B200_PUSH_CHAIN", '0') && h->side_stream != nullptr;
   if (h->chain_push && !h->ev_r) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_r, cudaEventDisableTiming));
+  // every boundary class must be in one of the warp launches (they come first in the plan) for its rows to leave early
+  bool early = h->chain_push && h->split_push && !h->fused_push && h->warp.v2f_on && plan->n_q > 0 &&
+               !fg_env_is("PYDCOP_B200_PUSH_EARLY", '0');
+  bool any_boundary = false;
+  for (const fg_varclass_t &vc : h->varclasses) {
+    if (!(vc.flags & FG_CLASS_BOUNDARY) || (vc.flags & FG_CLASS_GHOST) || vc.n_slots == 0) continue;
+    any_boundary = true;
+    if (!(fg_fast_dom(vc.dom) && vc.degree >= 1 && vc.degree <= 32)) early = false;
+  }
+  h->early_q = early && any_boundary;
+  if (h->early_q && !h->push_stream) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->push_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_vb, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
+  }
   return FG_OK;
 }
 

@@ -51,6 +51,7 @@ static_assert(sizeof(WClassEntry) == 48, "three 16-byte loads");
 struct WTileRange {   // one launch: the regular variable classes of one domain size
   int32_t dom, first, count;   // entries [first, first + count) of the plan's class table
   int32_t n_tiles;
+  int32_t boundary;            // multi-GPU: classes of variables with a remote factor (FG_CLASS_BOUNDARY), launched first
 };
 
 struct WTile {
@@ -384,10 +385,13 @@ k_v2f_warp(const WClassEntry *__restrict__ classes, int n_classes, int n_tiles, 
 // Class entries of the regular variable classes (degree 1..16, not ghosts) of domain size D, costly (high-degree)
 // classes first.  nv per tile: as many variables as fit 32 lanes, rounded down to the number of rows that
 // keeps every tile's q / unary offsets 16-byte aligned (bulk copies) when possible.  Returns the tile count.
-inline int v2fw_build_classes(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<WClassEntry> &out) {
+inline int v2fw_build_classes(const std::vector<fg_varclass_t> &vcs, int D, size_t elem, std::vector<WClassEntry> &out,
+                              int boundary) {
   std::vector<fg_varclass_t> order;
   for (const fg_varclass_t &vc : vcs)
-    if (vc.dom == D && vc.degree >= 1 && vc.degree <= 32 && vc.n_vars > 0 && !(vc.flags & FG_CLASS_GHOST)) order.push_back(vc);
+    if (vc.dom == D && vc.degree >= 1 && vc.degree <= 32 && vc.n_vars > 0 && !(vc.flags & FG_CLASS_GHOST) &&
+        ((vc.flags & FG_CLASS_BOUNDARY) != 0) == (boundary != 0))
+      order.push_back(vc);
   std::stable_sort(order.begin(), order.end(),
                    [](const fg_varclass_t &a, const fg_varclass_t &b) { return a.degree > b.degree; });
   const int unit = 16 / fg_gcd(16, D * (int)elem);  // rows per 16-byte multiple
@@ -502,15 +506,21 @@ inline int maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varc
     if (!(vc.flags & FG_CLASS_GHOST) && vc.degree >= 1 && fg_fast_dom(vc.dom) &&
         std::find(doms.begin(), doms.end(), vc.dom) == doms.end())
       doms.push_back(vc.dom);
-  for (int D : doms) {
-    WTileRange rg;
-    rg.dom = D;
-    rg.first = (int32_t)all.size();
-    rg.n_tiles = v2fw_build_classes(vcs, D, elem, all);
-    rg.count = (int32_t)all.size() - rg.first;
-    if (rg.count > FG_WARP_MAX_CLASSES) { all.resize(rg.first); continue; }   // (cannot happen: <= 16 degrees x 2 tags)
-    if (rg.count) plan.v2f.push_back(rg);
-  }
+  for (int boundary = 1; boundary >= 0; --boundary)   // boundary classes first: their rows can leave while the rest computes
+    for (int D : doms) {
+      WTileRange rg;
+      rg.dom = D;
+      rg.boundary = boundary;
+      rg.first = (int32_t)all.size();
+      rg.n_tiles = v2fw_build_classes(vcs, D, elem, all, boundary);
+      rg.count = (int32_t)all.size() - rg.first;
+      if (rg.count > FG_WARP_MAX_CLASSES) {   // (cannot happen: <= 16 degrees x 2 tags) — whole side back on the pipelined kernels
+        plan.v2f.clear();
+        plan.v2f_on = false;
+        return FG_OK;
+      }
+      if (rg.count) plan.v2f.push_back(rg);
+    }
   if (!all.empty()) {
     if (cudaMalloc(reinterpret_cast<void **>(&plan.dev_classes), all.size() * sizeof(WClassEntry)) != cudaSuccess) return FG_ERR_CUDA;
     if (cudaMemcpy(plan.dev_classes, all.data(), all.size() * sizeof(WClassEntry), cudaMemcpyHostToDevice) != cudaSuccess)

@@ -54,7 +54,7 @@ def _varclass_array(layout: FactorGraphLayout):
         vc.dom, vc.degree, vc.n_vars = c.dom, c.degree, c.n_vars
         vc.first_var, vc.first_slot, vc.n_slots = c.first_var, c.first_slot, c.n_slots
         vc.unary_base, vc.q_base = c.unary_base, c.q_base
-        vc.flags = 1 if c.tag else 0
+        vc.flags = (1 if c.tag == 2 else 0) | (2 if c.tag == 1 else 0)   # FG_CLASS_GHOST | FG_CLASS_BOUNDARY (multigpu.build_shard)
     return arr
 
 

@@ -159,7 +159,13 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int, partition="b
     g2l_var[own_v] = np.arange(n_own)
     g2l_var[ghost_vars] = n_own + np.arange(n_ghost)
     l_dom = np.concatenate([dom_size[own_v], dom_size[ghost_vars]]).astype(np.int32)
-    l_var_tag = np.concatenate([np.zeros(n_own, np.int32), np.ones(n_ghost, np.int32)])
+    # variable tags (classes never mix tags): 0 = own, interior; 1 = own with at least one REMOTE factor — its q rows
+    # towards those factors cross the cut, the engine computes these classes first so that their push overlaps the
+    # interior variables' compute; 2 = ghost of another rank's variable (never computed here)
+    own_tag = np.zeros(n_own, np.int32)
+    if len(stub_edges):
+        own_tag[g2l_var[edge_var[stub_edges]]] = 1
+    l_var_tag = np.concatenate([own_tag, np.full(n_ghost, 2, np.int32)])
 
     # local factors: own factors then one unary stub per remote-factor edge
     n_real, n_stub = len(own_f), len(stub_edges)
@@ -684,7 +690,7 @@ class ShardedMaxSum:
             n_ghost_el = int(np.asarray(p.local_inst["dom_size"], dtype=np.int64)[p.n_own_vars:].sum())
             local_unary = np.concatenate([np.asarray(unary, dtype=np.float64)[_ranges(uoff[own], dom[own])],
                                           np.zeros(n_ghost_el)])
-        n_own_internal = sum(c.n_vars for c in p.layout.var_classes if not c.tag)
+        n_own_internal = sum(c.n_vars for c in p.layout.var_classes if c.tag != 2)
         # a cut factor's entry needs the value of a variable another rank owns, and ghost variables are never
         # evaluated here: take them from the all-gathered assignment (local canonical order = own, then ghosts)
         full = self.values()

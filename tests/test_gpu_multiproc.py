@@ -64,8 +64,9 @@ def _maxsum_worker(rank, world, port, case, q):
         cost = sh.solution_cost(9.0, inst["unary"])     # table entries equal to 9 count as violations
         used = "p2p" if sh.peer is not None else "nccl"
         if sh.peer is not None and case.get("partition", "blocks") != "imbalanced":
-            # default: the warp kernels store the boundary rows themselves (all classes binary d=10, degrees <= 16)
-            assert sh.peer.fused == case.get("fused", True), sh.peer.fused
+            # default: push kernels, the q rows of the boundary classes leaving early; PYDCOP_B200_PUSH_FUSED=1: the warp
+            # kernels store the boundary rows themselves (all classes binary d=10, degrees <= 16)
+            assert sh.peer.fused == case.get("fused", False), sh.peer.fused
         if rank == 0:
             cur = 0
             for s in plan:     # cycles since the last init
@@ -145,9 +146,11 @@ MAXSUM_CASES = {
     "nccl": dict(mode="nccl"),
     "p2p": dict(mode="p2p"),
     "p2p-steps-reinit": dict(mode="p2p", steps=[1, 3, "init", 2, 5, 4]),
-    "p2p-split-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "0"}, steps=[4, 5], fused=False),
-    "p2p-joined-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "0", "PYDCOP_B200_PUSH_SPLIT": "0"}, steps=[4, 5], fused=False),
-    "p2p-per-row-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "0", "PYDCOP_B200_PUSH_RUNS": "0"}, steps=[4, 5], fused=False),
+    "p2p-fused": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "1"}, steps=[4, 5], fused=True),
+    "p2p-late-q-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_EARLY": "0"}, steps=[4, 5]),
+    "p2p-unchained": dict(mode="p2p", env={"PYDCOP_B200_PUSH_CHAIN": "0"}, steps=[4, 5]),
+    "p2p-joined-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_SPLIT": "0"}, steps=[4, 5]),
+    "p2p-per-row-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_RUNS": "0"}, steps=[4, 5]),
     "p2p-multilevel-f64": dict(mode="p2p", partition="multilevel", precision="f64"),
     "p2p-imbalanced": dict(mode="p2p", partition="imbalanced", n_vars=20000, steps=[12]),
 }

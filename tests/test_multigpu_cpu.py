@@ -58,7 +58,10 @@ def test_shards_cover_the_graph(kind, world):
     for p in plans:
         L = p.layout
         ghost_f = [c for c in L.classes if c.tag]
-        ghost_v = [c for c in L.var_classes if c.tag]
+        ghost_v = [c for c in L.var_classes if c.tag == 2]
+        bound_v = [c for c in L.var_classes if c.tag == 1]
+        # every q row this rank sends belongs to a variable of a boundary class, and every boundary variable sends
+        assert sum(c.n_vars for c in bound_v) == len(np.unique(inst["edge_var"][p.stub_edges]))
         assert sum(c.n_factors for c in ghost_f) == len(p.stub_edges)
         assert sum(c.n_slots for c in ghost_v) == len(p.send_r_len)
         # own variables keep their true degree (real + stub edges)
@@ -200,7 +203,7 @@ def test_rows_of_one_peer_land_in_one_block_and_push_order_follows_destinations(
                 rpos = sum(pbq.recv_q_rows[:a])
                 off = np.sort(np.asarray(pbq.recv_q_off[rpos:rpos + n]))
                 gaps = int((np.diff(off) != d).sum())
-                assert gaps <= len([c for c in pbq.layout.var_classes if c.tag]), (a, b, gaps)
+                assert gaps <= len([c for c in pbq.layout.var_classes if c.tag == 2]), (a, b, gaps)
             pos += n
 
 
