@@ -49,6 +49,7 @@ struct fg_maxsum {
   // early q push: the variable classes with a remote factor (FG_CLASS_BOUNDARY) are launched first and their rows leave on
   // a third stream while the interior classes are still being computed (PYDCOP_B200_PUSH_EARLY=0: off)
   bool early_q = false;
+  int early_mode = 1;   // 1: the q push follows the r push on the main stream; 2: on a third stream (PYDCOP_B200_PUSH_EARLY=2)
   cudaStream_t push_stream = nullptr;
   cudaEvent_t ev_vb = nullptr, ev_q = nullptr;
   fg_halo_plan_t halo;
@@ -249,9 +250,22 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
   }
   const bool chain = push_split && h->chain_push && fork;   // the side stream's last launch closes the cycle
   h->chained_now = chain;
-  if (chain) CUDA_TRY(h, cudaEventRecord(h->ev_r, st));
-  const bool early = chain && h->early_q && !fused;         // q rows of the boundary classes leave on the push stream
+  const bool early = chain && h->early_q && !fused;         // q rows of the boundary classes leave before the interior ones are done
+  const int early_mode = early ? h->early_mode : 0;
+  if (chain && early_mode != 1) CUDA_TRY(h, cudaEventRecord(h->ev_r, st));   // mode 1: recorded behind the early q push
   bool early_done = false;
+  // enqueue the q push behind the boundary classes (recorded on the side stream `sv`): on the main stream after the r
+  // push (mode 1) or on the push stream (mode 2)
+  auto early_push = [&](cudaStream_t sv) -> int {
+    if (cudaEventRecord(h->ev_vb, sv) != cudaSuccess) return FG_ERR_CUDA;
+    cudaStream_t ps = early_mode == 2 ? h->push_stream : st_f;
+    if (cudaStreamWaitEvent(ps, h->ev_vb, 0) != cudaSuccess) return FG_ERR_CUDA;
+    int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, ps, h->launches);
+    if (rc != FG_OK) return rc;
+    if (cudaEventRecord(early_mode == 2 ? h->ev_q : h->ev_r, ps) != cudaSuccess) return FG_ERR_CUDA;
+    early_done = true;
+    return FG_OK;
+  };
   if (h->prof) cudaEventRecord(h->prof[2], st);
   // variable -> factor (+ value selection).  Both sides only READ the current buffers and WRITE
   // disjoint next buffers (Jacobi), so from cycle 2 on the variable side runs on a second stream,
@@ -273,22 +287,14 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
         for (const WTileRange &rg : h->warp.v2f) {
           if (early && in_boundary && !rg.boundary) {   // every boundary class is enqueued: their q rows may leave now
             in_boundary = false;
-            CUDA_TRY(h, cudaEventRecord(h->ev_vb, st));
-            CUDA_TRY(h, cudaStreamWaitEvent(h->push_stream, h->ev_vb, 0));
-            int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, h->push_stream, h->launches);
+            int rc = early_push(st);
             if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, early) failed"); return rc; }
-            CUDA_TRY(h, cudaEventRecord(h->ev_q, h->push_stream));
-            early_done = true;
           }
           if (dispatch_v2f_warp<T>(h->warp.dev_classes, rg, d, r_cur, q_cur, q_next, p, st)) ++h->launches;
         }
         if (early && !early_done) {   // no interior range followed: push behind the last boundary launch
-          CUDA_TRY(h, cudaEventRecord(h->ev_vb, st));
-          CUDA_TRY(h, cudaStreamWaitEvent(h->push_stream, h->ev_vb, 0));
-          int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, h->halo.n_q, 0, 0, h->push_stream, h->launches);
+          int rc = early_push(st);
           if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, early) failed"); return rc; }
-          CUDA_TRY(h, cudaEventRecord(h->ev_q, h->push_stream));
-          early_done = true;
         }
       } else {
         for (size_t li = 0; li < h->fast.v2f.size(); ++li)
@@ -311,9 +317,10 @@ static int maxsum_compute_t(fg_maxsum *h, cudaStream_t st, bool push_split = fal
     }
   }
   if (h->prof) cudaEventRecord(h->prof[3], st);
+  if (chain && early_mode == 1 && !early_done) CUDA_TRY(h, cudaEventRecord(h->ev_r, st_f));   // (no warp launch ran)
   if (chain) {   // everything this rank sends in this cycle is on its way once the r push is done as well
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_r, 0));
-    if (early_done) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_q, 0));
+    if (early_done && early_mode == 2) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_q, 0));
     int rc = halo_push_launch(h->halo, r_next, q_next, nxt, 0, (fused || early_done) ? 0 : h->halo.n_q, 1, h->epoch + 1, st, h->launches, 1);
     if (rc != FG_OK) { snprintf(h->err, sizeof(h->err), "peer push (q rows, release, wait) failed"); return rc; }
   } else if (push_split && !fused && h->halo.n_q > 0) {  // q list only: the kernel indexes rows >= n_r as q rows
@@ -421,6 +428,7 @@ extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan)
   // every boundary class must be in one of the warp launches (they come first in the plan) for its rows to leave early
   bool early = h->chain_push && h->split_push && !h->fused_push && h->warp.v2f_on && plan->n_q > 0 &&
                !fg_env_is("PYDCOP_B200_PUSH_EARLY", '0');
+  h->early_mode = fg_env_is("PYDCOP_B200_PUSH_EARLY", '2') ? 2 : 1;
   bool any_boundary = false;
   for (const fg_varclass_t &vc : h->varclasses) {
     if (!(vc.flags & FG_CLASS_BOUNDARY) || (vc.flags & FG_CLASS_GHOST) || vc.n_slots == 0) continue;

@@ -390,7 +390,7 @@ inline int v2fw_build_classes(const std::vector<fg_varclass_t> &vcs, int D, size
   std::vector<fg_varclass_t> order;
   for (const fg_varclass_t &vc : vcs)
     if (vc.dom == D && vc.degree >= 1 && vc.degree <= 32 && vc.n_vars > 0 && !(vc.flags & FG_CLASS_GHOST) &&
-        ((vc.flags & FG_CLASS_BOUNDARY) != 0) == (boundary != 0))
+        (boundary < 0 || ((vc.flags & FG_CLASS_BOUNDARY) != 0) == (boundary != 0)))
       order.push_back(vc);
   std::stable_sort(order.begin(), order.end(),
                    [](const fg_varclass_t &a, const fg_varclass_t &b) { return a.degree > b.degree; });
@@ -506,11 +506,14 @@ inline int maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varc
     if (!(vc.flags & FG_CLASS_GHOST) && vc.degree >= 1 && fg_fast_dom(vc.dom) &&
         std::find(doms.begin(), doms.end(), vc.dom) == doms.end())
       doms.push_back(vc.dom);
-  for (int boundary = 1; boundary >= 0; --boundary)   // boundary classes first: their rows can leave while the rest computes
+  // boundary classes first, in launches of their own: their rows can leave while the rest computes
+  // (PYDCOP_B200_PUSH_EARLY=0: one launch per domain size over all classes, as on a single GPU)
+  const bool split_b = !fg_env_is("PYDCOP_B200_PUSH_EARLY", '0');
+  for (int boundary = split_b ? 1 : -1; boundary >= (split_b ? 0 : -1); --boundary)
     for (int D : doms) {
       WTileRange rg;
       rg.dom = D;
-      rg.boundary = boundary;
+      rg.boundary = boundary > 0;
       rg.first = (int32_t)all.size();
       rg.n_tiles = v2fw_build_classes(vcs, D, elem, all, boundary);
       rg.count = (int32_t)all.size() - rg.first;
