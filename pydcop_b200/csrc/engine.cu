@@ -46,8 +46,10 @@ struct fg_maxsum {
                             // releases in its last block — no separate release / wait kernels (PYDCOP_B200_PUSH_CHAIN=0: off)
   bool chained_now = false; // the cycle being enqueued was closed inside phase 0
   cudaEvent_t ev_r = nullptr;
-  // early q push: the variable classes with a remote factor (FG_CLASS_BOUNDARY) are launched first and their rows leave on
-  // a third stream while the interior classes are still being computed (PYDCOP_B200_PUSH_EARLY=0: off)
+  // early q push (EXPERIMENT, PYDCOP_B200_PUSH_EARLY=1|2): the variable classes with a remote factor (FG_CLASS_BOUNDARY) are
+  // launched first and their rows leave while the interior classes are still being computed.  The device-timed cycle
+  // improves (88 -> 87 us at N = 2, more as the cut grows) but 300 back-to-back enqueued cycles collapse to 330-445 us per
+  // cycle (profiles/r02_call18_*, r02_call21_*): not understood yet, so off by default
   bool early_q = false;
   int early_mode = 1;   // 1: the q push follows the r push on the main stream; 2: on a third stream (PYDCOP_B200_PUSH_EARLY=2)
   cudaStream_t push_stream = nullptr;
@@ -427,7 +429,7 @@ extern "C" int fg_maxsum_shard_attach(fg_maxsum_t h, const fg_halo_plan_t *plan)
   if (h->chain_push && !h->ev_r) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_r, cudaEventDisableTiming));
   // every boundary class must be in one of the warp launches (they come first in the plan) for its rows to leave early
   bool early = h->chain_push && h->split_push && !h->fused_push && h->warp.v2f_on && plan->n_q > 0 &&
-               !fg_env_is("PYDCOP_B200_PUSH_EARLY", '0');
+               (fg_env_is("PYDCOP_B200_PUSH_EARLY", '1') || fg_env_is("PYDCOP_B200_PUSH_EARLY", '2'));   // opt-in, see DESIGN.md §6
   h->early_mode = fg_env_is("PYDCOP_B200_PUSH_EARLY", '2') ? 2 : 1;
   bool any_boundary = false;
   for (const fg_varclass_t &vc : h->varclasses) {

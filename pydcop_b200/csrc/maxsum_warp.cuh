@@ -506,9 +506,9 @@ inline int maxsum_warp_plan(const fg_maxsum_desc_t &d, const std::vector<fg_varc
     if (!(vc.flags & FG_CLASS_GHOST) && vc.degree >= 1 && fg_fast_dom(vc.dom) &&
         std::find(doms.begin(), doms.end(), vc.dom) == doms.end())
       doms.push_back(vc.dom);
-  // boundary classes first, in launches of their own: their rows can leave while the rest computes
-  // (PYDCOP_B200_PUSH_EARLY=0: one launch per domain size over all classes, as on a single GPU)
-  const bool split_b = !fg_env_is("PYDCOP_B200_PUSH_EARLY", '0');
+  // PYDCOP_B200_PUSH_EARLY=1|2 (experiment): boundary classes first, in launches of their own, so that their rows can leave
+  // while the rest computes; default: one launch per domain size over all classes, as on a single GPU
+  const bool split_b = fg_env_is("PYDCOP_B200_PUSH_EARLY", '1') || fg_env_is("PYDCOP_B200_PUSH_EARLY", '2');
   for (int boundary = split_b ? 1 : -1; boundary >= (split_b ? 0 : -1); --boundary)
     for (int D : doms) {
       WTileRange rg;

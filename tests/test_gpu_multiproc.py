@@ -64,7 +64,7 @@ def _maxsum_worker(rank, world, port, case, q):
         cost = sh.solution_cost(9.0, inst["unary"])     # table entries equal to 9 count as violations
         used = "p2p" if sh.peer is not None else "nccl"
         if sh.peer is not None and case.get("partition", "blocks") != "imbalanced":
-            # default: push kernels, the q rows of the boundary classes leaving early; PYDCOP_B200_PUSH_FUSED=1: the warp
+            # default: push kernels behind each side; PYDCOP_B200_PUSH_FUSED=1: the warp
             # kernels store the boundary rows themselves (all classes binary d=10, degrees <= 16)
             assert sh.peer.fused == case.get("fused", False), sh.peer.fused
         if rank == 0:
@@ -147,7 +147,8 @@ MAXSUM_CASES = {
     "p2p": dict(mode="p2p"),
     "p2p-steps-reinit": dict(mode="p2p", steps=[1, 3, "init", 2, 5, 4]),
     "p2p-fused": dict(mode="p2p", env={"PYDCOP_B200_PUSH_FUSED": "1"}, steps=[4, 5], fused=True),
-    "p2p-late-q-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_EARLY": "0"}, steps=[4, 5]),
+    "p2p-early-q-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_EARLY": "1"}, steps=[4, 5]),
+    "p2p-early-q-push-third-stream": dict(mode="p2p", env={"PYDCOP_B200_PUSH_EARLY": "2"}, steps=[4, 5]),
     "p2p-unchained": dict(mode="p2p", env={"PYDCOP_B200_PUSH_CHAIN": "0"}, steps=[4, 5]),
     "p2p-joined-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_SPLIT": "0"}, steps=[4, 5]),
     "p2p-per-row-push": dict(mode="p2p", env={"PYDCOP_B200_PUSH_RUNS": "0"}, steps=[4, 5]),
