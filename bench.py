@@ -562,7 +562,7 @@ def main():
     peaks, peak_kind = load_peaks()
     peak = float(peaks["hbm_gbs"])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_c2_f32.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic_c2_f32.json")   # the final round-2 kernels (k_f2v_warp + k_v2f_warp)
     if world == 1 and args.precision == "f32" and args.vars_per_gpu == 100_000 and os.path.exists(tpath):
         traffic = json.load(open(tpath))["per_step_bytes"]   # from the committed ncu --set full capture
     per_gpu_bytes = alg_bytes / max(1, world)
@@ -574,8 +574,9 @@ def main():
         "config": config, "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": ("constant from the committed ncu --set full capture named in profiles/ (dram__bytes_read + "
-                                        "dram__bytes_write of one launch of each kernel), not a measurement of this run"
+                     "traffic_source": ("constant from the committed ncu --set full capture profiles/r02_traffic_c2_f32.json "
+                                        "(dram__bytes_read + dram__bytes_write of one launch of each kernel of this build), "
+                                        "not a measurement of this run"
                                         if traffic is not None else None),
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                      "algorithmic_bytes_per_step": int(per_gpu_bytes),
