@@ -72,6 +72,10 @@ class GeneratedNames(Sequence):
     def __len__(self):
         return self.n
 
+    def __iter__(self):   # Sequence's default goes through __getitem__ (bounds / slice checks) once per item
+        p = self.prefix
+        return (f"{p}{k}" for k in range(self.n))
+
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [f"{self.prefix}{k}" for k in range(*i.indices(self.n))]
@@ -694,7 +698,7 @@ def from_arrays(inst: Dict[str, np.ndarray], name="dcop", objective="min") -> Dc
     if a.get("init_value") is None:
         a["init_value"] = np.full(len(dom), -1, dtype=np.int32)
     a["dom_size"], a["factor_ptr"], a["edge_var"] = dom, fp, ev
-    sizes = sorted(set(int(d) for d in dom))
+    sizes = [int(d) for d in np.unique(dom)]
     return DcopArrays(name=name, objective=objective, arrays={k: a[k] for k in ARRAY_KEYS},
                       var_names=GeneratedNames("v", len(dom)), con_names=GeneratedNames("c", len(fp) - 1),
                       domain_values={f"d{d}": list(range(d)) for d in sizes},

@@ -170,6 +170,8 @@ def _unique_rows(key):
     another, and two 1-D integer sorts replace the row sort, which dominates the packing of 10^6 factors."""
     key = np.asarray(key)
     n, m = key.shape
+    if n and (key == key[0]).all():     # one shape (the usual generated instance): nothing to sort
+        return key[:1].copy(), np.zeros(n, dtype=np.int64)
     if n == 0 or m != MAX_ARITY + 1 or key.min() < 0 or key[:, :MAX_ARITY].max() > MAX_DOM:
         u, inv = np.unique(key, axis=0, return_inverse=True)
         return u, inv.reshape(-1)
@@ -268,8 +270,8 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
         efac = np.repeat(np.arange(F, dtype=np.int64), arity)
         epos = np.arange(E, dtype=np.int64) - factor_ptr[:-1][efac]
         key[efac, epos] = edge_dom
-    tsize = (np.where(key[:, :MAX_ARITY] > 0, key[:, :MAX_ARITY], 1).astype(np.int64).prod(axis=1)
-             if F else np.zeros(0, np.int64))
+    # arity >= 1 everywhere (checked above): the table size is the product over each factor's run of edges
+    tsize = np.multiply.reduceat(edge_dom.astype(np.int64), factor_ptr[:-1]) if F else np.zeros(0, np.int64)
     if factor_tag is not None and F:
         key[:, MAX_ARITY] = _as(factor_tag, np.int32)
     if table_off is None:
@@ -380,6 +382,7 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     ukeys, ustart, ucount = (np.unique(vkey[var_order], return_index=True, return_counts=True)
                              if V else (np.zeros(0, np.int64),) * 3)
     unary_base = q_base = 0
+    unary_parts = []
     for k, st, n in zip(ukeys, ustart, ucount):
         st, n = int(st), int(n)
         D = int(i_dom[st])
@@ -389,6 +392,9 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
                       int(i_deg[st:st + n].sum()), tag=int(k // ((MAX_DOM + 1) * (MAX_CLASS_DEGREE + 2))))
         var_classes.append(vc)
         i_unary_off[st:st + n] = unary_base + np.arange(n, dtype=np.int64) * D
+        # the class's rows of own costs, gathered from the canonical array (rows of D contiguous elements)
+        src0 = c_unary_off[:-1][var_order[st:st + n]]
+        unary_parts.append((unary_base, c_unary[(src0[:, None] + np.arange(D, dtype=np.int64)[None, :]).reshape(-1)]))
         slots_before = (i_var_ptr[st:st + n].astype(np.int64) - int(i_var_ptr[st]))
         var_qbase[st:st + n] = q_base + slots_before * D
         unary_base += n * D
@@ -398,12 +404,8 @@ def build_layout(dom_size, factor_ptr, edge_var, tables, table_off=None, unary=N
     i_unary_off[V] = unary_base
     var_qbase[V] = q_base
     i_unary = np.zeros(int(unary_base))
-    if V:
-        dst = np.repeat(i_unary_off[:-1], i_dom) + (np.arange(int(i_dom.sum()), dtype=np.int64)
-                                                    - np.repeat(np.cumsum(i_dom) - i_dom, i_dom))
-        srcu = np.repeat(c_unary_off[:-1][var_order], i_dom) + (
-            np.arange(int(i_dom.sum()), dtype=np.int64) - np.repeat(np.cumsum(i_dom) - i_dom, i_dom))
-        i_unary[dst] = c_unary[srcu]
+    for base, part in unary_parts:
+        i_unary[base:base + len(part)] = part
     slot_qoff = (var_qbase[:-1][slot_var]
                  + (np.arange(E, dtype=np.int64) - i_var_ptr[:-1].astype(np.int64)[slot_var])
                  * i_dom.astype(np.int64)[slot_var]) if E else np.zeros(0, np.int64)
