@@ -25,6 +25,10 @@
 //
 //  k_f2v_warp<T,D,NS,MX>   factor -> variable, binary factors over one even domain size (see below).
 //
+// Both kernels have a PEER instantiation (multi-GPU, opt-in fused halo): the lane that finishes a
+// boundary row also stores it into the consuming rank's buffer (an IPC-mapped NVLink address per edge / per slot,
+// MaxSumParams::edge_dst / slot_dst); PEER = false compiles that code out.
+//
 // Results are bit-identical to the generic kernels, the round-1 pipelined kernels and the CPU oracle
 // of the same precision.
 #pragma once
