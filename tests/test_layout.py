@@ -119,3 +119,26 @@ def test_table_packing_takes_slices_for_contiguous_runs_and_gathers_otherwise():
             canon = int(np.nonzero(L.factor_perm == c.first_factor + i)[0][0])
             assert np.array_equal(L.tables[c.table_base + i * c.table_size:c.table_base + (i + 1) * c.table_size],
                                   tabs[canon]), (c.dom, i)
+
+
+def test_stable_group_order_equals_stable_argsort():
+    """the counting sort behind the packing (scipy's COO -> CSR kernel) == np.argsort(kind='stable') + group pointers,
+    and so does the fallback taken when scipy's private kernel is missing"""
+    from pydcop_b200 import layout as LY
+    rng = np.random.default_rng(3)
+    for n, g in ((0, 0), (1, 1), (17, 5), (5000, 37), (20000, 20000)):
+        keys = rng.integers(0, max(g, 1), n).astype(np.int32)
+        order, ptr = LY.stable_group_order(keys, g)
+        want = np.argsort(keys, kind="stable")
+        assert np.array_equal(order, want) and order.dtype == np.int32
+        assert np.array_equal(np.diff(ptr), np.bincount(keys, minlength=g)) and ptr[0] == 0
+    # fallback path
+    import scipy.sparse._sparsetools as st
+    saved = st.coo_tocsr
+    try:
+        st.coo_tocsr = None
+        keys = rng.integers(0, 9, 300).astype(np.int64)
+        order, ptr = LY.stable_group_order(keys, 9)
+        assert np.array_equal(order, np.argsort(keys, kind="stable")) and ptr[-1] == 300
+    finally:
+        st.coo_tocsr = saved
