@@ -174,7 +174,7 @@ def build_shard(inst: Dict[str, np.ndarray], rank: int, world: int, partition="b
     np.cumsum(np.concatenate([real_ar, np.ones(n_stub, np.int64)]), out=l_factor_ptr[1:])
     l_edge_var = np.concatenate([g2l_var[edge_var[own_f_edges]], g2l_var[edge_var[stub_edges]]])
     l_factor_tag = np.concatenate([np.zeros(n_real, np.int32), np.ones(n_stub, np.int32)])
-    real_tab = tables[_ranges(table_off[own_f], tsize[own_f])] if n_real else np.zeros(0)
+    real_tab = _gather_blocks(tables, table_off, tsize, own_f) if n_real else np.zeros(0)
     l_tables = np.concatenate([real_tab, np.zeros(int(dom_size[edge_var[stub_edges]].sum()))])
     # global edge id -> local (canonical) edge id
     g2l_edge = np.full(E, -1, dtype=np.int64)
@@ -251,6 +251,19 @@ def _ranges(starts, lengths):
         return np.zeros(0, dtype=np.int64)
     rep = np.repeat(starts - np.concatenate([[0], np.cumsum(lengths)[:-1]]), lengths)
     return rep + np.arange(total, dtype=np.int64)
+
+
+def _gather_blocks(flat, off, size, which):
+    """Concatenation of flat[off[i] : off[i] + size[i]] for i in `which`.  When every block has the same size and
+    the blocks tile `flat` (the usual case: one table shape) this is a row gather of a 2-D view — a memcpy per row
+    instead of one index per ELEMENT (20 M indices for the 200k tables a rank of C2 x 8 owns: 3 s of a solve)."""
+    which = np.asarray(which, dtype=np.int64)
+    n = len(size)
+    if n and len(which):
+        s0 = int(size[0])
+        if s0 > 0 and len(flat) == n * s0 and (size == s0).all() and int(off[0]) == 0 and int(off[n - 1]) == (n - 1) * s0:
+            return flat.reshape(n, s0)[which].reshape(-1)
+    return flat[_ranges(off[which], size[which])]
 
 
 class HaloExchange:
